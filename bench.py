@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd interval-graph propagation throughput on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload gowalla] [--impl ours|reference]
+
+A "step" is one forward + one backward of the propagation over all T interval graphs and L
+layers of the workload: 4*L*sum(E_k) edge traversals.  Own arm (default):
+  value      edge traversals/s with all inputs resident in HBM (CUDA events, L2 flushed between
+             steps, whole step replayed from one CUDA graph);
+  e2e        the same metric through the C-ABI host entry point (sagnn_propagate_host) with
+             pinned HOST buffers: H2D of embeddings + upstream grads and D2H of outputs + grads
+             inside the timed region;
+  roofline   per-launch algorithmic bytes / measured duration of the layer kernel;
+  cpu_baseline  the TF1-graph restatement (oracle/tf1_mirror.py, torch CPU, all host threads).
+Reference arm (--impl reference): times that CPU restatement only (the reference itself needs
+TensorFlow 1.14, which cannot be installed here).
+Multi-GPU (torchrun, one rank per GPU): weak scaling -- every rank owns one full set of T
+interval graphs (interval sharding: intervals share nothing), no data-path collective in the
+propagation itself; the per-rank outputs are all-gathered over NCCL (north_star) on a side
+stream, overlapped with the backward, unless --no-allgather.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gowalla")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--layers", type=int, default=None)
+    ap.add_argument("--latdim", type=int, default=None)
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of a CUDA graph")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-allgather", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=100)
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def alg_bytes(nnz, U, I, d, L):
+    """algorithmic (compulsory, perfect-cache) bytes."""
+    n = U + I
+    fwd_layer = sum(8 * e + 4 * (n + 2) + 20 * d * n for e in nnz)
+    bwd_layer = sum(8 * e + 4 * (n + 2) + 16.125 * d * n for e in nnz)
+    return fwd_layer, bwd_layer, L * (fwd_layer + bwd_layer)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(args, rank):
+    from sagnn_b200 import data_handler as dh
+    shape = dict(dh.SHAPES[args.workload])
+    L = args.layers or shape["L"]
+    d = args.latdim or shape["d"]
+    g = dh.make_named(args.workload, seed=args.seed + 1000 * rank, scale=args.scale)
+    return g, L, d
+
+
+def cpu_reference_run(g, L, d, steps, warmup, seed):
+    """The TF1-graph restatement on the host cores; returns (seconds per step, threads)."""
+    import torch
+    from oracle import propagate_oracle as po, tf1_mirror
+    from sagnn_b200 import data_handler as dh
+    T, U, I = g.graph_num, g.n_user, g.n_item
+    adj = [torch.from_numpy(po.trans_to_lsts(m)[0].astype(np.int64)) for m in g.sub_mat]
+    tp = [torch.from_numpy(po.trans_to_lsts(po.transpose(m))[0].astype(np.int64)) for m in g.sub_mat]
+    uE = torch.from_numpy(dh.xavier_embeddings(T, U, d, seed))
+    iE = torch.from_numpy(dh.xavier_embeddings(T, I, d, seed + 1))
+    gen = torch.Generator().manual_seed(seed)
+    gU = torch.randn((T, U, d), generator=gen)
+    gI = torch.randn((T, I, d), generator=gen)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        tf1_mirror.propagate(adj, tp, uE, iE, gU, gI, L, 0.5)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    return float(np.mean(times)), int(torch.get_num_threads())
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        g, L, d = make_workload(args, 0)
+        edges = sum(g.nnz)
+        trav = 4 * L * edges
+        sec, threads = cpu_reference_run(g, L, d, args.steps, max(1, args.warmup), args.seed)
+        val = trav / sec
+        line = {
+            "impl": "reference", "metric": "fwd+bwd interval-graph SpMM edge traversals/s",
+            "value": val, "unit": "edge_traversals/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, g, L, d, world=1),
+            "cpu_baseline": {"value": val, "unit": "edge_traversals/s", "cores": threads, "kind": "port",
+                             "sample": "full %s workload, %d timed fwd+bwd steps of oracle/tf1_mirror.py "
+                                       "(torch-CPU op-by-op restatement of the TF1 graph; TF 1.14 itself is "
+                                       "not installable)" % (args.workload, args.steps)},
+            "e2e": {"value": val, "unit": "edge_traversals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ own arm
+    import torch
+    import sagnn_b200 as sg
+    from sagnn_b200 import data_handler as dh
+    from sagnn_b200.step import PropagationStep
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "bench.py needs a CUDA device; sagnn_b200 has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    g, L, d = make_workload(args, rank)
+    T, U, I = g.graph_num, g.n_user, g.n_item
+    edges = sum(g.nnz)
+    trav = 4 * L * edges
+
+    t0 = time.perf_counter()
+    plan = sg.build_plan(g.sub_mat, device=dev)
+    torch.cuda.synchronize()
+    plan_ms = (time.perf_counter() - t0) * 1e3
+
+    step = PropagationStep(plan, L, d, 0.5)
+    step.u_embed.copy_(torch.from_numpy(dh.xavier_embeddings(T, U, d, args.seed)))
+    step.i_embed.copy_(torch.from_numpy(dh.xavier_embeddings(T, I, d, args.seed + 1)))
+    gen = torch.Generator(device=dev).manual_seed(args.seed + rank)
+    step.g_user.normal_(generator=gen)
+    step.g_item.normal_(generator=gen)
+
+    do_gather = world > 1 and not args.no_allgather
+    if do_gather:
+        gat_u = torch.empty((world,) + tuple(step.user_out.shape), dtype=torch.float32, device=dev)
+        gat_i = torch.empty((world,) + tuple(step.item_out.shape), dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream()
+
+    use_graph = not args.no_graph and not do_gather
+    if use_graph:
+        step.capture()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def one_step():
+        if do_gather:
+            step.forward()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                           # overlaps the backward
+                dist.all_gather_into_tensor(gat_u, step.user_out)
+                dist.all_gather_into_tensor(gat_i, step.item_out)
+            step.backward()
+            torch.cuda.current_stream().wait_stream(side)
+        else:
+            step.replay()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        one_step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
+        ev[s][0].record()
+        one_step()
+        ev[s][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    per_step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(per_step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        e_all = torch.tensor([float(edges)], device=dev, dtype=torch.float64)
+        dist.all_reduce(e_all, op=dist.ReduceOp.SUM)
+        edges_all = float(e_all.item())
+    else:
+        edges_all = float(edges)
+    ms_per_step = total_ms / args.steps
+    value = 4 * L * edges_all / (ms_per_step * 1e-3)
+
+    # ---- per-kernel durations for the roofline (direct launches, events on the launch stream)
+    fwd_ms, bwd_ms = [], []
+    for _ in range(max(5, min(args.steps, 20))):
+        flush.zero_()
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record(); step.forward(); b.record(); step.backward(); c.record()
+        torch.cuda.synchronize()
+        fwd_ms.append(a.elapsed_time(b)); bwd_ms.append(b.elapsed_time(c))
+    fwd_ms, bwd_ms = float(np.mean(fwd_ms)), float(np.mean(bwd_ms))
+    peak, peak_src = load_peaks()
+    b_fwd_layer, b_bwd_layer, b_step = alg_bytes(g.nnz, U, I, d, L)
+    dom_is_fwd = fwd_ms >= bwd_ms
+    dom_ms = (fwd_ms if dom_is_fwd else bwd_ms) / L
+    dom_bytes = b_fwd_layer if dom_is_fwd else b_bwd_layer
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")    # dram bytes per launch from an ncu --set full capture
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload, {}).get("fwd" if dom_is_fwd else "bwd")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "peak_source": peak_src,
+        "kernel": "spmm_layer_kernel<%s> (one GNN layer, all T intervals, both orientations)"
+                  % ("FWD" if dom_is_fwd else "BWD"),
+        "alg_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
+        "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+        "step": {"alg_bytes": b_step, "achieved": b_step / (ms_per_step * 1e-3) / 1e9,
+                 "frac": b_step / (ms_per_step * 1e-3) / 1e9 / peak,
+                 "frac_of_nominal_8TBs": b_step / (ms_per_step * 1e-3) / 1e9 / 8000.0},
+    }
+
+    # ---- end to end through the C-ABI host entry point (pinned host buffers)
+    e2e = None
+    if not args.no_e2e:
+        host = {}
+        for name, src in (("uE", step.u_embed), ("iE", step.i_embed), ("gU", step.g_user), ("gI", step.g_item)):
+            host[name] = src.cpu().pin_memory()
+        for name, like in (("uO", step.user_out), ("iO", step.item_out), ("dU", step.d_u), ("dI", step.d_i)):
+            host[name] = torch.empty(like.shape, dtype=torch.float32).pin_memory()
+        h2d = sum(host[k].numel() * 4 for k in ("uE", "iE", "gU", "gI"))
+        d2h = sum(host[k].numel() * 4 for k in ("uO", "iO", "dU", "dI"))
+
+        def host_step():
+            sg.propagate_host(plan, host["uE"], host["iE"], host["gU"], host["gI"], host["uO"], host["iO"],
+                              host["dU"], host["dI"], L, 0.5)
+        for _ in range(3):
+            host_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            host_step()                    # synchronous: returns when the results are in host memory
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.steps
+        if world > 1:
+            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        chk = float(host["uO"][0, 0, 0])   # the device->host result is really there
+        e2e = {"value": 4 * L * edges_all / e2e_s, "unit": "edge_traversals/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "probe": chk,
+               "api": "sagnn_propagate_host (C ABI, pinned host buffers)"}
+
+    # ---- CPU baseline next to it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, threads = cpu_reference_run(g, L, d, args.cpu_steps, 1, args.seed)
+        cpu = {"value": trav / sec, "unit": "edge_traversals/s", "cores": threads, "kind": "port",
+               "ms_per_step": sec * 1e3,
+               "sample": "full %s workload, %d timed fwd+bwd steps of oracle/tf1_mirror.py (torch-CPU "
+                         "op-by-op restatement of the TF1 graph)" % (args.workload, args.cpu_steps)}
+        try:
+            from oracle import c_oracle, propagate_oracle as po
+            adj = [po.trans_to_lsts(m)[0] for m in g.sub_mat]
+            tpl = [po.trans_to_lsts(po.transpose(m))[0] for m in g.sub_mat]
+            arrs = [step.u_embed.cpu().numpy(), step.i_embed.cpu().numpy(), step.g_user.cpu().numpy(),
+                    step.g_item.cpu().numpy()]
+            c_oracle.propagate(adj, tpl, *arrs, L, 0.5, np.float32)
+            t0 = time.perf_counter()
+            c_oracle.propagate(adj, tpl, *arrs, L, 0.5, np.float32)
+            cs = time.perf_counter() - t0
+            cpu["fused_c_port"] = {"value": trav / cs, "cores": c_oracle.num_threads(),
+                                   "note": "oracle/csrc/sagnn_oracle.c (fused OpenMP fp32, incl. CSR build)"}
+        except Exception as e:   # the C port is optional colour, never fatal
+            cpu["fused_c_port"] = {"error": str(e)}
+
+    if rank == 0:
+        line = {
+            "metric": "fwd+bwd interval-graph SpMM edge traversals/s", "value": value,
+            "unit": "edge_traversals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, g, L, d, world, plan.stats(), use_graph, do_gather),
+            "graph_edges_per_s": edges_all / (ms_per_step * 1e-3),
+            "plan_build_ms": plan_ms, "wall_s_timed_region": wall,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": step.kernel_launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def workload_config(args, g, L, d, world, stats=None, use_graph=None, gather=None):
+    cfg = {
+        "workload": "%s-shaped synthetic power-law interval graphs (SURVEY app. D)" % args.workload,
+        "T": g.graph_num, "U": g.n_user, "I": g.n_item, "interval_edges": g.nnz, "edges": sum(g.nnz),
+        "layers": L, "latdim": d, "leaky": 0.5, "scale": args.scale, "seed": args.seed,
+        "edge_traversals_per_step": 4 * L * sum(g.nnz),
+        "per_gpu": "every rank owns one full set of T interval graphs (interval sharding, weak scaling)"
+                   if world > 1 else "single GPU",
+        "l2": "256 MB buffer written between timed steps (L2 flush), outside the event pairs",
+    }
+    if stats is not None:
+        cfg["schedule"] = stats
+    if use_graph is not None:
+        cfg["cuda_graph"] = bool(use_graph)
+    if gather is not None:
+        cfg["allgather_outputs"] = bool(gather)
+    return cfg
+
+
+if __name__ == "__main__":
+    sys.exit(main())

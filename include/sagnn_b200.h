@@ -1,0 +1,149 @@
+/*
+ * sagnn_b200 -- C ABI of the B200-native SelfGNN interval-graph propagation.
+ *
+ * Drop-in boundary for ONE path of LIU-YUXI/SA-GNN (paths below are in that repo):
+ * the per-time-interval user<->item propagation of model.py:118-134 (forward) and
+ * its TF1-autodiff backward (model.py:250), fed by the adjacency lists of
+ * DataHandler.transToLsts / transpose (DataHandler.py:9-11,47-69; call sites
+ * model.py:227-237).  The reference has no FFI of its own (pure Python on TF 1.14);
+ * these entry points are what a binding for that path would call -- see
+ * INTEGRATION.md for the ctypes stub and the model.py patch.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no torch / C++ types.
+ *   - every function returns a sagnn_status (0 = OK); sagnn_last_error() returns a
+ *     thread-local message for the last non-zero status.  Nothing throws.
+ *   - "_dev" pointers are device memory on the plan's device, "_host" host memory.
+ *   - the caller owns every tensor and the workspace; the library owns the plan.
+ *   - propagate_* enqueue work on the given stream and never synchronise or
+ *     allocate, so they can be captured into a CUDA graph.
+ *   - embeddings are fp32, row-major, contiguous: user tables [T, U, d], item
+ *     tables [T, I, d]; d in {32, 64, 128, 256}.
+ *   - there is no CPU fallback: every compute entry point needs a CUDA device.
+ */
+#ifndef SAGNN_B200_H_
+#define SAGNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sagnn_plan sagnn_plan;
+typedef void* sagnn_stream_t; /* a cudaStream_t (NULL = legacy default stream) */
+
+typedef enum sagnn_status {
+  SAGNN_OK = 0,
+  SAGNN_INVALID_ARG = 1,
+  SAGNN_UNSORTED_INPUT = 2,      /* segment ids not non-decreasing (TF SegmentSum rejects these too) */
+  SAGNN_CUDA_ERROR = 3,
+  SAGNN_WORKSPACE_TOO_SMALL = 4,
+  SAGNN_NOT_FINALIZED = 5,
+  SAGNN_OUT_OF_RANGE = 6         /* an edge id outside [0,U) x [0,I) */
+} sagnn_status;
+
+/* side of an interval graph: the A_k CSR (rows = users, model.py:122 'user' call) or
+ * the A_k^T CSR (rows = items, model.py:123 'item' call). */
+enum { SAGNN_SIDE_USER = 0, SAGNN_SIDE_ITEM = 1 };
+
+/* edge-weight modes for sagnn_plan_finalize */
+enum {
+  SAGNN_WEIGHTS_NONE = 0,     /* reference-exact: binary structure, stored values ignored (model.py:84-86) */
+  SAGNN_WEIGHTS_LIGHTGCN = 1, /* w = rowD*colD, D = 1/(sqrt(deg+1e-8)+1e-8) on structural degrees
+                                 (the formula of DataHandler.py:54-55, which the reference then truncates away) */
+  SAGNN_WEIGHTS_CUSTOM = 2    /* per-edge fp32 weights passed to sagnn_plan_set_interval */
+};
+
+const char* sagnn_last_error(void);
+const char* sagnn_version(void);
+
+/* ---- plan: device-side CSR (A_k) + CSC (= CSR of A_k^T) for T interval graphs ----------
+ * Replaces the 2T transToLsts() calls + tf.sparse.SparseTensor wrapping of
+ * model.py:227-237 and the transpose() of DataHandler.py:9-11. */
+
+/* nnz_host[T]: edge count of every interval (an empty interval must be passed as the
+ * reference's single fallback edge (0,0), DataHandler.py:66-68 -- the Python shim does). */
+int sagnn_plan_create(int T, int U, int I, const int64_t* nnz_host, sagnn_plan** out);
+
+/* Adjacency list of interval k in the order transToLsts emits it (row-major COO of the
+ * canonical CSR): row_dev/col_dev int32 [nnz] (user id, item id).  val_dev (nullable)
+ * are the stored int32 values (timestamps) -- only used for the value-sum degrees and
+ * sagnn_plan_norm_data.  w_dev (nullable) are custom fp32 edge weights (same order).
+ * Builds the A_k CSR, the stable transposed CSR and structural degrees on the device.
+ * Returns SAGNN_UNSORTED_INPUT if rows are not non-decreasing. Synchronises the stream. */
+int sagnn_plan_set_interval(sagnn_plan* plan, int k, const int32_t* row_dev, const int32_t* col_dev,
+                            const int32_t* val_dev, const float* w_dev, int64_t nnz,
+                            sagnn_stream_t stream);
+
+/* Row pointers over all intervals, optional edge weights, degree-binned schedule.
+ * Must be called once after every interval has been set. */
+int sagnn_plan_finalize(sagnn_plan* plan, int weight_mode, sagnn_stream_t stream);
+
+/* Parity hooks (bit-exact against transToLsts / transpose):
+ * indptr_dev int32 [R+1], indices_dev int32 [nnz_k] of the CSR of side `side`. */
+int sagnn_plan_get_csr(const sagnn_plan* plan, int k, int side, int32_t* indptr_dev,
+                       int32_t* indices_dev, sagnn_stream_t stream);
+/* deg_dev int32 [R] structural degrees; valsum_dev (nullable) int64 [R] sums of stored
+ * values (np.sum(mat, axis=...) of DataHandler.py:54-55; needs val_dev at set_interval). */
+int sagnn_plan_get_degrees(const sagnn_plan* plan, int k, int side, int32_t* deg_dev,
+                           int64_t* valsum_dev, sagnn_stream_t stream);
+/* data_dev int32 [nnz_k]: the reference's "normalised" values, i.e.
+ * (int32)((double)val * rowD[row] * colD[col]) of DataHandler.py:56-59 (all zeros on
+ * real data).  Needs val_dev at set_interval. */
+int sagnn_plan_norm_data(const sagnn_plan* plan, int k, int side, int32_t* data_dev,
+                         sagnn_stream_t stream);
+/* w_dev fp32 [nnz_k]: the edge weights in use for side `side` (CSR order). */
+int sagnn_plan_get_weights(const sagnn_plan* plan, int k, int side, float* w_dev,
+                           sagnn_stream_t stream);
+
+/* schedule statistics: out[0]=rows, out[1]=short rows, out[2]=long rows, out[3]=chunks,
+ * out[4]=max degree, out[5]=sum of edges over both sides, out[6]=grid blocks, out[7]=SMs */
+int sagnn_plan_stats(const sagnn_plan* plan, int64_t* out8);
+
+int sagnn_plan_destroy(sagnn_plan* plan);
+
+/* ---- propagation ------------------------------------------------------------------------
+ * Replaces the T x L x 2 messagePropagate() calls, residual adds and add_n of
+ * model.py:118-129 (forward) and their autodiff (backward). */
+
+/* Bytes of: forward scratch, saved activation-sign masks (forward output consumed by
+ * backward), backward scratch. */
+int sagnn_workspace_bytes(const sagnn_plan* plan, int n_layers, int d, size_t* fwd_bytes,
+                          size_t* mask_bytes, size_t* bwd_bytes);
+
+/* user_out[T,U,d], item_out[T,I,d] = sum_l E^l with E0^{l+1} = E0^l + lrelu(A E1^l),
+ * E1^{l+1} = E1^l + lrelu(A^T E0^l), lrelu(x) = max(leaky*x, x).
+ * masks_dev (mask_bytes, nullable when no backward will follow) receives the sign bits. */
+int sagnn_propagate_fwd(const sagnn_plan* plan, const float* u_embed_dev, const float* i_embed_dev,
+                        float* user_out_dev, float* item_out_dev, int n_layers, int d, float leaky,
+                        void* masks_dev, void* workspace_dev, size_t workspace_bytes,
+                        sagnn_stream_t stream);
+
+/* d_u_embed[T,U,d], d_i_embed[T,I,d] from dense upstream grads g_user[T,U,d], g_item[T,I,d]
+ * and the masks written by the matching forward. */
+int sagnn_propagate_bwd(const sagnn_plan* plan, const float* g_user_dev, const float* g_item_dev,
+                        float* d_u_embed_dev, float* d_i_embed_dev, int n_layers, int d, float leaky,
+                        const void* masks_dev, void* workspace_dev, size_t workspace_bytes,
+                        sagnn_stream_t stream);
+
+/* One messagePropagate() call (model.py:80-92): out[R,d] = lrelu(B_k,side * src[C,d]).
+ * workspace: forward scratch size. */
+int sagnn_message_propagate(const sagnn_plan* plan, int k, int side, const float* src_dev,
+                            float* out_dev, int d, float leaky, void* workspace_dev,
+                            size_t workspace_bytes, sagnn_stream_t stream);
+
+/* Host-buffer entry point (what a non-torch caller binds): copies the embeddings (and,
+ * when g_*_host != NULL, the upstream gradients) to the device, runs forward (+ backward),
+ * copies the results back and synchronises.  Device buffers are cached inside the plan.
+ * Pass pinned host memory for full PCIe bandwidth. */
+int sagnn_propagate_host(sagnn_plan* plan, const float* u_embed_host, const float* i_embed_host,
+                         const float* g_user_host, const float* g_item_host, float* user_out_host,
+                         float* item_out_host, float* d_u_embed_host, float* d_i_embed_host,
+                         int n_layers, int d, float leaky);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAGNN_B200_H_ */

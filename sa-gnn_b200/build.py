@@ -1,0 +1,46 @@
+"""Builds lib/libsagnn_b200.so (hand-written CUDA for sm_100a + the C ABI) in-tree with nvcc."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SOURCES = ["csrc/plan.cu", "csrc/spmm.cu"]
+HEADERS = ["csrc/common.cuh", "../include/sagnn_b200.h"]
+LIB = os.path.join(HERE, "lib", "libsagnn_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-Wno-deprecated-declarations",
+]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    cmd = [nvcc] + NVCC_FLAGS + ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "csrc")]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [os.path.join(HERE, s) for s in SOURCES] + ["-o", LIB]
+    env = dict(os.environ)
+    env.pop("CC", None)   # the image's CC points at a gcc wrapper without its spec files
+    env.pop("CXX", None)
+    subprocess.check_call(cmd, env=env)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,546 @@
+// Fused interval-graph propagation kernels (sm_100a) and their C-ABI drivers.
+//
+// One launch = one GNN layer over ALL T intervals and BOTH orientations
+// (LIU-YUXI/SA-GNN model.py:118-125: the 2T messagePropagate calls of one layer,
+// model.py:80-92, plus the residual add and the layer sum of model.py:124-127).
+// The backward is the same gather run on the same two CSRs with the sign-masked
+// upstream as the source -- no scatter, no float atomics, deterministic.
+//
+// Work decomposition: a "group" of LPR = d/4 lanes owns one task; each lane keeps a
+// float4 (128-bit loads) of the row.  A task is either a whole short row (deg <= 64)
+// or one <=64-edge chunk of a long row; chunk partial sums go through a workspace and
+// the group that finishes a row last (integer ticket) reduces them in fixed chunk
+// order, so results do not depend on scheduling.  Tasks are ordered longest-first and
+// dealt round-robin over a grid sized to the SM count x occupancy.
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace sagnn {
+
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_MSG = 2 };
+
+struct SpmmParams {
+  const int64_t* rowptr;
+  const int32_t* idx;
+  const float* w;
+  const uint32_t* order;
+  const uint32_t* long_row;
+  const int64_t* chunk_base;
+  const uint32_t* chunk_lr;
+  int64_t n_short, n_chunks;
+  int U, I;
+  uint32_t N;
+  uint32_t row_lo, row_hi;   // only global rows in [row_lo, row_hi) are processed
+  // gather sources: user rows read item-table rows (src_i), item rows read user-table rows (src_u)
+  const float* src_u;
+  const float* src_i;
+  const uint32_t* smask_u;   // BWD: sign masks of the source rows
+  const uint32_t* smask_i;
+  const float* a_u;          // FWD: E^l (residual)          BWD: G (dense upstream)
+  const float* a_i;
+  const float* b_u;          // FWD: sum_{j<l} E^j or NULL   BWD: running gradient g or NULL (== G)
+  const float* b_i;
+  float* o1_u;               // FWD: E^{l+1} or NULL         BWD / MSG: destination
+  float* o1_i;
+  float* o2_u;               // FWD: layer-sum output or NULL
+  float* o2_i;
+  uint32_t* mask_u;          // FWD: sign masks out or NULL
+  uint32_t* mask_i;
+  float* partials;           // [n_chunks, d]
+  uint32_t* tickets;         // [n_long], zero on entry, zero again on exit
+  float leaky;
+  int out_add_next;          // FWD: o2 = b + a (+ E^{l+1} when set)
+};
+
+__device__ __forceinline__ float4 ld_nc(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ float4 ld_stream(const float* p) {
+  return __ldcs(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ float4 ld_cg(const float* p) {
+  return __ldcg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st_stream(float* p, float4 v) {
+  __stcs(reinterpret_cast<float4*>(p), v);
+}
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+template <int LPR, int V, int MODE, bool WEIGHTED>
+__global__ void __launch_bounds__(kThreads)
+spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
+  constexpr int D = LPR * V * 4;
+  constexpr int WPR = D / 32;          // mask words per row
+  constexpr int UNR = 8;               // independent 128-bit gathers in flight per lane
+  static_assert(LPR % UNR == 0, "unroll must divide the group width");
+
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (lane - gl));
+  const int64_t n_groups = (int64_t)gridDim.x * (kThreads / LPR);
+  const int64_t n_tasks = p.n_chunks + p.n_short;
+
+  for (int64_t t = (int64_t)blockIdx.x * (kThreads / LPR) + threadIdx.x / LPR; t < n_tasks; t += n_groups) {
+    uint32_t grow;
+    int64_t e0, e1;
+    uint32_t lr = 0;
+    int64_t cb = 0;
+    int nch = 1;
+    if (t < p.n_chunks) {
+      lr = __ldg(p.chunk_lr + t);
+      grow = __ldg(p.long_row + lr);
+      cb = __ldg(p.chunk_base + lr);
+      nch = (int)(__ldg(p.chunk_base + lr + 1) - cb);
+      const int64_t rs = __ldg(p.rowptr + grow);
+      const int64_t deg = __ldg(p.rowptr + grow + 1) - rs;
+      const int64_t ci = t - cb;
+      e0 = rs + deg * ci / nch;
+      e1 = rs + deg * (ci + 1) / nch;
+    } else {
+      grow = __ldg(p.order + (t - p.n_chunks));
+      e0 = __ldg(p.rowptr + grow);
+      e1 = __ldg(p.rowptr + grow + 1);
+    }
+    if (grow < p.row_lo || grow >= p.row_hi) continue;
+    const uint32_t k = grow / p.N;
+    const uint32_t rem = grow - k * p.N;
+    const bool item_side = rem >= (uint32_t)p.U;
+    const uint32_t r = item_side ? rem - p.U : rem;
+    // this row's own table geometry and the geometry of the table it gathers from
+    const int64_t own_row = (int64_t)k * (item_side ? p.I : p.U) + r;
+    const int64_t src_row0 = (int64_t)k * (item_side ? p.U : p.I);
+    const float* __restrict__ src = (item_side ? p.src_u : p.src_i) + src_row0 * D;
+    const uint32_t* __restrict__ smask =
+        (MODE == MODE_BWD) ? (item_side ? p.smask_u : p.smask_i) + src_row0 * WPR : nullptr;
+
+    float4 acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // ---- gather-reduce over this task's edges -----------------------------------------
+    for (int64_t e = e0; e < e1; e += LPR) {
+      const int n = (int)((e1 - e) < (int64_t)LPR ? (e1 - e) : (int64_t)LPR);
+      int myc = 0;
+      float myw = 0.f;
+      if (gl < n) {
+        myc = __ldg(p.idx + e + gl);
+        if (WEIGHTED) myw = __ldg(p.w + e + gl);
+      }
+      for (int j = 0; j < n; j += UNR) {
+        float4 val[UNR][V];
+        uint32_t mw[UNR][V];
+        float wv[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int c = __shfl_sync(gmask, myc, j + u, LPR);
+          if (WEIGHTED) wv[u] = __shfl_sync(gmask, myw, j + u, LPR);
+          const bool on = (j + u) < n;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            mw[u][v] = 0xffffffffu;
+            if (on) {
+              val[u][v] = ld_nc(src + (int64_t)c * D + (v * LPR + gl) * 4);
+              if (MODE == MODE_BWD) mw[u][v] = __ldg(smask + (int64_t)c * WPR + ((v * LPR + gl) >> 3));
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            float4 x = val[u][v];
+            if (MODE == MODE_BWD) {   // source = sigma'(Z) (.) g : pass where Z > 0, else leaky
+              const uint32_t b = mw[u][v] >> ((gl & 7) * 4);
+              x.x = (b & 1u) ? x.x : p.leaky * x.x;
+              x.y = (b & 2u) ? x.y : p.leaky * x.y;
+              x.z = (b & 4u) ? x.z : p.leaky * x.z;
+              x.w = (b & 8u) ? x.w : p.leaky * x.w;
+            }
+            if (WEIGHTED) {
+              acc[v].x = fmaf(wv[u], x.x, acc[v].x);
+              acc[v].y = fmaf(wv[u], x.y, acc[v].y);
+              acc[v].z = fmaf(wv[u], x.z, acc[v].z);
+              acc[v].w = fmaf(wv[u], x.w, acc[v].w);
+            } else {
+              acc[v] = f4_add(acc[v], x);
+            }
+          }
+        }
+      }
+    }
+
+    // ---- long rows: publish the partial sum; the last chunk to arrive reduces ----------
+    if (nch > 1) {
+      float* mine = p.partials + t * D;
+#pragma unroll
+      for (int v = 0; v < V; ++v) st_f4(mine + (v * LPR + gl) * 4, acc[v]);
+      __threadfence();
+      __syncwarp(gmask);
+      unsigned old = 0;
+      if (gl == 0) old = atomicAdd(p.tickets + lr, 1u);
+      old = __shfl_sync(gmask, old, 0, LPR);
+      if (old != (unsigned)(nch - 1)) continue;
+      __threadfence();
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* part = p.partials + cb * D;
+      for (int c0 = 0; c0 < nch; c0 += UNR) {
+        float4 val[UNR][V];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            val[u][v] = (c0 + u < nch) ? ld_cg(part + (int64_t)(c0 + u) * D + (v * LPR + gl) * 4)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = f4_add(acc[v], val[u][v]);
+      }
+      if (gl == 0) p.tickets[lr] = 0u;   // ready for the next launch
+    }
+
+    // ---- fused epilogue -----------------------------------------------------------------
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int col = (v * LPR + gl) * 4;
+      const int64_t off = own_row * D + col;
+      if (MODE == MODE_BWD) {
+        // n = G + g + A (sigma' . g_other)      
+        const float* G = item_side ? p.a_i : p.a_u;
+        const float* g = item_side ? p.b_i : p.b_u;
+        float* dst = item_side ? p.o1_i : p.o1_u;
+        const float4 Gv = ld_nc(G + off);
+        const float4 gv = g ? ld_stream(g + off) : Gv;
+        st_f4(dst + off, f4_add(f4_add(Gv, gv), acc[v]));
+      } else {
+        const float4 z = acc[v];
+        const float lzx = p.leaky * z.x, lzy = p.leaky * z.y, lzz = p.leaky * z.z, lzw = p.leaky * z.w;
+        // LeakyReLU = max(leaky*z, z)  (Utils/NNLayers.py:135-136)
+        const float4 act = make_float4(fmaxf(lzx, z.x), fmaxf(lzy, z.y), fmaxf(lzz, z.z), fmaxf(lzw, z.w));
+        if (MODE == MODE_MSG) {
+          st_f4((item_side ? p.o1_i : p.o1_u) + off, act);
+        } else {
+          const float* a = item_side ? p.a_i : p.a_u;
+          const float* b = item_side ? p.b_i : p.b_u;
+          float* o1 = item_side ? p.o1_i : p.o1_u;
+          float* o2 = item_side ? p.o2_i : p.o2_u;
+          uint32_t* mk = item_side ? p.mask_i : p.mask_u;
+          const float4 cur = ld_nc(a + off);
+          const float4 nxt = f4_add(cur, act);                 // E^{l+1} = E^l + lrelu(Z^l)
+          if (o1) st_f4(o1 + off, nxt);
+          if (o2) {
+            float4 o = cur;
+            if (b) o = f4_add(ld_stream(b + off), cur);
+            if (p.out_add_next) o = f4_add(o, nxt);
+            st_stream(o2 + off, o);
+          }
+          if (mk) {
+            // TF MaximumGrad sends the gradient to leaky*z where leaky*z >= z: bit = pass-through
+            uint32_t nib = (!(lzx >= z.x) ? 1u : 0u) | (!(lzy >= z.y) ? 2u : 0u) |
+                           (!(lzz >= z.z) ? 4u : 0u) | (!(lzw >= z.w) ? 8u : 0u);
+            const uint32_t word = __reduce_or_sync(0xffu << (lane & ~7), nib << ((gl & 7) * 4));
+            if ((gl & 7) == 0) mk[own_row * WPR + ((v * LPR + gl) >> 3)] = word;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------
+template <int LPR, int V, int MODE, bool WEIGHTED>
+static int launch_t(const sagnn_plan* plan, const SpmmParams& prm, cudaStream_t st) {
+  static int blocks_per_sm = 0;   // same for every device of the same type
+  auto kern = spmm_layer_kernel<LPR, V, MODE, WEIGHTED>;
+  if (blocks_per_sm == 0) {
+    int b = 0;
+    SAGNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kThreads, 0));
+    blocks_per_sm = b > 0 ? b : 1;
+  }
+  const int64_t n_tasks = prm.n_chunks + prm.n_short;
+  if (n_tasks == 0) return SAGNN_OK;
+  const int64_t groups_per_block = kThreads / LPR;
+  int64_t want = (n_tasks + groups_per_block - 1) / groups_per_block;
+  int64_t cap = (int64_t)plan->num_sms * blocks_per_sm;
+  unsigned grid = (unsigned)(want < cap ? want : cap);
+  kern<<<grid, kThreads, 0, st>>>(prm);
+  SAGNN_CUDA(cudaGetLastError());
+  return SAGNN_OK;
+}
+
+template <int MODE>
+static int launch_mode(const sagnn_plan* plan, const SpmmParams& prm, int d, cudaStream_t st) {
+  const bool wt = prm.w != nullptr;
+  switch (d) {
+    case 32:  return wt ? launch_t<8, 1, MODE, true>(plan, prm, st)  : launch_t<8, 1, MODE, false>(plan, prm, st);
+    case 64:  return wt ? launch_t<16, 1, MODE, true>(plan, prm, st) : launch_t<16, 1, MODE, false>(plan, prm, st);
+    case 128: return wt ? launch_t<32, 1, MODE, true>(plan, prm, st) : launch_t<32, 1, MODE, false>(plan, prm, st);
+    case 256: return wt ? launch_t<32, 2, MODE, true>(plan, prm, st) : launch_t<32, 2, MODE, false>(plan, prm, st);
+  }
+  set_error("latdim d=%d unsupported (need 32, 64, 128 or 256)", d);
+  return SAGNN_INVALID_ARG;
+}
+
+static int launch(const sagnn_plan* plan, const SpmmParams& prm, int d, int mode, cudaStream_t st) {
+  switch (mode) {
+    case MODE_FWD: return launch_mode<MODE_FWD>(plan, prm, d, st);
+    case MODE_BWD: return launch_mode<MODE_BWD>(plan, prm, d, st);
+    default:       return launch_mode<MODE_MSG>(plan, prm, d, st);
+  }
+}
+
+static bool d_ok(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
+
+// workspace layout: [tickets | partials | table buffer 0 | table buffer 1]
+struct WsLayout {
+  size_t tickets_off, partials_off, buf_off[2], total;
+  size_t table_floats;   // T*(U+I)*d
+  size_t user_floats;    // T*U*d  (user part comes first inside a table buffer)
+};
+
+static WsLayout ws_layout(const sagnn_plan* p, int n_layers, int d) {
+  WsLayout w{};
+  size_t off = 0;
+  w.tickets_off = off;
+  off = align_up(off + sizeof(uint32_t) * (size_t)(p->n_long ? p->n_long : 1), 256);
+  w.partials_off = off;
+  off = align_up(off + sizeof(float) * (size_t)p->n_chunks * d, 256);
+  w.table_floats = (size_t)p->n_rows * d;
+  w.user_floats = (size_t)p->T * p->U * d;
+  int nbuf = n_layers - 1 < 2 ? n_layers - 1 : 2;
+  for (int b = 0; b < 2; ++b) {
+    w.buf_off[b] = off;
+    if (b < nbuf) off = align_up(off + sizeof(float) * w.table_floats, 256);
+  }
+  w.total = off;
+  return w;
+}
+
+static size_t mask_layer_words(const sagnn_plan* p, int d) { return (size_t)p->n_rows * (d / 32); }
+
+static void base_params(const sagnn_plan* p, SpmmParams& s) {
+  s = SpmmParams{};
+  s.rowptr = p->rowptr; s.idx = p->idx; s.w = p->w;
+  s.order = p->order; s.long_row = p->long_row; s.chunk_base = p->chunk_base; s.chunk_lr = p->chunk_lr;
+  s.n_short = p->n_short; s.n_chunks = p->n_chunks;
+  s.U = p->U; s.I = p->I; s.N = (uint32_t)p->N;
+  s.row_lo = 0; s.row_hi = (uint32_t)p->n_rows;
+}
+
+static int check_common(const sagnn_plan* p, int n_layers, int d, const char* fn) {
+  SAGNN_REQUIRE(p, SAGNN_INVALID_ARG, "%s: NULL plan", fn);
+  SAGNN_REQUIRE(p->finalized, SAGNN_NOT_FINALIZED, "%s: plan not finalized", fn);
+  SAGNN_REQUIRE(n_layers >= 1 && n_layers <= 64, SAGNN_INVALID_ARG, "%s: n_layers=%d", fn, n_layers);
+  SAGNN_REQUIRE(d_ok(d), SAGNN_INVALID_ARG, "%s: latdim d=%d unsupported (need 32, 64, 128 or 256)", fn, d);
+  return SAGNN_OK;
+}
+
+}  // namespace sagnn
+
+using namespace sagnn;
+
+extern "C" int sagnn_plan_stats(const sagnn_plan* p, int64_t* out8) {
+  SAGNN_REQUIRE(p && out8, SAGNN_INVALID_ARG, "plan_stats: NULL argument");
+  SAGNN_REQUIRE(p->finalized, SAGNN_NOT_FINALIZED, "plan_stats: plan not finalized");
+  out8[0] = p->n_rows; out8[1] = p->n_short; out8[2] = p->n_long; out8[3] = p->n_chunks;
+  out8[4] = p->max_deg; out8[5] = 2 * p->e_total; out8[6] = 0; out8[7] = p->num_sms;
+  return SAGNN_OK;
+}
+
+extern "C" int sagnn_workspace_bytes(const sagnn_plan* p, int n_layers, int d, size_t* fwd_bytes,
+                                     size_t* mask_bytes, size_t* bwd_bytes) {
+  if (int rc = check_common(p, n_layers, d, "workspace_bytes")) return rc;
+  WsLayout w = ws_layout(p, n_layers, d);
+  if (fwd_bytes) *fwd_bytes = w.total;
+  if (bwd_bytes) *bwd_bytes = w.total;
+  if (mask_bytes) *mask_bytes = sizeof(uint32_t) * mask_layer_words(p, d) * n_layers;
+  return SAGNN_OK;
+}
+
+extern "C" int sagnn_propagate_fwd(const sagnn_plan* p, const float* uE, const float* iE, float* uOut,
+                                   float* iOut, int L, int d, float leaky, void* masks, void* ws,
+                                   size_t ws_bytes, sagnn_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (int rc = check_common(p, L, d, "propagate_fwd")) return rc;
+  SAGNN_REQUIRE(uE && iE && uOut && iOut && ws, SAGNN_INVALID_ARG, "propagate_fwd: NULL tensor");
+  WsLayout w = ws_layout(p, L, d);
+  SAGNN_REQUIRE(ws_bytes >= w.total, SAGNN_WORKSPACE_TOO_SMALL,
+                "propagate_fwd: workspace %zu < %zu bytes", ws_bytes, w.total);
+  char* base = (char*)ws;
+  SpmmParams s;
+  base_params(p, s);
+  s.tickets = (uint32_t*)(base + w.tickets_off);
+  s.partials = (float*)(base + w.partials_off);
+  s.leaky = leaky;
+  SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, sizeof(uint32_t) * (size_t)(p->n_long ? p->n_long : 1), st));
+  float* buf[2] = {(float*)(base + w.buf_off[0]), (float*)(base + w.buf_off[1])};
+  const size_t mlw = mask_layer_words(p, d);
+  const size_t mu = (size_t)p->T * p->U * (d / 32);
+  for (int l = 0; l < L; ++l) {
+    const float* cur_u = l == 0 ? uE : buf[(l - 1) & 1];
+    const float* cur_i = l == 0 ? iE : buf[(l - 1) & 1] + w.user_floats;
+    const bool last = (l == L - 1);
+    s.src_u = cur_u; s.src_i = cur_i;
+    s.a_u = cur_u;   s.a_i = cur_i;
+    s.o1_u = last ? nullptr : buf[l & 1];
+    s.o1_i = last ? nullptr : buf[l & 1] + w.user_floats;
+    // layer sum: before layer l the output holds sum_{j<l} E^j (j=0 is the input itself)
+    if (l == 0) { s.b_u = nullptr; s.b_i = nullptr; }
+    else if (l == 1) { s.b_u = uE; s.b_i = iE; }
+    else { s.b_u = uOut; s.b_i = iOut; }
+    const bool write_out = last || l >= 1;
+    s.o2_u = write_out ? uOut : nullptr;
+    s.o2_i = write_out ? iOut : nullptr;
+    s.out_add_next = last ? 1 : 0;
+    s.mask_u = masks ? (uint32_t*)masks + (size_t)l * mlw : nullptr;
+    s.mask_i = masks ? (uint32_t*)masks + (size_t)l * mlw + mu : nullptr;
+    if (int rc = launch(p, s, d, MODE_FWD, st)) return rc;
+  }
+  return SAGNN_OK;
+}
+
+extern "C" int sagnn_propagate_bwd(const sagnn_plan* p, const float* gU, const float* gI, float* dU,
+                                   float* dI, int L, int d, float leaky, const void* masks, void* ws,
+                                   size_t ws_bytes, sagnn_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (int rc = check_common(p, L, d, "propagate_bwd")) return rc;
+  SAGNN_REQUIRE(gU && gI && dU && dI && masks && ws, SAGNN_INVALID_ARG, "propagate_bwd: NULL tensor");
+  WsLayout w = ws_layout(p, L, d);
+  SAGNN_REQUIRE(ws_bytes >= w.total, SAGNN_WORKSPACE_TOO_SMALL,
+                "propagate_bwd: workspace %zu < %zu bytes", ws_bytes, w.total);
+  char* base = (char*)ws;
+  SpmmParams s;
+  base_params(p, s);
+  s.tickets = (uint32_t*)(base + w.tickets_off);
+  s.partials = (float*)(base + w.partials_off);
+  s.leaky = leaky;
+  SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, sizeof(uint32_t) * (size_t)(p->n_long ? p->n_long : 1), st));
+  float* buf[2] = {(float*)(base + w.buf_off[0]), (float*)(base + w.buf_off[1])};
+  const size_t mlw = mask_layer_words(p, d);
+  const size_t mu = (size_t)p->T * p->U * (d / 32);
+  for (int l = L - 1, step = 0; l >= 0; --l, ++step) {
+    // g = total gradient w.r.t. E^{l+1}; at the top level it is the upstream itself
+    const float* g_u = step == 0 ? gU : buf[(step - 1) & 1];
+    const float* g_i = step == 0 ? gI : buf[(step - 1) & 1] + w.user_floats;
+    s.src_u = g_u; s.src_i = g_i;
+    s.smask_u = (const uint32_t*)masks + (size_t)l * mlw;        // sigma'(Z0^l): masks user-table rows
+    s.smask_i = (const uint32_t*)masks + (size_t)l * mlw + mu;   // sigma'(Z1^l): masks item-table rows
+    s.a_u = gU; s.a_i = gI;
+    s.b_u = step == 0 ? nullptr : g_u;
+    s.b_i = step == 0 ? nullptr : g_i;
+    s.o1_u = l == 0 ? dU : buf[step & 1];
+    s.o1_i = l == 0 ? dI : buf[step & 1] + w.user_floats;
+    if (int rc = launch(p, s, d, MODE_BWD, st)) return rc;
+  }
+  return SAGNN_OK;
+}
+
+extern "C" int sagnn_message_propagate(const sagnn_plan* p, int k, int side, const float* src, float* out,
+                                       int d, float leaky, void* ws, size_t ws_bytes,
+                                       sagnn_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (int rc = check_common(p, 1, d, "message_propagate")) return rc;
+  SAGNN_REQUIRE(k >= 0 && k < p->T && (side == 0 || side == 1), SAGNN_INVALID_ARG,
+                "message_propagate: bad interval %d / side %d", k, side);
+  SAGNN_REQUIRE(src && out && ws, SAGNN_INVALID_ARG, "message_propagate: NULL tensor");
+  WsLayout w = ws_layout(p, 1, d);
+  SAGNN_REQUIRE(ws_bytes >= w.total, SAGNN_WORKSPACE_TOO_SMALL,
+                "message_propagate: workspace %zu < %zu bytes", ws_bytes, w.total);
+  char* base = (char*)ws;
+  SpmmParams s;
+  base_params(p, s);
+  s.tickets = (uint32_t*)(base + w.tickets_off);
+  s.partials = (float*)(base + w.partials_off);
+  s.leaky = leaky;
+  SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, sizeof(uint32_t) * (size_t)(p->n_long ? p->n_long : 1), st));
+  s.row_lo = (uint32_t)((int64_t)k * p->N + (side ? p->U : 0));
+  s.row_hi = s.row_lo + (uint32_t)(side ? p->I : p->U);
+  // the kernel indexes tables as [T, rows, d]; shift the bases so that interval k lands on the
+  // caller's single-interval tensors
+  const intptr_t src_shift = (intptr_t)sizeof(float) * (intptr_t)k * (side ? p->U : p->I) * d;
+  const intptr_t out_shift = (intptr_t)sizeof(float) * (intptr_t)k * (side ? p->I : p->U) * d;
+  const float* vsrc = (const float*)((intptr_t)src - src_shift);
+  float* vout = (float*)((intptr_t)out - out_shift);
+  if (side) { s.src_u = vsrc; s.o1_i = vout; } else { s.src_i = vsrc; s.o1_u = vout; }
+  return launch(p, s, d, MODE_MSG, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// host-buffer entry point
+// ---------------------------------------------------------------------------------------
+void sagnn::free_host_cache(sagnn_plan* p) {
+  auto& h = p->hc;
+  cudaFree(h.uE); cudaFree(h.iE); cudaFree(h.gU); cudaFree(h.gI);
+  cudaFree(h.uO); cudaFree(h.iO); cudaFree(h.dU); cudaFree(h.dI);
+  cudaFree(h.masks); cudaFree(h.ws);
+  if (h.stream) cudaStreamDestroy(h.stream);
+  if (h.copy_in) cudaStreamDestroy(h.copy_in);
+  if (h.copy_out) cudaStreamDestroy(h.copy_out);
+  for (auto e : h.ev) cudaEventDestroy(e);
+  h = sagnn_plan::HostCache();
+}
+
+extern "C" int sagnn_propagate_host(sagnn_plan* p, const float* uE, const float* iE, const float* gU,
+                                    const float* gI, float* uO, float* iO, float* dU, float* dI, int L,
+                                    int d, float leaky) {
+  if (int rc = check_common(p, L, d, "propagate_host")) return rc;
+  SAGNN_REQUIRE(uE && iE && uO && iO, SAGNN_INVALID_ARG, "propagate_host: NULL embedding/output");
+  const bool bwd = gU != nullptr;
+  SAGNN_REQUIRE(!bwd || (gI && dU && dI), SAGNN_INVALID_ARG, "propagate_host: backward needs gI, dU, dI");
+  auto& h = p->hc;
+  const size_t nu = sizeof(float) * (size_t)p->T * p->U * d;
+  const size_t ni = sizeof(float) * (size_t)p->T * p->I * d;
+  if (h.L != L || h.d != d) {
+    free_host_cache(p);
+    size_t fb = 0, mb = 0, bb = 0;
+    if (int rc = sagnn_workspace_bytes(p, L, d, &fb, &mb, &bb)) return rc;
+    SAGNN_CUDA(cudaMalloc(&h.uE, nu)); SAGNN_CUDA(cudaMalloc(&h.iE, ni));
+    SAGNN_CUDA(cudaMalloc(&h.gU, nu)); SAGNN_CUDA(cudaMalloc(&h.gI, ni));
+    SAGNN_CUDA(cudaMalloc(&h.uO, nu)); SAGNN_CUDA(cudaMalloc(&h.iO, ni));
+    SAGNN_CUDA(cudaMalloc(&h.dU, nu)); SAGNN_CUDA(cudaMalloc(&h.dI, ni));
+    SAGNN_CUDA(cudaMalloc(&h.masks, mb ? mb : 1));
+    h.ws_bytes = fb > bb ? fb : bb;
+    SAGNN_CUDA(cudaMalloc(&h.ws, h.ws_bytes));
+    SAGNN_CUDA(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+    SAGNN_CUDA(cudaStreamCreateWithFlags(&h.copy_in, cudaStreamNonBlocking));
+    SAGNN_CUDA(cudaStreamCreateWithFlags(&h.copy_out, cudaStreamNonBlocking));
+    h.ev.resize(4);
+    for (auto& e : h.ev) SAGNN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h.L = L; h.d = d;
+  }
+  // embeddings in on the compute stream; upstream gradients in on a second copy stream
+  // (they are only needed by the backward); outputs leave on a third while backward runs.
+  SAGNN_CUDA(cudaMemcpyAsync(h.uE, uE, nu, cudaMemcpyHostToDevice, h.stream));
+  SAGNN_CUDA(cudaMemcpyAsync(h.iE, iE, ni, cudaMemcpyHostToDevice, h.stream));
+  if (bwd) {
+    SAGNN_CUDA(cudaMemcpyAsync(h.gU, gU, nu, cudaMemcpyHostToDevice, h.copy_in));
+    SAGNN_CUDA(cudaMemcpyAsync(h.gI, gI, ni, cudaMemcpyHostToDevice, h.copy_in));
+    SAGNN_CUDA(cudaEventRecord(h.ev[0], h.copy_in));
+  }
+  if (int rc = sagnn_propagate_fwd(p, h.uE, h.iE, h.uO, h.iO, L, d, leaky, bwd ? h.masks : nullptr, h.ws,
+                                   h.ws_bytes, h.stream))
+    return rc;
+  SAGNN_CUDA(cudaEventRecord(h.ev[1], h.stream));
+  SAGNN_CUDA(cudaStreamWaitEvent(h.copy_out, h.ev[1], 0));
+  SAGNN_CUDA(cudaMemcpyAsync(uO, h.uO, nu, cudaMemcpyDeviceToHost, h.copy_out));
+  SAGNN_CUDA(cudaMemcpyAsync(iO, h.iO, ni, cudaMemcpyDeviceToHost, h.copy_out));
+  if (bwd) {
+    SAGNN_CUDA(cudaStreamWaitEvent(h.stream, h.ev[0], 0));
+    if (int rc = sagnn_propagate_bwd(p, h.gU, h.gI, h.dU, h.dI, L, d, leaky, h.masks, h.ws, h.ws_bytes,
+                                     h.stream))
+      return rc;
+    SAGNN_CUDA(cudaMemcpyAsync(dU, h.dU, nu, cudaMemcpyDeviceToHost, h.stream));
+    SAGNN_CUDA(cudaMemcpyAsync(dI, h.dI, ni, cudaMemcpyDeviceToHost, h.stream));
+  }
+  SAGNN_CUDA(cudaStreamSynchronize(h.copy_out));
+  SAGNN_CUDA(cudaStreamSynchronize(h.stream));
+  return SAGNN_OK;
+}

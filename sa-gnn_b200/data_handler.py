@@ -1,0 +1,234 @@
+"""Host-side mirror of the reference's data layer for the propagation path.
+
+Mirrors (names, argument meaning, return layout, edge cases) the three pieces of
+``DataHandler.py`` the interval-graph propagation consumes:
+
+  * ``transpose``        -- DataHandler.py:9-11
+  * ``transToLsts``      -- DataHandler.py:47-69 (adjacency list, dead int32
+                            "normalisation", empty-matrix fallback edge (0,0))
+  * ``LoadData``'s ``trn_mat_time`` part -- DataHandler.py:92-94,126-129
+
+plus a writer of the same pickle layout and the synthetic power-law interval
+graph generator of SURVEY section 8(d) / appendix D (the real ``trn_mat_time``
+files are not shipped with the reference).
+
+Pure numpy/scipy host code: it only *prepares* inputs.  The CSR/CSC
+construction the model actually runs on is done on the device by the plan
+(``propagate.build_plan``); nothing here is a CPU fallback for it.
+"""
+from __future__ import annotations
+
+import pickle
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+
+TS_LO, TS_HI = 1388534400, 1406073600   # timestamp range of the stored values
+
+
+# --------------------------------------------------------------------------
+# reference-named helpers
+# --------------------------------------------------------------------------
+def transpose(mat):
+    """DataHandler.py:9-11 -- CSR of ``mat``'s transpose (rows = items, user ids ascending)."""
+    return sp.csr_matrix(sp.coo_matrix(mat).transpose())
+
+
+def transToLsts(mat, mask=False, norm=False):
+    """DataHandler.py:47-69 -- ``(indices int32 [E,2], data int32 [E], [R, C])``.
+
+    Vectorised, same results: COO order of the canonical CSR; ``norm`` multiplies
+    every stored value by ``rowD[row]*colD[col]`` in float64 and stores it back
+    into the int32 array (truncation -- all zeros for real data);
+    ``mask`` applies the reference's random half mask (:62-64); an empty matrix
+    becomes the single edge ``[[0, 0]]`` with data ``[0]`` (:66-68).
+    """
+    shape = [int(mat.shape[0]), int(mat.shape[1])]
+    coo = sp.coo_matrix(mat)
+    row = np.asarray(coo.row, dtype=np.int32)
+    col = np.asarray(coo.col, dtype=np.int32)
+    indices = np.stack([row, col], axis=1) if row.size else np.zeros((0, 2), np.int32)
+    data = np.asarray(coo.data).astype(np.int32)
+    if norm and data.size:
+        row_d = 1.0 / (np.sqrt(np.asarray(mat.sum(axis=1)).reshape(-1) + 1e-8) + 1e-8)
+        col_d = 1.0 / (np.sqrt(np.asarray(mat.sum(axis=0)).reshape(-1) + 1e-8) + 1e-8)
+        data = ((data * row_d[row]) * col_d[col]).astype(np.int32)
+    if mask:
+        data = data * ((np.random.uniform(size=data.shape) > 0.5) * 1.0)
+    if indices.shape[0] == 0:
+        indices = np.array([[0, 0]], dtype=np.int32)
+        data = np.array([0], dtype=np.int32)
+    return indices, data, shape
+
+
+trans_to_lsts = transToLsts
+
+
+# --------------------------------------------------------------------------
+# trn_mat_time  
+# --------------------------------------------------------------------------
+@dataclass
+class IntervalGraphs:
+    """What ``DataHandler.LoadData`` keeps for the path: ``subMat`` (T CSR, intc
+    timestamps), the global matrix (only its shape is used) and ``timeMat``."""
+    n_user: int
+    n_item: int
+    sub_mat: list                      # T x csr_matrix U x I, dtype intc  (trnMat[1])
+    trn_mat: object = None             # csr U x I float64                 (trnMat[0])
+    time_mat: object = None            # csr U x I intc                    (trnMat[2])
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def graph_num(self):
+        return len(self.sub_mat)
+
+    @property
+    def nnz(self):
+        return [int(m.nnz) for m in self.sub_mat]
+
+
+def load_trn_mat_time(path, graph_num=None):
+    """DataHandler.py:92-94,126-129: unpickle ``[trnMat, subMat[T], timeMat]``;
+    ``args.user, args.item = trnMat[0].shape``; ``--graphNum`` may select a prefix
+    of the stored intervals (model.py:230-231)."""
+    with open(path, "rb") as fs:
+        trn = pickle.load(fs)
+    n_user, n_item = trn[0].shape
+    sub = list(trn[1])
+    if graph_num is not None:
+        if graph_num > len(sub):
+            raise IndexError("graphNum %d > %d stored intervals" % (graph_num, len(sub)))
+        sub = sub[:graph_num]
+    return IntervalGraphs(int(n_user), int(n_item), [sp.csr_matrix(m) for m in sub], trn[0], trn[2])
+
+
+def write_trn_mat_time(path, graphs: IntervalGraphs):
+    """Writes the pickle layout of ``preprocess_to_trnmat.ipynb:1896``."""
+    U, I = graphs.n_user, graphs.n_item
+    trn = graphs.trn_mat
+    if trn is None:      # interaction counts: every pair lives in exactly one interval
+        trn = sp.csr_matrix((U, I), dtype=np.float64)
+        for m in graphs.sub_mat:
+            trn = trn + (m != 0).astype(np.float64)
+        trn = sp.csr_matrix(trn)
+    tm = graphs.time_mat
+    if tm is None:       # last interval id per pair; interval 0 vanishes (DOK drops zeros)
+        tm = sp.csr_matrix((U, I), dtype=np.intc)
+        for k, m in enumerate(graphs.sub_mat):
+            if k:
+                tm = tm + ((m != 0).astype(np.intc) * k)
+        tm = sp.csr_matrix(tm).astype(np.intc)
+    with open(path, "wb") as fs:
+        pickle.dump([trn, [m.astype(np.intc) for m in graphs.sub_mat], tm], fs)
+
+
+# --------------------------------------------------------------------------
+# synthetic power-law interval graphs  
+# --------------------------------------------------------------------------
+# name -> (U, I, T, total_edges or per-interval list, L, d, alpha_user, alpha_item)
+SHAPES = {
+    "gowalla":     dict(U=48653, I=52621, T=3, E=1807125, L=2, d=64, au=0.8, ai=1.0),
+    "amazon-book": dict(U=52643, I=91599, T=5, E=2984108, L=2, d=64, au=0.8, ai=1.0),
+    "amazon-ref":  dict(U=11199, I=30821, T=5, E=[72280, 78997, 79692, 78096, 45651], L=3, d=64,
+                        au=0.8, ai=1.0),
+    "ml10m":       dict(U=69878, I=10677, T=6, E=10000054, L=3, d=128, au=0.6, ai=1.2),
+    "scaled":      dict(U=10_000_000, I=2_000_000, T=8, E=1_000_000_000, L=2, d=64, au=0.8, ai=1.0),
+    # small cases for tests / smoke
+    "tiny":        dict(U=300, I=200, T=3, E=3000, L=2, d=64, au=0.8, ai=1.0),
+    "small":       dict(U=4000, I=3000, T=3, E=60000, L=2, d=64, au=0.8, ai=1.0),
+}
+
+
+def interval_sizes(total, T):
+    """Equal shares, the last interval ~0.6x (mirrors Amazon's 45,651 vs ~78 K)."""
+    w = np.ones(T)
+    if T > 1:
+        w[-1] = 0.6
+    sizes = np.floor(total * w / w.sum()).astype(np.int64)
+    sizes[0] += total - sizes.sum()
+    return [int(s) for s in sizes]
+
+
+def _zipf_cdf(n, alpha):
+    p = np.arange(1, n + 1, dtype=np.float64) ** (-alpha)
+    c = np.cumsum(p)
+    return c / c[-1]
+
+
+def make_interval_graphs(U, I, T, E, au=0.8, ai=1.0, seed=100, **_unused):
+    """Bipartite power-law interval graphs.
+
+    User activity ~ rank^-au, item popularity ~ rank^-ai, ids scattered by a fixed
+    random permutation, pairs de-duplicated globally so each (u,i) lives in exactly
+    one interval, intervals sized by ``interval_sizes`` (or the explicit list ``E``);
+    every interval gets one edge on the last user row and one on the last item
+    column so the reference's pad-100 hack (model.py:87) is in range; stored values
+    are int32 timestamps.  Canonical CSR (sorted, no duplicates) like
+    ``csr_matrix((v,(r,c)))`` at preprocess_to_trnmat.ipynb:379.
+    """
+    rng = np.random.default_rng(seed)
+    sizes = [int(e) for e in E] if isinstance(E, (list, tuple)) else interval_sizes(int(E), T)
+    assert len(sizes) == T
+    forced_per = 2 if (U > T and I > T) else 0
+    sizes_rand = [max(0, s - forced_per) for s in sizes]
+    total = int(sum(sizes_rand))
+    if total > U * I // 2:
+        raise ValueError("requested edges exceed half of the dense matrix")
+    ucdf, icdf = _zipf_cdf(U, au), _zipf_cdf(I, ai)
+    uperm, iperm = rng.permutation(U), rng.permutation(I)
+    forced = set()
+    if forced_per:
+        for k in range(T):
+            forced.add((U - 1) * I + k)           # (last user, item k)
+            forced.add(k * I + (I - 1))           # (user k, last item)
+    forced_keys = np.fromiter(forced, dtype=np.int64) if forced else np.zeros(0, np.int64)
+    keys = np.zeros(0, dtype=np.int64)
+    need = total
+    rounds = 0
+    while keys.size < total:
+        n_draw = int(max(1024, (need * 1.3) + 1024))
+        u = uperm[np.minimum(np.searchsorted(ucdf, rng.random(n_draw)), U - 1)]
+        i = iperm[np.minimum(np.searchsorted(icdf, rng.random(n_draw)), I - 1)]
+        new = u.astype(np.int64) * I + i
+        keys = np.unique(np.concatenate([keys, new]))
+        if forced_keys.size:
+            keys = keys[~np.isin(keys, forced_keys)]
+        need = total - keys.size
+        rounds += 1
+        if rounds > 200:
+            raise RuntimeError("generator did not converge (graph too dense for the power law)")
+    keys = rng.permutation(keys)[:total]
+    sub, off = [], 0
+    for k in range(T):
+        kk = keys[off:off + sizes_rand[k]]
+        off += sizes_rand[k]
+        if forced_per:
+            kk = np.concatenate([kk, np.array([(U - 1) * I + k, k * I + (I - 1)], dtype=np.int64)])
+        kk = np.sort(kk)
+        rows = (kk // I).astype(np.int32)
+        cols = (kk % I).astype(np.int32)
+        vals = np.random.default_rng(seed + 1000 + k).integers(TS_LO, TS_HI, size=kk.size, dtype=np.int64)
+        m = sp.csr_matrix((vals.astype(np.intc), (rows, cols)), shape=(U, I))
+        m.sort_indices()
+        sub.append(m)
+    return IntervalGraphs(U, I, sub, meta=dict(U=U, I=I, T=T, au=au, ai=ai, seed=seed))
+
+
+def make_named(name, seed=100, scale=1.0):
+    """Graphs for a named BASELINE shape; ``scale`` < 1 shrinks U, I and E together."""
+    s = dict(SHAPES[name])
+    if scale != 1.0:
+        s["U"] = max(8, int(s["U"] * scale))
+        s["I"] = max(8, int(s["I"] * scale))
+        s["E"] = [max(4, int(e * scale)) for e in s["E"]] if isinstance(s["E"], list) else max(16, int(s["E"] * scale))
+    g = make_interval_graphs(seed=seed, **s)
+    g.meta.update(name=name, L=s["L"], d=s["d"], scale=scale)
+    return g
+
+
+def xavier_embeddings(T, rows, d, seed, dtype=np.float32):
+    """``defineParam`` xavier-uniform for a 3-D shape (Utils/NNLayers.py:47-50):
+    U(-a, a) with a = sqrt(6 / (T*(rows + d)))  (SURVEY 8d)."""
+    a = np.sqrt(6.0 / (T * (rows + d)))
+    return np.random.default_rng(seed).uniform(-a, a, size=(T, rows, d)).astype(dtype)

@@ -1,0 +1,342 @@
+"""Python surface of the propagation path (thin shim over the C ABI).
+
+Keeps the reference's operator surface one level above ``messagePropagate``:
+
+    plan = build_plan(sub_mats, U, I)                      # model.py:227-237 (2T transToLsts calls)
+    user_vec, item_vec = propagate(plan, uEmbed, iEmbed,   # model.py:118-129 (T x L x 2 calls,
+                                   n_layers=L, leaky=0.5)  #   residuals, add_n)  + autograd backward
+    lat = message_propagate(srclats, plan, k, 'user')      # model.py:80-92, one call
+
+All arithmetic happens in ``libsagnn_b200.so`` (hand-written sm_100a kernels); torch only
+owns device memory and streams.  No CPU fallback: CPU tensors are rejected.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .data_handler import transToLsts
+
+PAD_ROWS = 100   # model.py:87
+_WEIGHT_MODES = {None: 0, "none": 0, "lightgcn": 1, "custom": 2}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Plan:
+    """Device-resident CSR (A_k) + transposed CSR (A_k^T) of the T interval graphs plus the
+    degree-binned schedule.  Immutable after ``build_plan``; owns no tensors but a scratch cache."""
+
+    def __init__(self, handle, T, U, I, nnz, device, weight_mode, has_val):
+        self._h = handle
+        self.T, self.U, self.I = T, U, I
+        self.nnz = list(nnz)
+        self.device = device
+        self.weight_mode = weight_mode
+        self.has_val = has_val
+        self._scratch = {}
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if self._h is not None:
+            _lib.load_library().sagnn_plan_destroy(self._h)
+            self._h = None
+            self._scratch.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise RuntimeError("plan already closed")
+        return self._h
+
+    # -- parity hooks -----------------------------------------------------------------
+    def _rows(self, side):
+        return self.I if side else self.U
+
+    def csr(self, k, side):
+        """(indptr int32 [R+1], indices int32 [nnz_k]) of A_k (side 0) or A_k^T (side 1)."""
+        lib = _lib.load_library()
+        with torch.cuda.device(self.device):
+            indptr = torch.empty(self._rows(side) + 1, dtype=torch.int32, device=self.device)
+            indices = torch.empty(self.nnz[k], dtype=torch.int32, device=self.device)
+            _lib.check(lib.sagnn_plan_get_csr(self.handle, k, side, _ptr(indptr), _ptr(indices),
+                                              _stream_ptr(self.device)))
+        return indptr, indices
+
+    def adjacency_list(self, k, side):
+        """int32 [nnz_k, 2] (row, col) list, the layout transToLsts returns."""
+        indptr, indices = self.csr(k, side)
+        counts = (indptr[1:] - indptr[:-1]).long()
+        rows = torch.repeat_interleave(torch.arange(self._rows(side), device=self.device, dtype=torch.int32), counts)
+        return torch.stack([rows, indices], dim=1)
+
+    def degrees(self, k, side, value_sum=False):
+        lib = _lib.load_library()
+        with torch.cuda.device(self.device):
+            deg = torch.empty(self._rows(side), dtype=torch.int32, device=self.device)
+            vs = torch.empty(self._rows(side), dtype=torch.int64, device=self.device) if value_sum else None
+            _lib.check(lib.sagnn_plan_get_degrees(self.handle, k, side, _ptr(deg), _ptr(vs),
+                                                  _stream_ptr(self.device)))
+        return (deg, vs) if value_sum else deg
+
+    def norm_data(self, k, side):
+        """The reference's int32-truncated 'normalised' values (DataHandler.py:56-59)."""
+        lib = _lib.load_library()
+        with torch.cuda.device(self.device):
+            out = torch.empty(self.nnz[k], dtype=torch.int32, device=self.device)
+            _lib.check(lib.sagnn_plan_norm_data(self.handle, k, side, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def weights(self, k, side):
+        lib = _lib.load_library()
+        with torch.cuda.device(self.device):
+            out = torch.empty(self.nnz[k], dtype=torch.float32, device=self.device)
+            _lib.check(lib.sagnn_plan_get_weights(self.handle, k, side, _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def stats(self):
+        out = (ctypes.c_int64 * 8)()
+        _lib.check(_lib.load_library().sagnn_plan_stats(self.handle, out))
+        keys = ["rows", "short_rows", "long_rows", "chunks", "max_degree", "edges_both_sides", "_", "sms"]
+        return {k: int(v) for k, v in zip(keys, out) if k != "_"}
+
+    # -- scratch ----------------------------------------------------------------------
+    def workspace_bytes(self, n_layers, d):
+        f, m, b = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(_lib.load_library().sagnn_workspace_bytes(self.handle, n_layers, d, ctypes.byref(f),
+                                                             ctypes.byref(m), ctypes.byref(b)))
+        return f.value, m.value, b.value
+
+    def scratch(self, n_layers, d):
+        """Cached (workspace tensor, mask_bytes): fwd and bwd of one step run back to back on one
+        stream and the backward needs nothing from the forward scratch, so they share it."""
+        key = (n_layers, d)
+        if key not in self._scratch:
+            f, m, b = self.workspace_bytes(n_layers, d)
+            ws = torch.empty(max(f, b, 1), dtype=torch.uint8, device=self.device)
+            self._scratch[key] = (ws, m)
+        return self._scratch[key]
+
+
+def _as_dev_i32(x, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.int32).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.int32)).to(device)
+
+
+def _split_interval(m):
+    """-> (row, col, val|None, shape|None) for one interval given in any accepted form."""
+    if hasattr(m, "tocoo"):                       # scipy sparse: the reference's own path
+        idx, data, shape = transToLsts(m)         # includes the (0,0) fallback for empty matrices
+        return idx[:, 0], idx[:, 1], data, shape
+    if isinstance(m, (tuple, list)):
+        if len(m) == 2:
+            return m[0], m[1], None, None
+        if len(m) == 3:
+            return m[0], m[1], m[2], None
+        raise ValueError("interval tuple must be (row, col) or (row, col, val)")
+    if getattr(m, "ndim", 0) == 2 and m.shape[1] == 2:     # transToLsts-style [E,2] list
+        if m.shape[0] == 0:
+            m = np.array([[0, 0]], dtype=np.int32)         # DataHandler.py:66-68
+        return m[:, 0], m[:, 1], None, None
+    raise TypeError("unsupported interval description: %r" % type(m))
+
+
+def build_plan(sub_mats, U=None, I=None, *, device=None, edge_weight=None, strict_pad=False):
+    """Builds the device plan for ``T = len(sub_mats)`` interval graphs.
+
+    sub_mats[k]: scipy sparse ``U x I`` matrix (``handler.subMat[k]``), or an ``[E,2]`` adjacency
+    list as ``transToLsts`` returns it, or ``(row, col[, val])`` arrays / tensors, row-major sorted.
+    edge_weight: None (reference-exact binary structure), ``"lightgcn"`` (1/sqrt(d_u d_i)) or a
+    list of per-interval fp32 arrays in the adjacency list's order.
+    strict_pad: raise like TF-CPU does when an interval's last populated row is more than 100
+    rows before the end (model.py:87-91); by default such rows are simply zero (TF-GPU).
+    """
+    if not torch.cuda.is_available():
+        raise RuntimeError("sagnn_b200.build_plan needs a CUDA device (there is no CPU fallback)")
+    lib = _lib.load_library()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    T = len(sub_mats)
+    if T == 0:
+        raise ValueError("need at least one interval graph")
+    parts = [_split_interval(m) for m in sub_mats]
+    for _, _, _, shape in parts:
+        if shape is not None:
+            U = shape[0] if U is None else U
+            I = shape[1] if I is None else I
+            if (U, I) != (shape[0], shape[1]):
+                raise ValueError("interval shape %s does not match (U, I) = (%d, %d)" % (shape, U, I))
+    if U is None or I is None:
+        raise ValueError("U and I are required when intervals are given as index arrays")
+    has_val = all(p[2] is not None for p in parts)
+    custom = isinstance(edge_weight, (list, tuple))
+    mode = 2 if custom else _WEIGHT_MODES[edge_weight]
+    if custom and len(edge_weight) != T:
+        raise ValueError("need one weight array per interval")
+    nnz = [int(len(p[0])) for p in parts]
+    if strict_pad:
+        for k, (row, col, _, _) in enumerate(parts):
+            rmax = int(row[-1]) if nnz[k] else 0
+            cmax = int(col.max()) if nnz[k] else 0
+            if rmax + 1 + PAD_ROWS < U or cmax + 1 + PAD_ROWS < I:
+                raise IndexError("interval %d: padded segment_sum has fewer rows than the lookup "
+                                 "range (model.py:87-91 would raise on TF-CPU)" % k)
+    handle = ctypes.c_void_p()
+    with torch.cuda.device(device):
+        nnz_arr = (ctypes.c_int64 * T)(*nnz)
+        _lib.check(lib.sagnn_plan_create(T, int(U), int(I), nnz_arr, ctypes.byref(handle)))
+        plan = Plan(handle, T, int(U), int(I), nnz, device, mode, has_val)
+        st = _stream_ptr(device)
+        for k, (row, col, val, _) in enumerate(parts):
+            row_d, col_d = _as_dev_i32(row, device), _as_dev_i32(col, device)
+            val_d = _as_dev_i32(val, device) if has_val else None
+            w_d = None
+            if custom:
+                w = edge_weight[k]
+                w_d = (w.to(device=device, dtype=torch.float32) if isinstance(w, torch.Tensor)
+                       else torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)).to(device)).contiguous()
+                if w_d.numel() != nnz[k]:
+                    raise ValueError("interval %d: %d weights for %d edges" % (k, w_d.numel(), nnz[k]))
+            _lib.check(lib.sagnn_plan_set_interval(handle, k, _ptr(row_d), _ptr(col_d), _ptr(val_d),
+                                                   _ptr(w_d), nnz[k], st))
+        _lib.check(lib.sagnn_plan_finalize(handle, mode, st))
+    return plan
+
+
+def _check_tables(plan, u, i):
+    if not (u.is_cuda and i.is_cuda):
+        raise RuntimeError("sagnn_b200.propagate: embeddings must be CUDA tensors (no CPU fallback)")
+    if u.dtype != torch.float32 or i.dtype != torch.float32:
+        raise TypeError("embeddings must be float32")
+    if u.dim() != 3 or i.dim() != 3 or u.shape[0] != plan.T or i.shape[0] != plan.T or \
+            u.shape[1] != plan.U or i.shape[1] != plan.I or u.shape[2] != i.shape[2]:
+        raise ValueError("expected uEmbed [%d,%d,d] and iEmbed [%d,%d,d], got %s and %s"
+                         % (plan.T, plan.U, plan.T, plan.I, tuple(u.shape), tuple(i.shape)))
+    if u.device != plan.device or i.device != plan.device:
+        raise ValueError("embeddings live on %s but the plan on %s" % (u.device, plan.device))
+
+
+class _Propagate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u_embed, i_embed, plan, n_layers, leaky):
+        _check_tables(plan, u_embed, i_embed)
+        lib = _lib.load_library()
+        u, i = u_embed.contiguous(), i_embed.contiguous()
+        d = u.shape[2]
+        need_bwd = u_embed.requires_grad or i_embed.requires_grad
+        with torch.cuda.device(plan.device):
+            ws, mask_bytes = plan.scratch(n_layers, d)
+            u_out, i_out = torch.empty_like(u), torch.empty_like(i)
+            masks = torch.empty(mask_bytes, dtype=torch.uint8, device=plan.device) if need_bwd else None
+            _lib.check(lib.sagnn_propagate_fwd(plan.handle, _ptr(u), _ptr(i), _ptr(u_out), _ptr(i_out),
+                                               n_layers, d, float(leaky), _ptr(masks), _ptr(ws), ws.numel(),
+                                               _stream_ptr(plan.device)))
+        ctx.plan, ctx.n_layers, ctx.leaky, ctx.d = plan, n_layers, float(leaky), d
+        ctx.masks = masks
+        return u_out, i_out
+
+    @staticmethod
+    def backward(ctx, g_user, g_item):
+        plan, d = ctx.plan, ctx.d
+        lib = _lib.load_library()
+        with torch.cuda.device(plan.device):
+            if g_user is None:
+                g_user = torch.zeros((plan.T, plan.U, d), dtype=torch.float32, device=plan.device)
+            if g_item is None:
+                g_item = torch.zeros((plan.T, plan.I, d), dtype=torch.float32, device=plan.device)
+            g_user, g_item = g_user.contiguous(), g_item.contiguous()
+            ws, _ = plan.scratch(ctx.n_layers, d)
+            d_u, d_i = torch.empty_like(g_user), torch.empty_like(g_item)
+            _lib.check(lib.sagnn_propagate_bwd(plan.handle, _ptr(g_user), _ptr(g_item), _ptr(d_u), _ptr(d_i),
+                                               ctx.n_layers, d, ctx.leaky, _ptr(ctx.masks), _ptr(ws),
+                                               ws.numel(), _stream_ptr(plan.device)))
+        return d_u, d_i, None, None, None
+
+
+def propagate(plan, u_embed, i_embed, n_layers, leaky=0.5):
+    """model.py:118-129 for all T intervals: returns (user_vector [T,U,d], item_vector [T,I,d]),
+    i.e. the stacked ``tf.add_n(embs0)`` / ``tf.add_n(embs1)`` of model.py:126-132.  Differentiable
+    w.r.t. both embedding tables (dense upstream gradients).  Edge dropout
+    (model.py:93-102) only rewrites the ignored edge values, so it has no counterpart here."""
+    return _Propagate.apply(u_embed, i_embed, plan, int(n_layers), float(leaky))
+
+
+def message_propagate(srclats, plan, k, type="user", leaky=0.5):
+    """One ``messagePropagate(srclats, mat, type)`` call (model.py:80-92) on interval ``k``:
+    ``type='user'`` uses subAdj[k] (srclats = item table [I,d] -> [U,d]), ``type='item'`` uses
+    subTpAdj[k] (srclats = user table [U,d] -> [I,d]).  Forward only (op-level parity hook)."""
+    if not srclats.is_cuda:
+        raise RuntimeError("sagnn_b200.message_propagate: srclats must be a CUDA tensor")
+    side = 0 if type == "user" else 1
+    rows, src_rows = (plan.U, plan.I) if side == 0 else (plan.I, plan.U)
+    if srclats.dim() != 2 or srclats.shape[0] != src_rows or srclats.dtype != torch.float32:
+        raise ValueError("srclats must be float32 [%d, d]" % src_rows)
+    lib = _lib.load_library()
+    src = srclats.contiguous()
+    d = src.shape[1]
+    with torch.cuda.device(plan.device):
+        ws, _ = plan.scratch(1, d)
+        out = torch.empty((rows, d), dtype=torch.float32, device=plan.device)
+        _lib.check(lib.sagnn_message_propagate(plan.handle, int(k), side, _ptr(src), _ptr(out), d, float(leaky),
+                                               _ptr(ws), ws.numel(), _stream_ptr(plan.device)))
+    return out
+
+
+def _host_ptr(a):
+    if a is None:
+        return ctypes.c_void_p(0)
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda or a.dtype != torch.float32 or not a.is_contiguous():
+            raise ValueError("host buffers must be contiguous float32 CPU tensors")
+        return ctypes.c_void_p(a.data_ptr())
+    if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("host buffers must be C-contiguous float32 arrays")
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def propagate_host(plan, u_embed, i_embed, g_user, g_item, user_out, item_out, d_u, d_i, n_layers, leaky=0.5):
+    """Host-buffer entry point (``sagnn_propagate_host``): numpy arrays or (pinned) CPU tensors in,
+    results written into the given host buffers; H2D/D2H copies happen inside the call.
+    ``g_user``/``g_item``/``d_u``/``d_i`` may be None for forward only."""
+    d = int(u_embed.shape[2])
+    with torch.cuda.device(plan.device):
+        _lib.check(_lib.load_library().sagnn_propagate_host(
+            plan.handle, _host_ptr(u_embed), _host_ptr(i_embed), _host_ptr(g_user), _host_ptr(g_item),
+            _host_ptr(user_out), _host_ptr(item_out), _host_ptr(d_u), _host_ptr(d_i), int(n_layers), d,
+            float(leaky)))
+
+
+class IntervalPropagation(torch.nn.Module):
+    """The short-term graph-propagation block of ``Recommender.ours()`` (model.py:108-134) as a
+    module: owns ``uEmbed [T,U,d]`` / ``iEmbed [T,I,d]`` (xavier, model.py:108-109) and returns the
+    stacked per-interval layer sums."""
+
+    def __init__(self, plan, latdim=64, gnn_layer=2, leaky=0.5):
+        super().__init__()
+        self.plan, self.gnn_layer, self.leaky = plan, gnn_layer, leaky
+        self.uEmbed = torch.nn.Parameter(torch.empty(plan.T, plan.U, latdim, device=plan.device))
+        self.iEmbed = torch.nn.Parameter(torch.empty(plan.T, plan.I, latdim, device=plan.device))
+        # tf.contrib xavier on a 3-D shape: fan_in = T*rows, fan_out = T*d (Utils/NNLayers.py:47-50)
+        for p_ in (self.uEmbed, self.iEmbed):
+            a = (6.0 / (plan.T * (p_.shape[1] + latdim))) ** 0.5
+            torch.nn.init.uniform_(p_, -a, a)
+
+    def forward(self):
+        return propagate(self.plan, self.uEmbed, self.iEmbed, self.gnn_layer, self.leaky)

@@ -1,0 +1,69 @@
+"""Pre-allocated fwd+bwd step over a plan (what a training loop calls once per batch; the
+reference re-runs the full-graph propagation on every ``sess.run``, model.py:373,459).
+
+All buffers are allocated once; ``run()`` only enqueues the C-ABI calls on the current stream,
+so the whole step can be captured into a CUDA graph (``capture()``) and replayed with no
+per-layer launch latency.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .propagate import _ptr, _stream_ptr
+
+
+class PropagationStep:
+    def __init__(self, plan, n_layers, d, leaky=0.5):
+        self.plan, self.L, self.d, self.leaky = plan, int(n_layers), int(d), float(leaky)
+        dev = plan.device
+        self.lib = _lib.load_library()
+        with torch.cuda.device(dev):
+            f, m, b = plan.workspace_bytes(self.L, self.d)
+            self.ws = torch.empty(max(f, b, 1), dtype=torch.uint8, device=dev)
+            self.masks = torch.empty(max(m, 1), dtype=torch.uint8, device=dev)
+            mk = lambda rows: torch.empty((plan.T, rows, self.d), dtype=torch.float32, device=dev)
+            self.u_embed, self.i_embed = mk(plan.U), mk(plan.I)
+            self.g_user, self.g_item = mk(plan.U), mk(plan.I)
+            self.user_out, self.item_out = mk(plan.U), mk(plan.I)
+            self.d_u, self.d_i = mk(plan.U), mk(plan.I)
+        self.graph = None
+        self.kernel_launches_per_step = 2 * self.L      # L forward + L backward layer kernels
+
+    def forward(self):
+        p = self.plan
+        _lib.check(self.lib.sagnn_propagate_fwd(p.handle, _ptr(self.u_embed), _ptr(self.i_embed),
+                                                _ptr(self.user_out), _ptr(self.item_out), self.L, self.d,
+                                                self.leaky, _ptr(self.masks), _ptr(self.ws), self.ws.numel(),
+                                                _stream_ptr(p.device)))
+
+    def backward(self):
+        p = self.plan
+        _lib.check(self.lib.sagnn_propagate_bwd(p.handle, _ptr(self.g_user), _ptr(self.g_item), _ptr(self.d_u),
+                                                _ptr(self.d_i), self.L, self.d, self.leaky, _ptr(self.masks),
+                                                _ptr(self.ws), self.ws.numel(), _stream_ptr(p.device)))
+
+    def run(self):
+        self.forward()
+        self.backward()
+
+    def capture(self):
+        """Captures fwd+bwd into a CUDA graph; afterwards ``replay()`` launches the whole step."""
+        with torch.cuda.device(self.plan.device):
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self.run()                                   # warm-up outside capture
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run()
+            self.graph = g
+        return self
+
+    def replay(self):
+        if self.graph is None:
+            self.run()
+        else:
+            self.graph.replay()

@@ -1,0 +1,323 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs the CPU oracle.
+
+Integer work (CSR/CSC indices, degrees, truncated norm data) must be bit-exact; fp32
+propagation must satisfy SURVEY 8(d): max|x-ref| / max|ref| <= 1e-5 per output tensor AND
+allclose(rtol=1e-5, atol=1e-5*max|ref|) against the fp64 oracle.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import sagnn_b200 as sg
+from sagnn_b200 import data_handler as dh
+from oracle import c_oracle, propagate_oracle as po
+from helpers import adj_lists, random_interval_mats, random_tables
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5   # north_star: 1e-5 relative, fp32
+
+
+def assert_parity(got, ref, what):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else got
+    ref = np.asarray(ref, dtype=np.float64)
+    scale = float(np.max(np.abs(ref)))
+    err = po.relerr(got, ref)
+    assert err <= TOL, "%s: max|x-ref|/max|ref| = %.3e" % (what, err)
+    assert np.allclose(got, ref, rtol=TOL, atol=TOL * scale), what
+
+
+def run_gpu(plan, uE, iE, gU, gI, L, leaky=0.5):
+    u = torch.from_numpy(uE).cuda().requires_grad_(True)
+    i = torch.from_numpy(iE).cuda().requires_grad_(True)
+    uv, iv = sg.propagate(plan, u, i, L, leaky)
+    torch.autograd.backward([uv, iv], [torch.from_numpy(gU).cuda(), torch.from_numpy(gI).cuda()])
+    torch.cuda.synchronize()
+    return uv, iv, u.grad, i.grad
+
+
+def check_against_oracle(mats, d, L, leaky=0.5, seed=0, use_c=False, edge_weight=None, scale=1.0):
+    T, (U, I) = len(mats), mats[0].shape
+    adj, tp = adj_lists(mats)
+    uE, iE, gU, gI = random_tables(T, U, I, d, seed=seed, scale=scale)
+    ew = tew = None
+    if edge_weight == "lightgcn":
+        ew = [po.lightgcn_edge_weights(a, U, I) for a in adj]
+        tew = [po.lightgcn_edge_weights(a, I, U) for a in tp]
+    oracle = c_oracle.propagate if use_c else po.propagate
+    ref = oracle(adj, tp, uE, iE, gU, gI, L, leaky, np.float64, ew, tew)
+    plan = sg.build_plan(mats, edge_weight=edge_weight)
+    got = run_gpu(plan, uE, iE, gU, gI, L, leaky)
+    for g, r, name in zip(got, ref, ("user_vec", "item_vec", "dU", "dI")):
+        assert_parity(g, r, name)
+    return plan
+
+
+# ---------------------------------------------------------------- plan: bit-exact integer work
+def _load_mat(z):
+    return sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"]))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "index_*.npz"))))
+def test_plan_indices_match_reference_fixtures(path):
+    """Device CSR/CSC vs the reference's own transToLsts / transpose outputs (golden fixtures)."""
+    z = np.load(path)
+    m = _load_mat(z)
+    if m.dtype != np.intc:
+        m = m.astype(np.intc)
+    plan = sg.build_plan([m])
+    np.testing.assert_array_equal(plan.adjacency_list(0, 0).cpu().numpy(), z["adj_idx_raw"])
+    np.testing.assert_array_equal(plan.adjacency_list(0, 1).cpu().numpy(), z["tp_idx_raw"])
+    if m.nnz:
+        ptr, idx = plan.csr(0, 1)
+        np.testing.assert_array_equal(ptr.cpu().numpy(), z["tp_indptr"])
+        np.testing.assert_array_equal(idx.cpu().numpy(), z["tp_indices"])
+        ptr, idx = plan.csr(0, 0)
+        np.testing.assert_array_equal(ptr.cpu().numpy(), z["indptr"])
+        np.testing.assert_array_equal(idx.cpu().numpy(), z["indices"])
+        if np.issubdtype(z["data"].dtype, np.integer):
+            deg_u, vs_u = plan.degrees(0, 0, value_sum=True)
+            deg_i, vs_i = plan.degrees(0, 1, value_sum=True)
+            np.testing.assert_array_equal(vs_u.cpu().numpy(), z["rowsum"].astype(np.int64))
+            np.testing.assert_array_equal(vs_i.cpu().numpy(), z["colsum"].astype(np.int64))
+            np.testing.assert_array_equal(deg_u.cpu().numpy(), np.diff(z["indptr"]))
+            np.testing.assert_array_equal(deg_i.cpu().numpy(), np.diff(z["tp_indptr"]))
+            np.testing.assert_array_equal(plan.norm_data(0, 0).cpu().numpy(), z["adj_data_norm"])
+            np.testing.assert_array_equal(plan.norm_data(0, 1).cpu().numpy(), z["tp_data_norm"])
+
+
+def test_plan_norm_data_nontrivial_values():
+    """Mixed-sign stored values make the truncated normalisation non-zero (positive values alone
+    can never exceed 1 before truncation): bit-exact vs the oracle, including truncation toward 0."""
+    A = np.array([[1000, -990, 0, 0], [-990, 1000, 0, 0], [0, 0, 5, 0], [0, 3, 0, 7]], dtype=np.intc)
+    rng = np.random.default_rng(2)
+    keys = rng.choice(50 * 40, size=300, replace=False)
+    R = sp.csr_matrix((rng.integers(1, 2000, size=300).astype(np.intc), (keys // 40, keys % 40)), shape=(50, 40))
+    for m in (sp.csr_matrix(A), R):
+        plan = sg.build_plan([m])
+        for side, mat in ((0, m), (1, po.transpose(m))):
+            _, ref, _ = po.trans_to_lsts(mat, norm=True)
+            np.testing.assert_array_equal(plan.norm_data(0, side).cpu().numpy(), ref)
+    ref = po.trans_to_lsts(sp.csr_matrix(A), norm=True)[1]
+    assert ref[0] == 99 and ref[2] == -98 and ref[4] == 0
+
+
+def test_plan_multi_interval_and_generator_shapes():
+    g = dh.make_named("small", seed=100)
+    plan = sg.build_plan(g.sub_mat)
+    for k, m in enumerate(g.sub_mat):
+        for side, mat in ((0, m), (1, po.transpose(m))):
+            ref_idx, _, _ = po.trans_to_lsts(mat)
+            np.testing.assert_array_equal(plan.adjacency_list(k, side).cpu().numpy(), ref_idx)
+            rs, cs = po.value_sum_degrees(mat)
+            deg, vs = plan.degrees(k, side, value_sum=True)
+            np.testing.assert_array_equal(vs.cpu().numpy(), rs)
+            np.testing.assert_array_equal(deg.cpu().numpy(), np.diff(sp.csr_matrix(mat).indptr))
+    st = plan.stats()
+    assert st["rows"] == 3 * (g.n_user + g.n_item) and st["edges_both_sides"] == 2 * sum(g.nnz)
+    assert st["short_rows"] + st["long_rows"] == st["rows"]
+
+
+def test_lightgcn_weights_match_oracle():
+    mats = random_interval_mats(2, 70, 50, 400, seed=3)
+    adj, tp = adj_lists(mats)
+    plan = sg.build_plan(mats, edge_weight="lightgcn")
+    for k in range(2):
+        np.testing.assert_allclose(plan.weights(k, 0).cpu().numpy(),
+                                   po.lightgcn_edge_weights(adj[k], 70, 50, np.float32), rtol=1e-7)
+        np.testing.assert_allclose(plan.weights(k, 1).cpu().numpy(),
+                                   po.lightgcn_edge_weights(tp[k], 50, 70, np.float32), rtol=1e-7)
+
+
+def test_unsorted_and_out_of_range_inputs_rejected():
+    row = np.array([0, 2, 1], dtype=np.int32)
+    col = np.array([0, 1, 2], dtype=np.int32)
+    with pytest.raises(sg.SagnnError) as e:
+        sg.build_plan([(row, col)], U=4, I=4)
+    assert e.value.code == 2 and "not increasing" in str(e.value)     # TF: "segment ids are not increasing"
+    with pytest.raises(sg.SagnnError) as e:
+        sg.build_plan([(np.array([0, 1], np.int32), np.array([0, 9], np.int32))], U=4, I=4)
+    assert e.value.code == 6
+
+
+def test_strict_pad_raises_like_tf_cpu(golden_dir):
+    z = np.load(os.path.join(golden_dir, "index_gap_300x200.npz"))
+    m = _load_mat(z)
+    with pytest.raises(IndexError):
+        sg.build_plan([m], strict_pad=True)
+    sg.build_plan([m])   # default: zero rows, like TF-GPU
+
+
+def test_cpu_tensors_are_rejected():
+    plan = sg.build_plan(random_interval_mats(1, 10, 10, 20))
+    with pytest.raises(RuntimeError):
+        sg.propagate(plan, torch.zeros(1, 10, 64), torch.zeros(1, 10, 64), 2)
+    with pytest.raises(sg.SagnnError):   # d not supported
+        sg.propagate(plan, torch.zeros(1, 10, 48).cuda(), torch.zeros(1, 10, 48).cuda(), 2)
+
+
+# ---------------------------------------------------------------- op-level: messagePropagate
+@pytest.mark.parametrize("d", [32, 64, 128, 256])
+def test_message_propagate_matches_oracle(d):
+    mats = random_interval_mats(3, 150, 90, 1500, seed=d)
+    adj, tp = adj_lists(mats)
+    plan = sg.build_plan(mats)
+    rng = np.random.default_rng(d)
+    for k in (0, 2):
+        src_i = rng.standard_normal((90, d)).astype(np.float32)
+        src_u = rng.standard_normal((150, d)).astype(np.float32)
+        got = sg.message_propagate(torch.from_numpy(src_i).cuda(), plan, k, "user", 0.5)
+        assert_parity(got, po.message_propagate(src_i.astype(np.float64), adj[k], 150, 0.5), "user side")
+        got = sg.message_propagate(torch.from_numpy(src_u).cuda(), plan, k, "item", 0.5)
+        assert_parity(got, po.message_propagate(src_u.astype(np.float64), tp[k], 90, 0.5), "item side")
+
+
+# ---------------------------------------------------------------- full path vs golden / oracle
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "prop_*.npz"))))
+def test_propagate_matches_golden_fixtures(path):
+    z = np.load(path)
+    T, U, I, L, leaky = int(z["T"]), int(z["U"]), int(z["I"]), int(z["L"]), float(z["leaky"])
+    plan = sg.build_plan([z[f"adj{k}"] for k in range(T)], U=U, I=I)
+    got = run_gpu(plan, z["uE"], z["iE"], z["gU"], z["gI"], L, leaky)
+    for g, name in zip(got, ("user_vec", "item_vec", "dU", "dI")):
+        assert_parity(g, z[name], name)
+
+
+@pytest.mark.parametrize("d,L", [(32, 1), (64, 2), (64, 3), (128, 3), (128, 4), (256, 2)])
+def test_propagate_small_random(d, L):
+    check_against_oracle(random_interval_mats(3, 120, 80, 900, seed=d + L), d, L, seed=L)
+
+
+def test_propagate_long_rows_chunked_reduction():
+    """Rows far above the 64-edge chunk (dense-ish block + one hub item / hub user)."""
+    U, I = 700, 300
+    rng = np.random.default_rng(1)
+    A = (rng.random((U, I)) < 0.05)
+    A[:, 7] = True            # hub item: 700 users  -> 11 chunks on the item side
+    A[13, :] = True           # hub user: 300 items
+    mats = [sp.csr_matrix(A.astype(np.intc)), sp.csr_matrix((rng.random((U, I)) < 0.3).astype(np.intc))]
+    plan = check_against_oracle(mats, 64, 2, seed=3, scale=0.1)
+    st = plan.stats()
+    assert st["long_rows"] > 0 and st["chunks"] > st["long_rows"] and st["max_degree"] == 700
+    check_against_oracle(mats, 128, 3, seed=4, scale=0.05)
+
+
+def test_propagate_empty_interval_and_empty_rows():
+    mats = random_interval_mats(3, 40, 30, 60, seed=8)
+    mats[1] = sp.csr_matrix((40, 30), dtype=np.intc)     # all-empty interval -> fallback edge (0,0)
+    check_against_oracle(mats, 64, 2, seed=1)
+
+
+def test_propagate_tie_rule_zero_inputs():
+    """Zero embeddings make every pre-activation exactly 0: sigma'(0) must be `leaky`."""
+    mats = random_interval_mats(1, 20, 20, 60, seed=2)
+    adj, tp = adj_lists(mats)
+    plan = sg.build_plan(mats)
+    z = np.zeros((1, 20, 64), np.float32)
+    g = np.ones((1, 20, 64), np.float32)
+    ref = po.propagate(adj, tp, z, z, g, g, 2, 0.25, np.float64)
+    got = run_gpu(plan, z, z, g, g, 2, 0.25)
+    for a, b in zip(got, ref):
+        np.testing.assert_allclose(a.cpu().numpy(), b, rtol=1e-6)
+
+
+def test_propagate_weighted_lightgcn_mode():
+    check_against_oracle(random_interval_mats(2, 200, 150, 2500, seed=6), 64, 2, seed=2, edge_weight="lightgcn")
+
+
+def test_propagate_custom_weights():
+    mats = random_interval_mats(2, 60, 50, 500, seed=12)
+    adj, tp = adj_lists(mats)
+    rng = np.random.default_rng(0)
+    ew = [rng.random(len(a)).astype(np.float32) for a in adj]
+    # weights of the transposed lists: same edges, transposed order
+    tew = []
+    for k, m in enumerate(mats):
+        w = sp.csr_matrix((ew[k], (adj[k][:, 0], adj[k][:, 1])), shape=m.shape)
+        tew.append(np.asarray(sp.csr_matrix(w.T).tocoo().data, dtype=np.float32))
+    uE, iE, gU, gI = random_tables(2, 60, 50, 64, seed=5)
+    ref = po.propagate(adj, tp, uE, iE, gU, gI, 2, 0.5, np.float64, ew, tew)
+    plan = sg.build_plan(mats, edge_weight=ew)
+    got = run_gpu(plan, uE, iE, gU, gI, 2)
+    for g, r, name in zip(got, ref, ("user_vec", "item_vec", "dU", "dI")):
+        assert_parity(g, r, name)
+
+
+def test_repeated_calls_are_bitwise_deterministic():
+    g = dh.make_named("small", seed=5)
+    plan = sg.build_plan(g.sub_mat)
+    uE, iE, gU, gI = random_tables(3, g.n_user, g.n_item, 64, seed=9)
+    a = run_gpu(plan, uE, iE, gU, gI, 2)
+    b = run_gpu(plan, uE, iE, gU, gI, 2)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_forward_only_and_partial_grad():
+    mats = random_interval_mats(2, 50, 40, 300, seed=4)
+    adj, tp = adj_lists(mats)
+    plan = sg.build_plan(mats)
+    uE, iE, gU, gI = random_tables(2, 50, 40, 64, seed=6)
+    with torch.no_grad():
+        uv, iv = sg.propagate(plan, torch.from_numpy(uE).cuda(), torch.from_numpy(iE).cuda(), 2)
+    ref = po.propagate(adj, tp, uE, iE, gU, np.zeros_like(gI), 2, 0.5, np.float64)
+    assert_parity(uv, ref[0], "user_vec")
+    assert_parity(iv, ref[1], "item_vec")
+    u = torch.from_numpy(uE).cuda().requires_grad_(True)
+    i = torch.from_numpy(iE).cuda().requires_grad_(True)
+    uv, iv = sg.propagate(plan, u, i, 2)
+    (uv * torch.from_numpy(gU).cuda()).sum().backward()     # item output unused -> zero upstream
+    assert_parity(u.grad, ref[2], "dU")
+    assert_parity(i.grad, ref[3], "dI")
+
+
+def test_host_entry_point_matches_oracle():
+    mats = random_interval_mats(2, 90, 70, 600, seed=14)
+    adj, tp = adj_lists(mats)
+    plan = sg.build_plan(mats)
+    uE, iE, gU, gI = random_tables(2, 90, 70, 64, seed=7)
+    ref = po.propagate(adj, tp, uE, iE, gU, gI, 2, 0.5, np.float64)
+    outs = [np.empty_like(x) for x in (uE, iE, uE, iE)]
+    sg.propagate_host(plan, uE, iE, gU, gI, outs[0], outs[1], outs[2], outs[3], 2, 0.5)
+    for g, r, name in zip(outs, ref, ("user_vec", "item_vec", "dU", "dI")):
+        assert_parity(g, r, name)
+    fo = [np.empty_like(uE), np.empty_like(iE)]
+    sg.propagate_host(plan, uE, iE, None, None, fo[0], fo[1], None, None, 2, 0.5)
+    np.testing.assert_array_equal(fo[0], outs[0])
+
+
+# ---------------------------------------------------------------- BASELINE shape families
+@pytest.mark.parametrize("name,scale", [("gowalla", 0.05), ("amazon-book", 0.05), ("amazon-ref", 0.25), ("ml10m", 0.03)])
+def test_baseline_shapes_reduced_scale(name, scale):
+    g = dh.make_named(name, seed=100, scale=scale)
+    check_against_oracle(g.sub_mat, g.meta["d"], g.meta["L"], seed=100, use_c=True, scale=0.05)
+
+
+def test_gowalla_full_size_parity_and_properties():
+    """BASELINE config 2 at full size: parity vs the (fast, fused) C oracle in fp64, plus
+    size-independent properties: linearity of the backward in the upstream gradient and
+    the edgeless-row identity user_vec = (L+1) * embedding."""
+    g = dh.make_named("gowalla", seed=100)
+    T, U, I, d, L = 3, g.n_user, g.n_item, 64, 2
+    adj, tp = adj_lists(g.sub_mat)
+    uE = dh.xavier_embeddings(T, U, d, 100)
+    iE = dh.xavier_embeddings(T, I, d, 101)
+    rng = np.random.default_rng(100)
+    gU = rng.standard_normal((T, U, d)).astype(np.float32)
+    gI = rng.standard_normal((T, I, d)).astype(np.float32)
+    ref = c_oracle.propagate(adj, tp, uE, iE, gU, gI, L, 0.5, np.float64)
+    plan = sg.build_plan(g.sub_mat)
+    got = run_gpu(plan, uE, iE, gU, gI, L)
+    for x, r, name in zip(got, ref, ("user_vec", "item_vec", "dU", "dI")):
+        assert_parity(x, r, name)
+    # edgeless rows: output = (L+1) * E
+    deg = plan.degrees(0, 0).cpu().numpy()
+    lonely = np.flatnonzero(deg == 0)[:50]
+    if lonely.size:
+        np.testing.assert_allclose(got[0][0].cpu().numpy()[lonely], 3 * uE[0][lonely], rtol=1e-6)
+    # backward is linear in the upstream for a fixed forward: bwd(2g) == 2 bwd(g) exactly (power of 2)
+    got2 = run_gpu(plan, uE, iE, 2 * gU, 2 * gI, L)
+    assert torch.equal(got2[2], 2 * got[2]) and torch.equal(got2[3], 2 * got[3])

@@ -1,0 +1,123 @@
+"""CPU tests: host-side mirror of the reference's data layer, the generator, the C-ABI surface."""
+import ctypes
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import sagnn_b200 as sg
+from sagnn_b200 import data_handler as dh, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load_mat(z):
+    return sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=tuple(z["shape"]))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "index_*.npz"))))
+def test_host_mirror_matches_reference_fixtures(path):
+    """sagnn_b200.transToLsts / transpose == the reference's DataHandler functions (golden)."""
+    z = np.load(path)
+    m = _load_mat(z)
+    for norm, tag in ((False, "raw"), (True, "norm")):
+        idx, dat, shp = sg.transToLsts(m, norm=norm)
+        np.testing.assert_array_equal(idx, z[f"adj_idx_{tag}"])
+        np.testing.assert_array_equal(dat, z[f"adj_data_{tag}"])
+        assert idx.dtype == np.int32 and dat.dtype == np.int32 and shp == list(z[f"adj_shape_{tag}"])
+        tidx, tdat, _ = sg.transToLsts(sg.transpose(m), norm=norm)
+        np.testing.assert_array_equal(tidx, z[f"tp_idx_{tag}"])
+        np.testing.assert_array_equal(tdat, z[f"tp_data_{tag}"])
+
+
+def test_trn_mat_time_round_trip(tmp_path):
+    g = dh.make_named("tiny", seed=3)
+    p = tmp_path / "trn_mat_time"
+    dh.write_trn_mat_time(str(p), g)
+    h = dh.load_trn_mat_time(str(p))
+    assert (h.n_user, h.n_item, h.graph_num) == (g.n_user, g.n_item, 3)
+    for a, b in zip(g.sub_mat, h.sub_mat):
+        assert b.dtype == np.intc and (a != b).nnz == 0
+    # trnMat[0] = interaction counts, timeMat = last interval id (interval 0 vanishes)
+    assert h.trn_mat.shape == (g.n_user, g.n_item) and h.trn_mat.nnz == sum(g.nnz)
+    assert h.time_mat.nnz == sum(g.nnz[1:])
+    assert dh.load_trn_mat_time(str(p), graph_num=2).graph_num == 2
+    with pytest.raises(IndexError):
+        dh.load_trn_mat_time(str(p), graph_num=4)
+
+
+def test_generator_properties():
+    g = dh.make_named("small", seed=100)
+    U, I = g.n_user, g.n_item
+    assert g.nnz == dh.interval_sizes(60000, 3) and g.nnz[-1] < g.nnz[0]
+    seen = sp.csr_matrix((U, I), dtype=np.int32)
+    for m in g.sub_mat:
+        assert m.has_canonical_format and m.dtype == np.intc
+        assert m.data.min() >= dh.TS_LO and m.data.max() < dh.TS_HI
+        idx, _, _ = sg.transToLsts(m)
+        assert idx[-1, 0] + 101 >= U                     # pad-100 hack in range (model.py:87)
+        assert sg.transToLsts(sg.transpose(m))[0][-1, 0] + 101 >= I
+        seen = seen + (m != 0).astype(np.int32)
+    assert seen.max() == 1                               # every (u,i) lives in exactly one interval
+    deg = np.sort(np.asarray((seen != 0).sum(axis=0)).ravel())[::-1]
+    assert deg[0] > 20 * max(1, np.median(deg))          # power-law head
+    g2 = dh.make_named("small", seed=100)
+    assert all((a != b).nnz == 0 for a, b in zip(g.sub_mat, g2.sub_mat))   # seeded
+
+
+def test_amazon_ref_exact_interval_sizes():
+    g = dh.make_named("amazon-ref", seed=100)
+    assert (g.n_user, g.n_item) == (11199, 30821)
+    assert g.nnz == [72280, 78997, 79692, 78096, 45651]   # preprocess_to_trnmat.ipynb:1911-1920
+
+
+def test_xavier_limits():
+    e = dh.xavier_embeddings(3, 48653, 64, 100)
+    a = np.sqrt(6.0 / (3 * (48653 + 64)))
+    assert e.dtype == np.float32 and np.abs(e).max() <= a and np.abs(e).max() > 0.99 * a
+
+
+# ---------------------------------------------------------------- C ABI surface (no compute)
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "sagnn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sagnn_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    syms = _header_symbols()
+    assert len(syms) >= 16
+    assert os.path.exists(_lib.lib_path()), "build the library first: python sa-gnn_b200/build.py"
+    lib = ctypes.CDLL(_lib.lib_path())
+    for s in syms:
+        assert hasattr(lib, s), "libsagnn_b200.so does not export %s" % s
+    assert sorted(_lib.SIGNATURES) == syms              # the ctypes binding covers the whole header
+
+
+def test_library_loads_and_reports_version():
+    lib = sg.load_library()
+    assert b"sm_100a" in lib.sagnn_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sg.build_plan([sp.csr_matrix(np.eye(3, dtype=np.intc))])
+    # the C ABI itself also fails loudly instead of computing on the host
+    h = ctypes.c_void_p()
+    nnz = (ctypes.c_int64 * 1)(3)
+    rc = sg.load_library().sagnn_plan_create(1, 3, 3, nnz, ctypes.byref(h))
+    assert rc == 3 and b"no CPU fallback" in sg.load_library().sagnn_last_error()
+
+
+def test_product_never_imports_oracle():
+    for path in glob.glob(os.path.join(ROOT, "sa-gnn_b200", "**", "*.py"), recursive=True) + \
+            glob.glob(os.path.join(ROOT, "sa-gnn_b200", "csrc", "*")) + [os.path.join(ROOT, "sagnn_b200.py")]:
+        src = open(path).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), path
+        assert "sagnn_oracle" not in src, path
