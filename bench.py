@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-allgather", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--seed", type=int, default=100)
     return ap.parse_args()
@@ -225,6 +226,11 @@ def main():
     if use_graph:
         step.capture()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    if args.no_flush:
+        class _NoFlush:
+            def zero_(self):
+                pass
+        flush = _NoFlush()
 
     def one_step():
         if do_gather:

@@ -52,9 +52,16 @@ def _p(a, ct):
 
 
 def propagate(adj, tp_adj, u_embed, i_embed, g_user, g_item, n_layers, leaky=0.5, dtype=np.float64,
-              edge_weight=None, tp_edge_weight=None):
+              edge_weight=None, tp_edge_weight=None, mask_in=None, mask_cmp=None, tie_tol=1e-5,
+              return_masks=False):
     """Same contract as propagate_oracle.propagate; g_user/g_item may be None (forward only).
-    Returns (user_vec, item_vec, dU, dI) (dU/dI None when forward only)."""
+    Returns (user_vec, item_vec, dU, dI) (dU/dI None when forward only).
+
+    Masks are uint8 arrays [T, L, (U+I)*d] (user part then item part; 1 = gradient passes
+    unscaled).  mask_in overrides the oracle's own MaximumGrad decisions in the backward;
+    mask_cmp is compared against them and the result carries ``stats = [mismatches,
+    mismatches that are not near-ties (|z| > tie_tol * sum|terms|)]``; return_masks appends
+    the oracle's masks.  Extra results are returned as a dict in a 5th tuple slot."""
     dtype = np.dtype(dtype)
     if dtype == np.float64:
         fn, ct = lib().sagnn_oracle_interval_f64, ctypes.c_double
@@ -73,6 +80,10 @@ def propagate(adj, tp_adj, u_embed, i_embed, g_user, g_item, n_layers, leaky=0.5
     uO, iO = np.empty_like(uE), np.empty_like(iE)
     dU = np.empty_like(uE) if bwd else None
     dI = np.empty_like(iE) if bwd else None
+    extra = mask_in is not None or mask_cmp is not None or return_masks
+    m_out = np.zeros((T, n_layers, (U + I) * d), dtype=np.uint8) if return_masks else None
+    stats = np.zeros(2, dtype=np.int64)
+    u8 = ctypes.c_uint8
     for k in range(T):
         uptr, ucol = indices_to_csr(adj[k], U)
         iptr, irow = indices_to_csr(tp_adj[k], I)
@@ -86,7 +97,13 @@ def propagate(adj, tp_adj, u_embed, i_embed, g_user, g_item, n_layers, leaky=0.5
                 _p(uE[k], ct), _p(iE[k], ct),
                 _p(gU[k], ct) if bwd else None, _p(gI[k], ct) if bwd else None,
                 _p(uO[k], ct), _p(iO[k], ct),
-                _p(dU[k], ct) if bwd else None, _p(dI[k], ct) if bwd else None)
+                _p(dU[k], ct) if bwd else None, _p(dI[k], ct) if bwd else None,
+                _p(m_out[k], u8) if m_out is not None else None,
+                _p(np.ascontiguousarray(mask_in[k], dtype=np.uint8), u8) if mask_in is not None else None,
+                _p(np.ascontiguousarray(mask_cmp[k], dtype=np.uint8), u8) if mask_cmp is not None else None,
+                ctypes.c_double(tie_tol), _p(stats, ctypes.c_int64))
         if rc != 0:
             raise MemoryError("sagnn_oracle_interval failed")
+    if extra:
+        return uO, iO, dU, dI, {"stats": stats, "masks": m_out}
     return uO, iO, dU, dI

@@ -62,12 +62,32 @@ void sagnn_oracle_set_threads(int n) {
     }                                                                                            \
   }                                                                                              \
                                                                                                  \
-  /* one interval, forward (+ backward when gU != NULL).  Returns 0, or -1 on OOM.           */  \
+  /* S[r,:] = sum_e |w_e * src[idx[e],:]|  -- the rounding scale of Z, for near-tie detection  */  \
+  static void spmm_abs_##SUFFIX(int R, int d, const int64_t* ptr, const int32_t* idx,            \
+                                const REAL* w, const REAL* src, REAL* z) {                       \
+    _Pragma("omp parallel for schedule(dynamic, 64)") for (int r = 0; r < R; ++r) {              \
+      REAL* zr = z + (size_t)r * d;                                                              \
+      for (int j = 0; j < d; ++j) zr[j] = (REAL)0;                                               \
+      for (int64_t e = ptr[r]; e < ptr[r + 1]; ++e) {                                            \
+        const REAL* s = src + (size_t)idx[e] * d;                                                \
+        REAL we = w ? w[e] : (REAL)1;                                                            \
+        for (int j = 0; j < d; ++j) { REAL t = we * s[j]; zr[j] += (t < 0 ? -t : t); }           \
+      }                                                                                          \
+    }                                                                                            \
+  }                                                                                              \
+                                                                                                 \
+  /* one interval, forward (+ backward when gU != NULL).  Returns 0, or -1 on OOM.              \
+   * masks are bytes, layout [L][U*d | I*d], 1 = MaximumGrad passes the gradient unscaled:      \
+   *   mask_out (nullable)  receives the oracle's own decisions;                                \
+   *   mask_in  (nullable)  overrides them in the backward (parity GIVEN the masks);            \
+   *   mask_cmp (nullable)  is compared with the oracle's: stats[0] += mismatches,              \
+   *                        stats[1] += mismatches with |z| > tie_tol * sum|terms| (not ties) */ \
   int sagnn_oracle_interval_##SUFFIX(                                                            \
       int U, int I, int d, int L, double leaky_d, const int64_t* uptr, const int32_t* ucol,      \
       const int64_t* iptr, const int32_t* irow, const REAL* uw, const REAL* iw, const REAL* uE,  \
       const REAL* iE, const REAL* gU, const REAL* gI, REAL* uOut, REAL* iOut, REAL* dU,          \
-      REAL* dI) {                                                                                \
+      REAL* dI, uint8_t* mask_out, const uint8_t* mask_in, const uint8_t* mask_cmp,              \
+      double tie_tol, int64_t* stats) {                                                          \
     const REAL leaky = (REAL)leaky_d;                                                            \
     const size_t nu = (size_t)U * d, ni = (size_t)I * d;                                         \
     REAL* e0 = (REAL*)malloc(nu * sizeof(REAL));                                                 \
@@ -87,6 +107,32 @@ void sagnn_oracle_set_threads(int n) {
       REAL* zl1 = z1 + (size_t)l * ni;                                                           \
       spmm_##SUFFIX(U, d, uptr, ucol, uw, e1, zl0);          /* both use layer-l inputs */       \
       spmm_##SUFFIX(I, d, iptr, irow, iw, e0, zl1);                                              \
+      if (mask_out) {                                                                            \
+        uint8_t* mo = mask_out + (size_t)l * (nu + ni);                                          \
+        for (size_t t = 0; t < nu; ++t) mo[t] = !(leaky * zl0[t] >= zl0[t]);                     \
+        for (size_t t = 0; t < ni; ++t) mo[nu + t] = !(leaky * zl1[t] >= zl1[t]);                \
+      }                                                                                          \
+      if (mask_cmp && stats) {                                                                   \
+        const uint8_t* mc = mask_cmp + (size_t)l * (nu + ni);                                    \
+        REAL* a0 = (REAL*)malloc(nu * sizeof(REAL));                                             \
+        REAL* a1 = (REAL*)malloc(ni * sizeof(REAL));                                             \
+        if (!a0 || !a1) { free(a0); free(a1); free(e0); free(e1); free(z0); free(z1); return -1; } \
+        spmm_abs_##SUFFIX(U, d, uptr, ucol, uw, e1, a0);                                         \
+        spmm_abs_##SUFFIX(I, d, iptr, irow, iw, e0, a1);                                         \
+        for (size_t t = 0; t < nu; ++t) {                                                        \
+          if (mc[t] != (uint8_t)(!(leaky * zl0[t] >= zl0[t]))) {                                 \
+            REAL az = zl0[t] < 0 ? -zl0[t] : zl0[t];                                             \
+            stats[0]++; if ((double)az > tie_tol * (double)a0[t]) stats[1]++;                    \
+          }                                                                                      \
+        }                                                                                        \
+        for (size_t t = 0; t < ni; ++t) {                                                        \
+          if (mc[nu + t] != (uint8_t)(!(leaky * zl1[t] >= zl1[t]))) {                            \
+            REAL az = zl1[t] < 0 ? -zl1[t] : zl1[t];                                             \
+            stats[0]++; if ((double)az > tie_tol * (double)a1[t]) stats[1]++;                    \
+          }                                                                                      \
+        }                                                                                        \
+        free(a0); free(a1);                                                                      \
+      }                                                                                          \
       _Pragma("omp parallel for") for (size_t t = 0; t < nu; ++t) {                              \
         REAL z = zl0[t], lz = leaky * z;                                                         \
         e0[t] += (lz > z ? lz : z);                                                              \
@@ -113,13 +159,16 @@ void sagnn_oracle_set_threads(int n) {
         const REAL* zl0 = z0 + (size_t)l * nu;                                                   \
         const REAL* zl1 = z1 + (size_t)l * ni;                                                   \
         /* MaximumGrad: gradient goes to leaky*z where leaky*z >= z */                           \
+        const uint8_t* mi = mask_in ? mask_in + (size_t)l * (nu + ni) : NULL;                    \
         _Pragma("omp parallel for") for (size_t t = 0; t < nu; ++t) {                            \
           REAL z = zl0[t];                                                                       \
-          s0[t] = (leaky * z >= z) ? leaky * g0[t] : g0[t];                                      \
+          int pass = mi ? mi[t] : !(leaky * z >= z);                                             \
+          s0[t] = pass ? g0[t] : leaky * g0[t];                                                  \
         }                                                                                        \
         _Pragma("omp parallel for") for (size_t t = 0; t < ni; ++t) {                            \
           REAL z = zl1[t];                                                                       \
-          s1[t] = (leaky * z >= z) ? leaky * g1[t] : g1[t];                                      \
+          int pass = mi ? mi[nu + t] : !(leaky * z >= z);                                        \
+          s1[t] = pass ? g1[t] : leaky * g1[t];                                                  \
         }                                                                                        \
         /* d/dE0^l of s(A^T E0^l) = A (m1 . g1): gather over the A-CSR; likewise for E1 */       \
         spmm_##SUFFIX(U, d, uptr, ucol, uw, s1, e0);         /* e0/e1 reused as scratch */       \

@@ -217,7 +217,7 @@ def propagate_forward(adj, tp_adj, u_embed, i_embed, n_layers, leaky=0.5, dtype=
 
 
 def propagate_backward(adj, tp_adj, tape, g_user, g_item, n_layers, leaky=0.5, dtype=np.float64,
-                       edge_weight=None, tp_edge_weight=None):
+                       edge_weight=None, tp_edge_weight=None, pass_masks=None):
     """Reverse-mode sweep over the op list of ``propagate_forward`` exactly as
     TF1 autodiff would build it (implied by model.py:250): AddN fans the
     upstream out to every ``embs*[j]``; the residual add passes the gradient to
@@ -227,6 +227,12 @@ def propagate_backward(adj, tp_adj, tape, g_user, g_item, n_layers, leaky=0.5, d
 
     g_user [T,U,d], g_item [T,I,d] dense upstream.  Returns
     (d_u_embed [T,U,d], d_i_embed [T,I,d]).
+
+    pass_masks (optional): ``pass_masks[k][l] = (bool [U,d], bool [I,d])`` replaces the
+    MaximumGrad decision (True = gradient passes unscaled).  LeakyReLU's derivative jumps at
+    0, so an fp32 implementation whose |z| ~ 1e-7 pre-activation rounds to the other sign
+    legitimately takes the other branch; parity tests therefore check the sign masks
+    separately (mismatches only at near-ties) and the backward GIVEN the masks.
     """
     T = len(adj)
     g_user = np.asarray(g_user, dtype=dtype)
@@ -245,8 +251,13 @@ def propagate_backward(adj, tp_adj, tape, g_user, g_item, n_layers, leaky=0.5, d
             ga1 = ge1[l + 1]
             ge0[l] = ge0[l] + ga0
             ge1[l] = ge1[l] + ga1
-            dz0 = leaky_relu_grad(z0s[l], ga0, leaky)           # [U,d]
-            dz1 = leaky_relu_grad(z1s[l], ga1, leaky)           # [I,d]
+            if pass_masks is None:
+                dz0 = leaky_relu_grad(z0s[l], ga0, leaky)       # [U,d]
+                dz1 = leaky_relu_grad(z1s[l], ga1, leaky)       # [I,d]
+            else:
+                lk = np.asarray(leaky, dtype=ga0.dtype)
+                dz0 = np.where(pass_masks[k][l][0], ga0, lk * ga0)
+                dz1 = np.where(pass_masks[k][l][1], ga1, lk * ga1)
             # user-side call: lat rows <- item table rows via adj[k]  (tgt=user, src=item)
             per_edge0 = dz0[adj[k][:, 0]]
             if ew is not None:
@@ -270,6 +281,15 @@ def propagate(adj, tp_adj, u_embed, i_embed, g_user, g_item, n_layers, leaky=0.5
     du, di = propagate_backward(adj, tp_adj, tape, g_user, g_item, n_layers, leaky, dtype,
                                 edge_weight, tp_edge_weight)
     return uv, iv, du, di
+
+
+def pass_masks_from_tape(tape, leaky=0.5):
+    """The MaximumGrad decisions of a forward tape: True where the gradient passes unscaled."""
+    out = []
+    for z0s, z1s in tape:
+        out.append([(~(np.asarray(leaky, z0.dtype) * z0 >= z0), ~(np.asarray(leaky, z1.dtype) * z1 >= z1))
+                    for z0, z1 in zip(z0s, z1s)])
+    return out
 
 
 def relerr(x, ref):
