@@ -5,7 +5,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "lib", "libsagnn_b200.so")
+# SAGNN_B200_LIB selects another build of the same C ABI (tuning experiments); default = in-tree build
+_LIB = os.environ.get("SAGNN_B200_LIB") or os.path.join(_HERE, "lib", "libsagnn_b200.so")
 _lib = None
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)

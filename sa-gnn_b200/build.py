@@ -26,21 +26,26 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: experiment variants, e.g. build(defines=["SAGNN_MIN_BLOCKS=4"], out="lib/x.so")."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     cmd = [nvcc] + NVCC_FLAGS + ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "csrc")]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(HERE, s) for s in SOURCES] + ["-o", LIB]
+    cmd += ["-D" + d for d in defines]
+    target = LIB if out is None else os.path.join(HERE, out)
+    cmd += [os.path.join(HERE, s) for s in SOURCES] + ["-o", target]
     env = dict(os.environ)
     env.pop("CC", None)   # the image's CC points at a gcc wrapper without its spec files
     env.pop("CXX", None)
     subprocess.check_call(cmd, env=env)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

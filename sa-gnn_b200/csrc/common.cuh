@@ -35,6 +35,13 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace sagnn
 
+// One unit of work for a lane group: a whole short row or one <=kChunk-edge slice of a long row.
+struct __align__(16) sagnn_task {
+  uint32_t grow;   // global row id
+  uint32_t meta;   // edge count (<= kChunk); bit 31 set for a slice of a long row
+  int64_t e0;      // first edge (offset into idx)
+};
+
 // Global row space: row g = k*(U+I) + (side ? U + r : r); edges of interval k are stored
 // as [A_k CSR column ids (item ids) | A_k^T CSR column ids (user ids)] starting at
 // idx[2*sum_{j<k} nnz_j], so one exclusive scan of the degrees in global row order is
@@ -68,6 +75,7 @@ struct sagnn_plan {
   uint32_t* long_row = nullptr;   // [n_long] global row ids
   int64_t* chunk_base = nullptr;  // [n_long + 1] first chunk of each long row
   uint32_t* chunk_lr = nullptr;   // [n_chunks] long-row rank of each chunk
+  sagnn_task* tasks = nullptr;    // [n_chunks + n_short] chunk tasks first (longest rows first), then short rows
   int64_t n_short = 0, n_long = 0, n_chunks = 0;
   int32_t max_deg = 0;
 

@@ -156,6 +156,29 @@ __global__ void chunk_fill_kernel(const int64_t* __restrict__ chunk_base, int64_
   chunk_lr[c] = (uint32_t)lo;
 }
 
+// task records: chunk c of long row lr covers edges [rs + deg*ci/nch, rs + deg*(ci+1)/nch)
+__global__ void task_fill_kernel(const int64_t* __restrict__ rowptr, const uint32_t* __restrict__ order,
+                                 const uint32_t* __restrict__ long_row, const int64_t* __restrict__ chunk_base,
+                                 const uint32_t* __restrict__ chunk_lr, int64_t n_chunks, int64_t n_short,
+                                 sagnn_task* __restrict__ tasks) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_chunks + n_short) return;
+  sagnn_task k;
+  if (t < n_chunks) {
+    const uint32_t lr = chunk_lr[t];
+    const int64_t cb = chunk_base[lr], nch = chunk_base[lr + 1] - cb, ci = t - cb;
+    k.grow = long_row[lr];
+    const int64_t rs = rowptr[k.grow], deg = rowptr[k.grow + 1] - rs;
+    k.e0 = rs + deg * ci / nch;
+    k.meta = (uint32_t)(rs + deg * (ci + 1) / nch - k.e0) | 0x80000000u;
+  } else {
+    k.grow = order[t - n_chunks];
+    k.e0 = rowptr[k.grow];
+    k.meta = (uint32_t)(rowptr[k.grow + 1] - k.e0);
+  }
+  tasks[t] = k;
+}
+
 struct CastI64 {
   __host__ __device__ int64_t operator()(int32_t v) const { return (int64_t)v; }
 };
@@ -231,7 +254,7 @@ extern "C" int sagnn_plan_destroy(sagnn_plan* p) {
   sagnn::free_host_cache(p);
   cudaFree(p->deg); cudaFree(p->rowptr); cudaFree(p->idx); cudaFree(p->val); cudaFree(p->w);
   cudaFree(p->valsum); cudaFree(p->order); cudaFree(p->long_row); cudaFree(p->chunk_base);
-  cudaFree(p->chunk_lr);
+  cudaFree(p->chunk_lr); cudaFree(p->tasks);
   delete p;
   return SAGNN_OK;
 }
@@ -393,6 +416,12 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
     chunk_fill_kernel<<<blocks_for(p->n_chunks), 256, 0, st>>>(p->chunk_base, p->n_long, p->n_chunks, p->chunk_lr);
   } else {
     SAGNN_CUDA(cudaMemsetAsync(p->chunk_base, 0, sizeof(int64_t), st));
+  }
+  {
+    const int64_t nt = p->n_chunks + p->n_short;
+    SAGNN_CUDA(cudaMalloc(&p->tasks, sizeof(sagnn_task) * (nt ? nt : 1)));
+    task_fill_kernel<<<blocks_for(nt), 256, 0, st>>>(p->rowptr, p->order, p->long_row, p->chunk_base,
+                                                     p->chunk_lr, p->n_chunks, p->n_short, p->tasks);
   }
   SAGNN_CUDA(cudaGetLastError());
   SAGNN_CUDA(cudaStreamSynchronize(st));

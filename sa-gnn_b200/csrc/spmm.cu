@@ -16,16 +16,18 @@
 
 #include "common.cuh"
 
+#ifndef SAGNN_MIN_BLOCKS
+#define SAGNN_MIN_BLOCKS 3   // CTAs per SM the register allocator must leave room for
+#endif
+
 namespace sagnn {
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_MSG = 2 };
 
 struct SpmmParams {
-  const int64_t* rowptr;
+  const sagnn_task* tasks;
   const int32_t* idx;
   const float* w;
-  const uint32_t* order;
-  const uint32_t* long_row;
   const int64_t* chunk_base;
   const uint32_t* chunk_lr;
   int64_t n_short, n_chunks;
@@ -59,8 +61,18 @@ __device__ __forceinline__ float4 ld_nc(const float* p) {
 __device__ __forceinline__ float4 ld_stream(const float* p) {
   return __ldcs(reinterpret_cast<const float4*>(p));
 }
-__device__ __forceinline__ float4 ld_cg(const float* p) {
-  return __ldcg(reinterpret_cast<const float4*>(p));
+// strong (L1-bypassing) load at GPU scope: used for data published by other SMs in this launch
+__device__ __forceinline__ float4 ld_strong(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// ticket increment with release semantics (MEMBAR.ALL.GPU + atomic, no L1 invalidate)
+__device__ __forceinline__ unsigned ticket_release_add(unsigned* p) {
+  unsigned old;
+  asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
+  return old;
 }
 __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void st_stream(float* p, float4 v) {
@@ -69,45 +81,72 @@ __device__ __forceinline__ void st_stream(float* p, float4 v) {
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
+__device__ __forceinline__ sagnn_task ld_task(const sagnn_task* tasks, int64_t t, int64_t n_tasks) {
+  sagnn_task k;
+  if (t < n_tasks) {
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(tasks + t));
+    k.grow = (uint32_t)raw.x;
+    k.meta = (uint32_t)raw.y;
+    k.e0 = ((int64_t)(uint32_t)raw.w << 32) | (uint32_t)raw.z;
+  } else {
+    k.grow = 0xffffffffu;   // sentinel: no work (fails the row filter)
+    k.meta = 0;
+    k.e0 = 0;
+  }
+  return k;
+}
+
+// The lane groups of a warp run in lock step (trip counts are warp maxima, loads are
+// predicated), so every shuffle uses the full mask and nothing serialises on divergence;
+// tasks arrive sorted by degree, so the groups sharing a warp have near-equal rows.
 template <int LPR, int V, int MODE, bool WEIGHTED>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, SAGNN_MIN_BLOCKS)
 spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
   constexpr int D = LPR * V * 4;
   constexpr int WPR = D / 32;          // mask words per row
+  constexpr int GPW = 32 / LPR;        // lane groups per warp
   constexpr int UNR = 8;               // independent 128-bit gathers in flight per lane
   static_assert(LPR % UNR == 0, "unroll must divide the group width");
+  constexpr unsigned FULL = 0xffffffffu;
 
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
-  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (lane - gl));
-  const int64_t n_groups = (int64_t)gridDim.x * (kThreads / LPR);
+  const int gbase = lane - gl;         // first lane of my group
   const int64_t n_tasks = p.n_chunks + p.n_short;
+  const int64_t stride = (int64_t)gridDim.x * (kThreads / 32) * GPW;
+  const int64_t warp_t0 = ((int64_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * GPW;
+  int64_t t = warp_t0 + lane / LPR;
 
-  for (int64_t t = (int64_t)blockIdx.x * (kThreads / LPR) + threadIdx.x / LPR; t < n_tasks; t += n_groups) {
-    uint32_t grow;
-    int64_t e0, e1;
-    uint32_t lr = 0;
-    int64_t cb = 0;
-    int nch = 1;
-    if (t < p.n_chunks) {
-      lr = __ldg(p.chunk_lr + t);
-      grow = __ldg(p.long_row + lr);
-      cb = __ldg(p.chunk_base + lr);
-      nch = (int)(__ldg(p.chunk_base + lr + 1) - cb);
-      const int64_t rs = __ldg(p.rowptr + grow);
-      const int64_t deg = __ldg(p.rowptr + grow + 1) - rs;
-      const int64_t ci = t - cb;
-      e0 = rs + deg * ci / nch;
-      e1 = rs + deg * (ci + 1) / nch;
-    } else {
-      grow = __ldg(p.order + (t - p.n_chunks));
-      e0 = __ldg(p.rowptr + grow);
-      e1 = __ldg(p.rowptr + grow + 1);
+  // software pipeline: task records two rounds ahead, the first index batch one round ahead
+  sagnn_task nxt = ld_task(p.tasks, t, n_tasks);
+  sagnn_task nxt2 = ld_task(p.tasks, t + stride, n_tasks);
+  int nxt_c = 0;
+  float nxt_w = 0.f;
+  if (gl < (int)(nxt.meta & 0xffu)) {
+    nxt_c = __ldg(p.idx + nxt.e0 + gl);
+    if (WEIGHTED) nxt_w = __ldg(p.w + nxt.e0 + gl);
+  }
+
+  for (int64_t tb = warp_t0; tb < n_tasks; tb += stride, t += stride) {   // warp-uniform trip count
+    const sagnn_task cur = nxt;
+    int myc = nxt_c;
+    float myw = nxt_w;
+    nxt = nxt2;
+    nxt2 = ld_task(p.tasks, t + 2 * stride, n_tasks);
+    nxt_c = 0;
+    if (gl < (int)(nxt.meta & 0xffu)) {
+      nxt_c = __ldg(p.idx + nxt.e0 + gl);
+      if (WEIGHTED) nxt_w = __ldg(p.w + nxt.e0 + gl);
     }
-    if (grow < p.row_lo || grow >= p.row_hi) continue;
-    const uint32_t k = grow / p.N;
-    const uint32_t rem = grow - k * p.N;
+
+    const uint32_t grow = cur.grow;
+    const bool valid = grow >= p.row_lo && grow < p.row_hi;
+    const bool is_chunk = (cur.meta >> 31) != 0;
+    const int n = valid ? (int)(cur.meta & 0xffu) : 0;
+    const uint32_t k = valid ? grow / p.N : 0u;
+    const uint32_t rem = valid ? grow - k * p.N : 0u;
     const bool item_side = rem >= (uint32_t)p.U;
     const uint32_t r = item_side ? rem - p.U : rem;
     // this row's own table geometry and the geometry of the table it gathers from
@@ -117,31 +156,56 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
     const uint32_t* __restrict__ smask =
         (MODE == MODE_BWD) ? (item_side ? p.smask_u : p.smask_i) + src_row0 * WPR : nullptr;
 
+    // chunk bookkeeping (long rows only), off the critical path
+    uint32_t lr = 0;
+    int64_t cb = 0;
+    int nch = 1;
+    if (valid && is_chunk) {
+      lr = __ldg(p.chunk_lr + t);
+      cb = __ldg(p.chunk_base + lr);
+      nch = (int)(__ldg(p.chunk_base + lr + 1) - cb);
+    }
+    const bool multi = nch > 1;
+
+    // the row's own dense operand is independent of the gather: issue it first
+    float4 own_a[V];
+    if (MODE != MODE_MSG) {
+      const float* a = item_side ? p.a_i : p.a_u;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        own_a[v] = valid ? ld_nc(a + own_row * D + (v * LPR + gl) * 4) : f4_zero();
+    }
+
     float4 acc[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int v = 0; v < V; ++v) acc[v] = f4_zero();
 
-    // ---- gather-reduce over this task's edges -----------------------------------------
-    for (int64_t e = e0; e < e1; e += LPR) {
-      const int n = (int)((e1 - e) < (int64_t)LPR ? (e1 - e) : (int64_t)LPR);
-      int myc = 0;
-      float myw = 0.f;
-      if (gl < n) {
-        myc = __ldg(p.idx + e + gl);
-        if (WEIGHTED) myw = __ldg(p.w + e + gl);
+    // ---- gather-reduce over this task's edges (lock step over the warp) -----------------
+    int nmax = n;
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+    for (int eb = 0; eb < nmax; eb += LPR) {
+      // prefetch the next batch of column ids while this one is gathered
+      int c_next = 0;
+      float w_next = 0.f;
+      if (eb + LPR + gl < n) {
+        c_next = __ldg(p.idx + cur.e0 + eb + LPR + gl);
+        if (WEIGHTED) w_next = __ldg(p.w + cur.e0 + eb + LPR + gl);
       }
-      for (int j = 0; j < n; j += UNR) {
+      const int nb = n - eb;               // edges of my group left (may be <= 0)
+      const int nbmax = min(LPR, nmax - eb);
+      for (int j = 0; j < nbmax; j += UNR) {
         float4 val[UNR][V];
         uint32_t mw[UNR][V];
         float wv[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-          const int c = __shfl_sync(gmask, myc, j + u, LPR);
-          if (WEIGHTED) wv[u] = __shfl_sync(gmask, myw, j + u, LPR);
-          const bool on = (j + u) < n;
+          const int c = __shfl_sync(FULL, myc, gbase + j + u);
+          if (WEIGHTED) wv[u] = __shfl_sync(FULL, myw, gbase + j + u);
+          const bool on = (j + u) < nb;
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            val[u][v] = f4_zero();
             mw[u][v] = 0xffffffffu;
             if (on) {
               val[u][v] = ld_nc(src + (int64_t)c * D + (v * LPR + gl) * 4);
@@ -172,80 +236,90 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
           }
         }
       }
+      myc = c_next;
+      myw = w_next;
     }
 
-    // ---- long rows: publish the partial sum; the last chunk to arrive reduces ----------
-    if (nch > 1) {
-      float* mine = p.partials + t * D;
+    // ---- long rows: publish the partial sum; the last slice to arrive reduces -----------
+    // (release-only ticket; the reducer reads with strong loads that bypass L1, so no
+    //  acquire fence / L1 invalidate is needed)
+    bool finish = valid;
+    if (__any_sync(FULL, multi)) {
+      if (multi) {
+        float* mine = p.partials + t * D;
 #pragma unroll
-      for (int v = 0; v < V; ++v) st_f4(mine + (v * LPR + gl) * 4, acc[v]);
-      __threadfence();
-      __syncwarp(gmask);
-      unsigned old = 0;
-      if (gl == 0) old = atomicAdd(p.tickets + lr, 1u);
-      old = __shfl_sync(gmask, old, 0, LPR);
-      if (old != (unsigned)(nch - 1)) continue;
-      __threadfence();
-#pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* part = p.partials + cb * D;
-      for (int c0 = 0; c0 < nch; c0 += UNR) {
-        float4 val[UNR][V];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u)
-#pragma unroll
-          for (int v = 0; v < V; ++v)
-            val[u][v] = (c0 + u < nch) ? ld_cg(part + (int64_t)(c0 + u) * D + (v * LPR + gl) * 4)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < UNR; ++u)
-#pragma unroll
-          for (int v = 0; v < V; ++v) acc[v] = f4_add(acc[v], val[u][v]);
+        for (int v = 0; v < V; ++v) st_f4(mine + (v * LPR + gl) * 4, acc[v]);
       }
-      if (gl == 0) p.tickets[lr] = 0u;   // ready for the next launch
+      __syncwarp();
+      unsigned old = 0;
+      if (multi && gl == 0) old = ticket_release_add(p.tickets + lr);
+      old = __shfl_sync(FULL, old, gbase);
+      if (multi) {
+        finish = (old == (unsigned)(nch - 1));
+        if (finish) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = f4_zero();
+          const float* part = p.partials + cb * D;
+          for (int c0 = 0; c0 < nch; c0 += UNR) {
+            float4 val[UNR][V];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+              for (int v = 0; v < V; ++v)
+                val[u][v] = (c0 + u < nch) ? ld_strong(part + (int64_t)(c0 + u) * D + (v * LPR + gl) * 4)
+                                           : f4_zero();
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+              for (int v = 0; v < V; ++v) acc[v] = f4_add(acc[v], val[u][v]);
+          }
+          if (gl == 0) p.tickets[lr] = 0u;   // ready for the next launch
+        }
+      }
+      __syncwarp();
     }
 
-    // ---- fused epilogue -----------------------------------------------------------------
+    // ---- fused epilogue (all lanes take part in the shuffles; stores are predicated) -----
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const int col = (v * LPR + gl) * 4;
       const int64_t off = own_row * D + col;
       if (MODE == MODE_BWD) {
         // n = G + g + A (sigma' . g_other)      
-        const float* G = item_side ? p.a_i : p.a_u;
-        const float* g = item_side ? p.b_i : p.b_u;
-        float* dst = item_side ? p.o1_i : p.o1_u;
-        const float4 Gv = ld_nc(G + off);
-        const float4 gv = g ? ld_stream(g + off) : Gv;
-        st_f4(dst + off, f4_add(f4_add(Gv, gv), acc[v]));
+        if (finish) {
+          const float* g = item_side ? p.b_i : p.b_u;
+          float* dst = item_side ? p.o1_i : p.o1_u;
+          const float4 gv = g ? ld_stream(g + off) : own_a[v];
+          st_f4(dst + off, f4_add(f4_add(own_a[v], gv), acc[v]));
+        }
       } else {
         const float4 z = acc[v];
         const float lzx = p.leaky * z.x, lzy = p.leaky * z.y, lzz = p.leaky * z.z, lzw = p.leaky * z.w;
         // LeakyReLU = max(leaky*z, z)  (Utils/NNLayers.py:135-136)
         const float4 act = make_float4(fmaxf(lzx, z.x), fmaxf(lzy, z.y), fmaxf(lzz, z.z), fmaxf(lzw, z.w));
         if (MODE == MODE_MSG) {
-          st_f4((item_side ? p.o1_i : p.o1_u) + off, act);
+          if (finish) st_f4((item_side ? p.o1_i : p.o1_u) + off, act);
         } else {
-          const float* a = item_side ? p.a_i : p.a_u;
           const float* b = item_side ? p.b_i : p.b_u;
           float* o1 = item_side ? p.o1_i : p.o1_u;
           float* o2 = item_side ? p.o2_i : p.o2_u;
           uint32_t* mk = item_side ? p.mask_i : p.mask_u;
-          const float4 cur = ld_nc(a + off);
-          const float4 nxt = f4_add(cur, act);                 // E^{l+1} = E^l + lrelu(Z^l)
-          if (o1) st_f4(o1 + off, nxt);
-          if (o2) {
-            float4 o = cur;
-            if (b) o = f4_add(ld_stream(b + off), cur);
-            if (p.out_add_next) o = f4_add(o, nxt);
+          const float4 nxt_e = f4_add(own_a[v], act);          // E^{l+1} = E^l + lrelu(Z^l)
+          if (finish && o1) st_f4(o1 + off, nxt_e);
+          if (finish && o2) {
+            float4 o = own_a[v];
+            if (b) o = f4_add(ld_stream(b + off), own_a[v]);
+            if (p.out_add_next) o = f4_add(o, nxt_e);
             st_stream(o2 + off, o);
           }
-          if (mk) {
+          if (p.mask_u) {   // warp-uniform
             // TF MaximumGrad sends the gradient to leaky*z where leaky*z >= z: bit = pass-through
-            uint32_t nib = (!(lzx >= z.x) ? 1u : 0u) | (!(lzy >= z.y) ? 2u : 0u) |
-                           (!(lzz >= z.z) ? 4u : 0u) | (!(lzw >= z.w) ? 8u : 0u);
-            const uint32_t word = __reduce_or_sync(0xffu << (lane & ~7), nib << ((gl & 7) * 4));
-            if ((gl & 7) == 0) mk[own_row * WPR + ((v * LPR + gl) >> 3)] = word;
+            uint32_t word = ((!(lzx >= z.x) ? 1u : 0u) | (!(lzy >= z.y) ? 2u : 0u) |
+                             (!(lzz >= z.z) ? 4u : 0u) | (!(lzw >= z.w) ? 8u : 0u)) << ((gl & 7) * 4);
+            word |= __shfl_xor_sync(FULL, word, 1);
+            word |= __shfl_xor_sync(FULL, word, 2);
+            word |= __shfl_xor_sync(FULL, word, 4);
+            if (finish && (gl & 7) == 0) mk[own_row * WPR + ((v * LPR + gl) >> 3)] = word;
           }
         }
       }
@@ -328,8 +402,8 @@ static size_t mask_layer_words(const sagnn_plan* p, int d) { return (size_t)p->n
 
 static void base_params(const sagnn_plan* p, SpmmParams& s) {
   s = SpmmParams{};
-  s.rowptr = p->rowptr; s.idx = p->idx; s.w = p->w;
-  s.order = p->order; s.long_row = p->long_row; s.chunk_base = p->chunk_base; s.chunk_lr = p->chunk_lr;
+  s.tasks = p->tasks; s.idx = p->idx; s.w = p->w;
+  s.chunk_base = p->chunk_base; s.chunk_lr = p->chunk_lr;
   s.n_short = p->n_short; s.n_chunks = p->n_chunks;
   s.U = p->U; s.I = p->I; s.N = (uint32_t)p->N;
   s.row_lo = 0; s.row_hi = (uint32_t)p->n_rows;

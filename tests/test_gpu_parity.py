@@ -238,7 +238,7 @@ def test_propagate_tie_rule_zero_inputs():
     ref = po.propagate(adj, tp, z, z, g, g, 2, 0.25, np.float64)
     got = run_gpu(plan, z, z, g, g, 2, 0.25)
     for a, b in zip(got, ref):
-        np.testing.assert_allclose(a.cpu().numpy(), b, rtol=1e-6)
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b, rtol=1e-6)
 
 
 def test_propagate_weighted_lightgcn_mode():
@@ -329,7 +329,7 @@ def test_gowalla_full_size_parity_and_properties():
     deg = plan.degrees(0, 0).cpu().numpy()
     lonely = np.flatnonzero(deg == 0)[:50]
     if lonely.size:
-        np.testing.assert_allclose(got[0][0].cpu().numpy()[lonely], 3 * uE[0][lonely], rtol=1e-6)
+        np.testing.assert_allclose(got[0][0].detach().cpu().numpy()[lonely], 3 * uE[0][lonely], rtol=1e-6)
     # backward is linear in the upstream for a fixed forward: bwd(2g) == 2 bwd(g) exactly (power of 2)
     got2 = run_gpu(plan, uE, iE, 2 * gU, 2 * gI, L)
     assert torch.equal(got2[2], 2 * got[2]) and torch.equal(got2[3], 2 * got[3])
