@@ -11,8 +11,8 @@
 
 namespace sagnn {
 
-constexpr int kChunk = 64;       // max edges one lane-group gathers for one task
-constexpr int kThreads = 256;    // CTA size of the propagation kernel
+constexpr int kChunk = 64;        // max edges one lane-group gathers for one task
+constexpr int kHotRows = 768;     // hot-slot capacity per source table (slots = degree rank)
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
@@ -35,11 +35,26 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace sagnn
 
-// One unit of work for a lane group: a whole short row or one <=kChunk-edge slice of a long row.
+// One unit of work for a lane group: a whole short row or one <=kChunk-edge slice of a long
+// row.  Edges of a row are stored hot-first in `enc`: the first n_hot codes are hot-slot
+// numbers (rows staged in shared memory), the rest are source-row ids.
 struct __align__(16) sagnn_task {
-  uint32_t grow;   // global row id
-  uint32_t meta;   // edge count (<= kChunk); bit 31 set for a slice of a long row
-  int64_t e0;      // first edge (offset into idx)
+  uint32_t row;     // row id inside its own table (user id or item id)
+  uint32_t meta;    // bits 0-6: edges n (<= kChunk); bits 8-14: hot edges; bit 31: slice of a long row
+  uint32_t e_off;   // first edge, relative to the segment's first edge
+  uint32_t aux;     // slices: global slice id (partial-sum slot)
+};
+
+// A segment = one CSR: (interval k, side).  seg = 2*k + side; its rows are the rows of table
+// `seg`, the rows it gathers from are the rows of table `seg ^ 1`.
+struct sagnn_seg {
+  int64_t edge_base;    // first edge of the segment in idx / enc
+  int64_t task_begin;   // its slice of the task list: long-row slices first (longest rows first),
+  int64_t task_end;     //   then short rows in descending-degree order
+};
+
+struct sagnn_cta {      // persistent CTA -> segment binding (CTAs are dealt out by segment cost)
+  int seg, rank, count, pad;
 };
 
 // Global row space: row g = k*(U+I) + (side ? U + r : r); edges of interval k are stored
@@ -61,22 +76,25 @@ struct sagnn_plan {
   bool finalized = false;
   int weight_mode = 0;
 
-  // device arrays
+  // canonical CSRs (what transToLsts / transpose produce; parity hooks read these)
   int32_t* deg = nullptr;         // [n_rows] structural degrees
   int64_t* rowptr = nullptr;      // [n_rows + 1]
-  int32_t* idx = nullptr;         // [2 * e_total] source ids
+  int32_t* idx = nullptr;         // [2 * e_total] source ids, canonical order
   int32_t* val = nullptr;         // [2 * e_total] stored values (optional)
-  float* w = nullptr;             // [2 * e_total] edge weights (optional)
+  float* w = nullptr;             // [2 * e_total] edge weights, canonical order (optional)
   int64_t* valsum = nullptr;      // [n_rows] value-sum degrees (optional)
 
-  // schedule (degree-binned): long rows (deg > kChunk) are cut into chunks, listed
-  // first and longest-first; short rows follow in descending-degree order.
-  uint32_t* order = nullptr;      // [n_short] global row ids
-  uint32_t* long_row = nullptr;   // [n_long] global row ids
-  int64_t* chunk_base = nullptr;  // [n_long + 1] first chunk of each long row
-  uint32_t* chunk_lr = nullptr;   // [n_chunks] long-row rank of each chunk
-  sagnn_task* tasks = nullptr;    // [n_chunks + n_short] chunk tasks first (longest rows first), then short rows
-  int64_t n_short = 0, n_long = 0, n_chunks = 0;
+  // kernel-side schedule
+  int32_t* enc = nullptr;         // [2 * e_total] edge codes, hot-first inside every row
+  float* w_enc = nullptr;         // [2 * e_total] weights in enc order (optional)
+  int32_t* hot_ids = nullptr;     // [2T, kHotRows] row ids (inside table t) of table t's hot slots
+  sagnn_task* tasks = nullptr;    // [n_tasks] grouped by segment
+  sagnn_seg* seg_dev = nullptr;   // [2T]
+  sagnn_cta* cta_dev = nullptr;   // [num_sms]
+  int64_t* chunk_base = nullptr;  // [n_long + 1] first slice of each long row
+  uint32_t* chunk_lr = nullptr;   // [n_chunks] long-row rank of each slice
+  std::vector<sagnn_seg> seg_host;
+  int64_t n_tasks = 0, n_short = 0, n_long = 0, n_chunks = 0;
   int32_t max_deg = 0;
 
   // host-entry cache (sagnn_propagate_host)

@@ -127,56 +127,121 @@ __global__ void rel_indptr_kernel(const int64_t* __restrict__ rowptr, int64_t ro
   if (i <= n) out[i] = (int32_t)(rowptr[row0 + i] - rowptr[row0]);
 }
 
-// sorted_deg is descending: count entries > kChunk (binary search, one thread), max degree
-__global__ void count_long_kernel(const int32_t* __restrict__ sorted_deg, int64_t n, int64_t* out) {
-  int64_t lo = 0, hi = n;   // first index with deg <= kChunk
-  while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    if (sorted_deg[mid] > kChunk) lo = mid + 1; else hi = mid;
-  }
-  out[0] = lo;
-  out[1] = n ? sorted_deg[0] : 0;
+// ---- schedule construction ---------------------------------------------------------------
+// table id (= segment id) of a global row / sorted position: 2*k + side
+__device__ __forceinline__ uint32_t table_of(int64_t g, int64_t N, int U) {
+  const int64_t k = g / N;
+  return (uint32_t)(2 * k + ((g - k * N) >= U ? 1 : 0));
+}
+__device__ __forceinline__ int64_t table_row0(uint32_t t, int64_t N, int U) {
+  return (int64_t)(t >> 1) * N + ((t & 1) ? U : 0);
 }
 
-__global__ void chunk_count_kernel(const int32_t* __restrict__ sorted_deg, int64_t n_long,
-                                   int64_t* __restrict__ nch) {
+// sort key: rows grouped by table, descending degree inside a table (stable => ascending id on ties)
+__global__ void sched_key_kernel(const int32_t* __restrict__ deg, int64_t n_rows, int64_t N, int U,
+                                 uint64_t* __restrict__ key, uint32_t* __restrict__ row) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_rows) return;
+  key[g] = ((uint64_t)table_of(g, N, U) << 32) | (uint32_t)(0x7fffffff - deg[g]);
+  row[g] = (uint32_t)g;
+}
+
+// hot slots = the kHotRows highest-degree rows of every table; per sorted position also the
+// number of tasks / slices / long rows it contributes (inputs of the three scans)
+__global__ void sched_slot_kernel(const uint32_t* __restrict__ srow, const int32_t* __restrict__ deg,
+                                  int64_t n_rows, int64_t N, int U, int32_t* __restrict__ slot_of,
+                                  int32_t* __restrict__ hot_ids, int64_t* __restrict__ n_task,
+                                  int64_t* __restrict__ n_chunk, int64_t* __restrict__ n_long) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_long) nch[i] = (sorted_deg[i] + kChunk - 1) / kChunk;
+  if (i > n_rows) return;
+  if (i == n_rows) { n_task[i] = 0; n_chunk[i] = 0; n_long[i] = 0; return; }
+  const uint32_t g = srow[i];
+  const uint32_t t = table_of(i, N, U);          // sorted positions keep the table layout
+  const int64_t pos = i - table_row0(t, N, U);
+  slot_of[g] = pos < kHotRows ? (int32_t)pos : -1;
+  if (pos < kHotRows) hot_ids[(int64_t)t * kHotRows + pos] = (int32_t)(g - table_row0(t, N, U));
+  const int d = deg[g];
+  const bool lg = d > kChunk;
+  const int64_t nt = lg ? (d + kChunk - 1) / kChunk : 1;
+  n_task[i] = nt;
+  n_chunk[i] = lg ? nt : 0;
+  n_long[i] = lg ? 1 : 0;
 }
 
-__global__ void chunk_fill_kernel(const int64_t* __restrict__ chunk_base, int64_t n_long,
-                                  int64_t n_chunks, uint32_t* __restrict__ chunk_lr) {
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_chunks) return;
-  int64_t lo = 0, hi = n_long;   // largest lr with chunk_base[lr] <= c
+// kernel-side edge codes: one warp per row, stable partition hot-first (hot = slot, cold = id)
+__global__ void sched_encode_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ idx,
+                                    const float* __restrict__ w, const int32_t* __restrict__ slot_of,
+                                    int64_t n_rows, int64_t N, int U, int32_t* __restrict__ enc,
+                                    float* __restrict__ w_enc, int32_t* __restrict__ nhot_row) {
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n_rows) return;
+  const uint32_t t = table_of(g, N, U);
+  const int64_t src0 = table_row0(t ^ 1u, N, U);
+  const int64_t rs = rowptr[g], re = rowptr[g + 1];
+  int nh = 0;
+  for (int64_t b0 = rs; b0 < re; b0 += 32) {            // warp-uniform trip count
+    const int64_t e = b0 + lane;
+    const bool hot = e < re && slot_of[src0 + idx[e]] >= 0;
+    nh += __popc(__ballot_sync(0xffffffffu, hot));
+  }
+  int64_t hp = rs, cp = rs + nh;
+  for (int64_t b0 = rs; b0 < re; b0 += 32) {
+    const int64_t e = b0 + lane;
+    const bool in = e < re;
+    int c = 0, s = -1;
+    float wv = 0.f;
+    if (in) { c = idx[e]; s = slot_of[src0 + c]; if (w) wv = w[e]; }
+    const bool hot = in && s >= 0;
+    const unsigned hb = __ballot_sync(0xffffffffu, hot), cbal = __ballot_sync(0xffffffffu, in && !hot);
+    const unsigned below = (1u << lane) - 1u;
+    if (hot) { const int64_t o = hp + __popc(hb & below); enc[o] = s; if (w) w_enc[o] = wv; }
+    else if (in) { const int64_t o = cp + __popc(cbal & below); enc[o] = c; if (w) w_enc[o] = wv; }
+    hp += __popc(hb);
+    cp += __popc(cbal);
+  }
+  if (lane == 0) nhot_row[g] = nh;
+}
+
+// one thread per task: the sorted position that owns it (binary search on the task scan), then
+// the slice [rs + deg*ci/nt, rs + deg*(ci+1)/nt) of that row
+__global__ void sched_task_kernel(const uint32_t* __restrict__ srow, const int32_t* __restrict__ deg,
+                                  const int64_t* __restrict__ rowptr, const int32_t* __restrict__ nhot_row,
+                                  const int64_t* __restrict__ task_off, const int64_t* __restrict__ chunk_off,
+                                  const int64_t* __restrict__ long_off, int64_t n_rows, int64_t n_tasks,
+                                  int64_t N, int U, sagnn_task* __restrict__ tasks,
+                                  int64_t* __restrict__ chunk_base, uint32_t* __restrict__ chunk_lr) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_tasks) return;
+  int64_t lo = 0, hi = n_rows;    // largest i with task_off[i] <= j
   while (hi - lo > 1) {
-    int64_t mid = (lo + hi) >> 1;
-    if (chunk_base[mid] <= c) lo = mid; else hi = mid;
+    const int64_t mid = (lo + hi) >> 1;
+    if (task_off[mid] <= j) lo = mid; else hi = mid;
   }
-  chunk_lr[c] = (uint32_t)lo;
-}
-
-// task records: chunk c of long row lr covers edges [rs + deg*ci/nch, rs + deg*(ci+1)/nch)
-__global__ void task_fill_kernel(const int64_t* __restrict__ rowptr, const uint32_t* __restrict__ order,
-                                 const uint32_t* __restrict__ long_row, const int64_t* __restrict__ chunk_base,
-                                 const uint32_t* __restrict__ chunk_lr, int64_t n_chunks, int64_t n_short,
-                                 sagnn_task* __restrict__ tasks) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_chunks + n_short) return;
+  const int64_t i = lo;
+  const uint32_t g = srow[i];
+  const uint32_t t = table_of(i, N, U);
+  const int64_t row0 = table_row0(t, N, U);
+  const int64_t d = deg[g];
+  const bool lg = d > kChunk;
+  const int64_t nt = lg ? (d + kChunk - 1) / kChunk : 1;
+  const int64_t ci = j - task_off[i];
+  const int64_t rs = rowptr[g];
+  const int64_t e0 = rs + d * ci / nt, e1 = rs + d * (ci + 1) / nt;
+  int64_t nh = rs + nhot_row[g] - e0;
+  nh = nh < 0 ? 0 : (nh > e1 - e0 ? e1 - e0 : nh);
   sagnn_task k;
-  if (t < n_chunks) {
-    const uint32_t lr = chunk_lr[t];
-    const int64_t cb = chunk_base[lr], nch = chunk_base[lr + 1] - cb, ci = t - cb;
-    k.grow = long_row[lr];
-    const int64_t rs = rowptr[k.grow], deg = rowptr[k.grow + 1] - rs;
-    k.e0 = rs + deg * ci / nch;
-    k.meta = (uint32_t)(rs + deg * (ci + 1) / nch - k.e0) | 0x80000000u;
-  } else {
-    k.grow = order[t - n_chunks];
-    k.e0 = rowptr[k.grow];
-    k.meta = (uint32_t)(rowptr[k.grow + 1] - k.e0);
+  k.row = (uint32_t)(g - row0);
+  k.meta = (uint32_t)(e1 - e0) | ((uint32_t)nh << 8) | (lg ? 0x80000000u : 0u);
+  k.e_off = (uint32_t)(e0 - rowptr[row0]);
+  k.aux = 0;
+  if (lg) {
+    const int64_t c = chunk_off[i] + ci;
+    k.aux = (uint32_t)c;
+    chunk_lr[c] = (uint32_t)long_off[i];
+    if (ci == 0) chunk_base[long_off[i]] = chunk_off[i];
   }
-  tasks[t] = k;
+  tasks[j] = k;
 }
 
 struct CastI64 {
@@ -253,8 +318,8 @@ extern "C" int sagnn_plan_destroy(sagnn_plan* p) {
   if (!p) return SAGNN_OK;
   sagnn::free_host_cache(p);
   cudaFree(p->deg); cudaFree(p->rowptr); cudaFree(p->idx); cudaFree(p->val); cudaFree(p->w);
-  cudaFree(p->valsum); cudaFree(p->order); cudaFree(p->long_row); cudaFree(p->chunk_base);
-  cudaFree(p->chunk_lr); cudaFree(p->tasks);
+  cudaFree(p->valsum); cudaFree(p->chunk_base); cudaFree(p->chunk_lr); cudaFree(p->tasks);
+  cudaFree(p->enc); cudaFree(p->w_enc); cudaFree(p->hot_ids); cudaFree(p->seg_dev); cudaFree(p->cta_dev);
   delete p;
   return SAGNN_OK;
 }
@@ -370,62 +435,125 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
     p->w = nullptr;
   }
 
-  // ---- degree-binned schedule ---------------------------------------------------------
-  int32_t *sorted_deg = nullptr; uint32_t *rows_in = nullptr, *rows_sorted = nullptr;
-  SAGNN_CUDA(cudaMalloc(&sorted_deg, sizeof(int32_t) * R));
-  SAGNN_CUDA(cudaMalloc(&rows_in, sizeof(uint32_t) * R));
-  SAGNN_CUDA(cudaMalloc(&rows_sorted, sizeof(uint32_t) * R));
-  iota_u32_kernel<<<blocks_for(R), 256, 0, st>>>(rows_in, R);
+  // ---- schedule: per-segment task lists, hot slots, hot-first edge codes ------------------
+  SAGNN_REQUIRE(2 * p->T <= p->num_sms, SAGNN_INVALID_ARG,
+                "finalize: %d segments exceed the %d SMs of the device", 2 * p->T, p->num_sms);
+  SAGNN_REQUIRE(2 * p->e_total < ((int64_t)1 << 32), SAGNN_INVALID_ARG,
+                "finalize: %lld edge entries exceed 2^32", (long long)(2 * p->e_total));
+  const int64_t N = p->N;
+  const int U = p->U;
+  uint64_t *key_in = nullptr, *key_out = nullptr;
+  uint32_t *row_in = nullptr, *srow = nullptr;
+  int32_t *slot_of = nullptr, *nhot_row = nullptr;
+  int64_t *cnt3 = nullptr, *off3 = nullptr;   // [3][R+1]: tasks, slices, long rows per sorted position
+  SAGNN_CUDA(cudaMalloc(&key_in, sizeof(uint64_t) * R));
+  SAGNN_CUDA(cudaMalloc(&key_out, sizeof(uint64_t) * R));
+  SAGNN_CUDA(cudaMalloc(&row_in, sizeof(uint32_t) * R));
+  SAGNN_CUDA(cudaMalloc(&srow, sizeof(uint32_t) * R));
+  SAGNN_CUDA(cudaMalloc(&slot_of, sizeof(int32_t) * R));
+  SAGNN_CUDA(cudaMalloc(&nhot_row, sizeof(int32_t) * R));
+  SAGNN_CUDA(cudaMalloc(&cnt3, sizeof(int64_t) * 3 * (R + 1)));
+  SAGNN_CUDA(cudaMalloc(&off3, sizeof(int64_t) * 3 * (R + 1)));
+  SAGNN_CUDA(cudaMalloc(&p->hot_ids, sizeof(int32_t) * 2 * p->T * kHotRows));
+  SAGNN_CUDA(cudaMemsetAsync(p->hot_ids, 0, sizeof(int32_t) * 2 * p->T * kHotRows, st));
+  sched_key_kernel<<<blocks_for(R), 256, 0, st>>>(p->deg, R, N, U, key_in, row_in);
   {
     void* tmp = nullptr; size_t tb = 0;
-    SAGNN_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, p->deg, sorted_deg, rows_in, rows_sorted, R, 0, 32, st));
+    const int end_bit = 32 + bits_for(2 * p->T);
+    SAGNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key_in, key_out, row_in, srow, R, 0, end_bit, st));
     SAGNN_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
-    SAGNN_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, tb, p->deg, sorted_deg, rows_in, rows_sorted, R, 0, 32, st));
+    SAGNN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, key_in, key_out, row_in, srow, R, 0, end_bit, st));
     SAGNN_CUDA(cudaStreamSynchronize(st));
     cudaFree(tmp);
   }
-  int64_t* cnt = nullptr;
-  SAGNN_CUDA(cudaMalloc(&cnt, 2 * sizeof(int64_t)));
-  count_long_kernel<<<1, 1, 0, st>>>(sorted_deg, R, cnt);
-  int64_t hcnt[2] = {0, 0};
-  SAGNN_CUDA(cudaMemcpyAsync(hcnt, cnt, sizeof(hcnt), cudaMemcpyDeviceToHost, st));
-  SAGNN_CUDA(cudaStreamSynchronize(st));
-  cudaFree(cnt);
-  p->n_long = hcnt[0];
-  p->max_deg = (int32_t)hcnt[1];
-  p->n_short = R - p->n_long;
-  SAGNN_CUDA(cudaMalloc(&p->order, sizeof(uint32_t) * (p->n_short ? p->n_short : 1)));
-  SAGNN_CUDA(cudaMemcpyAsync(p->order, rows_sorted + p->n_long, sizeof(uint32_t) * p->n_short, cudaMemcpyDeviceToDevice, st));
-  SAGNN_CUDA(cudaMalloc(&p->long_row, sizeof(uint32_t) * (p->n_long ? p->n_long : 1)));
-  SAGNN_CUDA(cudaMalloc(&p->chunk_base, sizeof(int64_t) * (p->n_long + 1)));
-  p->n_chunks = 0;
-  if (p->n_long) {
-    SAGNN_CUDA(cudaMemcpyAsync(p->long_row, rows_sorted, sizeof(uint32_t) * p->n_long, cudaMemcpyDeviceToDevice, st));
-    int64_t* nch = nullptr;
-    SAGNN_CUDA(cudaMalloc(&nch, sizeof(int64_t) * (p->n_long + 1)));
-    SAGNN_CUDA(cudaMemsetAsync(nch, 0, sizeof(int64_t) * (p->n_long + 1), st));
-    chunk_count_kernel<<<blocks_for(p->n_long), 256, 0, st>>>(sorted_deg, p->n_long, nch);
-    void* tmp = nullptr; size_t tb = 0;
-    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, nch, p->chunk_base, p->n_long + 1, st));
-    SAGNN_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
-    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, nch, p->chunk_base, p->n_long + 1, st));
-    SAGNN_CUDA(cudaMemcpyAsync(&p->n_chunks, p->chunk_base + p->n_long, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    SAGNN_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp); cudaFree(nch);
-    SAGNN_CUDA(cudaMalloc(&p->chunk_lr, sizeof(uint32_t) * p->n_chunks));
-    chunk_fill_kernel<<<blocks_for(p->n_chunks), 256, 0, st>>>(p->chunk_base, p->n_long, p->n_chunks, p->chunk_lr);
-  } else {
-    SAGNN_CUDA(cudaMemsetAsync(p->chunk_base, 0, sizeof(int64_t), st));
-  }
+  int64_t *n_task = cnt3, *n_chunk = cnt3 + (R + 1), *n_long = cnt3 + 2 * (R + 1);
+  int64_t *task_off = off3, *chunk_off = off3 + (R + 1), *long_off = off3 + 2 * (R + 1);
+  sched_slot_kernel<<<blocks_for(R + 1), 256, 0, st>>>(srow, p->deg, R, N, U, slot_of, p->hot_ids, n_task,
+                                                       n_chunk, n_long);
   {
-    const int64_t nt = p->n_chunks + p->n_short;
-    SAGNN_CUDA(cudaMalloc(&p->tasks, sizeof(sagnn_task) * (nt ? nt : 1)));
-    task_fill_kernel<<<blocks_for(nt), 256, 0, st>>>(p->rowptr, p->order, p->long_row, p->chunk_base,
-                                                     p->chunk_lr, p->n_chunks, p->n_short, p->tasks);
+    void* tmp = nullptr; size_t tb = 0;
+    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, n_task, task_off, R + 1, st));
+    SAGNN_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
+    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, n_task, task_off, R + 1, st));
+    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, n_chunk, chunk_off, R + 1, st));
+    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, n_long, long_off, R + 1, st));
+    SAGNN_CUDA(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+  }
+  SAGNN_CUDA(cudaMemcpy(&p->n_tasks, task_off + R, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  SAGNN_CUDA(cudaMemcpy(&p->n_chunks, chunk_off + R, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  SAGNN_CUDA(cudaMemcpy(&p->n_long, long_off + R, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  p->n_short = R - p->n_long;
+  {
+    void* tmp = nullptr; size_t tb = 0;
+    int32_t* dmax = nullptr;
+    SAGNN_CUDA(cudaMalloc(&dmax, sizeof(int32_t)));
+    SAGNN_CUDA(cub::DeviceReduce::Max(nullptr, tb, p->deg, dmax, R, st));
+    SAGNN_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
+    SAGNN_CUDA(cub::DeviceReduce::Max(tmp, tb, p->deg, dmax, R, st));
+    SAGNN_CUDA(cudaMemcpyAsync(&p->max_deg, dmax, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SAGNN_CUDA(cudaStreamSynchronize(st));
+    cudaFree(tmp); cudaFree(dmax);
+  }
+
+  SAGNN_CUDA(cudaMalloc(&p->enc, sizeof(int32_t) * 2 * p->e_total));
+  if (p->w) SAGNN_CUDA(cudaMalloc(&p->w_enc, sizeof(float) * 2 * p->e_total));
+  sched_encode_kernel<<<blocks_for(R * 32), 256, 0, st>>>(p->rowptr, p->idx, p->w, slot_of, R, N, U, p->enc,
+                                                          p->w_enc, nhot_row);
+
+  SAGNN_CUDA(cudaMalloc(&p->tasks, sizeof(sagnn_task) * (p->n_tasks ? p->n_tasks : 1)));
+  SAGNN_CUDA(cudaMalloc(&p->chunk_base, sizeof(int64_t) * (p->n_long + 1)));
+  SAGNN_CUDA(cudaMalloc(&p->chunk_lr, sizeof(uint32_t) * (p->n_chunks ? p->n_chunks : 1)));
+  SAGNN_CUDA(cudaMemcpyAsync(p->chunk_base + p->n_long, &p->n_chunks, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  sched_task_kernel<<<blocks_for(p->n_tasks), 256, 0, st>>>(srow, p->deg, p->rowptr, nhot_row, task_off, chunk_off,
+                                                            long_off, R, p->n_tasks, N, U, p->tasks, p->chunk_base,
+                                                            p->chunk_lr);
+  SAGNN_CUDA(cudaGetLastError());
+
+  // per-segment descriptors (task ranges come from the scan at the table boundaries)
+  const int S = 2 * p->T;
+  p->seg_host.resize(S);
+  {
+    std::vector<int64_t> tb(S + 1);
+    for (int t = 0; t <= S; ++t) {
+      const int64_t pos = t == S ? R : (int64_t)(t >> 1) * N + ((t & 1) ? U : 0);
+      SAGNN_CUDA(cudaMemcpyAsync(&tb[t], task_off + pos, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    }
+    SAGNN_CUDA(cudaStreamSynchronize(st));
+    for (int t = 0; t < S; ++t) {
+      p->seg_host[t].edge_base = p->base[t >> 1] + ((t & 1) ? p->nnz[t >> 1] : 0);
+      p->seg_host[t].task_begin = tb[t];
+      p->seg_host[t].task_end = tb[t + 1];
+    }
+  }
+  SAGNN_CUDA(cudaMalloc(&p->seg_dev, sizeof(sagnn_seg) * S));
+  SAGNN_CUDA(cudaMemcpyAsync(p->seg_dev, p->seg_host.data(), sizeof(sagnn_seg) * S, cudaMemcpyHostToDevice, st));
+
+  // persistent CTAs (one per SM) are dealt to segments in proportion to their cost
+  {
+    std::vector<double> cost(S);
+    for (int t = 0; t < S; ++t) cost[t] = (double)p->nnz[t >> 1] + 8.0 * ((t & 1) ? p->I : p->U);
+    std::vector<int> n(S, 1);
+    int left = p->num_sms - S;
+    while (left > 0) {   // give the next CTA to the segment with the largest cost per CTA
+      int best = 0;
+      for (int t = 1; t < S; ++t)
+        if (cost[t] / n[t] > cost[best] / n[best]) best = t;
+      n[best]++;
+      left--;
+    }
+    std::vector<sagnn_cta> cta(p->num_sms);
+    int c = 0;
+    for (int t = 0; t < S; ++t)
+      for (int r = 0; r < n[t]; ++r) cta[c++] = sagnn_cta{t, r, n[t], 0};
+    SAGNN_CUDA(cudaMalloc(&p->cta_dev, sizeof(sagnn_cta) * p->num_sms));
+    SAGNN_CUDA(cudaMemcpyAsync(p->cta_dev, cta.data(), sizeof(sagnn_cta) * p->num_sms, cudaMemcpyHostToDevice, st));
+    SAGNN_CUDA(cudaStreamSynchronize(st));
   }
   SAGNN_CUDA(cudaGetLastError());
   SAGNN_CUDA(cudaStreamSynchronize(st));
-  cudaFree(sorted_deg); cudaFree(rows_in); cudaFree(rows_sorted);
+  cudaFree(key_in); cudaFree(key_out); cudaFree(row_in); cudaFree(srow); cudaFree(slot_of);
+  cudaFree(nhot_row); cudaFree(cnt3); cudaFree(off3);
   p->finalized = true;
   return SAGNN_OK;
 }

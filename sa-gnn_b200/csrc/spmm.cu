@@ -16,24 +16,32 @@
 
 #include "common.cuh"
 
-#ifndef SAGNN_MIN_BLOCKS
-#define SAGNN_MIN_BLOCKS 3   // CTAs per SM the register allocator must leave room for
+#ifndef SAGNN_THREADS
+#define SAGNN_THREADS 1024     // one persistent CTA per SM
+#endif
+#ifndef SAGNN_UNR
+#define SAGNN_UNR 4            // independent 128-bit gathers in flight per lane
+#endif
+#ifndef SAGNN_HOT_BYTES
+#define SAGNN_HOT_BYTES (192 * 1024)   // shared memory given to staged hot rows
 #endif
 
 namespace sagnn {
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_MSG = 2 };
+constexpr int kThreads = SAGNN_THREADS;
 
 struct SpmmParams {
   const sagnn_task* tasks;
-  const int32_t* idx;
-  const float* w;
+  const int32_t* enc;
+  const float* w;            // weights in enc order or NULL
   const int64_t* chunk_base;
   const uint32_t* chunk_lr;
-  int64_t n_short, n_chunks;
+  const int32_t* hot_ids;
+  const sagnn_seg* seg;
+  const sagnn_cta* cta;
+  int single_seg;            // >= 0: every CTA works on this segment (messagePropagate); -1: use cta[]
   int U, I;
-  uint32_t N;
-  uint32_t row_lo, row_hi;   // only global rows in [row_lo, row_hi) are processed
   // gather sources: user rows read item-table rows (src_i), item rows read user-table rows (src_u)
   const float* src_u;
   const float* src_i;
@@ -83,131 +91,200 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
 }
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-__device__ __forceinline__ sagnn_task ld_task(const sagnn_task* tasks, int64_t t, int64_t n_tasks) {
+// ---- TMA bulk copy (global -> shared, mbarrier-completed) ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ sagnn_task ld_task(const sagnn_task* tasks, int64_t t, int64_t t_end) {
   sagnn_task k;
-  if (t < n_tasks) {
+  if (t < t_end) {
     const int4 raw = __ldg(reinterpret_cast<const int4*>(tasks + t));
-    k.grow = (uint32_t)raw.x;
-    k.meta = (uint32_t)raw.y;
-    k.e0 = ((int64_t)(uint32_t)raw.w << 32) | (uint32_t)raw.z;
+    k.row = (uint32_t)raw.x; k.meta = (uint32_t)raw.y; k.e_off = (uint32_t)raw.z; k.aux = (uint32_t)raw.w;
   } else {
-    k.grow = 0xffffffffu;   // sentinel: no work (fails the row filter)
-    k.meta = 0;
-    k.e0 = 0;
+    k.row = 0; k.meta = 0x40000000u; k.e_off = 0; k.aux = 0;   // bit 30: no work
   }
   return k;
 }
 
-// The lane groups of a warp run in lock step (trip counts are warp maxima, loads are
-// predicated), so every shuffle uses the full mask and nothing serialises on divergence;
-// tasks arrive sorted by degree, so the groups sharing a warp have near-equal rows.
+// One persistent CTA per SM, bound to one segment (interval, orientation).  It first stages
+// the segment's hottest source rows in shared memory with TMA bulk copies, then walks its
+// share of the segment's task list.  The lane groups of a warp run in lock step (trip
+// counts are warp maxima, loads are predicated), so every shuffle uses the full mask; tasks
+// arrive sorted by degree, so the groups sharing a warp have near-equal rows.
 template <int LPR, int V, int MODE, bool WEIGHTED>
-__global__ void __launch_bounds__(kThreads, SAGNN_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, 1)
 spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
   constexpr int D = LPR * V * 4;
-  constexpr int WPR = D / 32;          // mask words per row
-  constexpr int GPW = 32 / LPR;        // lane groups per warp
-  constexpr int UNR = 8;               // independent 128-bit gathers in flight per lane
+  constexpr int WPR = D / 32;                         // mask words per row
+  constexpr int GPW = 32 / LPR;                       // lane groups per warp
+  constexpr int UNR = SAGNN_UNR;
+  constexpr int KST = (SAGNN_HOT_BYTES / (4 * D)) < kHotRows ? (SAGNN_HOT_BYTES / (4 * D)) : kHotRows;
+  constexpr bool WARM = KST < kHotRows;               // hot slots that do not fit: read via their ids
   static_assert(LPR % UNR == 0, "unroll must divide the group width");
   constexpr unsigned FULL = 0xffffffffu;
 
+  extern __shared__ __align__(128) float hot[];       // [KST][D]
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int warm_ids[WARM ? kHotRows : 1];
+
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
-  const int gbase = lane - gl;         // first lane of my group
-  const int64_t n_tasks = p.n_chunks + p.n_short;
-  const int64_t stride = (int64_t)gridDim.x * (kThreads / 32) * GPW;
-  const int64_t warp_t0 = ((int64_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * GPW;
-  int64_t t = warp_t0 + lane / LPR;
+  const int gbase = lane - gl;                        // first lane of my group
 
-  // software pipeline: task records two rounds ahead, the first index batch one round ahead
-  sagnn_task nxt = ld_task(p.tasks, t, n_tasks);
-  sagnn_task nxt2 = ld_task(p.tasks, t + stride, n_tasks);
-  int nxt_c = 0;
-  float nxt_w = 0.f;
-  if (gl < (int)(nxt.meta & 0xffu)) {
-    nxt_c = __ldg(p.idx + nxt.e0 + gl);
-    if (WEIGHTED) nxt_w = __ldg(p.w + nxt.e0 + gl);
+  int seg, rank, count;
+  if (p.single_seg >= 0) { seg = p.single_seg; rank = blockIdx.x; count = gridDim.x; }
+  else { const sagnn_cta c = p.cta[blockIdx.x]; seg = c.seg; rank = c.rank; count = c.count; }
+  const int k = seg >> 1;
+  const bool item_side = seg & 1;
+  const int r_own = item_side ? p.I : p.U, r_src = item_side ? p.U : p.I;
+  const float* __restrict__ src = (item_side ? p.src_u : p.src_i) + (int64_t)k * r_src * D;
+  const uint32_t* __restrict__ smask =
+      (MODE == MODE_BWD) ? (item_side ? p.smask_u : p.smask_i) + (int64_t)k * r_src * WPR : nullptr;
+  const int64_t own0 = (int64_t)k * r_own;            // first row of my table
+  const sagnn_seg sg = p.seg[seg];
+  const int32_t* __restrict__ enc = p.enc + sg.edge_base;
+  const float* __restrict__ wts = WEIGHTED ? p.w + sg.edge_base : nullptr;
+
+  // ---- stage the hot rows of the source table (TMA bulk copies, one per row) -------------
+  {
+    const int32_t* ids = p.hot_ids + (int64_t)(seg ^ 1) * kHotRows;
+    const int n_stage = r_src < KST ? r_src : KST;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) mbar_expect_tx(&bar, (unsigned)(n_stage * D * 4));
+    for (int s = threadIdx.x; s < n_stage; s += kThreads)
+      tma_bulk_g2s(hot + (size_t)s * D, src + (int64_t)__ldg(ids + s) * D, D * 4, &bar);
+    if (WARM) {
+      const int n_hot = r_src < kHotRows ? r_src : kHotRows;
+      for (int s = threadIdx.x; s < n_hot; s += kThreads) warm_ids[s] = __ldg(ids + s);
+    }
+    mbar_wait(&bar, 0);
+    if (MODE == MODE_BWD) {
+      // the backward gathers sigma'(Z) (.) g: mask the staged rows once instead of per edge
+      __syncthreads();
+      for (int s = threadIdx.x / LPR; s < n_stage; s += kThreads / LPR) {
+        const int id = __ldg(ids + s);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float4* q = reinterpret_cast<float4*>(hot + (size_t)s * D + (v * LPR + gl) * 4);
+          float4 x = *q;
+          const uint32_t b = __ldg(smask + (int64_t)id * WPR + ((v * LPR + gl) >> 3)) >> ((gl & 7) * 4);
+          x.x = (b & 1u) ? x.x : p.leaky * x.x;
+          x.y = (b & 2u) ? x.y : p.leaky * x.y;
+          x.z = (b & 4u) ? x.z : p.leaky * x.z;
+          x.w = (b & 8u) ? x.w : p.leaky * x.w;
+          *q = x;
+        }
+      }
+    }
+    __syncthreads();
   }
 
-  for (int64_t tb = warp_t0; tb < n_tasks; tb += stride, t += stride) {   // warp-uniform trip count
+  // ---- my share of the segment's tasks ----------------------------------------------------
+  const int64_t t_end = sg.task_end;
+  const int64_t stride = (int64_t)count * (kThreads / 32) * GPW;
+  const int64_t warp_t0 = sg.task_begin + ((int64_t)rank * (kThreads / 32) + threadIdx.x / 32) * GPW;
+  int64_t t = warp_t0 + lane / LPR;
+
+  // software pipeline: task records two rounds ahead, the first code batch one round ahead
+  sagnn_task nxt = ld_task(p.tasks, t, t_end);
+  sagnn_task nxt2 = ld_task(p.tasks, t + stride, t_end);
+  int nxt_c = 0;
+  float nxt_w = 0.f;
+  if (gl < (int)(nxt.meta & 0x7fu)) {
+    nxt_c = __ldg(enc + nxt.e_off + gl);
+    if (WEIGHTED) nxt_w = __ldg(wts + nxt.e_off + gl);
+  }
+
+  for (int64_t tb = warp_t0; tb < t_end; tb += stride, t += stride) {   // warp-uniform trip count
     const sagnn_task cur = nxt;
     int myc = nxt_c;
     float myw = nxt_w;
     nxt = nxt2;
-    nxt2 = ld_task(p.tasks, t + 2 * stride, n_tasks);
+    nxt2 = ld_task(p.tasks, t + 2 * stride, t_end);
     nxt_c = 0;
-    if (gl < (int)(nxt.meta & 0xffu)) {
-      nxt_c = __ldg(p.idx + nxt.e0 + gl);
-      if (WEIGHTED) nxt_w = __ldg(p.w + nxt.e0 + gl);
+    if (gl < (int)(nxt.meta & 0x7fu)) {
+      nxt_c = __ldg(enc + nxt.e_off + gl);
+      if (WEIGHTED) nxt_w = __ldg(wts + nxt.e_off + gl);
     }
 
-    const uint32_t grow = cur.grow;
-    const bool valid = grow >= p.row_lo && grow < p.row_hi;
-    const bool is_chunk = (cur.meta >> 31) != 0;
-    const int n = valid ? (int)(cur.meta & 0xffu) : 0;
-    const uint32_t k = valid ? grow / p.N : 0u;
-    const uint32_t rem = valid ? grow - k * p.N : 0u;
-    const bool item_side = rem >= (uint32_t)p.U;
-    const uint32_t r = item_side ? rem - p.U : rem;
-    // this row's own table geometry and the geometry of the table it gathers from
-    const int64_t own_row = (int64_t)k * (item_side ? p.I : p.U) + r;
-    const int64_t src_row0 = (int64_t)k * (item_side ? p.U : p.I);
-    const float* __restrict__ src = (item_side ? p.src_u : p.src_i) + src_row0 * D;
-    const uint32_t* __restrict__ smask =
-        (MODE == MODE_BWD) ? (item_side ? p.smask_u : p.smask_i) + src_row0 * WPR : nullptr;
-
-    // chunk bookkeeping (long rows only), off the critical path
-    uint32_t lr = 0;
-    int64_t cb = 0;
-    int nch = 1;
-    if (valid && is_chunk) {
-      lr = __ldg(p.chunk_lr + t);
-      cb = __ldg(p.chunk_base + lr);
-      nch = (int)(__ldg(p.chunk_base + lr + 1) - cb);
-    }
-    const bool multi = nch > 1;
+    const bool valid = !(cur.meta & 0x40000000u);
+    const bool multi = (cur.meta >> 31) != 0;          // slice of a long row
+    const int n = (int)(cur.meta & 0x7fu);
+    const int nh = (int)((cur.meta >> 8) & 0x7fu);
+    const int64_t own_off = (own0 + cur.row) * D;
 
     // the row's own dense operand is independent of the gather: issue it first
     float4 own_a[V];
     if (MODE != MODE_MSG) {
       const float* a = item_side ? p.a_i : p.a_u;
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-        own_a[v] = valid ? ld_nc(a + own_row * D + (v * LPR + gl) * 4) : f4_zero();
+      for (int v = 0; v < V; ++v) own_a[v] = valid ? ld_nc(a + own_off + (v * LPR + gl) * 4) : f4_zero();
     }
 
     float4 acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = f4_zero();
 
-    // ---- gather-reduce over this task's edges (lock step over the warp) -----------------
+    // ---- gather-reduce over this task's edges (lock step over the warp) -------------------
     int nmax = n;
 #pragma unroll
     for (int o = LPR; o < 32; o <<= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
     for (int eb = 0; eb < nmax; eb += LPR) {
-      // prefetch the next batch of column ids while this one is gathered
+      // prefetch the next batch of codes while this one is gathered
       int c_next = 0;
       float w_next = 0.f;
       if (eb + LPR + gl < n) {
-        c_next = __ldg(p.idx + cur.e0 + eb + LPR + gl);
-        if (WEIGHTED) w_next = __ldg(p.w + cur.e0 + eb + LPR + gl);
+        c_next = __ldg(enc + cur.e_off + eb + LPR + gl);
+        if (WEIGHTED) w_next = __ldg(wts + cur.e_off + eb + LPR + gl);
       }
-      const int nb = n - eb;               // edges of my group left (may be <= 0)
+      const int nb = n - eb;                 // my group's edges left (may be <= 0)
+      const int nhb = nh - eb;               // ... of which hot (staged in shared memory)
       const int nbmax = min(LPR, nmax - eb);
       for (int j = 0; j < nbmax; j += UNR) {
         float4 val[UNR][V];
         uint32_t mw[UNR][V];
         float wv[UNR];
+        bool on[UNR], cold[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-          const int c = __shfl_sync(FULL, myc, gbase + j + u);
+          int c = __shfl_sync(FULL, myc, gbase + j + u);
           if (WEIGHTED) wv[u] = __shfl_sync(FULL, myw, gbase + j + u);
-          const bool on = (j + u) < nb;
+          on[u] = (j + u) < nb;
+          bool is_hot = (j + u) < nhb;
+          if (WARM) {
+            if (is_hot && c >= KST) { c = warm_ids[c]; is_hot = false; }
+          }
+          cold[u] = on[u] && !is_hot;
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            val[u][v] = f4_zero();
-            mw[u][v] = 0xffffffffu;
-            if (on) {
+            if (is_hot)
+              val[u][v] = *reinterpret_cast<const float4*>(hot + (size_t)c * D + (v * LPR + gl) * 4);
+            if (cold[u]) {
               val[u][v] = ld_nc(src + (int64_t)c * D + (v * LPR + gl) * 4);
               if (MODE == MODE_BWD) mw[u][v] = __ldg(smask + (int64_t)c * WPR + ((v * LPR + gl) >> 3));
             }
@@ -215,23 +292,27 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
+          if (on[u]) {
 #pragma unroll
-          for (int v = 0; v < V; ++v) {
-            float4 x = val[u][v];
-            if (MODE == MODE_BWD) {   // source = sigma'(Z) (.) g : pass where Z > 0, else leaky
-              const uint32_t b = mw[u][v] >> ((gl & 7) * 4);
-              x.x = (b & 1u) ? x.x : p.leaky * x.x;
-              x.y = (b & 2u) ? x.y : p.leaky * x.y;
-              x.z = (b & 4u) ? x.z : p.leaky * x.z;
-              x.w = (b & 8u) ? x.w : p.leaky * x.w;
-            }
-            if (WEIGHTED) {
-              acc[v].x = fmaf(wv[u], x.x, acc[v].x);
-              acc[v].y = fmaf(wv[u], x.y, acc[v].y);
-              acc[v].z = fmaf(wv[u], x.z, acc[v].z);
-              acc[v].w = fmaf(wv[u], x.w, acc[v].w);
-            } else {
-              acc[v] = f4_add(acc[v], x);
+            for (int v = 0; v < V; ++v) {
+              float4 x = val[u][v];
+              if (MODE == MODE_BWD) {
+                if (cold[u]) {   // source = sigma'(Z) (.) g : pass where Z > 0, else leaky
+                  const uint32_t b = mw[u][v] >> ((gl & 7) * 4);
+                  x.x = (b & 1u) ? x.x : p.leaky * x.x;
+                  x.y = (b & 2u) ? x.y : p.leaky * x.y;
+                  x.z = (b & 4u) ? x.z : p.leaky * x.z;
+                  x.w = (b & 8u) ? x.w : p.leaky * x.w;
+                }
+              }
+              if (WEIGHTED) {
+                acc[v].x = fmaf(wv[u], x.x, acc[v].x);
+                acc[v].y = fmaf(wv[u], x.y, acc[v].y);
+                acc[v].z = fmaf(wv[u], x.z, acc[v].z);
+                acc[v].w = fmaf(wv[u], x.w, acc[v].w);
+              } else {
+                acc[v] = f4_add(acc[v], x);
+              }
             }
           }
         }
@@ -240,13 +321,15 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
       myw = w_next;
     }
 
-    // ---- long rows: publish the partial sum; the last slice to arrive reduces -----------
+    // ---- long rows: publish the partial sum; the last slice to arrive reduces -------------
     // (release-only ticket; the reducer reads with strong loads that bypass L1, so no
     //  acquire fence / L1 invalidate is needed)
     bool finish = valid;
     if (__any_sync(FULL, multi)) {
+      uint32_t lr = 0;
       if (multi) {
-        float* mine = p.partials + t * D;
+        lr = __ldg(p.chunk_lr + cur.aux);
+        float* mine = p.partials + (int64_t)cur.aux * D;
 #pragma unroll
         for (int v = 0; v < V; ++v) st_f4(mine + (v * LPR + gl) * 4, acc[v]);
       }
@@ -255,21 +338,23 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
       if (multi && gl == 0) old = ticket_release_add(p.tickets + lr);
       old = __shfl_sync(FULL, old, gbase);
       if (multi) {
+        const int64_t cb = __ldg(p.chunk_base + lr);
+        const int nch = (int)(__ldg(p.chunk_base + lr + 1) - cb);
         finish = (old == (unsigned)(nch - 1));
         if (finish) {
 #pragma unroll
           for (int v = 0; v < V; ++v) acc[v] = f4_zero();
           const float* part = p.partials + cb * D;
-          for (int c0 = 0; c0 < nch; c0 += UNR) {
-            float4 val[UNR][V];
+          for (int c0 = 0; c0 < nch; c0 += 4) {
+            float4 val[4][V];
 #pragma unroll
-            for (int u = 0; u < UNR; ++u)
+            for (int u = 0; u < 4; ++u)
 #pragma unroll
               for (int v = 0; v < V; ++v)
                 val[u][v] = (c0 + u < nch) ? ld_strong(part + (int64_t)(c0 + u) * D + (v * LPR + gl) * 4)
                                            : f4_zero();
 #pragma unroll
-            for (int u = 0; u < UNR; ++u)
+            for (int u = 0; u < 4; ++u)
 #pragma unroll
               for (int v = 0; v < V; ++v) acc[v] = f4_add(acc[v], val[u][v]);
           }
@@ -279,11 +364,10 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
       __syncwarp();
     }
 
-    // ---- fused epilogue (all lanes take part in the shuffles; stores are predicated) -----
+    // ---- fused epilogue (all lanes take part in the shuffles; stores are predicated) -------
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const int col = (v * LPR + gl) * 4;
-      const int64_t off = own_row * D + col;
+      const int64_t off = own_off + (v * LPR + gl) * 4;
       if (MODE == MODE_BWD) {
         // n = G + g + A (sigma' . g_other)      
         if (finish) {
@@ -312,14 +396,14 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
             if (p.out_add_next) o = f4_add(o, nxt_e);
             st_stream(o2 + off, o);
           }
-          if (p.mask_u) {   // warp-uniform
+          if (mk) {   // CTA-uniform
             // TF MaximumGrad sends the gradient to leaky*z where leaky*z >= z: bit = pass-through
             uint32_t word = ((!(lzx >= z.x) ? 1u : 0u) | (!(lzy >= z.y) ? 2u : 0u) |
                              (!(lzz >= z.z) ? 4u : 0u) | (!(lzw >= z.w) ? 8u : 0u)) << ((gl & 7) * 4);
             word |= __shfl_xor_sync(FULL, word, 1);
             word |= __shfl_xor_sync(FULL, word, 2);
             word |= __shfl_xor_sync(FULL, word, 4);
-            if (finish && (gl & 7) == 0) mk[own_row * WPR + ((v * LPR + gl) >> 3)] = word;
+            if (finish && (gl & 7) == 0) mk[(own0 + cur.row) * WPR + ((v * LPR + gl) >> 3)] = word;
           }
         }
       }
@@ -332,20 +416,17 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
 // ---------------------------------------------------------------------------------------
 template <int LPR, int V, int MODE, bool WEIGHTED>
 static int launch_t(const sagnn_plan* plan, const SpmmParams& prm, cudaStream_t st) {
-  static int blocks_per_sm = 0;   // same for every device of the same type
+  constexpr int D = LPR * V * 4;
+  constexpr int KST = (SAGNN_HOT_BYTES / (4 * D)) < kHotRows ? (SAGNN_HOT_BYTES / (4 * D)) : kHotRows;
+  constexpr size_t smem = (size_t)KST * D * 4;
+  static bool configured = false;
   auto kern = spmm_layer_kernel<LPR, V, MODE, WEIGHTED>;
-  if (blocks_per_sm == 0) {
-    int b = 0;
-    SAGNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kThreads, 0));
-    blocks_per_sm = b > 0 ? b : 1;
+  if (!configured) {
+    SAGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
   }
-  const int64_t n_tasks = prm.n_chunks + prm.n_short;
-  if (n_tasks == 0) return SAGNN_OK;
-  const int64_t groups_per_block = kThreads / LPR;
-  int64_t want = (n_tasks + groups_per_block - 1) / groups_per_block;
-  int64_t cap = (int64_t)plan->num_sms * blocks_per_sm;
-  unsigned grid = (unsigned)(want < cap ? want : cap);
-  kern<<<grid, kThreads, 0, st>>>(prm);
+  if (plan->n_tasks == 0) return SAGNN_OK;
+  kern<<<plan->num_sms, kThreads, smem, st>>>(prm);
   SAGNN_CUDA(cudaGetLastError());
   return SAGNN_OK;
 }
@@ -402,11 +483,10 @@ static size_t mask_layer_words(const sagnn_plan* p, int d) { return (size_t)p->n
 
 static void base_params(const sagnn_plan* p, SpmmParams& s) {
   s = SpmmParams{};
-  s.tasks = p->tasks; s.idx = p->idx; s.w = p->w;
+  s.tasks = p->tasks; s.enc = p->enc; s.w = p->w_enc;
   s.chunk_base = p->chunk_base; s.chunk_lr = p->chunk_lr;
-  s.n_short = p->n_short; s.n_chunks = p->n_chunks;
-  s.U = p->U; s.I = p->I; s.N = (uint32_t)p->N;
-  s.row_lo = 0; s.row_hi = (uint32_t)p->n_rows;
+  s.hot_ids = p->hot_ids; s.seg = p->seg_dev; s.cta = p->cta_dev; s.single_seg = -1;
+  s.U = p->U; s.I = p->I;
 }
 
 static int check_common(const sagnn_plan* p, int n_layers, int d, const char* fn) {
@@ -535,8 +615,7 @@ extern "C" int sagnn_message_propagate(const sagnn_plan* p, int k, int side, con
   s.partials = (float*)(base + w.partials_off);
   s.leaky = leaky;
   SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, sizeof(uint32_t) * (size_t)(p->n_long ? p->n_long : 1), st));
-  s.row_lo = (uint32_t)((int64_t)k * p->N + (side ? p->U : 0));
-  s.row_hi = s.row_lo + (uint32_t)(side ? p->I : p->U);
+  s.single_seg = 2 * k + side;
   // the kernel indexes tables as [T, rows, d]; shift the bases so that interval k lands on the
   // caller's single-interval tensors
   const intptr_t src_shift = (intptr_t)sizeof(float) * (intptr_t)k * (side ? p->U : p->I) * d;
