@@ -130,6 +130,89 @@ __device__ __forceinline__ sagnn_task ld_task(const sagnn_task* tasks, int64_t t
   return k;
 }
 
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// One gather slot: slot u of the current block is hot (shared memory) when u < nhb, cold
+// (global, read-only path) when nhb <= u < nb, idle otherwise.  Both loads target the same
+// registers, so no moves are needed to merge them.
+template <int U_>
+__device__ __forceinline__ void gather_slot(float4& v, uint32_t hot_addr, const void* gaddr, int nhb, int nb) {
+  asm volatile(
+      "{\n\t.reg .pred ph, pc;\n\t"
+      "setp.gt.s32 ph, %6, %8;\n\t"
+      "setp.gt.s32 pc, %7, %8;\n\t"
+      "and.pred pc, pc, !ph;\n\t"
+      "@ph ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
+      "@pc ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5];\n\t}"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "r"(hot_addr), "l"(gaddr), "r"(nhb), "r"(nb), "n"(U_));
+}
+// same, with the hot / cold decision already made (warm slots: hot ids that are not staged)
+__device__ __forceinline__ void gather_slot_flags(float4& v, uint32_t hot_addr, const void* gaddr, int is_hot,
+                                                  int is_cold) {
+  asm volatile(
+      "{\n\t.reg .pred ph, pc;\n\t"
+      "setp.ne.s32 ph, %6, 0;\n\t"
+      "setp.ne.s32 pc, %7, 0;\n\t"
+      "@ph ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
+      "@pc ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5];\n\t}"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "r"(hot_addr), "l"(gaddr), "r"(is_hot), "r"(is_cold));
+}
+
+// keep a CTA-lifetime value in a register: the compiler must not rematerialise it from the
+// kernel parameters inside the gather loop (it does, under the 64-register cap)
+template <typename T>
+__device__ __forceinline__ void pin64(T*& p) { asm volatile("" : "+l"(p)); }
+__device__ __forceinline__ void pin32(uint32_t& v) { asm volatile("" : "+r"(v)); }
+
+template <int LPR, int V, int MODE, bool WARM, int KST, int UNR>
+__device__ __forceinline__ void gather_block(float4 (&val)[UNR][V], uint32_t (&mw)[UNR][V], bool (&cold)[UNR],
+                                             const int (&cs)[UNR], uint32_t hot_lane, const char* src_lane,
+                                             const char* smask_lane, const int* warm_ids, int nhb, int nb) {
+  constexpr int D = LPR * V * 4;
+  constexpr int WPR = D / 32;
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) {
+    int c = cs[u];
+    bool is_hot = u < nhb;
+    if (WARM) {
+      if (is_hot && c >= KST) { c = warm_ids[c]; is_hot = false; }
+    }
+    cold[u] = (u < nb) && !is_hot;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const uint32_t ha = hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16;
+      const char* ga = src_lane + (int64_t)c * (D * 4) + v * LPR * 16;
+      if (WARM) gather_slot_flags(val[u][v], ha, ga, is_hot ? 1 : 0, cold[u] ? 1 : 0);
+      else if (u == 0) gather_slot<0>(val[u][v], ha, ga, nhb, nb);
+      else if (u == 1) gather_slot<1>(val[u][v], ha, ga, nhb, nb);
+      else if (u == 2) gather_slot<2>(val[u][v], ha, ga, nhb, nb);
+      else if (u == 3) gather_slot<3>(val[u][v], ha, ga, nhb, nb);
+      else if (u == 4) gather_slot<4>(val[u][v], ha, ga, nhb, nb);
+      else if (u == 5) gather_slot<5>(val[u][v], ha, ga, nhb, nb);
+      else if (u == 6) gather_slot<6>(val[u][v], ha, ga, nhb, nb);
+      else gather_slot<7>(val[u][v], ha, ga, nhb, nb);
+      if (MODE == MODE_BWD) {
+        if (cold[u])
+          mw[u][v] = __ldg(reinterpret_cast<const uint32_t*>(smask_lane + (int64_t)c * (WPR * 4) + v * (LPR / 8) * 4));
+      }
+    }
+  }
+}
+
+struct SegPtrs {               // segment-uniform table pointers, written once per CTA to shared memory
+  const float* a;
+  const float* b;
+  float* o1;
+  float* o2;
+  uint32_t* mk;
+};
+
 // One persistent CTA per SM, bound to one segment (interval, orientation).  It first stages
 // the segment's hottest source rows in shared memory with TMA bulk copies, then walks its
 // share of the segment's task list.  The lane groups of a warp run in lock step (trip
@@ -149,6 +232,7 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
 
   extern __shared__ __align__(128) float hot[];       // [KST][D]
   __shared__ __align__(8) uint64_t bar;
+  __shared__ SegPtrs sp;
   __shared__ int warm_ids[WARM ? kHotRows : 1];
 
   const int lane = threadIdx.x & 31;
@@ -161,19 +245,31 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
   const int k = seg >> 1;
   const bool item_side = seg & 1;
   const int r_own = item_side ? p.I : p.U, r_src = item_side ? p.U : p.I;
-  const float* __restrict__ src = (item_side ? p.src_u : p.src_i) + (int64_t)k * r_src * D;
-  const uint32_t* __restrict__ smask =
+  const float* src = (item_side ? p.src_u : p.src_i) + (int64_t)k * r_src * D;
+  const uint32_t* smask =
       (MODE == MODE_BWD) ? (item_side ? p.smask_u : p.smask_i) + (int64_t)k * r_src * WPR : nullptr;
-  const int64_t own0 = (int64_t)k * r_own;            // first row of my table
   const sagnn_seg sg = p.seg[seg];
-  const int32_t* __restrict__ enc = p.enc + sg.edge_base;
-  const float* __restrict__ wts = WEIGHTED ? p.w + sg.edge_base : nullptr;
+  const int32_t* enc = p.enc + sg.edge_base;
+  const float* wts = WEIGHTED ? p.w + sg.edge_base : nullptr;
 
   // ---- stage the hot rows of the source table (TMA bulk copies, one per row) -------------
   {
     const int32_t* ids = p.hot_ids + (int64_t)(seg ^ 1) * kHotRows;
     const int n_stage = r_src < KST ? r_src : KST;
-    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      const int64_t own0 = (int64_t)k * r_own;
+      const float* a = item_side ? p.a_i : p.a_u;
+      const float* b = item_side ? p.b_i : p.b_u;
+      float* o1 = item_side ? p.o1_i : p.o1_u;
+      float* o2 = item_side ? p.o2_i : p.o2_u;
+      uint32_t* mk = item_side ? p.mask_i : p.mask_u;
+      sp.a = a ? a + own0 * D : nullptr;
+      sp.b = b ? b + own0 * D : nullptr;
+      sp.o1 = o1 ? o1 + own0 * D : nullptr;
+      sp.o2 = o2 ? o2 + own0 * D : nullptr;
+      sp.mk = mk ? mk + own0 * WPR : nullptr;
+    }
     __syncthreads();
     if (threadIdx.x == 0) mbar_expect_tx(&bar, (unsigned)(n_stage * D * 4));
     for (int s = threadIdx.x; s < n_stage; s += kThreads)
@@ -203,6 +299,16 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
     }
     __syncthreads();
   }
+
+  // lane-specific bases of everything the gather loop touches, pinned in registers
+  const char* src_lane = reinterpret_cast<const char*>(src) + gl * 16;
+  const char* smask_lane = reinterpret_cast<const char*>(smask) + (gl >> 3) * 4;
+  uint32_t hot_lane = smem_u32(hot) + gl * 16;
+  const float leaky = p.leaky;
+  pin64(src_lane);
+  if (MODE == MODE_BWD) pin64(smask_lane);
+  pin32(hot_lane);
+  pin64(enc);
 
   // ---- my share of the segment's tasks ----------------------------------------------------
   const int64_t t_end = sg.task_end;
@@ -236,14 +342,15 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
     const bool multi = (cur.meta >> 31) != 0;          // slice of a long row
     const int n = (int)(cur.meta & 0x7fu);
     const int nh = (int)((cur.meta >> 8) & 0x7fu);
-    const int64_t own_off = (own0 + cur.row) * D;
+    const uint32_t own_off = cur.row * (uint32_t)(D * 4) + gl * 16;   // byte offset inside my table (< 4 GB)
 
     // the row's own dense operand is independent of the gather: issue it first
     float4 own_a[V];
     if (MODE != MODE_MSG) {
-      const float* a = item_side ? p.a_i : p.a_u;
+      const char* a = reinterpret_cast<const char*>(sp.a);
 #pragma unroll
-      for (int v = 0; v < V; ++v) own_a[v] = valid ? ld_nc(a + own_off + (v * LPR + gl) * 4) : f4_zero();
+      for (int v = 0; v < V; ++v)
+        own_a[v] = valid ? ld_nc(reinterpret_cast<const float*>(a + own_off + v * LPR * 16)) : f4_zero();
     }
 
     float4 acc[V];
@@ -262,47 +369,34 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
         c_next = __ldg(enc + cur.e_off + eb + LPR + gl);
         if (WEIGHTED) w_next = __ldg(wts + cur.e_off + eb + LPR + gl);
       }
-      const int nb = n - eb;                 // my group's edges left (may be <= 0)
-      const int nhb = nh - eb;               // ... of which hot (staged in shared memory)
       const int nbmax = min(LPR, nmax - eb);
       for (int j = 0; j < nbmax; j += UNR) {
+        const int nb = n - eb - j;             // my group's edges left from slot j on (may be <= 0)
+        const int nhb = nh - eb - j;           // ... of which hot (staged in shared memory)
         float4 val[UNR][V];
         uint32_t mw[UNR][V];
         float wv[UNR];
-        bool on[UNR], cold[UNR];
+        bool cold[UNR];
+        int cs[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-          int c = __shfl_sync(FULL, myc, gbase + j + u);
+          cs[u] = __shfl_sync(FULL, myc, gbase + j + u);
           if (WEIGHTED) wv[u] = __shfl_sync(FULL, myw, gbase + j + u);
-          on[u] = (j + u) < nb;
-          bool is_hot = (j + u) < nhb;
-          if (WARM) {
-            if (is_hot && c >= KST) { c = warm_ids[c]; is_hot = false; }
-          }
-          cold[u] = on[u] && !is_hot;
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            if (is_hot)
-              val[u][v] = *reinterpret_cast<const float4*>(hot + (size_t)c * D + (v * LPR + gl) * 4);
-            if (cold[u]) {
-              val[u][v] = ld_nc(src + (int64_t)c * D + (v * LPR + gl) * 4);
-              if (MODE == MODE_BWD) mw[u][v] = __ldg(smask + (int64_t)c * WPR + ((v * LPR + gl) >> 3));
-            }
-          }
         }
+        gather_block<LPR, V, MODE, WARM, KST, UNR>(val, mw, cold, cs, hot_lane, src_lane, smask_lane, warm_ids, nhb, nb);
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-          if (on[u]) {
+          if (u < nb) {
 #pragma unroll
             for (int v = 0; v < V; ++v) {
               float4 x = val[u][v];
               if (MODE == MODE_BWD) {
-                if (cold[u]) {   // source = sigma'(Z) (.) g : pass where Z > 0, else leaky
+                if (cold[u]) {   // cold source = sigma'(Z) (.) g : pass where Z > 0, else leaky
                   const uint32_t b = mw[u][v] >> ((gl & 7) * 4);
-                  x.x = (b & 1u) ? x.x : p.leaky * x.x;
-                  x.y = (b & 2u) ? x.y : p.leaky * x.y;
-                  x.z = (b & 4u) ? x.z : p.leaky * x.z;
-                  x.w = (b & 8u) ? x.w : p.leaky * x.w;
+                  x.x = (b & 1u) ? x.x : leaky * x.x;
+                  x.y = (b & 2u) ? x.y : leaky * x.y;
+                  x.z = (b & 4u) ? x.z : leaky * x.z;
+                  x.w = (b & 8u) ? x.w : leaky * x.w;
                 }
               }
               if (WEIGHTED) {
@@ -367,34 +461,34 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
     // ---- fused epilogue (all lanes take part in the shuffles; stores are predicated) -------
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const int64_t off = own_off + (v * LPR + gl) * 4;
+      const uint32_t off = own_off + v * LPR * 16;     // bytes
       if (MODE == MODE_BWD) {
         // n = G + g + A (sigma' . g_other)      
         if (finish) {
-          const float* g = item_side ? p.b_i : p.b_u;
-          float* dst = item_side ? p.o1_i : p.o1_u;
-          const float4 gv = g ? ld_stream(g + off) : own_a[v];
-          st_f4(dst + off, f4_add(f4_add(own_a[v], gv), acc[v]));
+          const char* g = reinterpret_cast<const char*>(sp.b);
+          char* dst = reinterpret_cast<char*>(sp.o1);
+          const float4 gv = g ? ld_stream(reinterpret_cast<const float*>(g + off)) : own_a[v];
+          st_f4(reinterpret_cast<float*>(dst + off), f4_add(f4_add(own_a[v], gv), acc[v]));
         }
       } else {
         const float4 z = acc[v];
-        const float lzx = p.leaky * z.x, lzy = p.leaky * z.y, lzz = p.leaky * z.z, lzw = p.leaky * z.w;
+        const float lzx = leaky * z.x, lzy = leaky * z.y, lzz = leaky * z.z, lzw = leaky * z.w;
         // LeakyReLU = max(leaky*z, z)  (Utils/NNLayers.py:135-136)
         const float4 act = make_float4(fmaxf(lzx, z.x), fmaxf(lzy, z.y), fmaxf(lzz, z.z), fmaxf(lzw, z.w));
         if (MODE == MODE_MSG) {
-          if (finish) st_f4((item_side ? p.o1_i : p.o1_u) + off, act);
+          if (finish) st_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(sp.o1) + off), act);
         } else {
-          const float* b = item_side ? p.b_i : p.b_u;
-          float* o1 = item_side ? p.o1_i : p.o1_u;
-          float* o2 = item_side ? p.o2_i : p.o2_u;
-          uint32_t* mk = item_side ? p.mask_i : p.mask_u;
+          const char* b = reinterpret_cast<const char*>(sp.b);
+          char* o1 = reinterpret_cast<char*>(sp.o1);
+          char* o2 = reinterpret_cast<char*>(sp.o2);
+          uint32_t* mk = sp.mk;
           const float4 nxt_e = f4_add(own_a[v], act);          // E^{l+1} = E^l + lrelu(Z^l)
-          if (finish && o1) st_f4(o1 + off, nxt_e);
+          if (finish && o1) st_f4(reinterpret_cast<float*>(o1 + off), nxt_e);
           if (finish && o2) {
             float4 o = own_a[v];
-            if (b) o = f4_add(ld_stream(b + off), own_a[v]);
+            if (b) o = f4_add(ld_stream(reinterpret_cast<const float*>(b + off)), own_a[v]);
             if (p.out_add_next) o = f4_add(o, nxt_e);
-            st_stream(o2 + off, o);
+            st_stream(reinterpret_cast<float*>(o2 + off), o);
           }
           if (mk) {   // CTA-uniform
             // TF MaximumGrad sends the gradient to leaky*z where leaky*z >= z: bit = pass-through
@@ -403,7 +497,7 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
             word |= __shfl_xor_sync(FULL, word, 1);
             word |= __shfl_xor_sync(FULL, word, 2);
             word |= __shfl_xor_sync(FULL, word, 4);
-            if (finish && (gl & 7) == 0) mk[(own0 + cur.row) * WPR + ((v * LPR + gl) >> 3)] = word;
+            if (finish && (gl & 7) == 0) mk[(size_t)cur.row * WPR + ((v * LPR + gl) >> 3)] = word;
           }
         }
       }

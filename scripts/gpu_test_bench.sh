@@ -1,0 +1,12 @@
+# usage: bash scripts/gpu_test_bench.sh <tag> [bench args]   -- gpu tests + short bench (no ncu)
+TAG=$1; shift
+python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/test_$TAG.log; tail -3 gpurun_out/test_$TAG.log
+python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline $@ > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+python - <<PY
+import json
+try:
+    j=json.loads(open("gpurun_out/bench_$TAG.json").read().strip().splitlines()[-1])
+    print("$TAG", "ms/step", round(j["ms_per_step"],4), "fwd", round(j["roofline"]["fwd_ms"],4), "bwd", round(j["roofline"]["bwd_ms"],4), "frac", round(j["roofline"]["frac"],3), "step_frac", round(j["roofline"]["step"]["frac"],3))
+except Exception as e:
+    print("bench failed", e); print(open("gpurun_out/bench_$TAG.err").read()[-2000:])
+PY
