@@ -20,16 +20,23 @@
 #define SAGNN_THREADS 1024     // one persistent CTA per SM
 #endif
 #ifndef SAGNN_UNR
-#define SAGNN_UNR 4            // independent 128-bit gathers in flight per lane
+#define SAGNN_UNR 4            // gather slots per pipeline block
+#endif
+#ifndef SAGNN_GRAB
+#define SAGNN_GRAB 2           // task rounds a warp takes per queue atomic
 #endif
 #ifndef SAGNN_HOT_BYTES
-#define SAGNN_HOT_BYTES (192 * 1024)   // shared memory given to staged hot rows
+#define SAGNN_HOT_BYTES (80 * 1024)    // shared memory given to staged hot rows
+#endif
+#ifndef SAGNN_HOP
+#define SAGNN_HOP 0            // 1: CTAs whose segment is drained help the other segments
 #endif
 
 namespace sagnn {
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_MSG = 2 };
 constexpr int kThreads = SAGNN_THREADS;
+constexpr int kWarps = kThreads / 32;
 
 struct SpmmParams {
   const sagnn_task* tasks;
@@ -41,12 +48,13 @@ struct SpmmParams {
   const sagnn_seg* seg;
   const sagnn_cta* cta;
   int single_seg;            // >= 0: every CTA works on this segment (messagePropagate); -1: use cta[]
+  int n_seg_total;           // 2T
   int U, I;
   // gather sources: user rows read item-table rows (src_i), item rows read user-table rows (src_u)
   const float* src_u;
   const float* src_i;
-  const uint32_t* smask_u;   // BWD: sign masks of the source rows
-  const uint32_t* smask_i;
+  const uint8_t* smask_u;    // BWD: sign masks of the source rows (one byte = 4 sign bits per float4)
+  const uint8_t* smask_i;
   const float* a_u;          // FWD: E^l (residual)          BWD: G (dense upstream)
   const float* a_i;
   const float* b_u;          // FWD: sum_{j<l} E^j or NULL   BWD: running gradient g or NULL (== G)
@@ -55,10 +63,11 @@ struct SpmmParams {
   float* o1_i;
   float* o2_u;               // FWD: layer-sum output or NULL
   float* o2_i;
-  uint32_t* mask_u;          // FWD: sign masks out or NULL
-  uint32_t* mask_i;
+  uint8_t* mask_u;           // FWD: sign masks out or NULL
+  uint8_t* mask_i;
   float* partials;           // [n_chunks, d]
   uint32_t* tickets;         // [n_long], zero on entry, zero again on exit
+  unsigned* ctrs;            // [2T] per-segment task-queue heads, zero on entry
   float leaky;
   int out_add_next;          // FWD: o2 = b + a (+ E^{l+1} when set)
 };
@@ -91,7 +100,7 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
 }
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-// ---- TMA bulk copy (global -> shared, mbarrier-completed) ---------------------------------
+// ---- TMA bulk copy (global -> shared, mbarrier-completed): stages the hot rows ------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -119,389 +128,477 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                : "memory");
 }
 
-__device__ __forceinline__ sagnn_task ld_task(const sagnn_task* tasks, int64_t t, int64_t t_end) {
-  sagnn_task k;
-  if (t < t_end) {
-    const int4 raw = __ldg(reinterpret_cast<const int4*>(tasks + t));
-    k.row = (uint32_t)raw.x; k.meta = (uint32_t)raw.y; k.e_off = (uint32_t)raw.z; k.aux = (uint32_t)raw.w;
-  } else {
-    k.row = 0; k.meta = 0x40000000u; k.e_off = 0; k.aux = 0;   // bit 30: no work
-  }
-  return k;
+// ---- cp.async (LDGSTS): register-free gathers into the per-warp ring ----------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
-// One gather slot: slot u of the current block is hot (shared memory) when u < nhb, cold
-// (global, read-only path) when nhb <= u < nb, idle otherwise.  Both loads target the same
-// registers, so no moves are needed to merge them.
-template <int U_>
-__device__ __forceinline__ void gather_slot(float4& v, uint32_t hot_addr, const void* gaddr, int nhb, int nb) {
-  asm volatile(
-      "{\n\t.reg .pred ph, pc;\n\t"
-      "setp.gt.s32 ph, %6, %8;\n\t"
-      "setp.gt.s32 pc, %7, %8;\n\t"
-      "and.pred pc, pc, !ph;\n\t"
-      "@ph ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
-      "@pc ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5];\n\t}"
-      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-      : "r"(hot_addr), "l"(gaddr), "r"(nhb), "r"(nb), "n"(U_));
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
-// same, with the hot / cold decision already made (warm slots: hot ids that are not staged)
-__device__ __forceinline__ void gather_slot_flags(float4& v, uint32_t hot_addr, const void* gaddr, int is_hot,
-                                                  int is_cold) {
-  asm volatile(
-      "{\n\t.reg .pred ph, pc;\n\t"
-      "setp.ne.s32 ph, %6, 0;\n\t"
-      "setp.ne.s32 pc, %7, 0;\n\t"
-      "@ph ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
-      "@pc ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5];\n\t}"
-      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-      : "r"(hot_addr), "l"(gaddr), "r"(is_hot), "r"(is_cold));
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
 }
-
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 // keep a CTA-lifetime value in a register: the compiler must not rematerialise it from the
 // kernel parameters inside the gather loop (it does, under the 64-register cap)
 template <typename T>
 __device__ __forceinline__ void pin64(T*& p) { asm volatile("" : "+l"(p)); }
 __device__ __forceinline__ void pin32(uint32_t& v) { asm volatile("" : "+r"(v)); }
 
-template <int LPR, int V, int MODE, bool WARM, int KST, int UNR>
-__device__ __forceinline__ void gather_block(float4 (&val)[UNR][V], uint32_t (&mw)[UNR][V], bool (&cold)[UNR],
-                                             const int (&cs)[UNR], uint32_t hot_lane, const char* src_lane,
-                                             const char* smask_lane, const int* warm_ids, int nhb, int nb) {
-  constexpr int D = LPR * V * 4;
-  constexpr int WPR = D / 32;
-#pragma unroll
-  for (int u = 0; u < UNR; ++u) {
-    int c = cs[u];
-    bool is_hot = u < nhb;
-    if (WARM) {
-      if (is_hot && c >= KST) { c = warm_ids[c]; is_hot = false; }
+// ---- packed fp32x2 math (sm_100a FADD2 / FFMA2; same IEEE results as the scalar forms) ----
+struct f4p { float2 lo, hi; };
+__device__ __forceinline__ f4p f4p_zero() { return f4p{make_float2(0.f, 0.f), make_float2(0.f, 0.f)}; }
+__device__ __forceinline__ void acc_add(f4p& a, const float4& x) {
+  a.lo = __fadd2_rn(a.lo, make_float2(x.x, x.y));
+  a.hi = __fadd2_rn(a.hi, make_float2(x.z, x.w));
+}
+__device__ __forceinline__ float4 f4p_get(const f4p& a) { return make_float4(a.lo.x, a.lo.y, a.hi.x, a.hi.y); }
+
+// accumulate one gathered float4: plain, weighted, sign-masked (backward), or both
+template <bool WEIGHTED, bool MASKED>
+__device__ __forceinline__ void accumulate(f4p& a, const float4& x, float w, uint32_t bits, float leaky) {
+  if (!WEIGHTED && !MASKED) {
+    acc_add(a, x);
+  } else {
+    float s0 = WEIGHTED ? w : 1.f, s1 = s0, s2 = s0, s3 = s0;
+    if (MASKED) {   // source = sigma'(Z) (.) g : pass where the bit is set, else leaky
+      const float wl = s0 * leaky;
+      s0 = (bits & 1u) ? s0 : wl; s1 = (bits & 2u) ? s1 : wl;
+      s2 = (bits & 4u) ? s2 : wl; s3 = (bits & 8u) ? s3 : wl;
     }
-    cold[u] = (u < nb) && !is_hot;
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const uint32_t ha = hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16;
-      const char* ga = src_lane + (int64_t)c * (D * 4) + v * LPR * 16;
-      if (WARM) gather_slot_flags(val[u][v], ha, ga, is_hot ? 1 : 0, cold[u] ? 1 : 0);
-      else if (u == 0) gather_slot<0>(val[u][v], ha, ga, nhb, nb);
-      else if (u == 1) gather_slot<1>(val[u][v], ha, ga, nhb, nb);
-      else if (u == 2) gather_slot<2>(val[u][v], ha, ga, nhb, nb);
-      else if (u == 3) gather_slot<3>(val[u][v], ha, ga, nhb, nb);
-      else if (u == 4) gather_slot<4>(val[u][v], ha, ga, nhb, nb);
-      else if (u == 5) gather_slot<5>(val[u][v], ha, ga, nhb, nb);
-      else if (u == 6) gather_slot<6>(val[u][v], ha, ga, nhb, nb);
-      else gather_slot<7>(val[u][v], ha, ga, nhb, nb);
-      if (MODE == MODE_BWD) {
-        if (cold[u])
-          mw[u][v] = __ldg(reinterpret_cast<const uint32_t*>(smask_lane + (int64_t)c * (WPR * 4) + v * (LPR / 8) * 4));
-      }
-    }
+    a.lo = __ffma2_rn(make_float2(x.x, x.y), make_float2(s0, s1), a.lo);
+    a.hi = __ffma2_rn(make_float2(x.z, x.w), make_float2(s2, s3), a.hi);
   }
 }
 
-struct SegPtrs {               // segment-uniform table pointers, written once per CTA to shared memory
+struct SegPtrs {               // segment-uniform table pointers, written once per segment to shared memory
   const float* a;
   const float* b;
   float* o1;
   float* o2;
-  uint32_t* mk;
+  uint8_t* mk;
 };
 
-// One persistent CTA per SM, bound to one segment (interval, orientation).  It first stages
-// the segment's hottest source rows in shared memory with TMA bulk copies, then walks its
-// share of the segment's task list.  The lane groups of a warp run in lock step (trip
-// counts are warp maxima, loads are predicated), so every shuffle uses the full mask; tasks
-// arrive sorted by degree, so the groups sharing a warp have near-equal rows.
+// compile-time geometry shared by the kernel and its launcher
+template <int LPR, int V, int MODE, bool WEIGHTED>
+struct Geo {
+  static constexpr int D = LPR * V * 4;
+  static constexpr int MPR = D / 4;                           // mask bytes per row (4 sign bits per byte)
+  static constexpr int GPW = 32 / LPR;                        // lane groups per warp
+  static constexpr int UNR = (V == 2 && SAGNN_UNR > 1) ? SAGNN_UNR / 2 : SAGNN_UNR;
+  static constexpr int KST = (SAGNN_HOT_BYTES / (4 * D)) < kHotRows ? (SAGNN_HOT_BYTES / (4 * D)) : kHotRows;
+  static constexpr int SLOT = 32 * 16 * V;                    // ring bytes per gather slot per warp
+  static constexpr int RING_WARP = 2 * UNR * SLOT;            // two pipeline stages
+  static constexpr int MSLOT = GPW * MPR;                     // mask bytes per slot per warp (backward)
+  static constexpr int MRING_WARP = (MODE == MODE_BWD) ? 2 * UNR * MSLOT : 0;
+  static constexpr int WRING_WARP = WEIGHTED ? 2 * UNR * GPW * 4 : 0;
+  static constexpr size_t HOT = (size_t)KST * D * 4;
+  static constexpr size_t SMEM = HOT + (size_t)kWarps * (RING_WARP + MRING_WARP + WRING_WARP);
+};
+
+// One persistent CTA per SM, bound to one segment (interval, orientation).  It stages the
+// segment's hottest source rows in shared memory with TMA bulk copies, then drains the
+// segment's task queue.  Per warp, gathers run as a two-stage cp.async pipeline through a
+// shared-memory ring: while block b is accumulated, block b+1 -- the next block of the same
+// row or the first block of the next task -- is already in flight, without holding
+// registers.  Hot rows are read straight from the staged copy when a block is issued.
+// The lane groups of a warp run in lock step (trip counts are warp maxima), so every
+// shuffle uses the full mask; tasks arrive sorted by degree, so the groups sharing a warp
+// have near-equal rows.
 template <int LPR, int V, int MODE, bool WEIGHTED>
 __global__ void __launch_bounds__(kThreads, 1)
 spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
-  constexpr int D = LPR * V * 4;
-  constexpr int WPR = D / 32;                         // mask words per row
-  constexpr int GPW = 32 / LPR;                       // lane groups per warp
-  constexpr int UNR = SAGNN_UNR;
-  constexpr int KST = (SAGNN_HOT_BYTES / (4 * D)) < kHotRows ? (SAGNN_HOT_BYTES / (4 * D)) : kHotRows;
+  using G = Geo<LPR, V, MODE, WEIGHTED>;
+  constexpr int D = G::D, MPR = G::MPR, GPW = G::GPW, UNR = G::UNR, KST = G::KST;
+  constexpr int R = SAGNN_GRAB;
   constexpr bool WARM = KST < kHotRows;               // hot slots that do not fit: read via their ids
+  constexpr bool BWD = MODE == MODE_BWD;
   static_assert(LPR % UNR == 0, "unroll must divide the group width");
+  static_assert(SAGNN_GRAB >= 2, "the record pipeline looks two rounds ahead");
   constexpr unsigned FULL = 0xffffffffu;
 
-  extern __shared__ __align__(128) float hot[];       // [KST][D]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* hot = reinterpret_cast<float*>(smem_raw);    // [KST][D]
   __shared__ __align__(8) uint64_t bar;
   __shared__ SegPtrs sp;
+  __shared__ int skip_seg;
   __shared__ int warm_ids[WARM ? kHotRows : 1];
 
   const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const int gl = lane % LPR;
   const int gbase = lane - gl;                        // first lane of my group
+  const int grp = lane / LPR;
+  const float leaky = p.leaky;
 
-  int seg, rank, count;
-  if (p.single_seg >= 0) { seg = p.single_seg; rank = blockIdx.x; count = gridDim.x; }
-  else { const sagnn_cta c = p.cta[blockIdx.x]; seg = c.seg; rank = c.rank; count = c.count; }
-  const int k = seg >> 1;
-  const bool item_side = seg & 1;
-  const int r_own = item_side ? p.I : p.U, r_src = item_side ? p.U : p.I;
-  const float* src = (item_side ? p.src_u : p.src_i) + (int64_t)k * r_src * D;
-  const uint32_t* smask =
-      (MODE == MODE_BWD) ? (item_side ? p.smask_u : p.smask_i) + (int64_t)k * r_src * WPR : nullptr;
-  const sagnn_seg sg = p.seg[seg];
-  const int32_t* enc = p.enc + sg.edge_base;
-  const float* wts = WEIGHTED ? p.w + sg.edge_base : nullptr;
+  // per-warp ring: [stage][slot][v][lane] 16-byte cells; every lane reads back what it copied
+  uint32_t ring_lane = smem_u32(smem_raw + G::HOT + (size_t)warp * G::RING_WARP) + lane * 16;
+  uint32_t mring = smem_u32(smem_raw + G::HOT + (size_t)kWarps * G::RING_WARP + (size_t)warp * G::MRING_WARP);
+  uint32_t wring = smem_u32(smem_raw + G::HOT + (size_t)kWarps * (G::RING_WARP + G::MRING_WARP) +
+                            (size_t)warp * G::WRING_WARP);
+  pin32(ring_lane);
 
-  // ---- stage the hot rows of the source table (TMA bulk copies, one per row) -------------
-  {
-    const int32_t* ids = p.hot_ids + (int64_t)(seg ^ 1) * kHotRows;
-    const int n_stage = r_src < KST ? r_src : KST;
-    if (threadIdx.x == 0) {
-      mbar_init(&bar, 1);
-      const int64_t own0 = (int64_t)k * r_own;
-      const float* a = item_side ? p.a_i : p.a_u;
-      const float* b = item_side ? p.b_i : p.b_u;
-      float* o1 = item_side ? p.o1_i : p.o1_u;
-      float* o2 = item_side ? p.o2_i : p.o2_u;
-      uint32_t* mk = item_side ? p.mask_i : p.mask_u;
-      sp.a = a ? a + own0 * D : nullptr;
-      sp.b = b ? b + own0 * D : nullptr;
-      sp.o1 = o1 ? o1 + own0 * D : nullptr;
-      sp.o2 = o2 ? o2 + own0 * D : nullptr;
-      sp.mk = mk ? mk + own0 * WPR : nullptr;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) mbar_expect_tx(&bar, (unsigned)(n_stage * D * 4));
-    for (int s = threadIdx.x; s < n_stage; s += kThreads)
-      tma_bulk_g2s(hot + (size_t)s * D, src + (int64_t)__ldg(ids + s) * D, D * 4, &bar);
-    if (WARM) {
-      const int n_hot = r_src < kHotRows ? r_src : kHotRows;
-      for (int s = threadIdx.x; s < n_hot; s += kThreads) warm_ids[s] = __ldg(ids + s);
-    }
-    mbar_wait(&bar, 0);
-    if (MODE == MODE_BWD) {
-      // the backward gathers sigma'(Z) (.) g: mask the staged rows once instead of per edge
+  const int n_hops = (SAGNN_HOP && p.single_seg < 0) ? p.n_seg_total : 1;
+  const int seg0 = p.single_seg >= 0 ? p.single_seg : p.cta[blockIdx.x].seg;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  unsigned phase = 0;
+
+  for (int hop = 0; hop < n_hops; ++hop) {
+    int seg = seg0 + hop;
+    if (seg >= p.n_seg_total) seg -= p.n_seg_total;
+    const sagnn_seg sg = p.seg[seg];
+    const unsigned n_seg_tasks = (unsigned)(sg.task_end - sg.task_begin);
+    unsigned* ctr = p.ctrs + seg;
+    if (hop > 0) {     // help another segment only if its queue still has work (CTA-uniform decision)
       __syncthreads();
-      for (int s = threadIdx.x / LPR; s < n_stage; s += kThreads / LPR) {
-        const int id = __ldg(ids + s);
+      if (threadIdx.x == 0) skip_seg = (*(volatile unsigned*)ctr >= n_seg_tasks) ? 1 : 0;
+      __syncthreads();
+      if (skip_seg) continue;
+    }
+    const int k = seg >> 1;
+    const bool item_side = seg & 1;
+    const int r_own = item_side ? p.I : p.U, r_src = item_side ? p.U : p.I;
+    const float* src = (item_side ? p.src_u : p.src_i) + (int64_t)k * r_src * D;
+    const uint8_t* smask = BWD ? (item_side ? p.smask_u : p.smask_i) + (int64_t)k * r_src * MPR : nullptr;
+    const int32_t* enc = p.enc + sg.edge_base;
+    const float* wts = WEIGHTED ? p.w + sg.edge_base : nullptr;
+    const sagnn_task* tasks = p.tasks + sg.task_begin;
+
+    // ---- stage the hot rows of the source table (TMA bulk copies, one per row) -----------
+    {
+      __syncthreads();                                // everyone is done with the previous segment
+      const int32_t* ids = p.hot_ids + (int64_t)(seg ^ 1) * kHotRows;
+      const int n_stage = r_src < KST ? r_src : KST;
+      if (threadIdx.x == 0) {
+        const int64_t own0 = (int64_t)k * r_own;
+        const float* a = item_side ? p.a_i : p.a_u;
+        const float* b = item_side ? p.b_i : p.b_u;
+        float* o1 = item_side ? p.o1_i : p.o1_u;
+        float* o2 = item_side ? p.o2_i : p.o2_u;
+        uint8_t* mk = item_side ? p.mask_i : p.mask_u;
+        sp.a = a ? a + own0 * D : nullptr;
+        sp.b = b ? b + own0 * D : nullptr;
+        sp.o1 = o1 ? o1 + own0 * D : nullptr;
+        sp.o2 = o2 ? o2 + own0 * D : nullptr;
+        sp.mk = mk ? mk + own0 * MPR : nullptr;
+        mbar_expect_tx(&bar, (unsigned)(n_stage * D * 4));
+      }
+      __syncthreads();
+      for (int s = threadIdx.x; s < n_stage; s += kThreads)
+        tma_bulk_g2s(hot + (size_t)s * D, src + (int64_t)__ldg(ids + s) * D, D * 4, &bar);
+      if (WARM) {
+        const int n_hot = r_src < kHotRows ? r_src : kHotRows;
+        for (int s = threadIdx.x; s < n_hot; s += kThreads) warm_ids[s] = __ldg(ids + s);
+      }
+      mbar_wait(&bar, phase);
+      phase ^= 1u;
+      if (BWD) {
+        // the backward gathers sigma'(Z) (.) g: mask the staged rows once instead of per edge
+        __syncthreads();
+        for (int s = threadIdx.x / LPR; s < n_stage; s += kThreads / LPR) {
+          const int id = __ldg(ids + s);
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          float4* q = reinterpret_cast<float4*>(hot + (size_t)s * D + (v * LPR + gl) * 4);
-          float4 x = *q;
-          const uint32_t b = __ldg(smask + (int64_t)id * WPR + ((v * LPR + gl) >> 3)) >> ((gl & 7) * 4);
-          x.x = (b & 1u) ? x.x : p.leaky * x.x;
-          x.y = (b & 2u) ? x.y : p.leaky * x.y;
-          x.z = (b & 4u) ? x.z : p.leaky * x.z;
-          x.w = (b & 8u) ? x.w : p.leaky * x.w;
-          *q = x;
+          for (int v = 0; v < V; ++v) {
+            float4* q = reinterpret_cast<float4*>(hot + (size_t)s * D + (v * LPR + gl) * 4);
+            float4 x = *q;
+            const uint32_t b = __ldg(smask + (int64_t)id * MPR + v * LPR + gl);
+            x.x = (b & 1u) ? x.x : leaky * x.x;
+            x.y = (b & 2u) ? x.y : leaky * x.y;
+            x.z = (b & 4u) ? x.z : leaky * x.z;
+            x.w = (b & 8u) ? x.w : leaky * x.w;
+            *q = x;
+          }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
-  }
 
-  // lane-specific bases of everything the gather loop touches, pinned in registers
-  const char* src_lane = reinterpret_cast<const char*>(src) + gl * 16;
-  const char* smask_lane = reinterpret_cast<const char*>(smask) + (gl >> 3) * 4;
-  uint32_t hot_lane = smem_u32(hot) + gl * 16;
-  const float leaky = p.leaky;
-  pin64(src_lane);
-  if (MODE == MODE_BWD) pin64(smask_lane);
-  pin32(hot_lane);
-  pin64(enc);
+    // lane-specific bases of everything the gather loop touches, pinned in registers
+    const char* src_lane = reinterpret_cast<const char*>(src) + gl * 16;
+    uint32_t hot_lane = smem_u32(hot) + gl * 16;
+    pin64(src_lane);
+    pin32(hot_lane);
+    pin64(enc);
+    pin64(tasks);
 
-  // ---- my share of the segment's tasks ----------------------------------------------------
-  const int64_t t_end = sg.task_end;
-  const int64_t stride = (int64_t)count * (kThreads / 32) * GPW;
-  const int64_t warp_t0 = sg.task_begin + ((int64_t)rank * (kThreads / 32) + threadIdx.x / 32) * GPW;
-  int64_t t = warp_t0 + lane / LPR;
+    // ---- task queue -----------------------------------------------------------------------
+    // The list is ordered longest-first, so greedy grabbing (R rounds of GPW tasks per atomic)
+    // balances the warps; the atomic for the next grab is always in flight.
+    auto issue = [&]() -> unsigned { return lane == 0 ? atomicAdd(ctr, (unsigned)(R * GPW)) : 0u; };
+    auto ld_task = [&](unsigned t) -> sagnn_task {
+      sagnn_task q;
+      if (t < n_seg_tasks) {
+        const int4 raw = __ldg(reinterpret_cast<const int4*>(tasks + t));
+        q.row = (uint32_t)raw.x; q.meta = (uint32_t)raw.y; q.e_off = (uint32_t)raw.z; q.aux = (uint32_t)raw.w;
+      } else {
+        q.row = 0; q.meta = 0x40000000u; q.e_off = 0; q.aux = 0;   // bit 30: no work
+      }
+      return q;
+    };
+    unsigned b0 = __shfl_sync(FULL, issue(), 0);      // grab being processed
+    unsigned pend = issue();                          // next grab, still in flight
+    unsigned b1 = 0xffffffffu;                        // resolved lazily
+    int r = 0;
 
-  // software pipeline: task records two rounds ahead, the first code batch one round ahead
-  sagnn_task nxt = ld_task(p.tasks, t, t_end);
-  sagnn_task nxt2 = ld_task(p.tasks, t + stride, t_end);
-  int nxt_c = 0;
-  float nxt_w = 0.f;
-  if (gl < (int)(nxt.meta & 0x7fu)) {
-    nxt_c = __ldg(enc + nxt.e_off + gl);
-    if (WEIGHTED) nxt_w = __ldg(wts + nxt.e_off + gl);
-  }
-
-  for (int64_t tb = warp_t0; tb < t_end; tb += stride, t += stride) {   // warp-uniform trip count
-    const sagnn_task cur = nxt;
-    int myc = nxt_c;
-    float myw = nxt_w;
-    nxt = nxt2;
-    nxt2 = ld_task(p.tasks, t + 2 * stride, t_end);
-    nxt_c = 0;
+    // software pipeline: task records two rounds ahead, the first code batch one round ahead
+    sagnn_task nxt = ld_task(b0 + grp);
+    b1 = __shfl_sync(FULL, pend, 0);
+    pend = issue();
+    sagnn_task nxt2 = ld_task((R > 1 ? b0 + GPW : b1) + grp);
+    int nxt_c = 0;
+    float nxt_w = 0.f;
     if (gl < (int)(nxt.meta & 0x7fu)) {
       nxt_c = __ldg(enc + nxt.e_off + gl);
       if (WEIGHTED) nxt_w = __ldg(wts + nxt.e_off + gl);
     }
 
-    const bool valid = !(cur.meta & 0x40000000u);
-    const bool multi = (cur.meta >> 31) != 0;          // slice of a long row
-    const int n = (int)(cur.meta & 0x7fu);
-    const int nh = (int)((cur.meta >> 8) & 0x7fu);
-    const uint32_t own_off = cur.row * (uint32_t)(D * 4) + gl * 16;   // byte offset inside my table (< 4 GB)
-
-    // the row's own dense operand is independent of the gather: issue it first
-    float4 own_a[V];
-    if (MODE != MODE_MSG) {
-      const char* a = reinterpret_cast<const char*>(sp.a);
+    // ---- producer state: the next gather block to issue -------------------------------------
+    f4p acc[V], acc_n[V];                             // accumulators of the current / next task
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-        own_a[v] = valid ? ld_nc(reinterpret_cast<const float*>(a + own_off + v * LPR * 16)) : f4_zero();
-    }
+    for (int v = 0; v < V; ++v) { acc[v] = f4p_zero(); acc_n[v] = f4p_zero(); }
+    int p_n = 0, p_nh = 0, p_nmax = 0, p_off = 0;     // producer's task: edges, hot edges, warp max, next edge
+    uint32_t p_eoff = 0;
+    int p_codes = 0, p_cnext = 0;                     // codes of the producer's batch / the batch after
+    float p_w = 0.f, p_wnext = 0.f;
+    bool p_is_nxt = false;
+    int ps = 0, cs = 0;                               // producer / consumer ring stage
+    unsigned flags = 0;                               // per stage: which slots were issued as cp.async
 
-    float4 acc[V];
+    auto enter_next_task = [&]() {                    // producer moves on to `nxt`
+      p_is_nxt = true;
+      p_n = (int)(nxt.meta & 0x7fu);
+      p_nh = (int)((nxt.meta >> 8) & 0x7fu);
+      p_eoff = nxt.e_off;
+      p_nmax = p_n;
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = f4_zero();
-
-    // ---- gather-reduce over this task's edges (lock step over the warp) -------------------
-    int nmax = n;
-#pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
-    for (int eb = 0; eb < nmax; eb += LPR) {
-      // prefetch the next batch of codes while this one is gathered
-      int c_next = 0;
-      float w_next = 0.f;
-      if (eb + LPR + gl < n) {
-        c_next = __ldg(enc + cur.e_off + eb + LPR + gl);
-        if (WEIGHTED) w_next = __ldg(wts + cur.e_off + eb + LPR + gl);
+      for (int o = LPR; o < 32; o <<= 1) p_nmax = max(p_nmax, __shfl_xor_sync(FULL, p_nmax, o));
+      p_codes = nxt_c;
+      p_w = nxt_w;
+      p_off = 0;
+      p_cnext = 0;
+      if (LPR + gl < p_n) {
+        p_cnext = __ldg(enc + p_eoff + LPR + gl);
+        if (WEIGHTED) p_wnext = __ldg(wts + p_eoff + LPR + gl);
       }
-      const int nbmax = min(LPR, nmax - eb);
-      for (int j = 0; j < nbmax; j += UNR) {
-        const int nb = n - eb - j;             // my group's edges left from slot j on (may be <= 0)
-        const int nhb = nh - eb - j;           // ... of which hot (staged in shared memory)
-        float4 val[UNR][V];
-        uint32_t mw[UNR][V];
-        float wv[UNR];
-        bool cold[UNR];
-        int cs[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          cs[u] = __shfl_sync(FULL, myc, gbase + j + u);
-          if (WEIGHTED) wv[u] = __shfl_sync(FULL, myw, gbase + j + u);
+    };
+    auto produce = [&]() {                            // issue one block: hot -> accumulate now, cold -> cp.async
+      if (p_off > 0 && p_off >= p_nmax) enter_next_task();           // warp-uniform
+      const int j = p_off & (LPR - 1);
+      if (j == 0 && p_off > 0) {                      // next batch of codes
+        p_codes = p_cnext;
+        p_w = p_wnext;
+        p_cnext = 0;
+        if (p_off + LPR + gl < p_n) {
+          p_cnext = __ldg(enc + p_eoff + p_off + LPR + gl);
+          if (WEIGHTED) p_wnext = __ldg(wts + p_eoff + p_off + LPR + gl);
         }
-        gather_block<LPR, V, MODE, WARM, KST, UNR>(val, mw, cold, cs, hot_lane, src_lane, smask_lane, warm_ids, nhb, nb);
+      }
+      unsigned cold_bits = 0;
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        int c = __shfl_sync(FULL, p_codes, gbase + j + u);
+        const float w = WEIGHTED ? __shfl_sync(FULL, p_w, gbase + j + u) : 1.f;
+        bool is_hot = (p_off + u) < p_nh;
+        bool is_cold = !is_hot && (p_off + u) < p_n;
+        if (WARM) {     // hot slot that is not staged at this latdim: fetch it like a cold row
+          if (is_hot && c >= KST) { c = warm_ids[c]; is_hot = false; is_cold = true; }
+        }
+        if (is_cold) cold_bits |= 1u << u;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          if (is_hot) {
+            const float4 x = lds_f4(hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16);
+            if (p_is_nxt) accumulate<WEIGHTED, false>(acc_n[v], x, w, 0u, leaky);
+            else accumulate<WEIGHTED, false>(acc[v], x, w, 0u, leaky);
+          }
+          if (is_cold)
+            cp_async16(ring_lane + (ps * UNR + u) * G::SLOT + v * 512,
+                       src_lane + (int64_t)c * (D * 4) + v * LPR * 16);
+        }
+        if (BWD && is_cold) {                         // the row's mask bytes ride along (16 B per lane)
+          if (MPR >= 16) {
+            if (gl < MPR / 16)
+              cp_async16(mring + (ps * UNR + u) * G::MSLOT + grp * MPR + gl * 16, smask + (int64_t)c * MPR + gl * 16);
+          } else {
+            if (gl == 0) cp_async8(mring + (ps * UNR + u) * G::MSLOT + grp * MPR, smask + (int64_t)c * MPR);
+          }
+        }
+        if (WEIGHTED && is_cold && gl == 0) sts_f32(wring + ((ps * UNR + u) * GPW + grp) * 4, w);
+      }
+      flags = (flags & ~(0xffu << (ps * 8))) | (cold_bits << (ps * 8));   // tell the consumer which slots landed in the ring
+      cp_async_commit();
+      p_off += UNR;
+      ps ^= 1;
+    };
+
+    // prologue: first block of the first task
+    enter_next_task();
+    produce();
+
+    while (b0 < n_seg_tasks) {                          // warp-uniform
+      // ---- rotate: the task whose first block is in flight becomes current ----------------
+      const sagnn_task cur = nxt;
+#pragma unroll
+      for (int v = 0; v < V; ++v) { acc[v] = acc_n[v]; acc_n[v] = f4p_zero(); }
+      p_is_nxt = false;
+      nxt = nxt2;
+      nxt_c = 0;
+      if (gl < (int)(nxt.meta & 0x7fu)) {
+        nxt_c = __ldg(enc + nxt.e_off + gl);
+        if (WEIGHTED) nxt_w = __ldg(wts + nxt.e_off + gl);
+      }
+      nxt2 = ld_task((r + 2 < R ? b0 + (r + 2) * GPW : b1 + (r + 2 - R) * GPW) + grp);   // r = position of cur in b0
+      if (++r == R) {                                   // rotate the grabs
+        r = 0;
+        b0 = b1;
+        b1 = __shfl_sync(FULL, pend, 0);
+        pend = issue();
+      }
+
+      const bool valid = !(cur.meta & 0x40000000u);
+      const bool multi = (cur.meta >> 31) != 0;          // slice of a long row
+      const int n = (int)(cur.meta & 0x7fu);
+      const uint32_t own_off = cur.row * (uint32_t)(D * 4) + gl * 16;   // byte offset inside my table (< 4 GB)
+
+      // the row's own dense operand is independent of the gather: issue it first
+      float4 own_a[V];
+      if (MODE != MODE_MSG) {
+        const char* a = reinterpret_cast<const char*>(sp.a);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          own_a[v] = valid ? ld_nc(reinterpret_cast<const float*>(a + own_off + v * LPR * 16)) : f4_zero();
+      }
+
+      // ---- consume this task's blocks; the producer stays one block ahead -------------------
+      int nmax = n;
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+      const int n_blk = nmax > 0 ? (nmax + UNR - 1) / UNR : 1;
+      for (int b = 0; b < n_blk; ++b) {
+        produce();
+        cp_async_wait<1>();
+        __syncwarp();
+        const unsigned cold_bits = flags >> (cs * 8);
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-          if (u < nb) {
+          if (cold_bits & (1u << u)) {
+            const float w = WEIGHTED ? lds_f32(wring + ((cs * UNR + u) * GPW + grp) * 4) : 1.f;
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-              float4 x = val[u][v];
-              if (MODE == MODE_BWD) {
-                if (cold[u]) {   // cold source = sigma'(Z) (.) g : pass where Z > 0, else leaky
-                  const uint32_t b = mw[u][v] >> ((gl & 7) * 4);
-                  x.x = (b & 1u) ? x.x : leaky * x.x;
-                  x.y = (b & 2u) ? x.y : leaky * x.y;
-                  x.z = (b & 4u) ? x.z : leaky * x.z;
-                  x.w = (b & 8u) ? x.w : leaky * x.w;
-                }
+              const float4 x = lds_f4(ring_lane + (cs * UNR + u) * G::SLOT + v * 512);
+              const uint32_t mb = BWD ? lds_u8(mring + (cs * UNR + u) * G::MSLOT + grp * MPR + v * LPR + gl) : 0u;
+              accumulate<WEIGHTED, BWD>(acc[v], x, w, mb, leaky);
+            }
+          }
+        }
+        cs ^= 1;
+      }
+
+      // ---- long rows: publish the partial sum; the last slice to arrive reduces -----------
+      // (release-only ticket; the reducer reads with strong loads that bypass L1, so no
+      //  acquire fence / L1 invalidate is needed)
+      bool finish = valid;
+      if (__any_sync(FULL, multi)) {
+        uint32_t lr = 0;
+        if (multi) {
+          lr = __ldg(p.chunk_lr + cur.aux);
+          float* mine = p.partials + (int64_t)cur.aux * D;
+#pragma unroll
+          for (int v = 0; v < V; ++v) st_f4(mine + (v * LPR + gl) * 4, f4p_get(acc[v]));
+        }
+        __syncwarp();
+        unsigned old = 0;
+        if (multi && gl == 0) old = ticket_release_add(p.tickets + lr);
+        old = __shfl_sync(FULL, old, gbase);
+        if (multi) {
+          const int64_t cb = __ldg(p.chunk_base + lr);
+          const int nch = (int)(__ldg(p.chunk_base + lr + 1) - cb);
+          finish = (old == (unsigned)(nch - 1));
+          if (finish) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = f4p_zero();
+            const float* part = p.partials + cb * D;
+            for (int c0 = 0; c0 < nch; c0 += 4) {
+              float4 val[4][V];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                  val[u][v] = (c0 + u < nch) ? ld_strong(part + (int64_t)(c0 + u) * D + (v * LPR + gl) * 4)
+                                             : f4_zero();
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc_add(acc[v], val[u][v]);
+            }
+            if (gl == 0) p.tickets[lr] = 0u;   // ready for the next launch
+          }
+        }
+        __syncwarp();
+      }
+
+      // ---- fused epilogue ------------------------------------------------------------------
+      if (finish) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const uint32_t off = own_off + v * LPR * 16;     // bytes
+          const float4 z = f4p_get(acc[v]);
+          if (BWD) {
+            // n = G + g + A (sigma' . g_other)      
+            const char* g = reinterpret_cast<const char*>(sp.b);
+            char* dst = reinterpret_cast<char*>(sp.o1);
+            const float4 gv = g ? ld_stream(reinterpret_cast<const float*>(g + off)) : own_a[v];
+            st_f4(reinterpret_cast<float*>(dst + off), f4_add(f4_add(own_a[v], gv), z));
+          } else {
+            const float lzx = leaky * z.x, lzy = leaky * z.y, lzz = leaky * z.z, lzw = leaky * z.w;
+            // LeakyReLU = max(leaky*z, z)  (Utils/NNLayers.py:135-136)
+            const float4 act = make_float4(fmaxf(lzx, z.x), fmaxf(lzy, z.y), fmaxf(lzz, z.z), fmaxf(lzw, z.w));
+            if (MODE == MODE_MSG) {
+              st_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(sp.o1) + off), act);
+            } else {
+              const char* b = reinterpret_cast<const char*>(sp.b);
+              char* o1 = reinterpret_cast<char*>(sp.o1);
+              char* o2 = reinterpret_cast<char*>(sp.o2);
+              uint8_t* mk = sp.mk;
+              const float4 nxt_e = f4_add(own_a[v], act);          // E^{l+1} = E^l + lrelu(Z^l)
+              if (o1) st_f4(reinterpret_cast<float*>(o1 + off), nxt_e);
+              if (o2) {
+                float4 o = own_a[v];
+                if (b) o = f4_add(ld_stream(reinterpret_cast<const float*>(b + off)), own_a[v]);
+                if (p.out_add_next) o = f4_add(o, nxt_e);
+                st_stream(reinterpret_cast<float*>(o2 + off), o);
               }
-              if (WEIGHTED) {
-                acc[v].x = fmaf(wv[u], x.x, acc[v].x);
-                acc[v].y = fmaf(wv[u], x.y, acc[v].y);
-                acc[v].z = fmaf(wv[u], x.z, acc[v].z);
-                acc[v].w = fmaf(wv[u], x.w, acc[v].w);
-              } else {
-                acc[v] = f4_add(acc[v], x);
+              if (mk) {
+                // TF MaximumGrad sends the gradient to leaky*z where leaky*z >= z: bit = pass-through.
+                // One byte (4 sign bits) per lane: no cross-lane packing needed.
+                const uint32_t bits = (!(lzx >= z.x) ? 1u : 0u) | (!(lzy >= z.y) ? 2u : 0u) |
+                                      (!(lzz >= z.z) ? 4u : 0u) | (!(lzw >= z.w) ? 8u : 0u);
+                mk[(size_t)cur.row * MPR + v * LPR + gl] = (uint8_t)bits;
               }
             }
           }
         }
       }
-      myc = c_next;
-      myw = w_next;
     }
-
-    // ---- long rows: publish the partial sum; the last slice to arrive reduces -------------
-    // (release-only ticket; the reducer reads with strong loads that bypass L1, so no
-    //  acquire fence / L1 invalidate is needed)
-    bool finish = valid;
-    if (__any_sync(FULL, multi)) {
-      uint32_t lr = 0;
-      if (multi) {
-        lr = __ldg(p.chunk_lr + cur.aux);
-        float* mine = p.partials + (int64_t)cur.aux * D;
-#pragma unroll
-        for (int v = 0; v < V; ++v) st_f4(mine + (v * LPR + gl) * 4, acc[v]);
-      }
-      __syncwarp();
-      unsigned old = 0;
-      if (multi && gl == 0) old = ticket_release_add(p.tickets + lr);
-      old = __shfl_sync(FULL, old, gbase);
-      if (multi) {
-        const int64_t cb = __ldg(p.chunk_base + lr);
-        const int nch = (int)(__ldg(p.chunk_base + lr + 1) - cb);
-        finish = (old == (unsigned)(nch - 1));
-        if (finish) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) acc[v] = f4_zero();
-          const float* part = p.partials + cb * D;
-          for (int c0 = 0; c0 < nch; c0 += 4) {
-            float4 val[4][V];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-              for (int v = 0; v < V; ++v)
-                val[u][v] = (c0 + u < nch) ? ld_strong(part + (int64_t)(c0 + u) * D + (v * LPR + gl) * 4)
-                                           : f4_zero();
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-              for (int v = 0; v < V; ++v) acc[v] = f4_add(acc[v], val[u][v]);
-          }
-          if (gl == 0) p.tickets[lr] = 0u;   // ready for the next launch
-        }
-      }
-      __syncwarp();
-    }
-
-    // ---- fused epilogue (all lanes take part in the shuffles; stores are predicated) -------
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const uint32_t off = own_off + v * LPR * 16;     // bytes
-      if (MODE == MODE_BWD) {
-        // n = G + g + A (sigma' . g_other)      
-        if (finish) {
-          const char* g = reinterpret_cast<const char*>(sp.b);
-          char* dst = reinterpret_cast<char*>(sp.o1);
-          const float4 gv = g ? ld_stream(reinterpret_cast<const float*>(g + off)) : own_a[v];
-          st_f4(reinterpret_cast<float*>(dst + off), f4_add(f4_add(own_a[v], gv), acc[v]));
-        }
-      } else {
-        const float4 z = acc[v];
-        const float lzx = leaky * z.x, lzy = leaky * z.y, lzz = leaky * z.z, lzw = leaky * z.w;
-        // LeakyReLU = max(leaky*z, z)  (Utils/NNLayers.py:135-136)
-        const float4 act = make_float4(fmaxf(lzx, z.x), fmaxf(lzy, z.y), fmaxf(lzz, z.z), fmaxf(lzw, z.w));
-        if (MODE == MODE_MSG) {
-          if (finish) st_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(sp.o1) + off), act);
-        } else {
-          const char* b = reinterpret_cast<const char*>(sp.b);
-          char* o1 = reinterpret_cast<char*>(sp.o1);
-          char* o2 = reinterpret_cast<char*>(sp.o2);
-          uint32_t* mk = sp.mk;
-          const float4 nxt_e = f4_add(own_a[v], act);          // E^{l+1} = E^l + lrelu(Z^l)
-          if (finish && o1) st_f4(reinterpret_cast<float*>(o1 + off), nxt_e);
-          if (finish && o2) {
-            float4 o = own_a[v];
-            if (b) o = f4_add(ld_stream(reinterpret_cast<const float*>(b + off)), own_a[v]);
-            if (p.out_add_next) o = f4_add(o, nxt_e);
-            st_stream(reinterpret_cast<float*>(o2 + off), o);
-          }
-          if (mk) {   // CTA-uniform
-            // TF MaximumGrad sends the gradient to leaky*z where leaky*z >= z: bit = pass-through
-            uint32_t word = ((!(lzx >= z.x) ? 1u : 0u) | (!(lzy >= z.y) ? 2u : 0u) |
-                             (!(lzz >= z.z) ? 4u : 0u) | (!(lzw >= z.w) ? 8u : 0u)) << ((gl & 7) * 4);
-            word |= __shfl_xor_sync(FULL, word, 1);
-            word |= __shfl_xor_sync(FULL, word, 2);
-            word |= __shfl_xor_sync(FULL, word, 4);
-            if (finish && (gl & 7) == 0) mk[(size_t)cur.row * WPR + ((v * LPR + gl) >> 3)] = word;
-          }
-        }
-      }
-    }
+    cp_async_wait<0>();                                 // drain the look-ahead block before leaving
   }
 }
 
@@ -510,17 +607,16 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
 // ---------------------------------------------------------------------------------------
 template <int LPR, int V, int MODE, bool WEIGHTED>
 static int launch_t(const sagnn_plan* plan, const SpmmParams& prm, cudaStream_t st) {
-  constexpr int D = LPR * V * 4;
-  constexpr int KST = (SAGNN_HOT_BYTES / (4 * D)) < kHotRows ? (SAGNN_HOT_BYTES / (4 * D)) : kHotRows;
-  constexpr size_t smem = (size_t)KST * D * 4;
+  using G = Geo<LPR, V, MODE, WEIGHTED>;
+  static_assert(G::SMEM <= 227 * 1024 - 4096, "shared-memory budget exceeded");
   static bool configured = false;
   auto kern = spmm_layer_kernel<LPR, V, MODE, WEIGHTED>;
   if (!configured) {
-    SAGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SAGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
     configured = true;
   }
   if (plan->n_tasks == 0) return SAGNN_OK;
-  kern<<<plan->num_sms, kThreads, smem, st>>>(prm);
+  kern<<<plan->num_sms, kThreads, G::SMEM, st>>>(prm);
   SAGNN_CUDA(cudaGetLastError());
   return SAGNN_OK;
 }
@@ -551,6 +647,7 @@ static bool d_ok(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
 // workspace layout: [tickets | partials | table buffer 0 | table buffer 1]
 struct WsLayout {
   size_t tickets_off, partials_off, buf_off[2], total;
+  size_t zero_bytes;     // tickets + one set of per-segment queue heads per layer launch, zeroed per call
   size_t table_floats;   // T*(U+I)*d
   size_t user_floats;    // T*U*d  (user part comes first inside a table buffer)
 };
@@ -559,7 +656,8 @@ static WsLayout ws_layout(const sagnn_plan* p, int n_layers, int d) {
   WsLayout w{};
   size_t off = 0;
   w.tickets_off = off;
-  off = align_up(off + sizeof(uint32_t) * (size_t)(p->n_long ? p->n_long : 1), 256);
+  w.zero_bytes = sizeof(uint32_t) * ((size_t)p->n_long + 2 * (size_t)p->T * n_layers);
+  off = align_up(off + w.zero_bytes, 256);
   w.partials_off = off;
   off = align_up(off + sizeof(float) * (size_t)p->n_chunks * d, 256);
   w.table_floats = (size_t)p->n_rows * d;
@@ -573,13 +671,14 @@ static WsLayout ws_layout(const sagnn_plan* p, int n_layers, int d) {
   return w;
 }
 
-static size_t mask_layer_words(const sagnn_plan* p, int d) { return (size_t)p->n_rows * (d / 32); }
+static size_t mask_layer_bytes(const sagnn_plan* p, int d) { return (size_t)p->n_rows * (d / 4); }
 
 static void base_params(const sagnn_plan* p, SpmmParams& s) {
   s = SpmmParams{};
   s.tasks = p->tasks; s.enc = p->enc; s.w = p->w_enc;
   s.chunk_base = p->chunk_base; s.chunk_lr = p->chunk_lr;
   s.hot_ids = p->hot_ids; s.seg = p->seg_dev; s.cta = p->cta_dev; s.single_seg = -1;
+  s.n_seg_total = 2 * p->T;
   s.U = p->U; s.I = p->I;
 }
 
@@ -609,7 +708,7 @@ extern "C" int sagnn_workspace_bytes(const sagnn_plan* p, int n_layers, int d, s
   WsLayout w = ws_layout(p, n_layers, d);
   if (fwd_bytes) *fwd_bytes = w.total;
   if (bwd_bytes) *bwd_bytes = w.total;
-  if (mask_bytes) *mask_bytes = sizeof(uint32_t) * mask_layer_words(p, d) * n_layers;
+  if (mask_bytes) *mask_bytes = mask_layer_bytes(p, d) * n_layers;
   return SAGNN_OK;
 }
 
@@ -628,11 +727,13 @@ extern "C" int sagnn_propagate_fwd(const sagnn_plan* p, const float* uE, const f
   s.tickets = (uint32_t*)(base + w.tickets_off);
   s.partials = (float*)(base + w.partials_off);
   s.leaky = leaky;
-  SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, sizeof(uint32_t) * (size_t)(p->n_long ? p->n_long : 1), st));
+  SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, w.zero_bytes, st));
+  s.ctrs = s.tickets + p->n_long;
   float* buf[2] = {(float*)(base + w.buf_off[0]), (float*)(base + w.buf_off[1])};
-  const size_t mlw = mask_layer_words(p, d);
-  const size_t mu = (size_t)p->T * p->U * (d / 32);
+  const size_t mlw = mask_layer_bytes(p, d);
+  const size_t mu = (size_t)p->T * p->U * (d / 4);
   for (int l = 0; l < L; ++l) {
+    s.ctrs = s.tickets + p->n_long + (size_t)l * 2 * p->T;
     const float* cur_u = l == 0 ? uE : buf[(l - 1) & 1];
     const float* cur_i = l == 0 ? iE : buf[(l - 1) & 1] + w.user_floats;
     const bool last = (l == L - 1);
@@ -648,8 +749,8 @@ extern "C" int sagnn_propagate_fwd(const sagnn_plan* p, const float* uE, const f
     s.o2_u = write_out ? uOut : nullptr;
     s.o2_i = write_out ? iOut : nullptr;
     s.out_add_next = last ? 1 : 0;
-    s.mask_u = masks ? (uint32_t*)masks + (size_t)l * mlw : nullptr;
-    s.mask_i = masks ? (uint32_t*)masks + (size_t)l * mlw + mu : nullptr;
+    s.mask_u = masks ? (uint8_t*)masks + (size_t)l * mlw : nullptr;
+    s.mask_i = masks ? (uint8_t*)masks + (size_t)l * mlw + mu : nullptr;
     if (int rc = launch(p, s, d, MODE_FWD, st)) return rc;
   }
   return SAGNN_OK;
@@ -670,17 +771,19 @@ extern "C" int sagnn_propagate_bwd(const sagnn_plan* p, const float* gU, const f
   s.tickets = (uint32_t*)(base + w.tickets_off);
   s.partials = (float*)(base + w.partials_off);
   s.leaky = leaky;
-  SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, sizeof(uint32_t) * (size_t)(p->n_long ? p->n_long : 1), st));
+  SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, w.zero_bytes, st));
+  s.ctrs = s.tickets + p->n_long;
   float* buf[2] = {(float*)(base + w.buf_off[0]), (float*)(base + w.buf_off[1])};
-  const size_t mlw = mask_layer_words(p, d);
-  const size_t mu = (size_t)p->T * p->U * (d / 32);
+  const size_t mlw = mask_layer_bytes(p, d);
+  const size_t mu = (size_t)p->T * p->U * (d / 4);
   for (int l = L - 1, step = 0; l >= 0; --l, ++step) {
+    s.ctrs = s.tickets + p->n_long + (size_t)step * 2 * p->T;
     // g = total gradient w.r.t. E^{l+1}; at the top level it is the upstream itself
     const float* g_u = step == 0 ? gU : buf[(step - 1) & 1];
     const float* g_i = step == 0 ? gI : buf[(step - 1) & 1] + w.user_floats;
     s.src_u = g_u; s.src_i = g_i;
-    s.smask_u = (const uint32_t*)masks + (size_t)l * mlw;        // sigma'(Z0^l): masks user-table rows
-    s.smask_i = (const uint32_t*)masks + (size_t)l * mlw + mu;   // sigma'(Z1^l): masks item-table rows
+    s.smask_u = (const uint8_t*)masks + (size_t)l * mlw;        // sigma'(Z0^l): masks user-table rows
+    s.smask_i = (const uint8_t*)masks + (size_t)l * mlw + mu;   // sigma'(Z1^l): masks item-table rows
     s.a_u = gU; s.a_i = gI;
     s.b_u = step == 0 ? nullptr : g_u;
     s.b_i = step == 0 ? nullptr : g_i;
@@ -708,7 +811,8 @@ extern "C" int sagnn_message_propagate(const sagnn_plan* p, int k, int side, con
   s.tickets = (uint32_t*)(base + w.tickets_off);
   s.partials = (float*)(base + w.partials_off);
   s.leaky = leaky;
-  SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, sizeof(uint32_t) * (size_t)(p->n_long ? p->n_long : 1), st));
+  SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, w.zero_bytes, st));
+  s.ctrs = s.tickets + p->n_long;
   s.single_seg = 2 * k + side;
   // the kernel indexes tables as [T, rows, d]; shift the bases so that interval k lands on the
   // caller's single-interval tensors

@@ -30,16 +30,15 @@ def random_tables(T, U, I, d, seed=0, scale=1.0):
 
 def decode_gpu_masks(masks, T, U, I, d, L):
     """uint8 device buffer written by sagnn_propagate_fwd -> uint8 [T, L, (U+I)*d] in the C
-    oracle's layout (1 = gradient passes unscaled).  Device layout per layer: uint32 words
-    [T,U,d/32] then [T,I,d/32]; bit b of word w of a row is element 32*w + b."""
+    oracle's layout (1 = gradient passes unscaled).  Device layout per layer: bytes
+    [T,U,d/4] then [T,I,d/4]; bit i (i < 4) of byte j of a row is element 4*j + i."""
     raw = masks.detach().cpu().numpy().view(np.uint8)
-    wpr = d // 32
-    per_layer = T * (U + I) * wpr * 4
+    bpr = d // 4
+    per_layer = T * (U + I) * bpr
     out = np.empty((T, L, (U + I) * d), dtype=np.uint8)
     for l in range(L):
         lay = raw[l * per_layer:(l + 1) * per_layer]
-        ub = np.unpackbits(lay[:T * U * wpr * 4], bitorder="little").reshape(T, U * d)
-        ib = np.unpackbits(lay[T * U * wpr * 4:], bitorder="little").reshape(T, I * d)
-        out[:, l, :U * d] = ub
-        out[:, l, U * d:] = ib
+        bits = np.unpackbits(lay.reshape(-1, 1), axis=1, bitorder="little")[:, :4].reshape(-1)
+        out[:, l, :U * d] = bits[:T * U * d].reshape(T, U * d)
+        out[:, l, U * d:] = bits[T * U * d:].reshape(T, I * d)
     return out
