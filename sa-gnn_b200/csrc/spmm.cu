@@ -26,7 +26,10 @@
 #define SAGNN_GRAB 2           // task rounds a warp takes per queue atomic
 #endif
 #ifndef SAGNN_HOT_BYTES
-#define SAGNN_HOT_BYTES (80 * 1024)    // shared memory given to staged hot rows
+#define SAGNN_HOT_BYTES (192 * 1024)   // shared memory given to staged hot rows
+#endif
+#ifndef SAGNN_D64_LPR8
+#define SAGNN_D64_LPR8 0
 #endif
 #ifndef SAGNN_HOP
 #define SAGNN_HOP 0            // 1: CTAs whose segment is drained help the other segments
@@ -36,7 +39,6 @@ namespace sagnn {
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_MSG = 2 };
 constexpr int kThreads = SAGNN_THREADS;
-constexpr int kWarps = kThreads / 32;
 
 struct SpmmParams {
   const sagnn_task* tasks;
@@ -157,6 +159,44 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// One gather slot: hot edges come from the staged copy in shared memory, cold edges from global
+// memory through the read-only path; both loads target the same registers (no merge moves).
+__device__ __forceinline__ void gather_slot(float4& v, uint32_t hot_addr, const void* gaddr, int is_hot, int is_cold) {
+  asm volatile(
+      "{\n\t.reg .pred ph, pc;\n\t"
+      "setp.ne.s32 ph, %6, 0;\n\t"
+      "setp.ne.s32 pc, %7, 0;\n\t"
+      "@ph ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
+      "@pc ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5];\n\t}"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "r"(hot_addr), "l"(gaddr), "r"(is_hot), "r"(is_cold));
+}
+
+// same, deciding inside: slot U_ of the block is hot when U_ < nhb, cold when nhb <= U_ < nb
+template <int U_>
+__device__ __forceinline__ void gather_slot_u(float4& v, uint32_t hot_addr, const void* gaddr, int nhb, int nb) {
+  asm volatile(
+      "{\n\t.reg .pred ph, pc;\n\t"
+      "setp.gt.s32 ph, %6, %8;\n\t"
+      "setp.gt.s32 pc, %7, %8;\n\t"
+      "and.pred pc, pc, !ph;\n\t"
+      "@ph ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
+      "@pc ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5];\n\t}"
+      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+      : "r"(hot_addr), "l"(gaddr), "r"(nhb), "r"(nb), "n"(U_));
+}
+template <int UNR_, int U_ = 0>
+struct SlotDispatch {     // compile-time slot index for the in-asm compare
+  __device__ __forceinline__ static void run(int u, float4& v, uint32_t ha, const void* ga, int nhb, int nb) {
+    if (u == U_) gather_slot_u<U_>(v, ha, ga, nhb, nb);
+    else SlotDispatch<UNR_, U_ + 1>::run(u, v, ha, ga, nhb, nb);
+  }
+};
+template <int UNR_>
+struct SlotDispatch<UNR_, UNR_> {
+  __device__ __forceinline__ static void run(int, float4&, uint32_t, const void*, int, int) {}
+};
+
 // keep a CTA-lifetime value in a register: the compiler must not rematerialise it from the
 // kernel parameters inside the gather loop (it does, under the 64-register cap)
 template <typename T>
@@ -203,23 +243,21 @@ struct Geo {
   static constexpr int D = LPR * V * 4;
   static constexpr int MPR = D / 4;                           // mask bytes per row (4 sign bits per byte)
   static constexpr int GPW = 32 / LPR;                        // lane groups per warp
+#ifdef SAGNN_UNR_V2
+  static constexpr int UNR = (V == 2) ? SAGNN_UNR_V2 : SAGNN_UNR;
+#else
   static constexpr int UNR = (V == 2 && SAGNN_UNR > 1) ? SAGNN_UNR / 2 : SAGNN_UNR;
+#endif
   static constexpr int KST = (SAGNN_HOT_BYTES / (4 * D)) < kHotRows ? (SAGNN_HOT_BYTES / (4 * D)) : kHotRows;
-  static constexpr int SLOT = 32 * 16 * V;                    // ring bytes per gather slot per warp
-  static constexpr int RING_WARP = 2 * UNR * SLOT;            // two pipeline stages
-  static constexpr int MSLOT = GPW * MPR;                     // mask bytes per slot per warp (backward)
-  static constexpr int MRING_WARP = (MODE == MODE_BWD) ? 2 * UNR * MSLOT : 0;
-  static constexpr int WRING_WARP = WEIGHTED ? 2 * UNR * GPW * 4 : 0;
   static constexpr size_t HOT = (size_t)KST * D * 4;
-  static constexpr size_t SMEM = HOT + (size_t)kWarps * (RING_WARP + MRING_WARP + WRING_WARP);
+  static constexpr size_t SMEM = HOT;
 };
 
 // One persistent CTA per SM, bound to one segment (interval, orientation).  It stages the
 // segment's hottest source rows in shared memory with TMA bulk copies, then drains the
-// segment's task queue.  Per warp, gathers run as a two-stage cp.async pipeline through a
-// shared-memory ring: while block b is accumulated, block b+1 -- the next block of the same
-// row or the first block of the next task -- is already in flight, without holding
-// registers.  Hot rows are read straight from the staged copy when a block is issued.
+// segment's task queue (greedy, longest-first).  Each gather slot is one predicated pair of
+// loads into the same registers: from the staged copy when the edge is hot, from global
+// memory (read-only path, 128-bit) when it is cold.
 // The lane groups of a warp run in lock step (trip counts are warp maxima), so every
 // shuffle uses the full mask; tasks arrive sorted by degree, so the groups sharing a warp
 // have near-equal rows.
@@ -248,13 +286,6 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
   const int gbase = lane - gl;                        // first lane of my group
   const int grp = lane / LPR;
   const float leaky = p.leaky;
-
-  // per-warp ring: [stage][slot][v][lane] 16-byte cells; every lane reads back what it copied
-  uint32_t ring_lane = smem_u32(smem_raw + G::HOT + (size_t)warp * G::RING_WARP) + lane * 16;
-  uint32_t mring = smem_u32(smem_raw + G::HOT + (size_t)kWarps * G::RING_WARP + (size_t)warp * G::MRING_WARP);
-  uint32_t wring = smem_u32(smem_raw + G::HOT + (size_t)kWarps * (G::RING_WARP + G::MRING_WARP) +
-                            (size_t)warp * G::WRING_WARP);
-  pin32(ring_lane);
 
   const int n_hops = (SAGNN_HOP && p.single_seg < 0) ? p.n_seg_total : 1;
   const int seg0 = p.single_seg >= 0 ? p.single_seg : p.cta[blockIdx.x].seg;
@@ -370,95 +401,10 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
       if (WEIGHTED) nxt_w = __ldg(wts + nxt.e_off + gl);
     }
 
-    // ---- producer state: the next gather block to issue -------------------------------------
-    f4p acc[V], acc_n[V];                             // accumulators of the current / next task
-#pragma unroll
-    for (int v = 0; v < V; ++v) { acc[v] = f4p_zero(); acc_n[v] = f4p_zero(); }
-    int p_n = 0, p_nh = 0, p_nmax = 0, p_off = 0;     // producer's task: edges, hot edges, warp max, next edge
-    uint32_t p_eoff = 0;
-    int p_codes = 0, p_cnext = 0;                     // codes of the producer's batch / the batch after
-    float p_w = 0.f, p_wnext = 0.f;
-    bool p_is_nxt = false;
-    int ps = 0, cs = 0;                               // producer / consumer ring stage
-    unsigned flags = 0;                               // per stage: which slots were issued as cp.async
-
-    auto enter_next_task = [&]() {                    // producer moves on to `nxt`
-      p_is_nxt = true;
-      p_n = (int)(nxt.meta & 0x7fu);
-      p_nh = (int)((nxt.meta >> 8) & 0x7fu);
-      p_eoff = nxt.e_off;
-      p_nmax = p_n;
-#pragma unroll
-      for (int o = LPR; o < 32; o <<= 1) p_nmax = max(p_nmax, __shfl_xor_sync(FULL, p_nmax, o));
-      p_codes = nxt_c;
-      p_w = nxt_w;
-      p_off = 0;
-      p_cnext = 0;
-      if (LPR + gl < p_n) {
-        p_cnext = __ldg(enc + p_eoff + LPR + gl);
-        if (WEIGHTED) p_wnext = __ldg(wts + p_eoff + LPR + gl);
-      }
-    };
-    auto produce = [&]() {                            // issue one block: hot -> accumulate now, cold -> cp.async
-      if (p_off > 0 && p_off >= p_nmax) enter_next_task();           // warp-uniform
-      const int j = p_off & (LPR - 1);
-      if (j == 0 && p_off > 0) {                      // next batch of codes
-        p_codes = p_cnext;
-        p_w = p_wnext;
-        p_cnext = 0;
-        if (p_off + LPR + gl < p_n) {
-          p_cnext = __ldg(enc + p_eoff + p_off + LPR + gl);
-          if (WEIGHTED) p_wnext = __ldg(wts + p_eoff + p_off + LPR + gl);
-        }
-      }
-      unsigned cold_bits = 0;
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        int c = __shfl_sync(FULL, p_codes, gbase + j + u);
-        const float w = WEIGHTED ? __shfl_sync(FULL, p_w, gbase + j + u) : 1.f;
-        bool is_hot = (p_off + u) < p_nh;
-        bool is_cold = !is_hot && (p_off + u) < p_n;
-        if (WARM) {     // hot slot that is not staged at this latdim: fetch it like a cold row
-          if (is_hot && c >= KST) { c = warm_ids[c]; is_hot = false; is_cold = true; }
-        }
-        if (is_cold) cold_bits |= 1u << u;
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          if (is_hot) {
-            const float4 x = lds_f4(hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16);
-            if (p_is_nxt) accumulate<WEIGHTED, false>(acc_n[v], x, w, 0u, leaky);
-            else accumulate<WEIGHTED, false>(acc[v], x, w, 0u, leaky);
-          }
-          if (is_cold)
-            cp_async16(ring_lane + (ps * UNR + u) * G::SLOT + v * 512,
-                       src_lane + (int64_t)c * (D * 4) + v * LPR * 16);
-        }
-        if (BWD && is_cold) {                         // the row's mask bytes ride along (16 B per lane)
-          if (MPR >= 16) {
-            if (gl < MPR / 16)
-              cp_async16(mring + (ps * UNR + u) * G::MSLOT + grp * MPR + gl * 16, smask + (int64_t)c * MPR + gl * 16);
-          } else {
-            if (gl == 0) cp_async8(mring + (ps * UNR + u) * G::MSLOT + grp * MPR, smask + (int64_t)c * MPR);
-          }
-        }
-        if (WEIGHTED && is_cold && gl == 0) sts_f32(wring + ((ps * UNR + u) * GPW + grp) * 4, w);
-      }
-      flags = (flags & ~(0xffu << (ps * 8))) | (cold_bits << (ps * 8));   // tell the consumer which slots landed in the ring
-      cp_async_commit();
-      p_off += UNR;
-      ps ^= 1;
-    };
-
-    // prologue: first block of the first task
-    enter_next_task();
-    produce();
-
     while (b0 < n_seg_tasks) {                          // warp-uniform
-      // ---- rotate: the task whose first block is in flight becomes current ----------------
       const sagnn_task cur = nxt;
-#pragma unroll
-      for (int v = 0; v < V; ++v) { acc[v] = acc_n[v]; acc_n[v] = f4p_zero(); }
-      p_is_nxt = false;
+      int myc = nxt_c;
+      float myw = nxt_w;
       nxt = nxt2;
       nxt_c = 0;
       if (gl < (int)(nxt.meta & 0x7fu)) {
@@ -487,29 +433,68 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
           own_a[v] = valid ? ld_nc(reinterpret_cast<const float*>(a + own_off + v * LPR * 16)) : f4_zero();
       }
 
-      // ---- consume this task's blocks; the producer stays one block ahead -------------------
+      f4p acc[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] = f4p_zero();
+
+      // ---- gather-reduce over this task's edges (lock step over the warp) -------------------
+      const int nh = (int)((cur.meta >> 8) & 0x7fu);
       int nmax = n;
 #pragma unroll
       for (int o = LPR; o < 32; o <<= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
-      const int n_blk = nmax > 0 ? (nmax + UNR - 1) / UNR : 1;
-      for (int b = 0; b < n_blk; ++b) {
-        produce();
-        cp_async_wait<1>();
-        __syncwarp();
-        const unsigned cold_bits = flags >> (cs * 8);
+      for (int eb = 0; eb < nmax; eb += LPR) {
+        // prefetch the next batch of codes while this one is gathered
+        int c_next = 0;
+        float w_next = 0.f;
+        if (eb + LPR + gl < n) {
+          c_next = __ldg(enc + cur.e_off + eb + LPR + gl);
+          if (WEIGHTED) w_next = __ldg(wts + cur.e_off + eb + LPR + gl);
+        }
+        const int nbmax = min(LPR, nmax - eb);
+        for (int j = 0; j < nbmax; j += UNR) {
+          const int nb = n - eb - j;             // my group's edges left from slot j on (may be <= 0)
+          const int nhb = nh - eb - j;           // ... of which hot (staged in shared memory)
+          float4 val[UNR][V];
+          uint32_t mb[UNR][V];
+          float wv[UNR];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          if (cold_bits & (1u << u)) {
-            const float w = WEIGHTED ? lds_f32(wring + ((cs * UNR + u) * GPW + grp) * 4) : 1.f;
+          for (int u = 0; u < UNR; ++u) {
+            int c = __shfl_sync(FULL, myc, gbase + j + u);
+            wv[u] = WEIGHTED ? __shfl_sync(FULL, myw, gbase + j + u) : 1.f;
+            if (WARM) {
+              int hotf = u < nhb, coldf = (u < nb) && !hotf;
+              // hot slot that is not staged at this latdim: fetch it like a cold row
+              if (hotf && c >= KST) { c = warm_ids[c]; hotf = 0; coldf = 1; }
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-              const float4 x = lds_f4(ring_lane + (cs * UNR + u) * G::SLOT + v * 512);
-              const uint32_t mb = BWD ? lds_u8(mring + (cs * UNR + u) * G::MSLOT + grp * MPR + v * LPR + gl) : 0u;
-              accumulate<WEIGHTED, BWD>(acc[v], x, w, mb, leaky);
+              for (int v = 0; v < V; ++v) {
+                val[u][v] = f4_zero();
+                mb[u][v] = 0xfu;
+                gather_slot(val[u][v], hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16,
+                            src_lane + (int64_t)c * (D * 4) + v * LPR * 16, hotf, coldf);
+                if (BWD) {
+                  if (coldf) mb[u][v] = __ldg(smask + (int64_t)c * MPR + v * LPR + gl);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int v = 0; v < V; ++v) {
+                val[u][v] = f4_zero();
+                mb[u][v] = 0xfu;
+                SlotDispatch<UNR>::run(u, val[u][v], hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16,
+                                       src_lane + (int64_t)c * (D * 4) + v * LPR * 16, nhb, nb);
+                if (BWD) {
+                  if (u >= nhb && u < nb) mb[u][v] = __ldg(smask + (int64_t)c * MPR + v * LPR + gl);
+                }
+              }
             }
           }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u)
+#pragma unroll
+            for (int v = 0; v < V; ++v) accumulate<WEIGHTED, BWD>(acc[v], val[u][v], wv[u], mb[u][v], leaky);
         }
-        cs ^= 1;
+        myc = c_next;
+        myw = w_next;
       }
 
       // ---- long rows: publish the partial sum; the last slice to arrive reduces -----------
@@ -598,7 +583,6 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
         }
       }
     }
-    cp_async_wait<0>();                                 // drain the look-ahead block before leaving
   }
 }
 
@@ -626,7 +610,11 @@ static int launch_mode(const sagnn_plan* plan, const SpmmParams& prm, int d, cud
   const bool wt = prm.w != nullptr;
   switch (d) {
     case 32:  return wt ? launch_t<8, 1, MODE, true>(plan, prm, st)  : launch_t<8, 1, MODE, false>(plan, prm, st);
+#if SAGNN_D64_LPR8   // 8 lanes x 2 float4 per row: four rows per warp
+    case 64:  return wt ? launch_t<8, 2, MODE, true>(plan, prm, st) : launch_t<8, 2, MODE, false>(plan, prm, st);
+#else
     case 64:  return wt ? launch_t<16, 1, MODE, true>(plan, prm, st) : launch_t<16, 1, MODE, false>(plan, prm, st);
+#endif
     case 128: return wt ? launch_t<32, 1, MODE, true>(plan, prm, st) : launch_t<32, 1, MODE, false>(plan, prm, st);
     case 256: return wt ? launch_t<32, 2, MODE, true>(plan, prm, st) : launch_t<32, 2, MODE, false>(plan, prm, st);
   }
