@@ -281,7 +281,7 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
   __shared__ int warm_ids[WARM ? kHotRows : 1];
 
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+
   const int gl = lane % LPR;
   const int gbase = lane - gl;                        // first lane of my group
   const int grp = lane / LPR;
