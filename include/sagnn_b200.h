@@ -102,6 +102,11 @@ int sagnn_plan_get_weights(const sagnn_plan* plan, int k, int side, float* w_dev
  * out[4]=max degree, out[5]=sum of edges over both sides, out[6]=grid blocks, out[7]=SMs */
 int sagnn_plan_stats(const sagnn_plan* plan, int64_t* out8);
 
+/* Diagnostics: when trace_dev != NULL every following layer launch (up to capacity_launches)
+ * writes, per persistent CTA, 4 x uint64 {segment, t_start, t_hot_rows_staged, t_end} in ns
+ * (%globaltimer) at trace_dev + launch * SMs * 4.  Pass NULL to switch tracing off. */
+int sagnn_debug_trace(sagnn_plan* plan, uint64_t* trace_dev, int capacity_launches);
+
 int sagnn_plan_destroy(sagnn_plan* plan);
 
 /* ---- propagation ------------------------------------------------------------------------

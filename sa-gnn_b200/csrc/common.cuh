@@ -97,6 +97,11 @@ struct sagnn_plan {
   int64_t n_tasks = 0, n_short = 0, n_long = 0, n_chunks = 0;
   int32_t max_deg = 0;
 
+  // diagnostics (sagnn_debug_trace): per-launch, per-CTA {segment, start, staged, end} timestamps
+  unsigned long long* trace_dev = nullptr;
+  int trace_capacity = 0;
+  mutable int trace_launch = 0;
+
   // host-entry cache (sagnn_propagate_host)
   struct HostCache {
     int L = 0, d = 0;

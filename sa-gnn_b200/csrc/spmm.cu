@@ -72,7 +72,14 @@ struct SpmmParams {
   unsigned* ctrs;            // [2T] per-segment task-queue heads, zero on entry
   float leaky;
   int out_add_next;          // FWD: o2 = b + a (+ E^{l+1} when set)
+  unsigned long long* trace; // diagnostics: per CTA {seg, t_start, t_staged, t_end} (ns) or NULL
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ float4 ld_nc(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
@@ -291,6 +298,10 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
   const int seg0 = p.single_seg >= 0 ? p.single_seg : p.cta[blockIdx.x].seg;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   unsigned phase = 0;
+  if (p.trace && threadIdx.x == 0) {
+    p.trace[blockIdx.x * 4 + 0] = (unsigned long long)seg0;
+    p.trace[blockIdx.x * 4 + 1] = globaltimer_ns();
+  }
 
   for (int hop = 0; hop < n_hops; ++hop) {
     int seg = seg0 + hop;
@@ -361,6 +372,8 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
       }
       __syncthreads();
     }
+
+    if (p.trace && threadIdx.x == 0 && hop == 0) p.trace[blockIdx.x * 4 + 2] = globaltimer_ns();
 
     // lane-specific bases of everything the gather loop touches, pinned in registers
     const char* src_lane = reinterpret_cast<const char*>(src) + gl * 16;
@@ -584,13 +597,20 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
       }
     }
   }
+  if (p.trace) {
+    __syncthreads();
+    if (threadIdx.x == 0) p.trace[blockIdx.x * 4 + 3] = globaltimer_ns();
+  }
 }
 
 // ---------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------
 template <int LPR, int V, int MODE, bool WEIGHTED>
-static int launch_t(const sagnn_plan* plan, const SpmmParams& prm, cudaStream_t st) {
+static int launch_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaStream_t st) {
+  SpmmParams prm = prm_in;
+  if (plan->trace_dev && plan->trace_launch < plan->trace_capacity)   // diagnostics only
+    prm.trace = plan->trace_dev + (size_t)(plan->trace_launch++) * plan->num_sms * 4;
   using G = Geo<LPR, V, MODE, WEIGHTED>;
   static_assert(G::SMEM <= 227 * 1024 - 4096, "shared-memory budget exceeded");
   static bool configured = false;
@@ -666,6 +686,7 @@ static void base_params(const sagnn_plan* p, SpmmParams& s) {
   s.tasks = p->tasks; s.enc = p->enc; s.w = p->w_enc;
   s.chunk_base = p->chunk_base; s.chunk_lr = p->chunk_lr;
   s.hot_ids = p->hot_ids; s.seg = p->seg_dev; s.cta = p->cta_dev; s.single_seg = -1;
+  s.trace = nullptr;
   s.n_seg_total = 2 * p->T;
   s.U = p->U; s.I = p->I;
 }
@@ -681,6 +702,14 @@ static int check_common(const sagnn_plan* p, int n_layers, int d, const char* fn
 }  // namespace sagnn
 
 using namespace sagnn;
+
+extern "C" int sagnn_debug_trace(sagnn_plan* p, uint64_t* trace_dev, int capacity_launches) {
+  SAGNN_REQUIRE(p, SAGNN_INVALID_ARG, "debug_trace: NULL plan");
+  p->trace_dev = (unsigned long long*)trace_dev;
+  p->trace_capacity = trace_dev ? capacity_launches : 0;
+  p->trace_launch = 0;
+  return SAGNN_OK;
+}
 
 extern "C" int sagnn_plan_stats(const sagnn_plan* p, int64_t* out8) {
   SAGNN_REQUIRE(p && out8, SAGNN_INVALID_ARG, "plan_stats: NULL argument");
