@@ -38,11 +38,12 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // One unit of work for a lane group: a whole short row or one <=kChunk-edge slice of a long
 // row.  Edges of a row are stored hot-first in `enc`: the first n_hot codes are hot-slot
 // numbers (rows staged in shared memory), the rest are source-row ids.
-struct __align__(16) sagnn_task {
+struct __align__(32) sagnn_task {
   uint32_t row;     // row id inside its own table (user id or item id)
   uint32_t meta;    // bits 0-6: edges n (<= kChunk); bits 8-14: hot edges; bit 31: slice of a long row
   uint32_t e_off;   // first edge, relative to the segment's first edge
   uint32_t aux;     // slices: global slice id (partial-sum slot)
+  int32_t c[4];     // the first four edge codes, so short rows need no dependent code load
 };
 
 // A segment = one CSR: (interval k, side).  seg = 2*k + side; its rows are the rows of table

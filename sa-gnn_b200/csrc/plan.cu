@@ -208,7 +208,8 @@ __global__ void sched_encode_kernel(const int64_t* __restrict__ rowptr, const in
 __global__ void sched_task_kernel(const uint32_t* __restrict__ srow, const int32_t* __restrict__ deg,
                                   const int64_t* __restrict__ rowptr, const int32_t* __restrict__ nhot_row,
                                   const int64_t* __restrict__ task_off, const int64_t* __restrict__ chunk_off,
-                                  const int64_t* __restrict__ long_off, int64_t n_rows, int64_t n_tasks,
+                                  const int64_t* __restrict__ long_off, const int32_t* __restrict__ enc,
+                                  int64_t n_rows, int64_t n_tasks,
                                   int64_t N, int U, sagnn_task* __restrict__ tasks,
                                   int64_t* __restrict__ chunk_base, uint32_t* __restrict__ chunk_lr) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -235,6 +236,7 @@ __global__ void sched_task_kernel(const uint32_t* __restrict__ srow, const int32
   k.meta = (uint32_t)(e1 - e0) | ((uint32_t)nh << 8) | (lg ? 0x80000000u : 0u);
   k.e_off = (uint32_t)(e0 - rowptr[row0]);
   k.aux = 0;
+  for (int q = 0; q < 4; ++q) k.c[q] = (e0 + q < e1) ? enc[e0 + q] : 0;
   if (lg) {
     const int64_t c = chunk_off[i] + ci;
     k.aux = (uint32_t)c;
@@ -506,7 +508,7 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   SAGNN_CUDA(cudaMalloc(&p->chunk_lr, sizeof(uint32_t) * (p->n_chunks ? p->n_chunks : 1)));
   SAGNN_CUDA(cudaMemcpyAsync(p->chunk_base + p->n_long, &p->n_chunks, sizeof(int64_t), cudaMemcpyHostToDevice, st));
   sched_task_kernel<<<blocks_for(p->n_tasks), 256, 0, st>>>(srow, p->deg, p->rowptr, nhot_row, task_off, chunk_off,
-                                                            long_off, R, p->n_tasks, N, U, p->tasks, p->chunk_base,
+                                                            long_off, p->enc, R, p->n_tasks, N, U, p->tasks, p->chunk_base,
                                                             p->chunk_lr);
   SAGNN_CUDA(cudaGetLastError());
 
@@ -529,10 +531,32 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   SAGNN_CUDA(cudaMalloc(&p->seg_dev, sizeof(sagnn_seg) * S));
   SAGNN_CUDA(cudaMemcpyAsync(p->seg_dev, p->seg_host.data(), sizeof(sagnn_seg) * S, cudaMemcpyHostToDevice, st));
 
-  // persistent CTAs (one per SM) are dealt to segments in proportion to their cost
+  // persistent CTAs (one per SM) are dealt to segments in proportion to their cost.  Measured on
+  // B200 (scripts/trace_cta.py): a cold (global) edge costs ~4 units, a hot (staged) edge ~0.9,
+  // a row ~30 (task bookkeeping + epilogue).
   {
     std::vector<double> cost(S);
-    for (int t = 0; t < S; ++t) cost[t] = (double)p->nnz[t >> 1] + 8.0 * ((t & 1) ? p->I : p->U);
+    {
+      int64_t* hsum = nullptr;
+      void* tmp = nullptr; size_t tb = 0;
+      SAGNN_CUDA(cudaMalloc(&hsum, sizeof(int64_t) * S));
+      auto in = thrust::make_transform_iterator((const int32_t*)nhot_row, CastI64());
+      SAGNN_CUDA(cub::DeviceReduce::Sum(nullptr, tb, in, hsum, R, st));
+      SAGNN_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
+      for (int t = 0; t < S; ++t) {
+        const int64_t row0 = (int64_t)(t >> 1) * N + ((t & 1) ? U : 0);
+        const int64_t rows = (t & 1) ? p->I : p->U;
+        SAGNN_CUDA(cub::DeviceReduce::Sum(tmp, tb, in + row0, hsum + t, rows, st));
+      }
+      std::vector<int64_t> hot(S);
+      SAGNN_CUDA(cudaMemcpyAsync(hot.data(), hsum, sizeof(int64_t) * S, cudaMemcpyDeviceToHost, st));
+      SAGNN_CUDA(cudaStreamSynchronize(st));
+      cudaFree(tmp); cudaFree(hsum);
+      for (int t = 0; t < S; ++t) {
+        const double e = (double)p->nnz[t >> 1], h = (double)hot[t];
+        cost[t] = 4.0 * (e - h) + 0.9 * h + 30.0 * ((t & 1) ? p->I : p->U);
+      }
+    }
     std::vector<int> n(S, 1);
     int left = p->num_sms - S;
     while (left > 0) {   // give the next CTA to the segment with the largest cost per CTA

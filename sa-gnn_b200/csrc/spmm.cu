@@ -68,7 +68,8 @@ struct SpmmParams {
   uint8_t* mask_u;           // FWD: sign masks out or NULL
   uint8_t* mask_i;
   float* partials;           // [n_chunks, d]
-  uint32_t* tickets;         // [n_long], zero on entry, zero again on exit
+  uint32_t* tickets;         // slice-reduction tickets, one region per tree level; zero on entry and on exit
+  int64_t n_chunks;
   unsigned* ctrs;            // [2T] per-segment task-queue heads, zero on entry
   float leaky;
   int out_add_next;          // FWD: o2 = b + a (+ E^{l+1} when set)
@@ -390,10 +391,13 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
     auto ld_task = [&](unsigned t) -> sagnn_task {
       sagnn_task q;
       if (t < n_seg_tasks) {
-        const int4 raw = __ldg(reinterpret_cast<const int4*>(tasks + t));
-        q.row = (uint32_t)raw.x; q.meta = (uint32_t)raw.y; q.e_off = (uint32_t)raw.z; q.aux = (uint32_t)raw.w;
+        const int4 r0 = __ldg(reinterpret_cast<const int4*>(tasks + t));
+        const int4 r1 = __ldg(reinterpret_cast<const int4*>(tasks + t) + 1);
+        q.row = (uint32_t)r0.x; q.meta = (uint32_t)r0.y; q.e_off = (uint32_t)r0.z; q.aux = (uint32_t)r0.w;
+        q.c[0] = r1.x; q.c[1] = r1.y; q.c[2] = r1.z; q.c[3] = r1.w;
       } else {
         q.row = 0; q.meta = 0x40000000u; q.e_off = 0; q.aux = 0;   // bit 30: no work
+        q.c[0] = q.c[1] = q.c[2] = q.c[3] = 0;
       }
       return q;
     };
@@ -402,34 +406,27 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
     unsigned b1 = 0xffffffffu;                        // resolved lazily
     int r = 0;
 
-    // software pipeline: task records two rounds ahead, the first code batch one round ahead
+    // software pipeline: the next task record (which carries its first four edge codes) is
+    // always in flight, so a short row's gathers depend on nothing but that record
     sagnn_task nxt = ld_task(b0 + grp);
     b1 = __shfl_sync(FULL, pend, 0);
     pend = issue();
-    sagnn_task nxt2 = ld_task((R > 1 ? b0 + GPW : b1) + grp);
-    int nxt_c = 0;
-    float nxt_w = 0.f;
-    if (gl < (int)(nxt.meta & 0x7fu)) {
-      nxt_c = __ldg(enc + nxt.e_off + gl);
-      if (WEIGHTED) nxt_w = __ldg(wts + nxt.e_off + gl);
-    }
 
     while (b0 < n_seg_tasks) {                          // warp-uniform
       const sagnn_task cur = nxt;
-      int myc = nxt_c;
-      float myw = nxt_w;
-      nxt = nxt2;
-      nxt_c = 0;
-      if (gl < (int)(nxt.meta & 0x7fu)) {
-        nxt_c = __ldg(enc + nxt.e_off + gl);
-        if (WEIGHTED) nxt_w = __ldg(wts + nxt.e_off + gl);
-      }
-      nxt2 = ld_task((r + 2 < R ? b0 + (r + 2) * GPW : b1 + (r + 2 - R) * GPW) + grp);   // r = position of cur in b0
+      nxt = ld_task((r + 1 < R ? b0 + (r + 1) * GPW : b1) + grp);   // r = position of cur in grab b0
       if (++r == R) {                                   // rotate the grabs
         r = 0;
         b0 = b1;
         b1 = __shfl_sync(FULL, pend, 0);
         pend = issue();
+      }
+      // codes of the first batch beyond the four carried by the record
+      int myc = 0;
+      float myw = 0.f;
+      if (gl < (int)(cur.meta & 0x7fu) && (WEIGHTED || (int)(cur.meta & 0x7fu) > 4)) {
+        myc = __ldg(enc + cur.e_off + gl);
+        if (WEIGHTED) myw = __ldg(wts + cur.e_off + gl);
       }
 
       const bool valid = !(cur.meta & 0x40000000u);
@@ -472,7 +469,16 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
           float wv[UNR];
 #pragma unroll
           for (int u = 0; u < UNR; ++u) {
-            int c = __shfl_sync(FULL, myc, gbase + j + u);
+            int c;
+            if (UNR == 4) {
+              if (eb == 0 && j == 0) c = cur.c[u & 3];                     // carried by the task record
+              else c = __shfl_sync(FULL, myc, gbase + j + u);
+            } else {
+              const int e = j + u;                                         // first-batch edge index
+              const int rc = e == 0 ? cur.c[0] : e == 1 ? cur.c[1] : e == 2 ? cur.c[2] : cur.c[3];
+              const int sc = __shfl_sync(FULL, myc, gbase + j + u);
+              c = (eb == 0 && e < 4) ? rc : sc;
+            }
             wv[u] = WEIGHTED ? __shfl_sync(FULL, myw, gbase + j + u) : 1.f;
             if (WARM) {
               int hotf = u < nhb, coldf = (u < nb) && !hotf;
@@ -510,45 +516,70 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
         myw = w_next;
       }
 
-      // ---- long rows: publish the partial sum; the last slice to arrive reduces -----------
-      // (release-only ticket; the reducer reads with strong loads that bypass L1, so no
-      //  acquire fence / L1 invalidate is needed)
+      // ---- long rows: publish the partial sum; reduce through a fan-in-16 tree ----------------
+      // The last arriver of every group of 16 slices (then of 16 groups, ...) sums them in
+      // slice order, so the result does not depend on scheduling and no reduction chain is
+      // longer than 16 loads per level.  Release-only tickets; the reducer reads with strong
+      // loads that bypass L1, so no acquire fence / L1 invalidate is needed.
       bool finish = valid;
       if (__any_sync(FULL, multi)) {
-        uint32_t lr = 0;
+        int64_t cb = 0;
+        int nch = 1;
         if (multi) {
-          lr = __ldg(p.chunk_lr + cur.aux);
-          float* mine = p.partials + (int64_t)cur.aux * D;
-#pragma unroll
-          for (int v = 0; v < V; ++v) st_f4(mine + (v * LPR + gl) * 4, f4p_get(acc[v]));
+          const uint32_t lr = __ldg(p.chunk_lr + cur.aux);
+          cb = __ldg(p.chunk_base + lr);
+          nch = (int)(__ldg(p.chunk_base + lr + 1) - cb);
         }
-        __syncwarp();
-        unsigned old = 0;
-        if (multi && gl == 0) old = ticket_release_add(p.tickets + lr);
-        old = __shfl_sync(FULL, old, gbase);
-        if (multi) {
-          const int64_t cb = __ldg(p.chunk_base + lr);
-          const int nch = (int)(__ldg(p.chunk_base + lr + 1) - cb);
-          finish = (old == (unsigned)(nch - 1));
-          if (finish) {
+        int pos = multi ? (int)((int64_t)cur.aux - cb) : 0;   // my slice inside the row
+        bool active = multi;                                   // still climbing the tree
+        finish = valid && !multi;
+        unsigned* tk = p.tickets;                              // ticket region of the current level
+        for (int stride = 1; __any_sync(FULL, active); stride *= 16) {
+          // members of my group at this level: slots gs + j*stride, j < 16, below nch
+          const int gs = pos - pos % (16 * stride);
+          int members = (nch - gs + stride - 1) / stride;
+          members = members > 16 ? 16 : members;
+          if (active) {
+            float* mine = p.partials + (cb + pos) * D;
 #pragma unroll
-            for (int v = 0; v < V; ++v) acc[v] = f4p_zero();
-            const float* part = p.partials + cb * D;
-            for (int c0 = 0; c0 < nch; c0 += 4) {
-              float4 val[4][V];
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int v = 0; v < V; ++v)
-                  val[u][v] = (c0 + u < nch) ? ld_strong(part + (int64_t)(c0 + u) * D + (v * LPR + gl) * 4)
-                                             : f4_zero();
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int v = 0; v < V; ++v) acc_add(acc[v], val[u][v]);
-            }
-            if (gl == 0) p.tickets[lr] = 0u;   // ready for the next launch
+            for (int v = 0; v < V; ++v) st_f4(mine + (v * LPR + gl) * 4, f4p_get(acc[v]));
           }
+          __syncwarp();
+          unsigned old = 0;
+          unsigned* my_tk = tk + (cb + gs);                    // one ticket per group, named by its first slot
+          if (active && gl == 0) old = ticket_release_add(my_tk);
+          old = __shfl_sync(FULL, old, gbase);
+          if (active) {
+            if (old != (unsigned)(members - 1)) {
+              active = false;                                  // someone else finishes this group
+            } else {
+              if (gl == 0) *my_tk = 0u;                        // ready for the next launch
+#pragma unroll
+              for (int v = 0; v < V; ++v) acc[v] = f4p_zero();
+              const float* part = p.partials + (cb + gs) * D;
+              for (int c0 = 0; c0 < members; c0 += 4) {
+                float4 val[4][V];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                  for (int v = 0; v < V; ++v)
+                    val[u][v] = (c0 + u < members)
+                                    ? ld_strong(part + (int64_t)(c0 + u) * stride * D + (v * LPR + gl) * 4)
+                                    : f4_zero();
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                  for (int v = 0; v < V; ++v) acc_add(acc[v], val[u][v]);
+              }
+              if (gs == 0 && 16 * stride >= nch) {             // that was the whole row
+                finish = true;
+                active = false;
+              } else {
+                pos = gs;                                      // my sum becomes slot gs of the next level
+              }
+            }
+          }
+          tk += p.n_chunks;
         }
         __syncwarp();
       }
@@ -655,6 +686,7 @@ static bool d_ok(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
 // workspace layout: [tickets | partials | table buffer 0 | table buffer 1]
 struct WsLayout {
   size_t tickets_off, partials_off, buf_off[2], total;
+  size_t ticket_words;   // slice-reduction tickets of all tree levels
   size_t zero_bytes;     // tickets + one set of per-segment queue heads per layer launch, zeroed per call
   size_t table_floats;   // T*(U+I)*d
   size_t user_floats;    // T*U*d  (user part comes first inside a table buffer)
@@ -664,7 +696,10 @@ static WsLayout ws_layout(const sagnn_plan* p, int n_layers, int d) {
   WsLayout w{};
   size_t off = 0;
   w.tickets_off = off;
-  w.zero_bytes = sizeof(uint32_t) * ((size_t)p->n_long + 2 * (size_t)p->T * n_layers);
+  int levels = 1;        // fan-in-16 tree over the slices of the longest row
+  for (int64_t n = ((int64_t)p->max_deg + kChunk - 1) / kChunk; n > 16; n = (n + 15) / 16) ++levels;
+  w.ticket_words = (size_t)levels * (size_t)(p->n_chunks ? p->n_chunks : 1);
+  w.zero_bytes = sizeof(uint32_t) * (w.ticket_words + 2 * (size_t)p->T * n_layers);
   off = align_up(off + w.zero_bytes, 256);
   w.partials_off = off;
   off = align_up(off + sizeof(float) * (size_t)p->n_chunks * d, 256);
@@ -686,6 +721,7 @@ static void base_params(const sagnn_plan* p, SpmmParams& s) {
   s.tasks = p->tasks; s.enc = p->enc; s.w = p->w_enc;
   s.chunk_base = p->chunk_base; s.chunk_lr = p->chunk_lr;
   s.hot_ids = p->hot_ids; s.seg = p->seg_dev; s.cta = p->cta_dev; s.single_seg = -1;
+  s.n_chunks = p->n_chunks;
   s.trace = nullptr;
   s.n_seg_total = 2 * p->T;
   s.U = p->U; s.I = p->I;
@@ -745,12 +781,12 @@ extern "C" int sagnn_propagate_fwd(const sagnn_plan* p, const float* uE, const f
   s.partials = (float*)(base + w.partials_off);
   s.leaky = leaky;
   SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, w.zero_bytes, st));
-  s.ctrs = s.tickets + p->n_long;
+  s.ctrs = s.tickets + w.ticket_words;
   float* buf[2] = {(float*)(base + w.buf_off[0]), (float*)(base + w.buf_off[1])};
   const size_t mlw = mask_layer_bytes(p, d);
   const size_t mu = (size_t)p->T * p->U * (d / 4);
   for (int l = 0; l < L; ++l) {
-    s.ctrs = s.tickets + p->n_long + (size_t)l * 2 * p->T;
+    s.ctrs = s.tickets + w.ticket_words + (size_t)l * 2 * p->T;
     const float* cur_u = l == 0 ? uE : buf[(l - 1) & 1];
     const float* cur_i = l == 0 ? iE : buf[(l - 1) & 1] + w.user_floats;
     const bool last = (l == L - 1);
@@ -789,12 +825,12 @@ extern "C" int sagnn_propagate_bwd(const sagnn_plan* p, const float* gU, const f
   s.partials = (float*)(base + w.partials_off);
   s.leaky = leaky;
   SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, w.zero_bytes, st));
-  s.ctrs = s.tickets + p->n_long;
+  s.ctrs = s.tickets + w.ticket_words;
   float* buf[2] = {(float*)(base + w.buf_off[0]), (float*)(base + w.buf_off[1])};
   const size_t mlw = mask_layer_bytes(p, d);
   const size_t mu = (size_t)p->T * p->U * (d / 4);
   for (int l = L - 1, step = 0; l >= 0; --l, ++step) {
-    s.ctrs = s.tickets + p->n_long + (size_t)step * 2 * p->T;
+    s.ctrs = s.tickets + w.ticket_words + (size_t)step * 2 * p->T;
     // g = total gradient w.r.t. E^{l+1}; at the top level it is the upstream itself
     const float* g_u = step == 0 ? gU : buf[(step - 1) & 1];
     const float* g_i = step == 0 ? gI : buf[(step - 1) & 1] + w.user_floats;
@@ -829,7 +865,7 @@ extern "C" int sagnn_message_propagate(const sagnn_plan* p, int k, int side, con
   s.partials = (float*)(base + w.partials_off);
   s.leaky = leaky;
   SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, w.zero_bytes, st));
-  s.ctrs = s.tickets + p->n_long;
+  s.ctrs = s.tickets + w.ticket_words;
   s.single_seg = 2 * k + side;
   // the kernel indexes tables as [T, rows, d]; shift the bases so that interval k lands on the
   // caller's single-interval tensors
