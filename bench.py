@@ -75,49 +75,49 @@ def alg_bytes(nnz, U, I, d, L):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML polled from a thread every
+    ~2 ms; nvidia-smi -lms as a fallback)."""
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.sm, self.mx, self.reasons, self.stop_flag = gpu_index, [], [], set(), False
+        self.th = None
+        self.proc = None
+
+    def _poll_nvml(self):
+        import pynvml
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        names = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            self.mx.append(float(mx))
+            r = int(get_reasons(h))
+            for n, bit in names.items():
+                if r & bit:
+                    self.reasons.add(n)
+            time.sleep(0.002)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.th = threading.Thread(target=self._poll_nvml, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.th = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.th is not None:
+            self.th.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
 
 
 def make_workload(args, rank):

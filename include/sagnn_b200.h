@@ -148,6 +148,15 @@ int sagnn_propagate_host(sagnn_plan* plan, const float* u_embed_host, const floa
                          float* item_out_host, float* d_u_embed_host, float* d_i_embed_host,
                          int n_layers, int d, float leaky);
 
+/* The same, split for callers whose autodiff runs forward and backward at different times
+ * (a TF1 py_func pair): forward keeps the sign masks inside the plan when
+ * keep_masks != 0; backward uses them and fails with SAGNN_INVALID_ARG if there are none. */
+int sagnn_host_forward(sagnn_plan* plan, const float* u_embed_host, const float* i_embed_host,
+                       float* user_out_host, float* item_out_host, int n_layers, int d, float leaky,
+                       int keep_masks);
+int sagnn_host_backward(sagnn_plan* plan, const float* g_user_host, const float* g_item_host,
+                        float* d_u_embed_host, float* d_i_embed_host, int n_layers, int d, float leaky);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,8 @@ struct sagnn_plan {
     float *uO = nullptr, *iO = nullptr, *dU = nullptr, *dI = nullptr;
     void *masks = nullptr, *ws = nullptr;
     size_t ws_bytes = 0;
+    bool masks_valid = false;     // the masks of the last host forward are still in `masks`
+    float leaky = 0.f;
     cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
     std::vector<cudaEvent_t> ev;
   } hc;

@@ -892,6 +892,72 @@ void sagnn::free_host_cache(sagnn_plan* p) {
   h = sagnn_plan::HostCache();
 }
 
+// device buffers / streams of the host-buffer entry points, (re)allocated when L or d change
+static int host_ensure(sagnn_plan* p, int L, int d) {
+  auto& h = p->hc;
+  if (h.L == L && h.d == d) return SAGNN_OK;
+  const size_t nu = sizeof(float) * (size_t)p->T * p->U * d;
+  const size_t ni = sizeof(float) * (size_t)p->T * p->I * d;
+  free_host_cache(p);
+  size_t fb = 0, mb = 0, bb = 0;
+  if (int rc = sagnn_workspace_bytes(p, L, d, &fb, &mb, &bb)) return rc;
+  SAGNN_CUDA(cudaMalloc(&h.uE, nu)); SAGNN_CUDA(cudaMalloc(&h.iE, ni));
+  SAGNN_CUDA(cudaMalloc(&h.gU, nu)); SAGNN_CUDA(cudaMalloc(&h.gI, ni));
+  SAGNN_CUDA(cudaMalloc(&h.uO, nu)); SAGNN_CUDA(cudaMalloc(&h.iO, ni));
+  SAGNN_CUDA(cudaMalloc(&h.dU, nu)); SAGNN_CUDA(cudaMalloc(&h.dI, ni));
+  SAGNN_CUDA(cudaMalloc(&h.masks, mb ? mb : 1));
+  h.ws_bytes = fb > bb ? fb : bb;
+  SAGNN_CUDA(cudaMalloc(&h.ws, h.ws_bytes));
+  SAGNN_CUDA(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+  SAGNN_CUDA(cudaStreamCreateWithFlags(&h.copy_in, cudaStreamNonBlocking));
+  SAGNN_CUDA(cudaStreamCreateWithFlags(&h.copy_out, cudaStreamNonBlocking));
+  h.ev.resize(4);
+  for (auto& e : h.ev) SAGNN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  h.L = L; h.d = d;
+  h.masks_valid = false;
+  return SAGNN_OK;
+}
+
+extern "C" int sagnn_host_forward(sagnn_plan* p, const float* uE, const float* iE, float* uO, float* iO, int L,
+                                  int d, float leaky, int keep_masks) {
+  if (int rc = check_common(p, L, d, "host_forward")) return rc;
+  SAGNN_REQUIRE(uE && iE && uO && iO, SAGNN_INVALID_ARG, "host_forward: NULL embedding/output");
+  if (int rc = host_ensure(p, L, d)) return rc;
+  auto& h = p->hc;
+  const size_t nu = sizeof(float) * (size_t)p->T * p->U * d;
+  const size_t ni = sizeof(float) * (size_t)p->T * p->I * d;
+  SAGNN_CUDA(cudaMemcpyAsync(h.uE, uE, nu, cudaMemcpyHostToDevice, h.stream));
+  SAGNN_CUDA(cudaMemcpyAsync(h.iE, iE, ni, cudaMemcpyHostToDevice, h.stream));
+  if (int rc = sagnn_propagate_fwd(p, h.uE, h.iE, h.uO, h.iO, L, d, leaky, keep_masks ? h.masks : nullptr, h.ws,
+                                   h.ws_bytes, h.stream))
+    return rc;
+  SAGNN_CUDA(cudaMemcpyAsync(uO, h.uO, nu, cudaMemcpyDeviceToHost, h.stream));
+  SAGNN_CUDA(cudaMemcpyAsync(iO, h.iO, ni, cudaMemcpyDeviceToHost, h.stream));
+  SAGNN_CUDA(cudaStreamSynchronize(h.stream));
+  h.masks_valid = keep_masks != 0;
+  h.leaky = leaky;
+  return SAGNN_OK;
+}
+
+extern "C" int sagnn_host_backward(sagnn_plan* p, const float* gU, const float* gI, float* dU, float* dI, int L,
+                                   int d, float leaky) {
+  if (int rc = check_common(p, L, d, "host_backward")) return rc;
+  SAGNN_REQUIRE(gU && gI && dU && dI, SAGNN_INVALID_ARG, "host_backward: NULL gradient buffer");
+  auto& h = p->hc;
+  SAGNN_REQUIRE(h.L == L && h.d == d && h.masks_valid, SAGNN_INVALID_ARG,
+                "host_backward: no matching sagnn_host_forward(keep_masks=1) on this plan");
+  const size_t nu = sizeof(float) * (size_t)p->T * p->U * d;
+  const size_t ni = sizeof(float) * (size_t)p->T * p->I * d;
+  SAGNN_CUDA(cudaMemcpyAsync(h.gU, gU, nu, cudaMemcpyHostToDevice, h.stream));
+  SAGNN_CUDA(cudaMemcpyAsync(h.gI, gI, ni, cudaMemcpyHostToDevice, h.stream));
+  if (int rc = sagnn_propagate_bwd(p, h.gU, h.gI, h.dU, h.dI, L, d, leaky, h.masks, h.ws, h.ws_bytes, h.stream))
+    return rc;
+  SAGNN_CUDA(cudaMemcpyAsync(dU, h.dU, nu, cudaMemcpyDeviceToHost, h.stream));
+  SAGNN_CUDA(cudaMemcpyAsync(dI, h.dI, ni, cudaMemcpyDeviceToHost, h.stream));
+  SAGNN_CUDA(cudaStreamSynchronize(h.stream));
+  return SAGNN_OK;
+}
+
 extern "C" int sagnn_propagate_host(sagnn_plan* p, const float* uE, const float* iE, const float* gU,
                                     const float* gI, float* uO, float* iO, float* dU, float* dI, int L,
                                     int d, float leaky) {
@@ -899,27 +965,12 @@ extern "C" int sagnn_propagate_host(sagnn_plan* p, const float* uE, const float*
   SAGNN_REQUIRE(uE && iE && uO && iO, SAGNN_INVALID_ARG, "propagate_host: NULL embedding/output");
   const bool bwd = gU != nullptr;
   SAGNN_REQUIRE(!bwd || (gI && dU && dI), SAGNN_INVALID_ARG, "propagate_host: backward needs gI, dU, dI");
+  if (int rc = host_ensure(p, L, d)) return rc;
   auto& h = p->hc;
   const size_t nu = sizeof(float) * (size_t)p->T * p->U * d;
   const size_t ni = sizeof(float) * (size_t)p->T * p->I * d;
-  if (h.L != L || h.d != d) {
-    free_host_cache(p);
-    size_t fb = 0, mb = 0, bb = 0;
-    if (int rc = sagnn_workspace_bytes(p, L, d, &fb, &mb, &bb)) return rc;
-    SAGNN_CUDA(cudaMalloc(&h.uE, nu)); SAGNN_CUDA(cudaMalloc(&h.iE, ni));
-    SAGNN_CUDA(cudaMalloc(&h.gU, nu)); SAGNN_CUDA(cudaMalloc(&h.gI, ni));
-    SAGNN_CUDA(cudaMalloc(&h.uO, nu)); SAGNN_CUDA(cudaMalloc(&h.iO, ni));
-    SAGNN_CUDA(cudaMalloc(&h.dU, nu)); SAGNN_CUDA(cudaMalloc(&h.dI, ni));
-    SAGNN_CUDA(cudaMalloc(&h.masks, mb ? mb : 1));
-    h.ws_bytes = fb > bb ? fb : bb;
-    SAGNN_CUDA(cudaMalloc(&h.ws, h.ws_bytes));
-    SAGNN_CUDA(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
-    SAGNN_CUDA(cudaStreamCreateWithFlags(&h.copy_in, cudaStreamNonBlocking));
-    SAGNN_CUDA(cudaStreamCreateWithFlags(&h.copy_out, cudaStreamNonBlocking));
-    h.ev.resize(4);
-    for (auto& e : h.ev) SAGNN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    h.L = L; h.d = d;
-  }
+  h.masks_valid = bwd;
+  h.leaky = leaky;
   // embeddings in on the compute stream; upstream gradients in on a second copy stream
   // (they are only needed by the backward); outputs leave on a third while backward runs.
   SAGNN_CUDA(cudaMemcpyAsync(h.uE, uE, nu, cudaMemcpyHostToDevice, h.stream));

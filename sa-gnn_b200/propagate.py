@@ -323,6 +323,23 @@ def propagate_host(plan, u_embed, i_embed, g_user, g_item, user_out, item_out, d
             float(leaky)))
 
 
+def host_forward(plan, u_embed, i_embed, user_out, item_out, n_layers, leaky=0.5, keep_masks=True):
+    """``sagnn_host_forward``: host buffers in/out, forward only; the sign masks stay inside the plan
+    for a later ``host_backward`` (what a TF1 ``py_func`` forward op would call)."""
+    with torch.cuda.device(plan.device):
+        _lib.check(_lib.load_library().sagnn_host_forward(
+            plan.handle, _host_ptr(u_embed), _host_ptr(i_embed), _host_ptr(user_out), _host_ptr(item_out),
+            int(n_layers), int(u_embed.shape[2]), float(leaky), 1 if keep_masks else 0))
+
+
+def host_backward(plan, g_user, g_item, d_u, d_i, n_layers, leaky=0.5):
+    """``sagnn_host_backward``: gradients for the last ``host_forward(keep_masks=True)`` on this plan."""
+    with torch.cuda.device(plan.device):
+        _lib.check(_lib.load_library().sagnn_host_backward(
+            plan.handle, _host_ptr(g_user), _host_ptr(g_item), _host_ptr(d_u), _host_ptr(d_i),
+            int(n_layers), int(g_user.shape[2]), float(leaky)))
+
+
 class IntervalPropagation(torch.nn.Module):
     """The short-term graph-propagation block of ``Recommender.ours()`` (model.py:108-134) as a
     module: owns ``uEmbed [T,U,d]`` / ``iEmbed [T,I,d]`` (xavier, model.py:108-109) and returns the

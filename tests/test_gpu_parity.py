@@ -304,6 +304,14 @@ def test_host_entry_point_matches_oracle():
     fo = [np.empty_like(uE), np.empty_like(iE)]
     sg.propagate_host(plan, uE, iE, None, None, fo[0], fo[1], None, None, 2, 0.5)
     np.testing.assert_array_equal(fo[0], outs[0])
+    # split entry points (forward now, backward later) give the same bits
+    so = [np.empty_like(x) for x in (uE, iE, uE, iE)]
+    with pytest.raises(sg.SagnnError):
+        sg.host_backward(plan, gU, gI, so[2], so[3], 2, 0.5)        # no forward with masks yet
+    sg.host_forward(plan, uE, iE, so[0], so[1], 2, 0.5, keep_masks=True)
+    sg.host_backward(plan, gU, gI, so[2], so[3], 2, 0.5)
+    for a, b in zip(so, outs):
+        np.testing.assert_array_equal(a, b)
 
 
 # ---------------------------------------------------------------- BASELINE shape families
