@@ -74,50 +74,71 @@ def alg_bytes(nnz, U, I, d, L):
     return fwd_layer, bwd_layer, L * (fwd_layer + bwd_layer)
 
 
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml
+pynvml.nvmlInit()
+h = pynvml.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+get = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+print("max", mx, flush=True)
+while True:
+    print(time.time(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), int(get(h)), flush=True)
+    time.sleep(0.001)
+"""
+
+
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region (NVML polled from a thread every
-    ~2 ms; nvidia-smi -lms as a fallback)."""
+    """SM clock + throttle reasons sampled DURING the timed region: a helper process polls NVML
+    every ~1 ms (a thread would starve behind the launch loop's GIL); samples are cut to the
+    timed window by wall-clock time."""
+    REASONS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20,
+               "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
-        self.idx, self.sm, self.mx, self.reasons, self.stop_flag = gpu_index, [], [], set(), False
-        self.th = None
-        self.proc = None
-
-    def _poll_nvml(self):
-        import pynvml
-        h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
-        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-        names = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
-                 "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-                 "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
-                 "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
-        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
-            getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
-        while not self.stop_flag:
-            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-            self.mx.append(float(mx))
-            r = int(get_reasons(h))
-            for n, bit in names.items():
-                if r & bit:
-                    self.reasons.add(n)
-            time.sleep(0.002)
+        self.idx, self.proc, self.t0, self.t1 = gpu_index, None, None, None
 
     def start(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.th = threading.Thread(target=self._poll_nvml, daemon=True)
-            self.th.start()
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.5)          # let it import and start polling before the window opens
         except Exception:
-            self.th = None
+            self.proc = None
+
+    def open_window(self):
+        self.t0 = time.time()
+
+    def close_window(self):
+        self.t1 = time.time()
 
     def stop(self):
-        self.stop_flag = True
-        if self.th is not None:
-            self.th.join(timeout=2)
-        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
-                "sm_max_mhz": max(self.mx) if self.mx else None,
-                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.01)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=3)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        for line in out.splitlines():
+            f = line.split()
+            try:
+                if f[0] == "max":
+                    mx = float(f[1])
+                    continue
+                t, clk, r = float(f[0]), float(f[1]), int(f[2])
+            except Exception:
+                continue
+            if self.t0 is not None and self.t0 <= t <= (self.t1 or t):
+                sm.append(clk)
+                for n, bit in self.REASONS.items():
+                    if r & bit:
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml, 1 ms polling, timed window only"}
 
 
 def make_workload(args, rank):
@@ -260,6 +281,7 @@ def main():
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    sampler.open_window()
     wall0 = time.perf_counter()
     for s in range(args.steps):
         flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
@@ -268,6 +290,7 @@ def main():
         ev[s][1].record()
     barrier()
     wall = time.perf_counter() - wall0
+    sampler.close_window()
     clocks = sampler.stop() if rank == 0 else None
     per_step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(per_step_ms))
