@@ -133,6 +133,18 @@ int sagnn_propagate_bwd(const sagnn_plan* plan, const float* g_user_dev, const f
                         const void* masks_dev, void* workspace_dev, size_t workspace_bytes,
                         sagnn_stream_t stream);
 
+/* The same restricted to interval k (rows of the other intervals are not touched): all SMs work on
+ * that interval's two CSRs, so a caller can pipeline per-interval copies with compute.  Tensors,
+ * masks and workspace are the full [T, ...] buffers; calls must be stream-ordered. */
+int sagnn_propagate_fwd_interval(const sagnn_plan* plan, int k, const float* u_embed_dev,
+                                 const float* i_embed_dev, float* user_out_dev, float* item_out_dev,
+                                 int n_layers, int d, float leaky, void* masks_dev, void* workspace_dev,
+                                 size_t workspace_bytes, sagnn_stream_t stream);
+int sagnn_propagate_bwd_interval(const sagnn_plan* plan, int k, const float* g_user_dev,
+                                 const float* g_item_dev, float* d_u_embed_dev, float* d_i_embed_dev,
+                                 int n_layers, int d, float leaky, const void* masks_dev,
+                                 void* workspace_dev, size_t workspace_bytes, sagnn_stream_t stream);
+
 /* One messagePropagate() call (model.py:80-92): out[R,d] = lrelu(B_k,side * src[C,d]).
  * workspace: forward scratch size. */
 int sagnn_message_propagate(const sagnn_plan* plan, int k, int side, const float* src_dev,

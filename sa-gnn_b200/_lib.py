@@ -37,6 +37,10 @@ SIGNATURES = {
                                            vp, vp, ctypes.c_size_t, vp]),
     "sagnn_propagate_bwd": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                            vp, vp, ctypes.c_size_t, vp]),
+    "sagnn_propagate_fwd_interval": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,
+                                                    ctypes.c_float, vp, vp, ctypes.c_size_t, vp]),
+    "sagnn_propagate_bwd_interval": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,
+                                                    ctypes.c_float, vp, vp, ctypes.c_size_t, vp]),
     "sagnn_message_propagate": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int,
                                                ctypes.c_float, vp, ctypes.c_size_t, vp]),
     "sagnn_host_forward": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int]),

@@ -91,7 +91,8 @@ struct sagnn_plan {
   int32_t* hot_ids = nullptr;     // [2T, kHotRows] row ids (inside table t) of table t's hot slots
   sagnn_task* tasks = nullptr;    // [n_tasks] grouped by segment
   sagnn_seg* seg_dev = nullptr;   // [2T]
-  sagnn_cta* cta_dev = nullptr;   // [num_sms]
+  sagnn_cta* cta_dev = nullptr;   // [num_sms] all intervals in one launch
+  sagnn_cta* cta_int_dev = nullptr;  // [T][num_sms] one interval per launch
   int64_t* chunk_base = nullptr;  // [n_long + 1] first slice of each long row
   uint32_t* chunk_lr = nullptr;   // [n_chunks] long-row rank of each slice
   std::vector<sagnn_seg> seg_host;

@@ -321,7 +321,7 @@ extern "C" int sagnn_plan_destroy(sagnn_plan* p) {
   sagnn::free_host_cache(p);
   cudaFree(p->deg); cudaFree(p->rowptr); cudaFree(p->idx); cudaFree(p->val); cudaFree(p->w);
   cudaFree(p->valsum); cudaFree(p->chunk_base); cudaFree(p->chunk_lr); cudaFree(p->tasks);
-  cudaFree(p->enc); cudaFree(p->w_enc); cudaFree(p->hot_ids); cudaFree(p->seg_dev); cudaFree(p->cta_dev);
+  cudaFree(p->enc); cudaFree(p->w_enc); cudaFree(p->hot_ids); cudaFree(p->seg_dev); cudaFree(p->cta_dev); cudaFree(p->cta_int_dev);
   delete p;
   return SAGNN_OK;
 }
@@ -572,6 +572,19 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
       for (int r = 0; r < n[t]; ++r) cta[c++] = sagnn_cta{t, r, n[t], 0};
     SAGNN_CUDA(cudaMalloc(&p->cta_dev, sizeof(sagnn_cta) * p->num_sms));
     SAGNN_CUDA(cudaMemcpyAsync(p->cta_dev, cta.data(), sizeof(sagnn_cta) * p->num_sms, cudaMemcpyHostToDevice, st));
+    // per-interval tables: all CTAs on the two segments of one interval (pipelined host entry point)
+    std::vector<sagnn_cta> cta_int((size_t)p->T * p->num_sms);
+    for (int k = 0; k < p->T; ++k) {
+      const double cu = cost[2 * k], ci = cost[2 * k + 1];
+      int nu = (int)(p->num_sms * cu / (cu + ci) + 0.5);
+      nu = nu < 1 ? 1 : (nu > p->num_sms - 1 ? p->num_sms - 1 : nu);
+      for (int c2 = 0; c2 < p->num_sms; ++c2)
+        cta_int[(size_t)k * p->num_sms + c2] =
+            c2 < nu ? sagnn_cta{2 * k, c2, nu, 0} : sagnn_cta{2 * k + 1, c2 - nu, p->num_sms - nu, 0};
+    }
+    SAGNN_CUDA(cudaMalloc(&p->cta_int_dev, sizeof(sagnn_cta) * cta_int.size()));
+    SAGNN_CUDA(cudaMemcpyAsync(p->cta_int_dev, cta_int.data(), sizeof(sagnn_cta) * cta_int.size(),
+                               cudaMemcpyHostToDevice, st));
     SAGNN_CUDA(cudaStreamSynchronize(st));
   }
   SAGNN_CUDA(cudaGetLastError());

@@ -411,7 +411,24 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
     sagnn_task nxt = ld_task(b0 + grp);
     b1 = __shfl_sync(FULL, pend, 0);
     pend = issue();
+    int nxt_c = 0;                                      // first code batch of `nxt` (rows with > 4 edges)
+    float nxt_w = 0.f;
+    auto request_codes = [&]() {                        // needs nxt's record: called late in the iteration
+      const int nn = (int)(nxt.meta & 0x7fu);
+      nxt_c = 0;
+      if (gl < nn && (WEIGHTED || nn > 4)) {
+        nxt_c = __ldg(enc + nxt.e_off + gl);
+        if (WEIGHTED) nxt_w = __ldg(wts + nxt.e_off + gl);
+      }
+    };
+    request_codes();
 
+#if defined(SAGNN_PHASES)
+    long long ph[4] = {0, 0, 0, 0}, pt = clock64();
+#define PHASE(i) do { long long _t = clock64(); ph[i] += _t - pt; pt = _t; } while (0)
+#else
+#define PHASE(i) do {} while (0)
+#endif
     while (b0 < n_seg_tasks) {                          // warp-uniform
       const sagnn_task cur = nxt;
       nxt = ld_task((r + 1 < R ? b0 + (r + 1) * GPW : b1) + grp);   // r = position of cur in grab b0
@@ -421,17 +438,17 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
         b1 = __shfl_sync(FULL, pend, 0);
         pend = issue();
       }
-      // codes of the first batch beyond the four carried by the record
-      int myc = 0;
-      float myw = 0.f;
-      if (gl < (int)(cur.meta & 0x7fu) && (WEIGHTED || (int)(cur.meta & 0x7fu) > 4)) {
-        myc = __ldg(enc + cur.e_off + gl);
-        if (WEIGHTED) myw = __ldg(wts + cur.e_off + gl);
-      }
+      // codes of the first batch beyond the four carried by the record: requested one task ahead
+      int myc = nxt_c;
+      float myw = nxt_w;
 
       const bool valid = !(cur.meta & 0x40000000u);
       const bool multi = (cur.meta >> 31) != 0;          // slice of a long row
+#if defined(SAGNN_X3)
+      const int n = 0;                                    // experiment: no gathers at all
+#else
       const int n = (int)(cur.meta & 0x7fu);
+#endif
       const uint32_t own_off = cur.row * (uint32_t)(D * 4) + gl * 16;   // byte offset inside my table (< 4 GB)
 
       // the row's own dense operand is independent of the gather: issue it first
@@ -446,6 +463,7 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
       f4p acc[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) acc[v] = f4p_zero();
+      PHASE(0);
 
       // ---- gather-reduce over this task's edges (lock step over the warp) -------------------
       const int nh = (int)((cur.meta >> 8) & 0x7fu);
@@ -480,6 +498,11 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
               c = (eb == 0 && e < 4) ? rc : sc;
             }
             wv[u] = WEIGHTED ? __shfl_sync(FULL, myw, gbase + j + u) : 1.f;
+#if defined(SAGNN_X1)
+            if (!(u < nhb)) c &= 1023;          // experiment: cold gathers confined to 1024 rows
+#elif defined(SAGNN_X2)
+            if (!(u < nhb)) c &= 511;           // experiment: every edge reads the staged copy
+#endif
             if (WARM) {
               int hotf = u < nhb, coldf = (u < nb) && !hotf;
               // hot slot that is not staged at this latdim: fetch it like a cold row
@@ -499,8 +522,13 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
               for (int v = 0; v < V; ++v) {
                 val[u][v] = f4_zero();
                 mb[u][v] = 0xfu;
+#if defined(SAGNN_X2)
+                SlotDispatch<UNR>::run(u, val[u][v], hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16,
+                                       src_lane + (int64_t)c * (D * 4) + v * LPR * 16, nb, nb);
+#else
                 SlotDispatch<UNR>::run(u, val[u][v], hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16,
                                        src_lane + (int64_t)c * (D * 4) + v * LPR * 16, nhb, nb);
+#endif
                 if (BWD) {
                   if (u >= nhb && u < nb) mb[u][v] = __ldg(smask + (int64_t)c * MPR + v * LPR + gl);
                 }
@@ -516,6 +544,11 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
         myw = w_next;
       }
 
+#if defined(SAGNN_PHASES)
+      { volatile float sink = acc[0].lo.x; (void)sink; }   // force the gathers to complete here
+#endif
+      PHASE(1);
+      request_codes();                                    // the next task's record has arrived by now
       // ---- long rows: publish the partial sum; reduce through a fan-in-16 tree ----------------
       // The last arriver of every group of 16 slices (then of 16 groups, ...) sums them in
       // slice order, so the result does not depend on scheduling and no reduction chain is
@@ -584,6 +617,7 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
         __syncwarp();
       }
 
+      PHASE(2);
       // ---- fused epilogue ------------------------------------------------------------------
       if (finish) {
 #pragma unroll
@@ -626,7 +660,14 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
           }
         }
       }
+      PHASE(3);
     }
+#if defined(SAGNN_PHASES)
+    if (p.trace && lane == 0) {
+      unsigned long long* o = p.trace + (size_t)gridDim.x * 4 + ((size_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * 4;
+      for (int i = 0; i < 4; ++i) o[i] = (unsigned long long)ph[i];
+    }
+#endif
   }
   if (p.trace) {
     __syncthreads();
@@ -765,11 +806,13 @@ extern "C" int sagnn_workspace_bytes(const sagnn_plan* p, int n_layers, int d, s
   return SAGNN_OK;
 }
 
-extern "C" int sagnn_propagate_fwd(const sagnn_plan* p, const float* uE, const float* iE, float* uOut,
-                                   float* iOut, int L, int d, float leaky, void* masks, void* ws,
-                                   size_t ws_bytes, sagnn_stream_t stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
+// interval < 0: all T intervals in one launch per layer; otherwise only that interval's two
+// segments (all 148 CTAs work on them) -- lets a caller pipeline copies with compute
+static int fwd_impl(const sagnn_plan* p, int interval, const float* uE, const float* iE, float* uOut,
+                    float* iOut, int L, int d, float leaky, void* masks, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
   if (int rc = check_common(p, L, d, "propagate_fwd")) return rc;
+  SAGNN_REQUIRE(interval < p->T, SAGNN_INVALID_ARG, "propagate_fwd: interval %d outside [0,%d)", interval, p->T);
   SAGNN_REQUIRE(uE && iE && uOut && iOut && ws, SAGNN_INVALID_ARG, "propagate_fwd: NULL tensor");
   WsLayout w = ws_layout(p, L, d);
   SAGNN_REQUIRE(ws_bytes >= w.total, SAGNN_WORKSPACE_TOO_SMALL,
@@ -780,6 +823,7 @@ extern "C" int sagnn_propagate_fwd(const sagnn_plan* p, const float* uE, const f
   s.tickets = (uint32_t*)(base + w.tickets_off);
   s.partials = (float*)(base + w.partials_off);
   s.leaky = leaky;
+  if (interval >= 0) s.cta = p->cta_int_dev + (size_t)interval * p->num_sms;
   SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, w.zero_bytes, st));
   s.ctrs = s.tickets + w.ticket_words;
   float* buf[2] = {(float*)(base + w.buf_off[0]), (float*)(base + w.buf_off[1])};
@@ -809,11 +853,23 @@ extern "C" int sagnn_propagate_fwd(const sagnn_plan* p, const float* uE, const f
   return SAGNN_OK;
 }
 
-extern "C" int sagnn_propagate_bwd(const sagnn_plan* p, const float* gU, const float* gI, float* dU,
-                                   float* dI, int L, int d, float leaky, const void* masks, void* ws,
-                                   size_t ws_bytes, sagnn_stream_t stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
+extern "C" int sagnn_propagate_fwd(const sagnn_plan* p, const float* uE, const float* iE, float* uOut,
+                                   float* iOut, int L, int d, float leaky, void* masks, void* ws,
+                                   size_t ws_bytes, sagnn_stream_t stream) {
+  return fwd_impl(p, -1, uE, iE, uOut, iOut, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int sagnn_propagate_fwd_interval(const sagnn_plan* p, int k, const float* uE, const float* iE,
+                                            float* uOut, float* iOut, int L, int d, float leaky, void* masks,
+                                            void* ws, size_t ws_bytes, sagnn_stream_t stream) {
+  SAGNN_REQUIRE(k >= 0, SAGNN_INVALID_ARG, "propagate_fwd_interval: k=%d", k);
+  return fwd_impl(p, k, uE, iE, uOut, iOut, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const float* gI, float* dU, float* dI,
+                    int L, int d, float leaky, const void* masks, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (int rc = check_common(p, L, d, "propagate_bwd")) return rc;
+  SAGNN_REQUIRE(interval < p->T, SAGNN_INVALID_ARG, "propagate_bwd: interval %d outside [0,%d)", interval, p->T);
   SAGNN_REQUIRE(gU && gI && dU && dI && masks && ws, SAGNN_INVALID_ARG, "propagate_bwd: NULL tensor");
   WsLayout w = ws_layout(p, L, d);
   SAGNN_REQUIRE(ws_bytes >= w.total, SAGNN_WORKSPACE_TOO_SMALL,
@@ -829,6 +885,7 @@ extern "C" int sagnn_propagate_bwd(const sagnn_plan* p, const float* gU, const f
   float* buf[2] = {(float*)(base + w.buf_off[0]), (float*)(base + w.buf_off[1])};
   const size_t mlw = mask_layer_bytes(p, d);
   const size_t mu = (size_t)p->T * p->U * (d / 4);
+  if (interval >= 0) s.cta = p->cta_int_dev + (size_t)interval * p->num_sms;
   for (int l = L - 1, step = 0; l >= 0; --l, ++step) {
     s.ctrs = s.tickets + w.ticket_words + (size_t)step * 2 * p->T;
     // g = total gradient w.r.t. E^{l+1}; at the top level it is the upstream itself
@@ -845,6 +902,19 @@ extern "C" int sagnn_propagate_bwd(const sagnn_plan* p, const float* gU, const f
     if (int rc = launch(p, s, d, MODE_BWD, st)) return rc;
   }
   return SAGNN_OK;
+}
+
+extern "C" int sagnn_propagate_bwd(const sagnn_plan* p, const float* gU, const float* gI, float* dU,
+                                   float* dI, int L, int d, float leaky, const void* masks, void* ws,
+                                   size_t ws_bytes, sagnn_stream_t stream) {
+  return bwd_impl(p, -1, gU, gI, dU, dI, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int sagnn_propagate_bwd_interval(const sagnn_plan* p, int k, const float* gU, const float* gI,
+                                            float* dU, float* dI, int L, int d, float leaky, const void* masks,
+                                            void* ws, size_t ws_bytes, sagnn_stream_t stream) {
+  SAGNN_REQUIRE(k >= 0, SAGNN_INVALID_ARG, "propagate_bwd_interval: k=%d", k);
+  return bwd_impl(p, k, gU, gI, dU, dI, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int sagnn_message_propagate(const sagnn_plan* p, int k, int side, const float* src, float* out,
@@ -971,29 +1041,48 @@ extern "C" int sagnn_propagate_host(sagnn_plan* p, const float* uE, const float*
   const size_t ni = sizeof(float) * (size_t)p->T * p->I * d;
   h.masks_valid = bwd;
   h.leaky = leaky;
-  // embeddings in on the compute stream; upstream gradients in on a second copy stream
-  // (they are only needed by the backward); outputs leave on a third while backward runs.
-  SAGNN_CUDA(cudaMemcpyAsync(h.uE, uE, nu, cudaMemcpyHostToDevice, h.stream));
-  SAGNN_CUDA(cudaMemcpyAsync(h.iE, iE, ni, cudaMemcpyHostToDevice, h.stream));
-  if (bwd) {
-    SAGNN_CUDA(cudaMemcpyAsync(h.gU, gU, nu, cudaMemcpyHostToDevice, h.copy_in));
-    SAGNN_CUDA(cudaMemcpyAsync(h.gI, gI, ni, cudaMemcpyHostToDevice, h.copy_in));
-    SAGNN_CUDA(cudaEventRecord(h.ev[0], h.copy_in));
+  // Pipelined per interval over three streams: embeddings (then upstream gradients) stream in on
+  // copy_in, interval k is propagated as soon as its slice has landed, and its outputs
+  // (then gradients) stream out on copy_out while later intervals are still computing.
+  const int T = p->T;
+  if ((int)h.ev.size() < 4 * T) {
+    for (auto e : h.ev) cudaEventDestroy(e);
+    h.ev.resize(4 * T);
+    for (auto& e : h.ev) SAGNN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  if (int rc = sagnn_propagate_fwd(p, h.uE, h.iE, h.uO, h.iO, L, d, leaky, bwd ? h.masks : nullptr, h.ws,
-                                   h.ws_bytes, h.stream))
-    return rc;
-  SAGNN_CUDA(cudaEventRecord(h.ev[1], h.stream));
-  SAGNN_CUDA(cudaStreamWaitEvent(h.copy_out, h.ev[1], 0));
-  SAGNN_CUDA(cudaMemcpyAsync(uO, h.uO, nu, cudaMemcpyDeviceToHost, h.copy_out));
-  SAGNN_CUDA(cudaMemcpyAsync(iO, h.iO, ni, cudaMemcpyDeviceToHost, h.copy_out));
+  const size_t su = (size_t)p->U * d, si = (size_t)p->I * d;       // floats per interval slice
+  for (int k = 0; k < T; ++k) {
+    SAGNN_CUDA(cudaMemcpyAsync(h.uE + k * su, uE + k * su, su * 4, cudaMemcpyHostToDevice, h.copy_in));
+    SAGNN_CUDA(cudaMemcpyAsync(h.iE + k * si, iE + k * si, si * 4, cudaMemcpyHostToDevice, h.copy_in));
+    SAGNN_CUDA(cudaEventRecord(h.ev[k], h.copy_in));
+  }
   if (bwd) {
-    SAGNN_CUDA(cudaStreamWaitEvent(h.stream, h.ev[0], 0));
-    if (int rc = sagnn_propagate_bwd(p, h.gU, h.gI, h.dU, h.dI, L, d, leaky, h.masks, h.ws, h.ws_bytes,
-                                     h.stream))
+    for (int k = 0; k < T; ++k) {
+      SAGNN_CUDA(cudaMemcpyAsync(h.gU + k * su, gU + k * su, su * 4, cudaMemcpyHostToDevice, h.copy_in));
+      SAGNN_CUDA(cudaMemcpyAsync(h.gI + k * si, gI + k * si, si * 4, cudaMemcpyHostToDevice, h.copy_in));
+      SAGNN_CUDA(cudaEventRecord(h.ev[T + k], h.copy_in));
+    }
+  }
+  for (int k = 0; k < T; ++k) {
+    SAGNN_CUDA(cudaStreamWaitEvent(h.stream, h.ev[k], 0));
+    if (int rc = fwd_impl(p, k, h.uE, h.iE, h.uO, h.iO, L, d, leaky, bwd ? h.masks : nullptr, h.ws, h.ws_bytes,
+                          h.stream))
       return rc;
-    SAGNN_CUDA(cudaMemcpyAsync(dU, h.dU, nu, cudaMemcpyDeviceToHost, h.stream));
-    SAGNN_CUDA(cudaMemcpyAsync(dI, h.dI, ni, cudaMemcpyDeviceToHost, h.stream));
+    SAGNN_CUDA(cudaEventRecord(h.ev[2 * T + k], h.stream));
+    SAGNN_CUDA(cudaStreamWaitEvent(h.copy_out, h.ev[2 * T + k], 0));
+    SAGNN_CUDA(cudaMemcpyAsync(uO + k * su, h.uO + k * su, su * 4, cudaMemcpyDeviceToHost, h.copy_out));
+    SAGNN_CUDA(cudaMemcpyAsync(iO + k * si, h.iO + k * si, si * 4, cudaMemcpyDeviceToHost, h.copy_out));
+  }
+  if (bwd) {
+    for (int k = 0; k < T; ++k) {
+      SAGNN_CUDA(cudaStreamWaitEvent(h.stream, h.ev[T + k], 0));
+      if (int rc = bwd_impl(p, k, h.gU, h.gI, h.dU, h.dI, L, d, leaky, h.masks, h.ws, h.ws_bytes, h.stream))
+        return rc;
+      SAGNN_CUDA(cudaEventRecord(h.ev[3 * T + k], h.stream));
+      SAGNN_CUDA(cudaStreamWaitEvent(h.copy_out, h.ev[3 * T + k], 0));
+      SAGNN_CUDA(cudaMemcpyAsync(dU + k * su, h.dU + k * su, su * 4, cudaMemcpyDeviceToHost, h.copy_out));
+      SAGNN_CUDA(cudaMemcpyAsync(dI + k * si, h.dI + k * si, si * 4, cudaMemcpyDeviceToHost, h.copy_out));
+    }
   }
   SAGNN_CUDA(cudaStreamSynchronize(h.copy_out));
   SAGNN_CUDA(cudaStreamSynchronize(h.stream));

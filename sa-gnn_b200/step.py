@@ -43,6 +43,21 @@ class PropagationStep:
                                                 _ptr(self.d_i), self.L, self.d, self.leaky, _ptr(self.masks),
                                                 _ptr(self.ws), self.ws.numel(), _stream_ptr(p.device)))
 
+    def forward_interval(self, k):
+        """Forward restricted to interval k (all SMs on its two CSRs); see sagnn_propagate_fwd_interval."""
+        p = self.plan
+        _lib.check(self.lib.sagnn_propagate_fwd_interval(p.handle, int(k), _ptr(self.u_embed), _ptr(self.i_embed),
+                                                         _ptr(self.user_out), _ptr(self.item_out), self.L, self.d,
+                                                         self.leaky, _ptr(self.masks), _ptr(self.ws),
+                                                         self.ws.numel(), _stream_ptr(p.device)))
+
+    def backward_interval(self, k):
+        p = self.plan
+        _lib.check(self.lib.sagnn_propagate_bwd_interval(p.handle, int(k), _ptr(self.g_user), _ptr(self.g_item),
+                                                         _ptr(self.d_u), _ptr(self.d_i), self.L, self.d, self.leaky,
+                                                         _ptr(self.masks), _ptr(self.ws), self.ws.numel(),
+                                                         _stream_ptr(p.device)))
+
     def run(self):
         self.forward()
         self.backward()
