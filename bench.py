@@ -226,7 +226,7 @@ def main():
     trav = 4 * L * edges
 
     t0 = time.perf_counter()
-    plan = sg.build_plan(g.sub_mat, device=dev)
+    plan = sg.build_plan(g.sub_mat, device=dev, latdim=d)
     torch.cuda.synchronize()
     plan_ms = (time.perf_counter() - t0) * 1e3
 

@@ -77,6 +77,11 @@ int sagnn_plan_set_interval(sagnn_plan* plan, int k, const int32_t* row_dev, con
                             const int32_t* val_dev, const float* w_dev, int64_t nnz,
                             sagnn_stream_t stream);
 
+/* Optional, before finalize: the latdim the plan will mostly be run with (default 64).  It sizes
+ * the hot-row set so that all of it fits the shared-memory staging area at that d; other d still
+ * work (hot rows that do not fit are read through their ids). */
+int sagnn_plan_set_latdim_hint(sagnn_plan* plan, int d);
+
 /* Row pointers over all intervals, optional edge weights, degree-binned schedule.
  * Must be called once after every interval has been set. */
 int sagnn_plan_finalize(sagnn_plan* plan, int weight_mode, sagnn_stream_t stream);

@@ -12,7 +12,8 @@
 namespace sagnn {
 
 constexpr int kChunk = 64;        // max edges one lane-group gathers for one task
-constexpr int kHotRows = 768;     // hot-slot capacity per source table (slots = degree rank)
+constexpr int kHotRows = 768;     // max hot slots per source table (slot = degree rank); array stride
+constexpr int kHotBytes = 192 * 1024;   // shared memory the kernels give to staged hot rows
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
@@ -76,6 +77,7 @@ struct sagnn_plan {
   bool has_custom_w = false;
   bool finalized = false;
   int weight_mode = 0;
+  int hot_rows = sagnn::kHotRows; // hot slots actually used: min(kHotRows, kHotBytes / (4 * latdim hint))
 
   // canonical CSRs (what transToLsts / transpose produce; parity hooks read these)
   int32_t* deg = nullptr;         // [n_rows] structural degrees

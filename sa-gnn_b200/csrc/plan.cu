@@ -149,7 +149,7 @@ __global__ void sched_key_kernel(const int32_t* __restrict__ deg, int64_t n_rows
 // hot slots = the kHotRows highest-degree rows of every table; per sorted position also the
 // number of tasks / slices / long rows it contributes (inputs of the three scans)
 __global__ void sched_slot_kernel(const uint32_t* __restrict__ srow, const int32_t* __restrict__ deg,
-                                  int64_t n_rows, int64_t N, int U, int32_t* __restrict__ slot_of,
+                                  int64_t n_rows, int64_t N, int U, int K, int32_t* __restrict__ slot_of,
                                   int32_t* __restrict__ hot_ids, int64_t* __restrict__ n_task,
                                   int64_t* __restrict__ n_chunk, int64_t* __restrict__ n_long) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -158,8 +158,8 @@ __global__ void sched_slot_kernel(const uint32_t* __restrict__ srow, const int32
   const uint32_t g = srow[i];
   const uint32_t t = table_of(i, N, U);          // sorted positions keep the table layout
   const int64_t pos = i - table_row0(t, N, U);
-  slot_of[g] = pos < kHotRows ? (int32_t)pos : -1;
-  if (pos < kHotRows) hot_ids[(int64_t)t * kHotRows + pos] = (int32_t)(g - table_row0(t, N, U));
+  slot_of[g] = pos < K ? (int32_t)pos : -1;
+  if (pos < K) hot_ids[(int64_t)t * kHotRows + pos] = (int32_t)(g - table_row0(t, N, U));
   const int d = deg[g];
   const bool lg = d > kChunk;
   const int64_t nt = lg ? (d + kChunk - 1) / kChunk : 1;
@@ -393,6 +393,14 @@ extern "C" int sagnn_plan_set_interval(sagnn_plan* p, int k, const int32_t* row,
   return SAGNN_OK;
 }
 
+extern "C" int sagnn_plan_set_latdim_hint(sagnn_plan* p, int d) {
+  SAGNN_REQUIRE(p && !p->finalized, SAGNN_INVALID_ARG, "set_latdim_hint: NULL or finalized plan");
+  SAGNN_REQUIRE(d >= 4 && d % 4 == 0, SAGNN_INVALID_ARG, "set_latdim_hint: d=%d", d);
+  const int k = kHotBytes / (4 * d);
+  p->hot_rows = k < kHotRows ? (k < 1 ? 1 : k) : kHotRows;
+  return SAGNN_OK;
+}
+
 extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   SAGNN_REQUIRE(p, SAGNN_INVALID_ARG, "finalize: NULL plan");
@@ -470,7 +478,7 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   }
   int64_t *n_task = cnt3, *n_chunk = cnt3 + (R + 1), *n_long = cnt3 + 2 * (R + 1);
   int64_t *task_off = off3, *chunk_off = off3 + (R + 1), *long_off = off3 + 2 * (R + 1);
-  sched_slot_kernel<<<blocks_for(R + 1), 256, 0, st>>>(srow, p->deg, R, N, U, slot_of, p->hot_ids, n_task,
+  sched_slot_kernel<<<blocks_for(R + 1), 256, 0, st>>>(srow, p->deg, R, N, U, p->hot_rows, slot_of, p->hot_ids, n_task,
                                                        n_chunk, n_long);
   {
     void* tmp = nullptr; size_t tb = 0;

@@ -26,7 +26,7 @@
 #define SAGNN_GRAB 2           // task rounds a warp takes per queue atomic
 #endif
 #ifndef SAGNN_HOT_BYTES
-#define SAGNN_HOT_BYTES (192 * 1024)   // shared memory given to staged hot rows
+#define SAGNN_HOT_BYTES kHotBytes      // shared memory given to staged hot rows
 #endif
 #ifndef SAGNN_D64_LPR8
 #define SAGNN_D64_LPR8 0
@@ -49,6 +49,7 @@ struct SpmmParams {
   const int32_t* hot_ids;
   const sagnn_seg* seg;
   const sagnn_cta* cta;
+  int hot_rows;              // hot slots per table used by the plan's edge codes
   int single_seg;            // >= 0: every CTA works on this segment (messagePropagate); -1: use cta[]
   int n_seg_total;           // 2T
   int U, I;
@@ -275,7 +276,8 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
   using G = Geo<LPR, V, MODE, WEIGHTED>;
   constexpr int D = G::D, MPR = G::MPR, GPW = G::GPW, UNR = G::UNR, KST = G::KST;
   constexpr int R = SAGNN_GRAB;
-  constexpr bool WARM = KST < kHotRows;               // hot slots that do not fit: read via their ids
+  constexpr bool WARM = KST < kHotRows;               // this latdim may meet hot slots that do not fit
+  const bool warm = WARM && p.hot_rows > KST;         // ... and this plan has them: read those via their ids
   constexpr bool BWD = MODE == MODE_BWD;
   static_assert(LPR % UNR == 0, "unroll must divide the group width");
   static_assert(SAGNN_GRAB >= 2, "the record pipeline looks two rounds ahead");
@@ -348,8 +350,10 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
       for (int s = threadIdx.x; s < n_stage; s += kThreads)
         tma_bulk_g2s(hot + (size_t)s * D, src + (int64_t)__ldg(ids + s) * D, D * 4, &bar);
       if (WARM) {
-        const int n_hot = r_src < kHotRows ? r_src : kHotRows;
-        for (int s = threadIdx.x; s < n_hot; s += kThreads) warm_ids[s] = __ldg(ids + s);
+        if (warm) {
+          const int n_hot = r_src < p.hot_rows ? r_src : p.hot_rows;
+          for (int s = threadIdx.x; s < n_hot; s += kThreads) warm_ids[s] = __ldg(ids + s);
+        }
       }
       mbar_wait(&bar, phase);
       phase ^= 1u;
@@ -482,8 +486,7 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
         for (int j = 0; j < nbmax; j += UNR) {
           const int nb = n - eb - j;             // my group's edges left from slot j on (may be <= 0)
           const int nhb = nh - eb - j;           // ... of which hot (staged in shared memory)
-          float4 val[UNR][V];
-          uint32_t mb[UNR][V];
+          int cs[UNR];
           float wv[UNR];
 #pragma unroll
           for (int u = 0; u < UNR; ++u) {
@@ -497,48 +500,84 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
               const int sc = __shfl_sync(FULL, myc, gbase + j + u);
               c = (eb == 0 && e < 4) ? rc : sc;
             }
-            wv[u] = WEIGHTED ? __shfl_sync(FULL, myw, gbase + j + u) : 1.f;
 #if defined(SAGNN_X1)
             if (!(u < nhb)) c &= 1023;          // experiment: cold gathers confined to 1024 rows
 #elif defined(SAGNN_X2)
             if (!(u < nhb)) c &= 511;           // experiment: every edge reads the staged copy
 #endif
-            if (WARM) {
-              int hotf = u < nhb, coldf = (u < nb) && !hotf;
-              // hot slot that is not staged at this latdim: fetch it like a cold row
-              if (hotf && c >= KST) { c = warm_ids[c]; hotf = 0; coldf = 1; }
+            cs[u] = c;
+            wv[u] = WEIGHTED ? __shfl_sync(FULL, myw, gbase + j + u) : 1.f;
+          }
+          if (!warm && __all_sync(FULL, nhb >= UNR)) {
+            // fast path: every group has a full block of staged rows (sign-masked already in bwd)
+            float4 val[UNR][V];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+              for (int v = 0; v < V; ++v) val[u][v] = lds_f4(hot_lane + (uint32_t)cs[u] * (D * 4) + v * LPR * 16);
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+              for (int v = 0; v < V; ++v) accumulate<WEIGHTED, false>(acc[v], val[u][v], wv[u], 0u, leaky);
+          } else if (__all_sync(FULL, nhb <= 0 && nb >= UNR)) {
+            // fast path: every group has a full block of rows in global memory
+            float4 val[UNR][V];
+            uint32_t mb[UNR][V];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
 #pragma unroll
               for (int v = 0; v < V; ++v) {
-                val[u][v] = f4_zero();
-                mb[u][v] = 0xfu;
-                gather_slot(val[u][v], hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16,
-                            src_lane + (int64_t)c * (D * 4) + v * LPR * 16, hotf, coldf);
-                if (BWD) {
-                  if (coldf) mb[u][v] = __ldg(smask + (int64_t)c * MPR + v * LPR + gl);
-                }
+                val[u][v] = ld_nc(reinterpret_cast<const float*>(src_lane + (int64_t)cs[u] * (D * 4) + v * LPR * 16));
+                mb[u][v] = BWD ? __ldg(smask + (int64_t)cs[u] * MPR + v * LPR + gl) : 0u;
               }
-            } else {
 #pragma unroll
-              for (int v = 0; v < V; ++v) {
-                val[u][v] = f4_zero();
-                mb[u][v] = 0xfu;
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+              for (int v = 0; v < V; ++v) accumulate<WEIGHTED, BWD>(acc[v], val[u][v], wv[u], mb[u][v], leaky);
+          } else {
+            // general path: per-slot hot / cold / idle predicates
+            float4 val[UNR][V];
+            uint32_t mb[UNR][V];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              int c = cs[u];
+              if (WARM) {
+                int hotf = u < nhb, coldf = (u < nb) && !hotf;
+                // hot slot that is not staged at this latdim: fetch it like a cold row
+                if (warm && hotf && c >= KST) { c = warm_ids[c]; hotf = 0; coldf = 1; }
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                  val[u][v] = f4_zero();
+                  mb[u][v] = 0xfu;
+                  gather_slot(val[u][v], hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16,
+                              src_lane + (int64_t)c * (D * 4) + v * LPR * 16, hotf, coldf);
+                  if (BWD) {
+                    if (coldf) mb[u][v] = __ldg(smask + (int64_t)c * MPR + v * LPR + gl);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                  val[u][v] = f4_zero();
+                  mb[u][v] = 0xfu;
 #if defined(SAGNN_X2)
-                SlotDispatch<UNR>::run(u, val[u][v], hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16,
-                                       src_lane + (int64_t)c * (D * 4) + v * LPR * 16, nb, nb);
+                  SlotDispatch<UNR>::run(u, val[u][v], hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16,
+                                         src_lane + (int64_t)c * (D * 4) + v * LPR * 16, nb, nb);
 #else
-                SlotDispatch<UNR>::run(u, val[u][v], hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16,
-                                       src_lane + (int64_t)c * (D * 4) + v * LPR * 16, nhb, nb);
+                  SlotDispatch<UNR>::run(u, val[u][v], hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16,
+                                         src_lane + (int64_t)c * (D * 4) + v * LPR * 16, nhb, nb);
 #endif
-                if (BWD) {
-                  if (u >= nhb && u < nb) mb[u][v] = __ldg(smask + (int64_t)c * MPR + v * LPR + gl);
+                  if (BWD) {
+                    if (u >= nhb && u < nb) mb[u][v] = __ldg(smask + (int64_t)c * MPR + v * LPR + gl);
+                  }
                 }
               }
             }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+              for (int v = 0; v < V; ++v) accumulate<WEIGHTED, BWD>(acc[v], val[u][v], wv[u], mb[u][v], leaky);
           }
-#pragma unroll
-          for (int u = 0; u < UNR; ++u)
-#pragma unroll
-            for (int v = 0; v < V; ++v) accumulate<WEIGHTED, BWD>(acc[v], val[u][v], wv[u], mb[u][v], leaky);
         }
         myc = c_next;
         myw = w_next;
@@ -762,6 +801,7 @@ static void base_params(const sagnn_plan* p, SpmmParams& s) {
   s.tasks = p->tasks; s.enc = p->enc; s.w = p->w_enc;
   s.chunk_base = p->chunk_base; s.chunk_lr = p->chunk_lr;
   s.hot_ids = p->hot_ids; s.seg = p->seg_dev; s.cta = p->cta_dev; s.single_seg = -1;
+  s.hot_rows = p->hot_rows;
   s.n_chunks = p->n_chunks;
   s.trace = nullptr;
   s.n_seg_total = 2 * p->T;

@@ -157,13 +157,14 @@ def _split_interval(m):
     raise TypeError("unsupported interval description: %r" % type(m))
 
 
-def build_plan(sub_mats, U=None, I=None, *, device=None, edge_weight=None, strict_pad=False):
+def build_plan(sub_mats, U=None, I=None, *, device=None, edge_weight=None, strict_pad=False, latdim=64):
     """Builds the device plan for ``T = len(sub_mats)`` interval graphs.
 
     sub_mats[k]: scipy sparse ``U x I`` matrix (``handler.subMat[k]``), or an ``[E,2]`` adjacency
     list as ``transToLsts`` returns it, or ``(row, col[, val])`` arrays / tensors, row-major sorted.
     edge_weight: None (reference-exact binary structure), ``"lightgcn"`` (1/sqrt(d_u d_i)) or a
     list of per-interval fp32 arrays in the adjacency list's order.
+    latdim: the embedding width the plan will mostly run with (sizes the shared-memory hot-row set).
     strict_pad: raise like TF-CPU does when an interval's last populated row is more than 100
     rows before the end (model.py:87-91); by default such rows are simply zero (TF-GPU).
     """
@@ -216,6 +217,7 @@ def build_plan(sub_mats, U=None, I=None, *, device=None, edge_weight=None, stric
                     raise ValueError("interval %d: %d weights for %d edges" % (k, w_d.numel(), nnz[k]))
             _lib.check(lib.sagnn_plan_set_interval(handle, k, _ptr(row_d), _ptr(col_d), _ptr(val_d),
                                                    _ptr(w_d), nnz[k], st))
+        _lib.check(lib.sagnn_plan_set_latdim_hint(handle, int(latdim)))
         _lib.check(lib.sagnn_plan_finalize(handle, mode, st))
     return plan
 
