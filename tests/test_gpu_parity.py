@@ -353,6 +353,40 @@ def test_baseline_shapes_reduced_scale(name, scale):
     check_against_oracle(g.sub_mat, g.meta["d"], g.meta["L"], seed=100, scale=0.05)
 
 
+def test_config1_trn_mat_time_plumbing(tmp_path):
+    """BASELINE config 1 (plumbing): a `trn_mat_time` pickle in the reference's on-disk layout
+    (preprocess_to_trnmat.ipynb:1896) -> LoadData mirror -> transToLsts lists -> plan -> propagate
+    with the gowalla.sh settings (graphNum 3, gnn_layer 2, latdim 64, leaky 0.5), at reduced scale."""
+    g = dh.make_named("gowalla", seed=100, scale=0.04)
+    path = str(tmp_path / "trn_mat_time")
+    dh.write_trn_mat_time(path, g)
+    h = dh.load_trn_mat_time(path, graph_num=3)                 # args.user, args.item from trnMat[0].shape
+    assert (h.n_user, h.n_item) == (g.n_user, g.n_item)
+    lists = [sg.transToLsts(m, norm=True) for m in h.sub_mat]   # what model.py:230-233 feeds TF
+    assert all(np.all(d == 0) for _, d, _ in lists)             # the dead normalisation (SURVEY F3)
+    plan = sg.build_plan([l[0] for l in lists], U=h.n_user, I=h.n_item)
+    check_against_oracle(h.sub_mat, 64, 2, leaky=0.5, seed=100, scale=0.05)
+    # the plan built from adjacency lists equals the one built from the matrices
+    plan2 = sg.build_plan(h.sub_mat)
+    for k in range(3):
+        for side in (0, 1):
+            assert torch.equal(plan.adjacency_list(k, side), plan2.adjacency_list(k, side))
+
+
+@pytest.mark.parametrize("name", ["amazon-book", "ml10m"])
+def test_other_baseline_shapes_full_size(name):
+    """BASELINE configs 3 and 4 at full size (three-part parity vs the fused C oracle, fp64)."""
+    g = dh.make_named(name, seed=100)
+    L, d = g.meta["L"], g.meta["d"]
+    T, U, I = g.graph_num, g.n_user, g.n_item
+    uE = dh.xavier_embeddings(T, U, d, 100)
+    iE = dh.xavier_embeddings(T, I, d, 101)
+    rng = np.random.default_rng(100)
+    gU = rng.standard_normal((T, U, d), dtype=np.float32)
+    gI = rng.standard_normal((T, I, d), dtype=np.float32)
+    check_against_oracle(g.sub_mat, d, L, tables=(uE, iE, gU, gI), max_ties=256)
+
+
 def test_gowalla_full_size_parity_and_properties():
     """BASELINE config 2 at full size: three-part parity vs the (fast, fused) C oracle in fp64,
     plus size-independent properties: the backward is linear in the upstream gradient and
