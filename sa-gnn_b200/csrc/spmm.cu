@@ -1077,8 +1077,6 @@ extern "C" int sagnn_propagate_host(sagnn_plan* p, const float* uE, const float*
   SAGNN_REQUIRE(!bwd || (gI && dU && dI), SAGNN_INVALID_ARG, "propagate_host: backward needs gI, dU, dI");
   if (int rc = host_ensure(p, L, d)) return rc;
   auto& h = p->hc;
-  const size_t nu = sizeof(float) * (size_t)p->T * p->U * d;
-  const size_t ni = sizeof(float) * (size_t)p->T * p->I * d;
   h.masks_valid = bwd;
   h.leaky = leaky;
   // Pipelined per interval over three streams: embeddings (then upstream gradients) stream in on

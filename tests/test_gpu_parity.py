@@ -387,6 +387,26 @@ def test_other_baseline_shapes_full_size(name):
     check_against_oracle(g.sub_mat, d, L, tables=(uE, iE, gU, gI), max_ties=256)
 
 
+def test_monster_rows_three_level_slice_tree():
+    """Rows far beyond 16*16*64 edges (as in BASELINE config 5, where head items collect millions
+    of users) are reduced through a three-level ticket tree: a hub item linked to 90 % of 120 K
+    users and a hub user linked to every item, on top of a sparse random graph."""
+    U, I = 120_000, 3000
+    rng = np.random.default_rng(5)
+    n = 600_000
+    r = rng.integers(0, U, n)
+    c = rng.integers(0, I, n)
+    hub_users = np.flatnonzero(rng.random(U) < 0.9)
+    r = np.concatenate([r, hub_users, np.full(I, 77)])
+    c = np.concatenate([c, np.full(hub_users.size, 5), np.arange(I)])
+    m = sp.csr_matrix((np.ones(r.size, np.intc), (r, c)), shape=(U, I))
+    m.data[:] = 1
+    m.sort_indices()
+    plan = check_against_oracle([m], 64, 2, seed=9, scale=0.02, max_ties=64)
+    st = plan.stats()
+    assert st["max_degree"] > 16 * 16 * 64 and st["chunks"] > 1700
+
+
 def test_gowalla_full_size_parity_and_properties():
     """BASELINE config 2 at full size: three-part parity vs the (fast, fused) C oracle in fp64,
     plus size-independent properties: the backward is linear in the upstream gradient and
