@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-allgather", action="store_true")
+    ap.add_argument("--no-calibrate", action="store_true", help="keep the static cost-model CTA split")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--seed", type=int, default=100)
@@ -243,6 +244,9 @@ def main():
         gat_i = torch.empty((world,) + tuple(step.item_out.shape), dtype=torch.float32, device=dev)
         side = torch.cuda.Stream()
 
+    split = None
+    if not args.no_calibrate:
+        split = step.calibrate(rounds=2)        # measured load balance (setup, like the plan build)
     use_graph = not args.no_graph and not do_gather
     if use_graph:
         step.capture()
@@ -400,7 +404,8 @@ def main():
             "unit": "edge_traversals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, g, L, d, world, plan.stats(), use_graph, do_gather),
+            "config": dict(workload_config(args, g, L, d, world, plan.stats(), use_graph, do_gather),
+                           cta_split=split),
             "graph_edges_per_s": edges_all / (ms_per_step * 1e-3),
             "plan_build_ms": plan_ms, "wall_s_timed_region": wall,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

@@ -107,6 +107,13 @@ int sagnn_plan_get_weights(const sagnn_plan* plan, int k, int side, float* w_dev
  * out[4]=max degree, out[5]=sum of edges over both sides, out[6]=grid blocks, out[7]=SMs */
 int sagnn_plan_stats(const sagnn_plan* plan, int64_t* out8);
 
+/* Load balance.  Persistent CTAs are dealt to the 2T segments (seg = 2k + side) from a static cost
+ * model; sagnn_plan_rebalance re-deals them from measured per-segment work (e.g. mean CTA time x
+ * CTAs of a traced launch, see sagnn_debug_trace) -- the device tables are updated in place, so
+ * captured CUDA graphs stay valid.  sagnn_plan_get_split returns the current CTAs per segment. */
+int sagnn_plan_rebalance(sagnn_plan* plan, const double* seg_work /* [2T] */, sagnn_stream_t stream);
+int sagnn_plan_get_split(const sagnn_plan* plan, int* ctas_per_segment /* [2T] */);
+
 /* Diagnostics: when trace_dev != NULL every following layer launch (up to capacity_launches)
  * writes, per persistent CTA, 4 x uint64 {segment, t_start, t_hot_rows_staged, t_end} in ns
  * (%globaltimer) at trace_dev + launch * SMs * 4.  Pass NULL to switch tracing off. */

@@ -32,6 +32,8 @@ SIGNATURES = {
     "sagnn_plan_get_weights": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, vp]),
     "sagnn_plan_stats": (ctypes.c_int, [vp, c_i64p]),
     "sagnn_plan_destroy": (ctypes.c_int, [vp]),
+    "sagnn_plan_rebalance": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_double), vp]),
+    "sagnn_plan_get_split": (ctypes.c_int, [vp, ctypes.POINTER(ctypes.c_int)]),
     "sagnn_debug_trace": (ctypes.c_int, [vp, vp, ctypes.c_int]),
     "sagnn_workspace_bytes": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_szp, c_szp, c_szp]),
     "sagnn_propagate_fwd": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float,

@@ -98,6 +98,8 @@ struct sagnn_plan {
   int64_t* chunk_base = nullptr;  // [n_long + 1] first slice of each long row
   uint32_t* chunk_lr = nullptr;   // [n_chunks] long-row rank of each slice
   std::vector<sagnn_seg> seg_host;
+  std::vector<double> seg_cost;   // per-segment work estimate behind the CTA split
+  std::vector<int> seg_ctas;      // CTAs per segment (all-interval launches)
   int64_t n_tasks = 0, n_short = 0, n_long = 0, n_chunks = 0;
   int32_t max_deg = 0;
 
@@ -122,4 +124,5 @@ struct sagnn_plan {
 
 namespace sagnn {
 void free_host_cache(sagnn_plan* p);
+int apply_cta_split(sagnn_plan* p, const std::vector<double>& cost, cudaStream_t st);
 }

@@ -262,6 +262,44 @@ static int bits_for(int64_t n) {   // number of key bits needed for values in [0
 
 }  // namespace sagnn
 
+namespace sagnn {
+// persistent CTAs (one per SM) dealt to segments so that max(work / CTAs) is smallest; also the
+// per-interval tables (all CTAs on the two segments of one interval)
+int apply_cta_split(sagnn_plan* p, const std::vector<double>& cost, cudaStream_t st) {
+  const int S = 2 * p->T;
+  std::vector<int> n(S, 1);
+  int left = p->num_sms - S;
+  while (left > 0) {   // give the next CTA to the segment with the largest work per CTA
+    int best = 0;
+    for (int t = 1; t < S; ++t)
+      if (cost[t] / n[t] > cost[best] / n[best]) best = t;
+    n[best]++;
+    left--;
+  }
+  std::vector<sagnn_cta> cta(p->num_sms);
+  int c = 0;
+  for (int t = 0; t < S; ++t)
+    for (int r = 0; r < n[t]; ++r) cta[c++] = sagnn_cta{t, r, n[t], 0};
+  if (!p->cta_dev) SAGNN_CUDA(cudaMalloc(&p->cta_dev, sizeof(sagnn_cta) * p->num_sms));
+  SAGNN_CUDA(cudaMemcpyAsync(p->cta_dev, cta.data(), sizeof(sagnn_cta) * p->num_sms, cudaMemcpyHostToDevice, st));
+  std::vector<sagnn_cta> cta_int((size_t)p->T * p->num_sms);
+  for (int k = 0; k < p->T; ++k) {
+    const double cu = cost[2 * k], ci = cost[2 * k + 1];
+    int nu = (int)(p->num_sms * cu / (cu + ci) + 0.5);
+    nu = nu < 1 ? 1 : (nu > p->num_sms - 1 ? p->num_sms - 1 : nu);
+    for (int c2 = 0; c2 < p->num_sms; ++c2)
+      cta_int[(size_t)k * p->num_sms + c2] =
+          c2 < nu ? sagnn_cta{2 * k, c2, nu, 0} : sagnn_cta{2 * k + 1, c2 - nu, p->num_sms - nu, 0};
+  }
+  if (!p->cta_int_dev) SAGNN_CUDA(cudaMalloc(&p->cta_int_dev, sizeof(sagnn_cta) * cta_int.size()));
+  SAGNN_CUDA(cudaMemcpyAsync(p->cta_int_dev, cta_int.data(), sizeof(sagnn_cta) * cta_int.size(),
+                             cudaMemcpyHostToDevice, st));
+  SAGNN_CUDA(cudaStreamSynchronize(st));
+  p->seg_ctas = n;
+  return SAGNN_OK;
+}
+}  // namespace sagnn
+
 using namespace sagnn;
 
 // ---------------------------------------------------------------------------------------
@@ -390,6 +428,20 @@ extern "C" int sagnn_plan_set_interval(sagnn_plan* p, int k, const int32_t* row,
   SAGNN_CUDA(cudaStreamSynchronize(st));
   cudaFree(tmp); cudaFree(keys_out); cudaFree(perm_in); cudaFree(perm);
   p->is_set[k] = 1;
+  return SAGNN_OK;
+}
+
+extern "C" int sagnn_plan_rebalance(sagnn_plan* p, const double* seg_work, sagnn_stream_t stream) {
+  SAGNN_REQUIRE(p && p->finalized && seg_work, SAGNN_INVALID_ARG, "rebalance: NULL or unfinalized plan");
+  std::vector<double> w(seg_work, seg_work + 2 * p->T);
+  for (double x : w) SAGNN_REQUIRE(x > 0, SAGNN_INVALID_ARG, "rebalance: work must be positive");
+  p->seg_cost = w;
+  return apply_cta_split(p, w, (cudaStream_t)stream);
+}
+
+extern "C" int sagnn_plan_get_split(const sagnn_plan* p, int* ctas_per_segment) {
+  SAGNN_REQUIRE(p && p->finalized && ctas_per_segment, SAGNN_INVALID_ARG, "get_split: NULL or unfinalized plan");
+  for (int t = 0; t < 2 * p->T; ++t) ctas_per_segment[t] = p->seg_ctas[t];
   return SAGNN_OK;
 }
 
@@ -565,35 +617,8 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
         cost[t] = 4.0 * (e - h) + 0.9 * h + 30.0 * ((t & 1) ? p->I : p->U);
       }
     }
-    std::vector<int> n(S, 1);
-    int left = p->num_sms - S;
-    while (left > 0) {   // give the next CTA to the segment with the largest cost per CTA
-      int best = 0;
-      for (int t = 1; t < S; ++t)
-        if (cost[t] / n[t] > cost[best] / n[best]) best = t;
-      n[best]++;
-      left--;
-    }
-    std::vector<sagnn_cta> cta(p->num_sms);
-    int c = 0;
-    for (int t = 0; t < S; ++t)
-      for (int r = 0; r < n[t]; ++r) cta[c++] = sagnn_cta{t, r, n[t], 0};
-    SAGNN_CUDA(cudaMalloc(&p->cta_dev, sizeof(sagnn_cta) * p->num_sms));
-    SAGNN_CUDA(cudaMemcpyAsync(p->cta_dev, cta.data(), sizeof(sagnn_cta) * p->num_sms, cudaMemcpyHostToDevice, st));
-    // per-interval tables: all CTAs on the two segments of one interval (pipelined host entry point)
-    std::vector<sagnn_cta> cta_int((size_t)p->T * p->num_sms);
-    for (int k = 0; k < p->T; ++k) {
-      const double cu = cost[2 * k], ci = cost[2 * k + 1];
-      int nu = (int)(p->num_sms * cu / (cu + ci) + 0.5);
-      nu = nu < 1 ? 1 : (nu > p->num_sms - 1 ? p->num_sms - 1 : nu);
-      for (int c2 = 0; c2 < p->num_sms; ++c2)
-        cta_int[(size_t)k * p->num_sms + c2] =
-            c2 < nu ? sagnn_cta{2 * k, c2, nu, 0} : sagnn_cta{2 * k + 1, c2 - nu, p->num_sms - nu, 0};
-    }
-    SAGNN_CUDA(cudaMalloc(&p->cta_int_dev, sizeof(sagnn_cta) * cta_int.size()));
-    SAGNN_CUDA(cudaMemcpyAsync(p->cta_int_dev, cta_int.data(), sizeof(sagnn_cta) * cta_int.size(),
-                               cudaMemcpyHostToDevice, st));
-    SAGNN_CUDA(cudaStreamSynchronize(st));
+    p->seg_cost = cost;
+    if (int rc = sagnn::apply_cta_split(p, cost, st)) return rc;
   }
   SAGNN_CUDA(cudaGetLastError());
   SAGNN_CUDA(cudaStreamSynchronize(st));

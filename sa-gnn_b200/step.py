@@ -62,6 +62,39 @@ class PropagationStep:
         self.forward()
         self.backward()
 
+    def calibrate(self, rounds=2):
+        """Measured load balancing: trace one step per round (per-CTA timestamps from the kernels),
+        take work(segment) = sum over the step's launches of mean CTA busy time x CTAs, and re-deal
+        the persistent CTAs accordingly (``sagnn_plan_rebalance``).  Uses the step's current buffers;
+        results are unaffected (only the CTA -> segment table changes).  Returns the final split."""
+        import ctypes
+        import numpy as np
+        p = self.plan
+        sms = p.stats()["sms"]
+        S = 2 * p.T
+        n_launch = 2 * self.L
+        with torch.cuda.device(p.device):
+            for _ in range(rounds):
+                buf = torch.zeros(n_launch * sms * 4, dtype=torch.int64, device=p.device)
+                _lib.check(self.lib.sagnn_debug_trace(p.handle, ctypes.c_void_p(buf.data_ptr()), n_launch))
+                self.run()
+                torch.cuda.synchronize(p.device)
+                _lib.check(self.lib.sagnn_debug_trace(p.handle, None, 0))
+                t = buf.cpu().numpy().reshape(n_launch, sms, 4)
+                work = np.zeros(S)
+                for l in range(n_launch):
+                    seg, busy = t[l, :, 0], (t[l, :, 3] - t[l, :, 1]).astype(np.float64)
+                    for s in range(S):
+                        m = seg == s
+                        if m.any():
+                            work[s] += busy[m].mean() * m.sum()
+                work = np.maximum(work, 1.0)
+                arr = (ctypes.c_double * S)(*work.tolist())
+                _lib.check(self.lib.sagnn_plan_rebalance(p.handle, arr, _stream_ptr(p.device)))
+            out = (ctypes.c_int * S)()
+            _lib.check(self.lib.sagnn_plan_get_split(p.handle, out))
+        return list(out)
+
     def capture(self):
         """Captures fwd+bwd into a CUDA graph; afterwards ``replay()`` launches the whole step."""
         with torch.cuda.device(self.plan.device):

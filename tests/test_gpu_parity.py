@@ -337,6 +337,8 @@ def test_interval_launches_equal_full_launch_bitwise():
         torch.cuda.synchronize()
         for a, b in zip(ref, (st.user_out, st.item_out, st.d_u, st.d_i)):
             assert torch.equal(a, b)
+        split = st.calibrate(rounds=1)                    # re-dealing the CTAs must not change a bit
+        assert sum(split) == plan.stats()["sms"] and min(split) >= 1
         st.capture()
         for t in (st.user_out, st.item_out, st.d_u, st.d_i):
             t.zero_()
