@@ -134,6 +134,8 @@ SHAPES = {
                         au=0.8, ai=1.0),
     "ml10m":       dict(U=69878, I=10677, T=6, E=10000054, L=3, d=128, au=0.6, ai=1.2),
     "scaled":      dict(U=10_000_000, I=2_000_000, T=8, E=1_000_000_000, L=2, d=64, au=0.8, ai=1.0),
+    # the scaled config with U, I divided by 10 and E by 100 (same density): tables far beyond L2
+    "scaled-s10":  dict(U=1_000_000, I=200_000, T=8, E=10_000_000, L=2, d=64, au=0.8, ai=1.0),
     # small cases for tests / smoke
     "tiny":        dict(U=300, I=200, T=3, E=3000, L=2, d=64, au=0.8, ai=1.0),
     "small":       dict(U=4000, I=3000, T=3, E=60000, L=2, d=64, au=0.8, ai=1.0),
