@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-allgather", action="store_true")
+    ap.add_argument("--exchange", default="allgather", choices=["allgather", "alltoall", "none"],
+                    help="multi-GPU hand-off of the outputs: all-gather (replicated consumer, north_star), "
+                         "all-to-all of row blocks (row-sharded consumer) or none")
     ap.add_argument("--no-calibrate", action="store_true", help="keep the static cost-model CTA split")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
     ap.add_argument("--cpu-steps", type=int, default=3)
@@ -238,7 +241,9 @@ def main():
     step.g_user.normal_(generator=gen)
     step.g_item.normal_(generator=gen)
 
-    do_gather = world > 1 and not args.no_allgather
+    if args.no_allgather:
+        args.exchange = "none"
+    do_gather = world > 1 and args.exchange != "none"
     if do_gather:
         gat_u = torch.empty((world,) + tuple(step.user_out.shape), dtype=torch.float32, device=dev)
         gat_i = torch.empty((world,) + tuple(step.item_out.shape), dtype=torch.float32, device=dev)
@@ -262,8 +267,13 @@ def main():
             step.forward()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                           # overlaps the backward
-                dist.all_gather_into_tensor(gat_u, step.user_out)
-                dist.all_gather_into_tensor(gat_i, step.item_out)
+                if args.exchange == "allgather":
+                    dist.all_gather_into_tensor(gat_u, step.user_out)
+                    dist.all_gather_into_tensor(gat_i, step.item_out)
+                else:
+                    from sagnn_b200.dist import exchange_rows
+                    exchange_rows(step.user_out)
+                    exchange_rows(step.item_out)
             step.backward()
             torch.cuda.current_stream().wait_stream(side)
         else:
@@ -434,7 +444,8 @@ def workload_config(args, g, L, d, world, stats=None, use_graph=None, gather=Non
     if use_graph is not None:
         cfg["cuda_graph"] = bool(use_graph)
     if gather is not None:
-        cfg["allgather_outputs"] = bool(gather)
+        cfg["allgather_outputs"] = bool(gather) and args.exchange == "allgather"
+        cfg["exchange"] = args.exchange if world > 1 else "none"
     return cfg
 
 

@@ -69,6 +69,30 @@ def gather_intervals(local, owners, rank=None, group=None):
     return _GatherIntervals.apply(local, owners, rank, group)
 
 
+def row_blocks(n_rows, world):
+    """Equal row blocks (the last one may be short): block b = rows [b*size, min((b+1)*size, n_rows))."""
+    size = (n_rows + world - 1) // world
+    return size, [(min(b * size, n_rows), min((b + 1) * size, n_rows)) for b in range(world)]
+
+
+def exchange_rows(local, group=None):
+    """Hand-off to a ROW-sharded consumer: instead of gathering every interval
+    everywhere, rank j receives only its block of rows of every rank's intervals.
+
+    local [T_local, R, d] (the same T_local on every rank) -> [world*T_local, block, d]: the
+    caller's row block of all intervals, in rank order.  One all-to-all of 1/world the all-gather
+    volume.  Rows are padded to a multiple of world (pad rows are zero)."""
+    world = dist.get_world_size(group)
+    T, R, d = local.shape
+    size, _ = row_blocks(R, world)
+    if size * world != R:
+        local = torch.cat([local, local.new_zeros((T, size * world - R, d))], dim=1)
+    send = local.view(T, world, size, d).permute(1, 0, 2, 3).contiguous()      # [dst, T, block, d]
+    recv = torch.empty_like(send)                                               # [src, T, block, d]
+    dist.all_to_all_single(recv.view(world, -1), send.view(world, -1), group=group)
+    return recv.view(world * T, size, d)
+
+
 class ShardedPropagation:
     """Interval-sharded drop-in for ``propagate``: every rank passes the FULL parameter tables
     (or just its own slices via ``local_only``) and gets the full ``[T,U,d]`` / ``[T,I,d]`` back."""

@@ -71,6 +71,45 @@ def _worker(rank, world, port, T, out_q):
         dist.destroy_process_group()
 
 
+def _a2a_worker(rank, world, port, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        T, R, d = 2, 7, 3                                   # R not divisible by world: padding path
+        full = torch.arange(world * T * R * d, dtype=torch.float32).view(world, T, R, d)
+        try:
+            got = sd.exchange_rows(full[rank].clone())
+        except Exception as e:                              # gloo builds without all_to_all
+            out_q.put((rank, "skip", str(e)))
+            return
+        size, blocks = sd.row_blocks(R, world)
+        lo, hi = blocks[rank]
+        want = torch.zeros(world * T, size, d)
+        want[:, :hi - lo] = full[:, :, lo:hi].reshape(world * T, hi - lo, d)
+        out_q.put((rank, "ok" if torch.equal(got, want) else "mismatch", ""))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_block_exchange_gloo_world2():
+    """The all-to-all hand-off to a row-sharded consumer delivers, on every rank, its row block of
+    every rank's intervals (rank order), with zero padding."""
+    assert sd.row_blocks(7, 2) == (4, [(0, 4), (4, 7)])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_a2a_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    if any(r[1] == "skip" for r in res):
+        pytest.skip("gloo without all_to_all: " + res[0][2])
+    assert all(r[1] == "ok" for r in res), res
+
+
 @pytest.mark.parametrize("T", [3, 5, 1])
 def test_interval_sharding_gloo_world2(T):
     """1-vs-2 rank equality of outputs and gradients is bitwise (interval sharding)."""
