@@ -1,6 +1,15 @@
-# usage: bash scripts/gpu_multi.sh N   -- N-GPU torchrun bench (with and without the output all-gather)
+# usage: bash scripts/gpu_multi.sh N   -- N-GPU torchrun bench: all-gather (default), all-to-all, compute only
 N=${1:-2}
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
-tail -c 1500 gpurun_out/bench_n$N.json; tail -c 400 gpurun_out/bench_n$N.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 20 --warmup 5 --no-allgather --no-e2e > gpurun_out/bench_n${N}_nogather.json 2> gpurun_out/bench_n${N}_nogather.err
-tail -c 700 gpurun_out/bench_n${N}_nogather.json
+P=29517
+for X in allgather alltoall none; do
+  P=$((P+1))
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N --steps 20 --warmup 5 --exchange $X --no-e2e > gpurun_out/bench_n${N}_$X.json 2> gpurun_out/bench_n${N}_$X.err
+  python - <<PY
+import json
+try:
+    j=json.loads(open("gpurun_out/bench_n${N}_$X.json").read().strip().splitlines()[-1])
+    print("N=$N exchange=$X value %.3e ms/step %.4f"%(j["value"], j["ms_per_step"]))
+except Exception as e:
+    print("N=$N $X FAILED", e); print(open("gpurun_out/bench_n${N}_$X.err").read()[-600:])
+PY
+done
