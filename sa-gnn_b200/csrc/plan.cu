@@ -250,6 +250,15 @@ struct CastI64 {
   __host__ __device__ int64_t operator()(int32_t v) const { return (int64_t)v; }
 };
 
+// scratch device buffer released on every exit path (error returns included)
+template <typename T>
+struct DevTmp {
+  T* p = nullptr;
+  ~DevTmp() { cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * (n ? n : 1)); }
+  operator T*() const { return p; }
+};
+
 static inline unsigned blocks_for(int64_t n, int threads = 256) {
   return (unsigned)((n + threads - 1) / threads);
 }
@@ -384,14 +393,13 @@ extern "C" int sagnn_plan_set_interval(sagnn_plan* p, int k, const int32_t* row,
   p->has_custom_w = w != nullptr;
 
   const int U = p->U, I = p->I;
-  int* flags = nullptr;
-  SAGNN_CUDA(cudaMalloc(&flags, sizeof(int)));
+  DevTmp<int> flags;
+  SAGNN_CUDA(flags.alloc(1));
   SAGNN_CUDA(cudaMemsetAsync(flags, 0, sizeof(int), st));
   check_coo_kernel<<<blocks_for(nnz), 256, 0, st>>>(row, col, nnz, U, I, flags);
   int hflags = 0;
   SAGNN_CUDA(cudaMemcpyAsync(&hflags, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
   SAGNN_CUDA(cudaStreamSynchronize(st));
-  cudaFree(flags);
   SAGNN_REQUIRE(!(hflags & 2), SAGNN_OUT_OF_RANGE,
                 "set_interval: interval %d has an edge outside [0,%d) x [0,%d)", k, U, I);
   SAGNN_REQUIRE(!(hflags & 1), SAGNN_UNSORTED_INPUT,
@@ -410,23 +418,22 @@ extern "C" int sagnn_plan_set_interval(sagnn_plan* p, int k, const int32_t* row,
 
   // A_k^T CSR: stable sort of the edges by item id; edges arrive ordered by user id, so
   // every item row lists its users ascending (== csr_matrix(coo.transpose()), DataHandler.py:9-11)
-  int32_t *keys_out = nullptr, *perm_in = nullptr, *perm = nullptr;
-  void* tmp = nullptr;
+  DevTmp<int32_t> keys_out, perm_in, perm;
+  DevTmp<char> tmp;
   size_t tmp_bytes = 0;
-  SAGNN_CUDA(cudaMalloc(&keys_out, sizeof(int32_t) * nnz));
-  SAGNN_CUDA(cudaMalloc(&perm_in, sizeof(int32_t) * nnz));
-  SAGNN_CUDA(cudaMalloc(&perm, sizeof(int32_t) * nnz));
+  SAGNN_CUDA(keys_out.alloc(nnz));
+  SAGNN_CUDA(perm_in.alloc(nnz));
+  SAGNN_CUDA(perm.alloc(nnz));
   iota_kernel<<<blocks_for(nnz), 256, 0, st>>>(perm_in, nnz);
   int end_bit = bits_for(I);
-  SAGNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, col, keys_out, perm_in, perm, nnz, 0, end_bit, st));
-  SAGNN_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
-  SAGNN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, col, keys_out, perm_in, perm, nnz, 0, end_bit, st));
+  SAGNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, col, keys_out.p, perm_in.p, perm.p, nnz, 0, end_bit, st));
+  SAGNN_CUDA(tmp.alloc(tmp_bytes));
+  SAGNN_CUDA(cub::DeviceRadixSort::SortPairs((void*)tmp.p, tmp_bytes, col, keys_out.p, perm_in.p, perm.p, nnz, 0, end_bit, st));
   gather_kernel<int32_t><<<blocks_for(nnz), 256, 0, st>>>(row, perm, nnz, idx_i);
   if (val) gather_kernel<int32_t><<<blocks_for(nnz), 256, 0, st>>>(val, perm, nnz, p->val + p->base[k] + nnz);
   if (w) gather_kernel<float><<<blocks_for(nnz), 256, 0, st>>>(w, perm, nnz, p->w + p->base[k] + nnz);
   SAGNN_CUDA(cudaGetLastError());
   SAGNN_CUDA(cudaStreamSynchronize(st));
-  cudaFree(tmp); cudaFree(keys_out); cudaFree(perm_in); cudaFree(perm);
   p->is_set[k] = 1;
   return SAGNN_OK;
 }
@@ -467,14 +474,13 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   // row pointers: one exclusive scan over the degrees in global row order
   {
     auto in = thrust::make_transform_iterator((const int32_t*)p->deg, CastI64());
-    void* tmp = nullptr; size_t tb = 0;
+    DevTmp<char> tmp; size_t tb = 0;
     SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, p->rowptr, R, st));
-    SAGNN_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
-    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, in, p->rowptr, R, st));
+    SAGNN_CUDA(tmp.alloc(tb));
+    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum((void*)tmp.p, tb, in, p->rowptr, R, st));
     int64_t total = 2 * p->e_total;
     SAGNN_CUDA(cudaMemcpyAsync(p->rowptr + R, &total, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     SAGNN_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp);
   }
 
   if (p->has_val) {
@@ -504,58 +510,56 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
                 "finalize: %lld edge entries exceed 2^32", (long long)(2 * p->e_total));
   const int64_t N = p->N;
   const int U = p->U;
-  uint64_t *key_in = nullptr, *key_out = nullptr;
-  uint32_t *row_in = nullptr, *srow = nullptr;
-  int32_t *slot_of = nullptr, *nhot_row = nullptr;
-  int64_t *cnt3 = nullptr, *off3 = nullptr;   // [3][R+1]: tasks, slices, long rows per sorted position
-  SAGNN_CUDA(cudaMalloc(&key_in, sizeof(uint64_t) * R));
-  SAGNN_CUDA(cudaMalloc(&key_out, sizeof(uint64_t) * R));
-  SAGNN_CUDA(cudaMalloc(&row_in, sizeof(uint32_t) * R));
-  SAGNN_CUDA(cudaMalloc(&srow, sizeof(uint32_t) * R));
-  SAGNN_CUDA(cudaMalloc(&slot_of, sizeof(int32_t) * R));
-  SAGNN_CUDA(cudaMalloc(&nhot_row, sizeof(int32_t) * R));
-  SAGNN_CUDA(cudaMalloc(&cnt3, sizeof(int64_t) * 3 * (R + 1)));
-  SAGNN_CUDA(cudaMalloc(&off3, sizeof(int64_t) * 3 * (R + 1)));
+  DevTmp<uint64_t> key_in, key_out;
+  DevTmp<uint32_t> row_in, srow;
+  DevTmp<int32_t> slot_of, nhot_row;
+  DevTmp<int64_t> cnt3, off3;   // [3][R+1]: tasks, slices, long rows per sorted position
+  SAGNN_CUDA(key_in.alloc(R));
+  SAGNN_CUDA(key_out.alloc(R));
+  SAGNN_CUDA(row_in.alloc(R));
+  SAGNN_CUDA(srow.alloc(R));
+  SAGNN_CUDA(slot_of.alloc(R));
+  SAGNN_CUDA(nhot_row.alloc(R));
+  SAGNN_CUDA(cnt3.alloc(3 * (R + 1)));
+  SAGNN_CUDA(off3.alloc(3 * (R + 1)));
   SAGNN_CUDA(cudaMalloc(&p->hot_ids, sizeof(int32_t) * 2 * p->T * kHotRows));
   SAGNN_CUDA(cudaMemsetAsync(p->hot_ids, 0, sizeof(int32_t) * 2 * p->T * kHotRows, st));
   sched_key_kernel<<<blocks_for(R), 256, 0, st>>>(p->deg, R, N, U, key_in, row_in);
   {
-    void* tmp = nullptr; size_t tb = 0;
+    DevTmp<char> tmp; size_t tb = 0;
     const int end_bit = 32 + bits_for(2 * p->T);
-    SAGNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key_in, key_out, row_in, srow, R, 0, end_bit, st));
-    SAGNN_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
-    SAGNN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, key_in, key_out, row_in, srow, R, 0, end_bit, st));
+    SAGNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key_in.p, key_out.p, row_in.p, srow.p, R, 0, end_bit, st));
+    SAGNN_CUDA(tmp.alloc(tb));
+    SAGNN_CUDA(cub::DeviceRadixSort::SortPairs((void*)tmp.p, tb, key_in.p, key_out.p, row_in.p, srow.p, R, 0, end_bit, st));
     SAGNN_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp);
   }
-  int64_t *n_task = cnt3, *n_chunk = cnt3 + (R + 1), *n_long = cnt3 + 2 * (R + 1);
-  int64_t *task_off = off3, *chunk_off = off3 + (R + 1), *long_off = off3 + 2 * (R + 1);
+  int64_t *n_task = cnt3.p, *n_chunk = cnt3.p + (R + 1), *n_long = cnt3.p + 2 * (R + 1);
+  int64_t *task_off = off3.p, *chunk_off = off3.p + (R + 1), *long_off = off3.p + 2 * (R + 1);
   sched_slot_kernel<<<blocks_for(R + 1), 256, 0, st>>>(srow, p->deg, R, N, U, p->hot_rows, slot_of, p->hot_ids, n_task,
                                                        n_chunk, n_long);
   {
-    void* tmp = nullptr; size_t tb = 0;
+    DevTmp<char> tmp; size_t tb = 0;
     SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, n_task, task_off, R + 1, st));
-    SAGNN_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
-    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, n_task, task_off, R + 1, st));
-    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, n_chunk, chunk_off, R + 1, st));
-    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, n_long, long_off, R + 1, st));
+    SAGNN_CUDA(tmp.alloc(tb));
+    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum((void*)tmp.p, tb, n_task, task_off, R + 1, st));
+    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum((void*)tmp.p, tb, n_chunk, chunk_off, R + 1, st));
+    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum((void*)tmp.p, tb, n_long, long_off, R + 1, st));
     SAGNN_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp);
   }
   SAGNN_CUDA(cudaMemcpy(&p->n_tasks, task_off + R, sizeof(int64_t), cudaMemcpyDeviceToHost));
   SAGNN_CUDA(cudaMemcpy(&p->n_chunks, chunk_off + R, sizeof(int64_t), cudaMemcpyDeviceToHost));
   SAGNN_CUDA(cudaMemcpy(&p->n_long, long_off + R, sizeof(int64_t), cudaMemcpyDeviceToHost));
   p->n_short = R - p->n_long;
   {
-    void* tmp = nullptr; size_t tb = 0;
-    int32_t* dmax = nullptr;
-    SAGNN_CUDA(cudaMalloc(&dmax, sizeof(int32_t)));
-    SAGNN_CUDA(cub::DeviceReduce::Max(nullptr, tb, p->deg, dmax, R, st));
-    SAGNN_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
-    SAGNN_CUDA(cub::DeviceReduce::Max(tmp, tb, p->deg, dmax, R, st));
+    DevTmp<char> tmp; size_t tb = 0;
+    DevTmp<int32_t> dmax;
+    SAGNN_CUDA(dmax.alloc(1));
+    SAGNN_CUDA(cub::DeviceReduce::Max(nullptr, tb, p->deg, dmax.p, R, st));
+    SAGNN_CUDA(tmp.alloc(tb));
+    SAGNN_CUDA(cub::DeviceReduce::Max((void*)tmp.p, tb, p->deg, dmax.p, R, st));
     SAGNN_CUDA(cudaMemcpyAsync(&p->max_deg, dmax, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SAGNN_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp); cudaFree(dmax);
+    
   }
 
   SAGNN_CUDA(cudaMalloc(&p->enc, sizeof(int32_t) * 2 * p->e_total));
@@ -597,21 +601,20 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   {
     std::vector<double> cost(S);
     {
-      int64_t* hsum = nullptr;
-      void* tmp = nullptr; size_t tb = 0;
-      SAGNN_CUDA(cudaMalloc(&hsum, sizeof(int64_t) * S));
+      DevTmp<int64_t> hsum;
+      DevTmp<char> tmp; size_t tb = 0;
+      SAGNN_CUDA(hsum.alloc(S));
       auto in = thrust::make_transform_iterator((const int32_t*)nhot_row, CastI64());
-      SAGNN_CUDA(cub::DeviceReduce::Sum(nullptr, tb, in, hsum, R, st));
-      SAGNN_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
+      SAGNN_CUDA(cub::DeviceReduce::Sum(nullptr, tb, in, hsum.p, R, st));
+      SAGNN_CUDA(tmp.alloc(tb));
       for (int t = 0; t < S; ++t) {
         const int64_t row0 = (int64_t)(t >> 1) * N + ((t & 1) ? U : 0);
         const int64_t rows = (t & 1) ? p->I : p->U;
-        SAGNN_CUDA(cub::DeviceReduce::Sum(tmp, tb, in + row0, hsum + t, rows, st));
+        SAGNN_CUDA(cub::DeviceReduce::Sum((void*)tmp.p, tb, in + row0, hsum.p + t, rows, st));
       }
       std::vector<int64_t> hot(S);
       SAGNN_CUDA(cudaMemcpyAsync(hot.data(), hsum, sizeof(int64_t) * S, cudaMemcpyDeviceToHost, st));
       SAGNN_CUDA(cudaStreamSynchronize(st));
-      cudaFree(tmp); cudaFree(hsum);
       for (int t = 0; t < S; ++t) {
         const double e = (double)p->nnz[t >> 1], h = (double)hot[t];
         cost[t] = 4.0 * (e - h) + 0.9 * h + 30.0 * ((t & 1) ? p->I : p->U);
@@ -622,8 +625,6 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   }
   SAGNN_CUDA(cudaGetLastError());
   SAGNN_CUDA(cudaStreamSynchronize(st));
-  cudaFree(key_in); cudaFree(key_out); cudaFree(row_in); cudaFree(srow); cudaFree(slot_of);
-  cudaFree(nhot_row); cudaFree(cnt3); cudaFree(off3);
   p->finalized = true;
   return SAGNN_OK;
 }

@@ -12,6 +12,7 @@
 // the group that finishes a row last (integer ticket) reduces them in fixed chunk
 // order, so results do not depend on scheduling.  Tasks are ordered longest-first and
 // dealt round-robin over a grid sized to the SM count x occupancy.
+#include <atomic>
 #include <cstdio>
 
 #include "common.cuh"
@@ -724,11 +725,12 @@ static int launch_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaStream
     prm.trace = plan->trace_dev + (size_t)(plan->trace_launch++) * plan->num_sms * 4;
   using G = Geo<LPR, V, MODE, WEIGHTED>;
   static_assert(G::SMEM <= 227 * 1024 - 4096, "shared-memory budget exceeded");
-  static bool configured = false;
+  static std::atomic<uint64_t> configured{0};   // bit per device: the attribute is per device
   auto kern = spmm_layer_kernel<LPR, V, MODE, WEIGHTED>;
-  if (!configured) {
+  const uint64_t bit = 1ull << (plan->device & 63);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {
     SAGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-    configured = true;
+    configured.fetch_or(bit, std::memory_order_release);
   }
   if (plan->n_tasks == 0) return SAGNN_OK;
   kern<<<plan->num_sms, kThreads, G::SMEM, st>>>(prm);
