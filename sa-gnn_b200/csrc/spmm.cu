@@ -471,7 +471,11 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
       PHASE(0);
 
       // ---- gather-reduce over this task's edges (lock step over the warp) -------------------
+#if defined(SAGNN_NOHOT)
+      const int nh = 0;                                   // experiment: every edge is gathered from global memory
+#else
       const int nh = (int)((cur.meta >> 8) & 0x7fu);
+#endif
       int nmax = n;
 #pragma unroll
       for (int o = LPR; o < 32; o <<= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
