@@ -93,7 +93,8 @@ struct sagnn_plan {
   int32_t* hot_ids = nullptr;     // [2T, kHotRows] row ids (inside table t) of table t's hot slots
   sagnn_task* tasks = nullptr;    // [n_tasks] grouped by segment
   sagnn_seg* seg_dev = nullptr;   // [2T]
-  sagnn_cta* cta_dev = nullptr;   // [num_sms] all intervals in one launch
+  sagnn_cta* cta_dev = nullptr;   // [n_waves][num_sms] all intervals: one launch per wave (normally one wave)
+  int n_waves = 1;
   sagnn_cta* cta_int_dev = nullptr;  // [T][num_sms] one interval per launch
   int64_t* chunk_base = nullptr;  // [n_long + 1] first slice of each long row
   uint32_t* chunk_lr = nullptr;   // [n_chunks] long-row rank of each slice

@@ -274,37 +274,44 @@ static int bits_for(int64_t n) {   // number of key bits needed for values in [0
 namespace sagnn {
 // persistent CTAs (one per SM) dealt to segments so that max(work / CTAs) is smallest; also the
 // per-interval tables (all CTAs on the two segments of one interval)
-int apply_cta_split(sagnn_plan* p, const std::vector<double>& cost, cudaStream_t st) {
-  const int S = 2 * p->T;
+// deal `n_cta` persistent CTAs to the segments [seg_lo, seg_hi) so that max(work / CTAs) is smallest
+static void deal_ctas(const std::vector<double>& cost, int seg_lo, int seg_hi, int n_cta, sagnn_cta* out,
+                      std::vector<int>* counts) {
+  const int S = seg_hi - seg_lo;
   std::vector<int> n(S, 1);
-  int left = p->num_sms - S;
-  while (left > 0) {   // give the next CTA to the segment with the largest work per CTA
+  for (int left = n_cta - S; left > 0; --left) {   // next CTA -> segment with the largest work per CTA
     int best = 0;
     for (int t = 1; t < S; ++t)
-      if (cost[t] / n[t] > cost[best] / n[best]) best = t;
+      if (cost[seg_lo + t] / n[t] > cost[seg_lo + best] / n[best]) best = t;
     n[best]++;
-    left--;
   }
-  std::vector<sagnn_cta> cta(p->num_sms);
   int c = 0;
   for (int t = 0; t < S; ++t)
-    for (int r = 0; r < n[t]; ++r) cta[c++] = sagnn_cta{t, r, n[t], 0};
-  if (!p->cta_dev) SAGNN_CUDA(cudaMalloc(&p->cta_dev, sizeof(sagnn_cta) * p->num_sms));
-  SAGNN_CUDA(cudaMemcpyAsync(p->cta_dev, cta.data(), sizeof(sagnn_cta) * p->num_sms, cudaMemcpyHostToDevice, st));
-  std::vector<sagnn_cta> cta_int((size_t)p->T * p->num_sms);
-  for (int k = 0; k < p->T; ++k) {
-    const double cu = cost[2 * k], ci = cost[2 * k + 1];
-    int nu = (int)(p->num_sms * cu / (cu + ci) + 0.5);
-    nu = nu < 1 ? 1 : (nu > p->num_sms - 1 ? p->num_sms - 1 : nu);
-    for (int c2 = 0; c2 < p->num_sms; ++c2)
-      cta_int[(size_t)k * p->num_sms + c2] =
-          c2 < nu ? sagnn_cta{2 * k, c2, nu, 0} : sagnn_cta{2 * k + 1, c2 - nu, p->num_sms - nu, 0};
+    for (int r = 0; r < n[t]; ++r) out[c++] = sagnn_cta{seg_lo + t, r, n[t], 0};
+  if (counts)
+    for (int t = 0; t < S; ++t) (*counts)[seg_lo + t] = n[t];
+}
+
+// CTA -> segment tables: one per wave (a wave = as many whole intervals as fit one CTA per segment;
+// usually a single wave with all T intervals) and one per interval (pipelined host entry point)
+int apply_cta_split(sagnn_plan* p, const std::vector<double>& cost, cudaStream_t st) {
+  const int sms = p->num_sms;
+  const int per_wave = sms / 2 < 1 ? 1 : sms / 2;          // intervals per wave
+  p->n_waves = (p->T + per_wave - 1) / per_wave;
+  p->seg_ctas.assign(2 * p->T, 0);
+  std::vector<sagnn_cta> cta((size_t)p->n_waves * sms);
+  for (int w = 0; w < p->n_waves; ++w) {
+    const int k_lo = w * per_wave, k_hi = (w + 1) * per_wave < p->T ? (w + 1) * per_wave : p->T;
+    deal_ctas(cost, 2 * k_lo, 2 * k_hi, sms, cta.data() + (size_t)w * sms, &p->seg_ctas);
   }
+  if (!p->cta_dev) SAGNN_CUDA(cudaMalloc(&p->cta_dev, sizeof(sagnn_cta) * cta.size()));
+  SAGNN_CUDA(cudaMemcpyAsync(p->cta_dev, cta.data(), sizeof(sagnn_cta) * cta.size(), cudaMemcpyHostToDevice, st));
+  std::vector<sagnn_cta> cta_int((size_t)p->T * sms);
+  for (int k = 0; k < p->T; ++k) deal_ctas(cost, 2 * k, 2 * k + 2, sms, cta_int.data() + (size_t)k * sms, nullptr);
   if (!p->cta_int_dev) SAGNN_CUDA(cudaMalloc(&p->cta_int_dev, sizeof(sagnn_cta) * cta_int.size()));
   SAGNN_CUDA(cudaMemcpyAsync(p->cta_int_dev, cta_int.data(), sizeof(sagnn_cta) * cta_int.size(),
                              cudaMemcpyHostToDevice, st));
   SAGNN_CUDA(cudaStreamSynchronize(st));
-  p->seg_ctas = n;
   return SAGNN_OK;
 }
 }  // namespace sagnn
@@ -504,8 +511,7 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   }
 
   // ---- schedule: per-segment task lists, hot slots, hot-first edge codes ------------------
-  SAGNN_REQUIRE(2 * p->T <= p->num_sms, SAGNN_INVALID_ARG,
-                "finalize: %d segments exceed the %d SMs of the device", 2 * p->T, p->num_sms);
+  SAGNN_REQUIRE(p->num_sms >= 2, SAGNN_INVALID_ARG, "finalize: need at least 2 SMs");
   SAGNN_REQUIRE(2 * p->e_total < ((int64_t)1 << 32), SAGNN_INVALID_ARG,
                 "finalize: %lld edge entries exceed 2^32", (long long)(2 * p->e_total));
   const int64_t N = p->N;

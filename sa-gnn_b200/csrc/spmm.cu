@@ -894,7 +894,10 @@ static int fwd_impl(const sagnn_plan* p, int interval, const float* uE, const fl
     s.out_add_next = last ? 1 : 0;
     s.mask_u = masks ? (uint8_t*)masks + (size_t)l * mlw : nullptr;
     s.mask_i = masks ? (uint8_t*)masks + (size_t)l * mlw + mu : nullptr;
-    if (int rc = launch(p, s, d, MODE_FWD, st)) return rc;
+    for (int wv = 0; wv < (interval >= 0 ? 1 : p->n_waves); ++wv) {   // one launch unless 2T exceeds the SM count
+      if (interval < 0) s.cta = p->cta_dev + (size_t)wv * p->num_sms;
+      if (int rc = launch(p, s, d, MODE_FWD, st)) return rc;
+    }
   }
   return SAGNN_OK;
 }
@@ -945,7 +948,10 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
     s.b_i = step == 0 ? nullptr : g_i;
     s.o1_u = l == 0 ? dU : buf[step & 1];
     s.o1_i = l == 0 ? dI : buf[step & 1] + w.user_floats;
-    if (int rc = launch(p, s, d, MODE_BWD, st)) return rc;
+    for (int wv = 0; wv < (interval >= 0 ? 1 : p->n_waves); ++wv) {
+      if (interval < 0) s.cta = p->cta_dev + (size_t)wv * p->num_sms;
+      if (int rc = launch(p, s, d, MODE_BWD, st)) return rc;
+    }
   }
   return SAGNN_OK;
 }

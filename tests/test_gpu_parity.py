@@ -228,6 +228,12 @@ def test_propagate_empty_interval_and_empty_rows():
     check_against_oracle(mats, 64, 2, seed=1)
 
 
+def test_more_intervals_than_half_the_sms():
+    """T = 80 intervals (160 segments > 148 SMs): the layer runs in waves of whole intervals."""
+    mats = random_interval_mats(80, 40, 30, 90, seed=80)
+    check_against_oracle(mats, 64, 2, seed=8)
+
+
 def test_propagate_tie_rule_zero_inputs():
     """Zero embeddings make every pre-activation exactly 0: sigma'(0) must be `leaky`."""
     mats = random_interval_mats(1, 20, 20, 60, seed=2)
