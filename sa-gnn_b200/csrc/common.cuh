@@ -126,4 +126,5 @@ struct sagnn_plan {
 namespace sagnn {
 void free_host_cache(sagnn_plan* p);
 int apply_cta_split(sagnn_plan* p, const std::vector<double>& cost, cudaStream_t st);
+bool use_rpw();   // row-per-warp kernel selected (default; SAGNN_KERNEL=v7 selects the half-warp kernel)
 }

@@ -511,6 +511,7 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   }
 
   // ---- schedule: per-segment task lists, hot slots, hot-first edge codes ------------------
+  if (sagnn::use_rpw()) p->hot_rows = 0;   // the row-per-warp kernel stages no hot rows: every code is a source-row id
   SAGNN_REQUIRE(p->num_sms >= 2, SAGNN_INVALID_ARG, "finalize: need at least 2 SMs");
   SAGNN_REQUIRE(2 * p->e_total < ((int64_t)1 << 32), SAGNN_INVALID_ARG,
                 "finalize: %lld edge entries exceed 2^32", (long long)(2 * p->e_total));

@@ -14,6 +14,7 @@
 // dealt round-robin over a grid sized to the SM count x occupancy.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -75,6 +76,14 @@ struct SpmmParams {
   unsigned* ctrs;            // [2T] per-segment task-queue heads, zero on entry
   float leaky;
   int out_add_next;          // FWD: o2 = b + a (+ E^{l+1} when set)
+  int T;                     // number of intervals (row stride of the [R,T,d] layout)
+  // layout flags (row-per-warp kernel only): 0 = [T,R,d] (default), 1 = [R,T,d], the transposed
+  // hand-off of model.py:133-134
+  int a_rtd, b_rtd, o2_rtd, src_rtd;
+  // row-per-warp backward: sign masks one level down (of the rows being written); the pre-masked
+  // copy sigma'(Z^{l-1}) (.) n goes to o2 and is the gather source of the next level
+  const uint8_t* pmask_u;
+  const uint8_t* pmask_i;
   unsigned long long* trace; // diagnostics: per CTA {seg, t_start, t_staged, t_end} (ns) or NULL
 };
 
@@ -245,6 +254,7 @@ struct SegPtrs {               // segment-uniform table pointers, written once p
   float* o1;
   float* o2;
   uint8_t* mk;
+  uint32_t a_stride, b_stride, o2_stride, pad;   // bytes between consecutive rows of a / b / o2
 };
 
 // compile-time geometry shared by the kernel and its launcher
@@ -719,9 +729,65 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
   }
 }
 
+}  // namespace sagnn
+#include "spmm_rpw.cuh"
+namespace sagnn {
+
 // ---------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------
+// SAGNN_KERNEL=v7 selects the half-warp lock-step kernel (kept for A/B runs); default: row per warp
+bool use_rpw() {
+  static const bool v = [] {
+    const char* e = getenv("SAGNN_KERNEL");
+    return !(e && (e[0] == 'v' || e[0] == 'V') && e[1] == '7');
+  }();
+  return v;
+}
+
+template <int VPL, int MODE, bool WEIGHTED, bool MASKED>
+static int launch_rpw_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaStream_t st) {
+  SpmmParams prm = prm_in;
+  if (plan->trace_dev && plan->trace_launch < plan->trace_capacity)   // diagnostics only
+    prm.trace = plan->trace_dev + (size_t)(plan->trace_launch++) * plan->num_sms * 4;
+  using G = RowGeo<VPL, MASKED>;
+  static_assert(G::SMEM <= 227 * 1024, "shared-memory budget exceeded");
+  static std::atomic<uint64_t> configured{0};   // bit per device: the attribute is per device
+  auto kern = spmm_rpw_kernel<VPL, MODE, WEIGHTED, MASKED>;
+  const uint64_t bit = 1ull << (plan->device & 63);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {
+    SAGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+    configured.fetch_or(bit, std::memory_order_release);
+  }
+  if (plan->n_tasks == 0) return SAGNN_OK;
+  kern<<<plan->num_sms, kRpwThreads, G::SMEM, st>>>(prm);
+  SAGNN_CUDA(cudaGetLastError());
+  return SAGNN_OK;
+}
+
+template <int VPL, int MODE>
+static int launch_rpw_v(const sagnn_plan* plan, const SpmmParams& prm, cudaStream_t st) {
+  const bool wt = prm.w != nullptr;
+  if constexpr (MODE == MODE_BWD) {
+    if (prm.smask_u)   // raw upstream as the source: sign masks per edge
+      return wt ? launch_rpw_t<VPL, MODE, true, true>(plan, prm, st) : launch_rpw_t<VPL, MODE, false, true>(plan, prm, st);
+  }
+  return wt ? launch_rpw_t<VPL, MODE, true, false>(plan, prm, st) : launch_rpw_t<VPL, MODE, false, false>(plan, prm, st);
+}
+
+template <int MODE>
+static int launch_rpw_mode(const sagnn_plan* plan, const SpmmParams& prm, int d, cudaStream_t st) {
+  SAGNN_REQUIRE(plan->hot_rows == 0, SAGNN_INVALID_ARG, "the row-per-warp kernel needs a plan without hot slots");
+  switch (d) {
+    case 32:  return launch_rpw_v<1, MODE>(plan, prm, st);
+    case 64:  return launch_rpw_v<2, MODE>(plan, prm, st);
+    case 128: return launch_rpw_v<4, MODE>(plan, prm, st);
+    case 256: return launch_rpw_v<8, MODE>(plan, prm, st);
+  }
+  set_error("latdim d=%d unsupported (need 32, 64, 128 or 256)", d);
+  return SAGNN_INVALID_ARG;
+}
+
 template <int LPR, int V, int MODE, bool WEIGHTED>
 static int launch_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaStream_t st) {
   SpmmParams prm = prm_in;
@@ -760,6 +826,15 @@ static int launch_mode(const sagnn_plan* plan, const SpmmParams& prm, int d, cud
 }
 
 static int launch(const sagnn_plan* plan, const SpmmParams& prm, int d, int mode, cudaStream_t st) {
+  if (use_rpw()) {
+    switch (mode) {
+      case MODE_FWD: return launch_rpw_mode<MODE_FWD>(plan, prm, d, st);
+      case MODE_BWD: return launch_rpw_mode<MODE_BWD>(plan, prm, d, st);
+      default:       return launch_rpw_mode<MODE_MSG>(plan, prm, d, st);
+    }
+  }
+  SAGNN_REQUIRE(!(prm.a_rtd | prm.b_rtd | prm.o2_rtd | prm.src_rtd), SAGNN_INVALID_ARG,
+                "the v7 kernel has no [R,T,d] layouts");
   switch (mode) {
     case MODE_FWD: return launch_mode<MODE_FWD>(plan, prm, d, st);
     case MODE_BWD: return launch_mode<MODE_BWD>(plan, prm, d, st);
@@ -771,7 +846,7 @@ static bool d_ok(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
 
 // workspace layout: [tickets | partials | table buffer 0 | table buffer 1]
 struct WsLayout {
-  size_t tickets_off, partials_off, buf_off[2], total;
+  size_t tickets_off, partials_off, buf_off[2], pm_off[2], total;
   size_t ticket_words;   // slice-reduction tickets of all tree levels
   size_t zero_bytes;     // tickets + one set of per-segment queue heads per layer launch, zeroed per call
   size_t table_floats;   // T*(U+I)*d
@@ -796,6 +871,10 @@ static WsLayout ws_layout(const sagnn_plan* p, int n_layers, int d) {
     w.buf_off[b] = off;
     if (b < nbuf) off = align_up(off + sizeof(float) * w.table_floats, 256);
   }
+  for (int b = 0; b < 2; ++b) {   // row-per-warp backward: pre-masked copies of the running gradient
+    w.pm_off[b] = off;
+    if (b < nbuf && use_rpw()) off = align_up(off + sizeof(float) * w.table_floats, 256);
+  }
   w.total = off;
   return w;
 }
@@ -808,6 +887,7 @@ static void base_params(const sagnn_plan* p, SpmmParams& s) {
   s.chunk_base = p->chunk_base; s.chunk_lr = p->chunk_lr;
   s.hot_ids = p->hot_ids; s.seg = p->seg_dev; s.cta = p->cta_dev; s.single_seg = -1;
   s.hot_rows = p->hot_rows;
+  s.T = p->T;
   s.n_chunks = p->n_chunks;
   s.trace = nullptr;
   s.n_seg_total = 2 * p->T;
@@ -932,8 +1012,10 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
   SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, w.zero_bytes, st));
   s.ctrs = s.tickets + w.ticket_words;
   float* buf[2] = {(float*)(base + w.buf_off[0]), (float*)(base + w.buf_off[1])};
+  float* pmb[2] = {(float*)(base + w.pm_off[0]), (float*)(base + w.pm_off[1])};
   const size_t mlw = mask_layer_bytes(p, d);
   const size_t mu = (size_t)p->T * p->U * (d / 4);
+  const bool rpw = use_rpw();
   if (interval >= 0) s.cta = p->cta_int_dev + (size_t)interval * p->num_sms;
   for (int l = L - 1, step = 0; l >= 0; --l, ++step) {
     s.ctrs = s.tickets + w.ticket_words + (size_t)step * 2 * p->T;
@@ -943,6 +1025,20 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
     s.src_u = g_u; s.src_i = g_i;
     s.smask_u = (const uint8_t*)masks + (size_t)l * mlw;        // sigma'(Z0^l): masks user-table rows
     s.smask_i = (const uint8_t*)masks + (size_t)l * mlw + mu;   // sigma'(Z1^l): masks item-table rows
+    if (rpw) {
+      // below the top level the source is the copy the level above already multiplied by sigma'(Z^l)
+      if (step > 0) {
+        s.src_u = pmb[(step - 1) & 1]; s.src_i = pmb[(step - 1) & 1] + w.user_floats;
+        s.smask_u = nullptr; s.smask_i = nullptr;
+      }
+      if (l > 0) {   // hand the next level its pre-masked source: sigma'(Z^{l-1}) (.) n
+        s.o2_u = pmb[step & 1]; s.o2_i = pmb[step & 1] + w.user_floats;
+        s.pmask_u = (const uint8_t*)masks + (size_t)(l - 1) * mlw;
+        s.pmask_i = (const uint8_t*)masks + (size_t)(l - 1) * mlw + mu;
+      } else {
+        s.o2_u = nullptr; s.o2_i = nullptr; s.pmask_u = nullptr; s.pmask_i = nullptr;
+      }
+    }
     s.a_u = gU; s.a_i = gI;
     s.b_u = step == 0 ? nullptr : g_u;
     s.b_i = step == 0 ? nullptr : g_i;
