@@ -79,7 +79,7 @@ struct SpmmParams {
   int T;                     // number of intervals (row stride of the [R,T,d] layout)
   // layout flags (row-per-warp kernel only): 0 = [T,R,d] (default), 1 = [R,T,d], the transposed
   // hand-off of model.py:133-134
-  int a_rtd, b_rtd, o2_rtd, src_rtd;
+  int a_rtd, o2_rtd, src_rtd;
   // row-per-warp backward: sign masks one level down (of the rows being written); the pre-masked
   // copy sigma'(Z^{l-1}) (.) n goes to o2 and is the gather source of the next level
   const uint8_t* pmask_u;
@@ -733,6 +733,33 @@ spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
 #include "spmm_rpw.cuh"
 namespace sagnn {
 
+// Backward, top level: the gather source is sigma'(Z^{L-1}) (.) G.  One streaming pass writes it
+// (both tables, 128-bit accesses, one mask byte per float4) so that the gather kernel reads plain
+// rows: cheaper than a mask load + selects per gathered edge (12 per row on the Gowalla shape).
+__global__ void __launch_bounds__(256)
+premask_kernel(const float4* __restrict__ in_u, const float4* __restrict__ in_i, const uint8_t* __restrict__ m_u,
+               const uint8_t* __restrict__ m_i, float4* __restrict__ out_u, float4* __restrict__ out_i, int64_t n4_u,
+               int64_t n4_i, float leaky) {
+  const int64_t n = n4_u + n4_i, step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const bool it = i >= n4_u;
+    const int64_t j = it ? i - n4_u : i;
+    float4 x = it ? in_i[j] : in_u[j];
+    const uint32_t b = it ? m_i[j] : m_u[j];
+    x.x = (b & 1u) ? x.x : leaky * x.x;
+    x.y = (b & 2u) ? x.y : leaky * x.y;
+    x.z = (b & 4u) ? x.z : leaky * x.z;
+    x.w = (b & 8u) ? x.w : leaky * x.w;
+    (it ? out_i : out_u)[j] = x;
+  }
+}
+
+// SAGNN_BWD_PREMASK=0 keeps the per-edge masks of the top backward level (A/B runs)
+static bool use_premask() {
+  static const bool v = [] { const char* e = getenv("SAGNN_BWD_PREMASK"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------
@@ -745,7 +772,7 @@ bool use_rpw() {
   return v;
 }
 
-template <int VPL, int MODE, bool WEIGHTED, bool MASKED>
+template <int VPL, int MODE, bool WEIGHTED, bool MASKED, bool RTD>
 static int launch_rpw_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaStream_t st) {
   SpmmParams prm = prm_in;
   if (plan->trace_dev && plan->trace_launch < plan->trace_capacity)   // diagnostics only
@@ -753,7 +780,7 @@ static int launch_rpw_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaSt
   using G = RowGeo<VPL, MASKED>;
   static_assert(G::SMEM <= 227 * 1024, "shared-memory budget exceeded");
   static std::atomic<uint64_t> configured{0};   // bit per device: the attribute is per device
-  auto kern = spmm_rpw_kernel<VPL, MODE, WEIGHTED, MASKED>;
+  auto kern = spmm_rpw_kernel<VPL, MODE, WEIGHTED, MASKED, RTD>;
   const uint64_t bit = 1ull << (plan->device & 63);
   if (!(configured.load(std::memory_order_acquire) & bit)) {
     SAGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
@@ -765,14 +792,21 @@ static int launch_rpw_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaSt
   return SAGNN_OK;
 }
 
+template <int VPL, int MODE, bool WEIGHTED, bool MASKED>
+static int launch_rpw_l(const sagnn_plan* plan, const SpmmParams& prm, cudaStream_t st) {
+  if (MODE != MODE_MSG && (prm.a_rtd | prm.o2_rtd | prm.src_rtd))
+    return launch_rpw_t<VPL, MODE, WEIGHTED, MASKED, MODE != MODE_MSG>(plan, prm, st);
+  return launch_rpw_t<VPL, MODE, WEIGHTED, MASKED, false>(plan, prm, st);
+}
+
 template <int VPL, int MODE>
 static int launch_rpw_v(const sagnn_plan* plan, const SpmmParams& prm, cudaStream_t st) {
   const bool wt = prm.w != nullptr;
   if constexpr (MODE == MODE_BWD) {
     if (prm.smask_u)   // raw upstream as the source: sign masks per edge
-      return wt ? launch_rpw_t<VPL, MODE, true, true>(plan, prm, st) : launch_rpw_t<VPL, MODE, false, true>(plan, prm, st);
+      return wt ? launch_rpw_l<VPL, MODE, true, true>(plan, prm, st) : launch_rpw_l<VPL, MODE, false, true>(plan, prm, st);
   }
-  return wt ? launch_rpw_t<VPL, MODE, true, false>(plan, prm, st) : launch_rpw_t<VPL, MODE, false, false>(plan, prm, st);
+  return wt ? launch_rpw_l<VPL, MODE, true, false>(plan, prm, st) : launch_rpw_l<VPL, MODE, false, false>(plan, prm, st);
 }
 
 template <int MODE>
@@ -833,7 +867,7 @@ static int launch(const sagnn_plan* plan, const SpmmParams& prm, int d, int mode
       default:       return launch_rpw_mode<MODE_MSG>(plan, prm, d, st);
     }
   }
-  SAGNN_REQUIRE(!(prm.a_rtd | prm.b_rtd | prm.o2_rtd | prm.src_rtd), SAGNN_INVALID_ARG,
+  SAGNN_REQUIRE(!(prm.a_rtd | prm.o2_rtd | prm.src_rtd), SAGNN_INVALID_ARG,
                 "the v7 kernel has no [R,T,d] layouts");
   switch (mode) {
     case MODE_FWD: return launch_mode<MODE_FWD>(plan, prm, d, st);
@@ -871,9 +905,10 @@ static WsLayout ws_layout(const sagnn_plan* p, int n_layers, int d) {
     w.buf_off[b] = off;
     if (b < nbuf) off = align_up(off + sizeof(float) * w.table_floats, 256);
   }
-  for (int b = 0; b < 2; ++b) {   // row-per-warp backward: pre-masked copies of the running gradient
+  const int npm = n_layers < 2 ? n_layers : 2;
+  for (int b = 0; b < 2; ++b) {   // row-per-warp backward: pre-masked copies of the upstream / running gradient
     w.pm_off[b] = off;
-    if (b < nbuf && use_rpw()) off = align_up(off + sizeof(float) * w.table_floats, 256);
+    if (b < npm && use_rpw()) off = align_up(off + sizeof(float) * w.table_floats, 256);
   }
   w.total = off;
   return w;
@@ -1026,7 +1061,20 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
     s.smask_u = (const uint8_t*)masks + (size_t)l * mlw;        // sigma'(Z0^l): masks user-table rows
     s.smask_i = (const uint8_t*)masks + (size_t)l * mlw + mu;   // sigma'(Z1^l): masks item-table rows
     if (rpw) {
-      // below the top level the source is the copy the level above already multiplied by sigma'(Z^l)
+      // below the top level the source is the copy the level above already multiplied by sigma'(Z^l);
+      // at the top level one streaming pass makes that copy of the upstream
+      if (step == 0 && use_premask()) {
+        float* pu = pmb[L >= 2 ? 1 : 0]; float* pi = pu + w.user_floats;
+        const int64_t ru = interval >= 0 ? p->U : (int64_t)p->T * p->U, ri = interval >= 0 ? p->I : (int64_t)p->T * p->I;
+        const int64_t ou = interval >= 0 ? (int64_t)interval * p->U : 0, oi = interval >= 0 ? (int64_t)interval * p->I : 0;
+        const int64_t q = d / 4;
+        premask_kernel<<<p->num_sms * 8, 256, 0, st>>>(
+            (const float4*)gU + ou * q, (const float4*)gI + oi * q, s.smask_u + ou * q, s.smask_i + oi * q,
+            (float4*)pu + ou * q, (float4*)pi + oi * q, ru * q, ri * q, leaky);
+        SAGNN_CUDA(cudaGetLastError());
+        s.src_u = pu; s.src_i = pi;
+        s.smask_u = nullptr; s.smask_i = nullptr;
+      }
       if (step > 0) {
         s.src_u = pmb[(step - 1) & 1]; s.src_i = pmb[(step - 1) & 1] + w.user_floats;
         s.smask_u = nullptr; s.smask_i = nullptr;

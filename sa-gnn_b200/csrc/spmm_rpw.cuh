@@ -68,6 +68,20 @@ __device__ __forceinline__ void cp_async_b(uint32_t dst_smem, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 
+// same, issued only when `pred` is non-zero (keeps a run of copies free of branches)
+template <int BYTES>
+__device__ __forceinline__ void cp_async_p(uint32_t dst_smem, const void* src, int pred) {
+  if constexpr (BYTES == 16)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                 ::"r"(dst_smem), "l"(src), "r"(pred) : "memory");
+  else if constexpr (BYTES == 8)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 8;\n\t}"
+                 ::"r"(dst_smem), "l"(src), "r"(pred) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 4;\n\t}"
+                 ::"r"(dst_smem), "l"(src), "r"(pred) : "memory");
+}
+
 // ---- per-lane chunk loads / stores (CW floats = 4, 8 or 16 bytes) ---------------------------
 template <int CW>
 __device__ __forceinline__ void ldg_chunk(float* v, const char* p) {            // read-only path
@@ -155,7 +169,9 @@ __device__ __forceinline__ void rpw_accumulate(float* acc, const float* x, float
 
 // MODE_FWD / MODE_MSG: MASKED must be false.  MODE_BWD: MASKED = the source is the raw upstream
 // (top level, sign masks applied per edge); !MASKED = the source was pre-multiplied by sigma'.
-template <int VPL, int MODE, bool WEIGHTED, bool MASKED>
+// RTD: some tensor of this launch uses the [R,T,d] layout (runtime row strides); otherwise every
+// row stride is the compile-time d*4.
+template <int VPL, int MODE, bool WEIGHTED, bool MASKED, bool RTD>
 __global__ void __launch_bounds__(kRpwThreads, 1)
 spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
   using G = RowGeo<VPL, MASKED>;
@@ -172,6 +188,9 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
   const float leaky = p.leaky;
   // everything below is derived from a shuffled value, so the compiler keeps it in uniform registers
   const int seg = __shfl_sync(FULL, p.single_seg >= 0 ? p.single_seg : p.cta[blockIdx.x].seg, 0);
+  // the first grab of every warp is static (CTA rank inside its segment), the queue serves the rest
+  const unsigned seg_rank = p.single_seg >= 0 ? blockIdx.x : (unsigned)p.cta[blockIdx.x].rank;
+  const unsigned seg_ctas = p.single_seg >= 0 ? gridDim.x : (unsigned)p.cta[blockIdx.x].count;
   if (p.trace && threadIdx.x == 0) {
     p.trace[blockIdx.x * 4 + 0] = (unsigned long long)seg;
     p.trace[blockIdx.x * 4 + 1] = globaltimer_ns();
@@ -187,9 +206,10 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
   const int64_t own0 = (int64_t)k * r_own;
   // [T,R,d]: interval k starts at row k*R, rows are D floats apart;
   // [R,T,d]: interval k starts at float k*D of row 0, rows are T*D floats apart (model.py:133-134)
+  const bool src_rtd = RTD && p.src_rtd, a_rtd = RTD && p.a_rtd, o2_rtd = RTD && p.o2_rtd;
   const char* src = reinterpret_cast<const char*>((item_side ? p.src_u : p.src_i) +
-                                                  (p.src_rtd ? (int64_t)k * D : (int64_t)k * r_src * D));
-  const uint32_t src_stride = (uint32_t)ROWB * (p.src_rtd ? p.T : 1);   // bytes between source rows
+                                                  (src_rtd ? (int64_t)k * D : (int64_t)k * r_src * D));
+  const uint32_t src_stride = (uint32_t)ROWB * (src_rtd ? p.T : 1);   // bytes between source rows
   const uint8_t* smask = MASKED ? (item_side ? p.smask_u : p.smask_i) + (int64_t)k * r_src * MPR : nullptr;
   const int32_t* enc = p.enc + sg.edge_base;
   const float* wts = WEIGHTED ? p.w + sg.edge_base : nullptr;
@@ -200,19 +220,23 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
   float* o2_f = item_side ? p.o2_i : p.o2_u;
   uint8_t* mk_f = item_side ? p.mask_i : p.mask_u;
   const uint8_t* pm_f = item_side ? p.pmask_i : p.pmask_u;
-  const char* a_base = a_f ? reinterpret_cast<const char*>(a_f + (p.a_rtd ? (int64_t)k * D : own0 * D)) : nullptr;
-  const char* b_base = b_f ? reinterpret_cast<const char*>(b_f + (p.b_rtd ? (int64_t)k * D : own0 * D)) : nullptr;
+  const char* a_base = a_f ? reinterpret_cast<const char*>(a_f + (a_rtd ? (int64_t)k * D : own0 * D)) : nullptr;
+  const char* b_base = b_f ? reinterpret_cast<const char*>(b_f + own0 * D) : nullptr;   // internal tensor: always [T,R,d]
   char* o1_base = o1_f ? reinterpret_cast<char*>(o1_f + own0 * D) : nullptr;
-  char* o2_base = o2_f ? reinterpret_cast<char*>(o2_f + (p.o2_rtd ? (int64_t)k * D : own0 * D)) : nullptr;
+  char* o2_base = o2_f ? reinterpret_cast<char*>(o2_f + (o2_rtd ? (int64_t)k * D : own0 * D)) : nullptr;
   uint8_t* mk_base = mk_f ? mk_f + own0 * MPR : nullptr;
   const uint8_t* pm_base = pm_f ? pm_f + own0 * MPR : nullptr;
-  const uint32_t a_stride = (uint32_t)ROWB * (p.a_rtd ? p.T : 1);
-  const uint32_t b_stride = (uint32_t)ROWB * (p.b_rtd ? p.T : 1);
-  const uint32_t o2_stride = (uint32_t)ROWB * (p.o2_rtd ? p.T : 1);
-  const bool has_b = b_base != nullptr;
+  const uint32_t a_stride = (uint32_t)ROWB * (a_rtd ? p.T : 1);
+  const uint32_t o2_stride = (uint32_t)ROWB * (o2_rtd ? p.T : 1);
+  // which optional tensors this launch has: one pinned register instead of pointer tests per task
+  enum { F_B = 1, F_O1 = 2, F_O2 = 4, F_MK = 8, F_ADDNEXT = 16, F_PM = 32 };
+  uint32_t flags = (b_base ? F_B : 0) | (o1_base ? F_O1 : 0) | (o2_base ? F_O2 : 0) | (mk_base ? F_MK : 0) |
+                   (p.out_add_next ? F_ADDNEXT : 0) | (pm_base ? F_PM : 0);
+  pin32(flags);
 
   // my bytes inside a chunk; my sign bits inside a row's mask bytes: byte (chunk v) = v*32 + mbyte
-  const uint32_t lane_off = (uint32_t)lane * (CW * 4);
+  uint32_t lane_off = (uint32_t)lane * (CW * 4);
+  pin32(lane_off);
   const int mbyte = CW == 4 ? lane : (CW == 2 ? lane >> 1 : lane >> 2);
   const int mshift = CW == 4 ? 0 : (CW == 2 ? (lane & 1) * 2 : (lane & 3));
   auto mask_bits = [&](const uint8_t* base, uint32_t c) -> uint32_t {   // sign bits of row c that belong to my elements
@@ -224,11 +248,21 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
   };
 
   // ---- per-warp ring -----------------------------------------------------------------------
-  const uint32_t ring = smem_u32(smem_raw) + (uint32_t)warp * G::WARP_BYTES;
-  const uint32_t rec_ring = ring + G::REC_OFF, code_ring = ring + G::CODE_OFF, wt_ring = ring + G::WT_OFF,
-                 own_ring = ring + G::OWN_OFF;
+  // (pinned: the compiler must not rebuild these from %tid / the kernel parameters at every use)
+  uint32_t rec_ring = smem_u32(smem_raw) + (uint32_t)warp * G::WARP_BYTES + G::REC_OFF;
+  uint32_t code_lane = rec_ring + (G::CODE_OFF - G::REC_OFF) + lane * 4;      // my word of code-ring slot 0
+  uint32_t own_lane = rec_ring + (G::OWN_OFF - G::REC_OFF) + lane_off;        // my bytes of own-ring slot 0
+  pin32(rec_ring);
+  pin32(code_lane);
+  pin32(own_lane);
+  const uint32_t code_ring = rec_ring + (G::CODE_OFF - G::REC_OFF), wt_ring = rec_ring + (G::WT_OFF - G::REC_OFF);
+  const char* src_lane = src + lane_off;
+  uint32_t src_stride_r = src_stride;
+  pin64(src_lane);
+  pin32(src_stride_r);
 
-  auto issue = [&]() -> unsigned { return lane == 0 ? atomicAdd(ctr, (unsigned)kRpwGrab) : 0u; };
+  const unsigned q_base = seg_ctas * (unsigned)(kRpwThreads / 32) * kRpwGrab;   // tasks handed out statically
+  auto issue = [&]() -> unsigned { return lane == 0 ? atomicAdd(ctr, (unsigned)kRpwGrab) + q_base : 0u; };
   // records of the grab starting at task b -> half `h` of the record ring (16 bytes each)
   auto fetch_records = [&](unsigned b, int h) {
     if (lane < kRpwGrab) {
@@ -243,32 +277,31 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
     const int4 rq = lds_i4(rec_ring + (uint32_t)(q & 15) * 16);
     if (!(rq.y & NOWORK)) {
       const int nn = rq.y & 0x7f;
-      const uint32_t cdst = code_ring + (uint32_t)slot * 256 + lane * 4;
-      const int32_t* csrc = enc + (uint32_t)rq.z + lane;
-      if (lane < nn) cp_async_b<4>(cdst, csrc);
-      if (lane + 32 < nn) cp_async_b<4>(cdst + 128, csrc + 32);
+      const uint32_t ln = lane_off / (CW * 4);
+      const uint32_t cdst = code_lane + (uint32_t)slot * 256;
+      const int32_t* csrc = enc + ((uint32_t)rq.z + ln);
+      cp_async_p<4>(cdst, csrc, ln < (uint32_t)nn);
+      cp_async_p<4>(cdst + 128, csrc + 32, ln + 32 < (uint32_t)nn);
       if (WEIGHTED) {
-        const uint32_t wdst = wt_ring + (uint32_t)slot * 256 + lane * 4;
-        const float* wsrc = wts + (uint32_t)rq.z + lane;
-        if (lane < nn) cp_async_b<4>(wdst, wsrc);
-        if (lane + 32 < nn) cp_async_b<4>(wdst + 128, wsrc + 32);
+        const uint32_t wdst = cdst + (G::WT_OFF - G::CODE_OFF);
+        const float* wsrc = wts + ((uint32_t)rq.z + ln);
+        cp_async_p<4>(wdst, wsrc, ln < (uint32_t)nn);
+        cp_async_p<4>(wdst + 128, wsrc + 32, ln + 32 < (uint32_t)nn);
       }
       if (MODE != MODE_MSG) {
-        const uint32_t odst = own_ring + (uint32_t)slot * (2 * ROWB) + lane_off;
-        const char* pa = a_base + (uint64_t)(uint32_t)rq.x * a_stride + lane_off;
+        const uint32_t odst = own_lane + (uint32_t)slot * (2 * ROWB);
+        const uint64_t ra = (uint64_t)(uint32_t)rq.x * a_stride + lane_off;
+        const uint64_t rb = RTD ? (uint64_t)(uint32_t)rq.x * ROWB + lane_off : ra;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) cp_async_b<CW * 4>(odst + v * CHB, pa + v * CHB);
-        if (has_b) {
-          const char* pb = b_base + (uint64_t)(uint32_t)rq.x * b_stride + lane_off;
+        for (int v = 0; v < NV; ++v) cp_async_b<CW * 4>(odst + v * CHB, a_base + ra + v * CHB);
 #pragma unroll
-          for (int v = 0; v < NV; ++v) cp_async_b<CW * 4>(odst + ROWB + v * CHB, pb + v * CHB);
-        }
+        for (int v = 0; v < NV; ++v) cp_async_p<CW * 4>(odst + ROWB + v * CHB, b_base + rb + v * CHB, flags & F_B);
       }
     }
   };
 
   // ---- start-up: first grab's records, then the first LA requests --------------------------
-  const unsigned b_first = __shfl_sync(FULL, issue(), 0);
+  const unsigned b_first = (seg_rank * (unsigned)(kRpwThreads / 32) + (unsigned)warp) * kRpwGrab;
   unsigned pend = issue();                            // base of the next grab, still in flight
   fetch_records(b_first, 0);
   cp_async_commit();
@@ -280,7 +313,6 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
     cp_async_commit();
   }
 
-  const char* src_lane = src + lane_off;
   int slot_t = 0, slot_q = LA % RD;                   // ring slots of the current task / of the request
   for (int t = 0;; ++t) {
     cp_async_wait<LA - 1>();                          // task t's operands (requested LA iterations ago) have landed
@@ -301,7 +333,7 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
     const uint32_t cb = code_ring + (uint32_t)slot_t * 256;
     const uint32_t wb = wt_ring + (uint32_t)slot_t * 256;
     uint32_t pbits = 0;                               // backward: my sign bits one level down (for the pre-masked copy)
-    if (BWD && pm_base && !multi) pbits = mask_bits(pm_base, row);
+    if (BWD && (flags & F_PM) && !multi) pbits = mask_bits(pm_base, row);
 
     float acc[VPL];
 #pragma unroll
@@ -330,7 +362,7 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
       for (int u = 0; u < K; ++u) {
 #pragma unroll
         for (int v = 0; v < NV; ++v)
-          ldg_chunk<CW>(val[s0 + u] + v * CW, src_lane + (uint64_t)(uint32_t)c[u] * src_stride + v * CHB);
+          ldg_chunk<CW>(val[s0 + u] + v * CW, src_lane + (uint64_t)(uint32_t)c[u] * src_stride_r + v * CHB);
         if constexpr (MASKED) mb[s0 + u] = mask_bits(smask, (uint32_t)c[u]);
       }
     };
@@ -377,9 +409,10 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
       bool active = true;
       finish = false;
       unsigned* tk = p.tickets;                        // ticket region of the current level
-      for (int stride = 1; active; stride *= 16) {
-        const int gs = pos - pos % (16 * stride);      // members: slots gs + j*stride, j < 16, below nch
-        int members = (nch - gs + stride - 1) / stride;
+      for (int sh = 0; active; sh += 4) {              // level stride = 16^level = 1 << sh
+        const int stride = 1 << sh;
+        const int gs = pos & ~((16 << sh) - 1);        // members: slots gs + j*stride, j < 16, below nch
+        int members = (nch - gs + stride - 1) >> sh;
         members = members > 16 ? 16 : members;
         char* mine = reinterpret_cast<char*>(p.partials + (cbase + pos) * D) + lane_off;
 #pragma unroll
@@ -422,7 +455,7 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
         tk += p.n_chunks;
       }
       __syncwarp();
-      if (BWD && pm_base && finish) pbits = mask_bits(pm_base, row);
+      if (BWD && (flags & F_PM) && finish) pbits = mask_bits(pm_base, row);
     }
 
     // ---- fused epilogue ------------------------------------------------------------------------
@@ -431,10 +464,10 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
 #pragma unroll
       for (int i = 0; i < VPL; ++i) { own_a[i] = 0.f; own_b[i] = 0.f; }
       if (MODE != MODE_MSG) {
-        const uint32_t o = own_ring + (uint32_t)slot_t * (2 * ROWB) + lane_off;
+        const uint32_t o = own_lane + (uint32_t)slot_t * (2 * ROWB);
 #pragma unroll
         for (int v = 0; v < NV; ++v) lds_chunk<CW>(own_a + v * CW, o + v * CHB);
-        if (has_b) {
+        if (flags & F_B) {
 #pragma unroll
           for (int v = 0; v < NV; ++v) lds_chunk<CW>(own_b + v * CW, o + ROWB + v * CHB);
         }
@@ -444,10 +477,10 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
         // n = G + g + A (sigma' . g_other)      (SURVEY A.2); at the top level g == G
         float o[VPL];
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) o[i] = own_a[i] + (has_b ? own_b[i] : own_a[i]) + acc[i];
+        for (int i = 0; i < VPL; ++i) o[i] = own_a[i] + ((flags & F_B) ? own_b[i] : own_a[i]) + acc[i];
 #pragma unroll
         for (int v = 0; v < NV; ++v) st_chunk<CW>(o1_base + off + v * CHB, o + v * CW);
-        if (o2_base) {                                             // the source of the next level down: sigma'(Z^{l-1}) (.) n
+        if (flags & F_O2) {                                        // the source of the next level down: sigma'(Z^{l-1}) (.) n
           float om[VPL];
 #pragma unroll
           for (int i = 0; i < VPL; ++i) om[i] = ((pbits >> i) & 1u) ? o[i] : leaky * o[i];
@@ -472,22 +505,22 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
           float nxt_e[VPL];                                         // E^{l+1} = E^l + lrelu(Z^l)
 #pragma unroll
           for (int i = 0; i < VPL; ++i) nxt_e[i] = own_a[i] + act[i];
-          if (o1_base) {
+          if (flags & F_O1) {
 #pragma unroll
             for (int v = 0; v < NV; ++v) st_chunk<CW>(o1_base + off + v * CHB, nxt_e + v * CW);
           }
-          if (o2_base) {
+          if (flags & F_O2) {
             float o[VPL];
 #pragma unroll
             for (int i = 0; i < VPL; ++i) {
-              o[i] = has_b ? own_b[i] + own_a[i] : own_a[i];
-              if (p.out_add_next) o[i] += nxt_e[i];
+              o[i] = (flags & F_B) ? own_b[i] + own_a[i] : own_a[i];
+              if (flags & F_ADDNEXT) o[i] += nxt_e[i];
             }
             char* dst = o2_base + (uint64_t)row * o2_stride + lane_off;
 #pragma unroll
             for (int v = 0; v < NV; ++v) stcs_chunk<CW>(dst + v * CHB, o + v * CW);
           }
-          if (mk_base) {
+          if (flags & F_MK) {
             uint8_t* mrow = mk_base + (uint64_t)row * MPR;
             if constexpr (CW == 4) {
 #pragma unroll

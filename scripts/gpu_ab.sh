@@ -1,5 +1,6 @@
-# usage: bash scripts/gpu_ab.sh   -- gpu tests on the default kernel, then bench default / v7 / lib variants
-python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/test_ab.log; tail -3 gpurun_out/test_ab.log
+# usage: [TESTSEL="pytest -k expr"] [NOV7=1] bash scripts/gpu_ab.sh [lib variants]
+# gpu tests on the default kernel, then bench default / v7 / lib/libsagnn_<variant>.so
+python -m pytest tests -m gpu -x -q ${TESTSEL:+-k "$TESTSEL"} 2>&1 | tail -25 > gpurun_out/test_ab.log; tail -3 gpurun_out/test_ab.log
 run() {  # tag, env...
   TAG=$1; shift
   env "$@" python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline $BARGS > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
@@ -13,5 +14,5 @@ except Exception as e:
 PY
 }
 run rpw SAGNN_KERNEL=v8
-run v7 SAGNN_KERNEL=v7
+[ -z "$NOV7" ] && run v7 SAGNN_KERNEL=v7
 for v in "$@"; do run $v SAGNN_B200_LIB=$PWD/sa-gnn_b200/lib/libsagnn_$v.so; done
