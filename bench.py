@@ -345,7 +345,7 @@ def main():
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src,
-        "kernel": "spmm_layer_kernel<%s> (one GNN layer, all T intervals, both orientations)"
+        "kernel": "spmm_rpw_kernel<%s> (one GNN layer, all T intervals, both orientations)"
                   % ("FWD" if dom_is_fwd else "BWD"),
         "alg_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
         "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,

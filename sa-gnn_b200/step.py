@@ -7,6 +7,8 @@ per-layer launch latency.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -28,7 +30,8 @@ class PropagationStep:
             self.user_out, self.item_out = mk(plan.U), mk(plan.I)
             self.d_u, self.d_i = mk(plan.U), mk(plan.I)
         self.graph = None
-        self.kernel_launches_per_step = 2 * self.L      # L forward + L backward layer kernels
+        # L forward + L backward layer kernels + the streaming pre-mask of the upstream (row-per-warp kernel)
+        self.kernel_launches_per_step = 2 * self.L + (0 if os.environ.get("SAGNN_KERNEL", "").lower().startswith("v7") else 1)
 
     def forward(self):
         p = self.plan

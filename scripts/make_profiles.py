@@ -9,13 +9,15 @@ def val(r, k): return float(r[idx[k]])
 launch = []
 for r in rows[2:]:
     name = r[idx["Kernel Name"]]
-    launch.append(dict(kernel=name, mode="fwd" if "1, 0, 0>" in name.replace("(int)", "") or ", 0, 0>" in name else "bwd",
+    short = name.replace("(int)", "").replace("(bool)", "")
+    mode = "premask" if "premask" in short else ("fwd" if "_kernel<2, 0," in short else "bwd")
+    launch.append(dict(kernel=name, mode=mode,
                        dur_us=val(r, "gpu__time_duration.sum"), dram_read_MB=val(r, "dram__bytes_read.sum"),
                        dram_write_MB=val(r, "dram__bytes_write.sum")))
 # unit handling: ncu prints Mbyte / us for these sizes (checked in the header row)
 units = rows[1]
 assert units[idx["dram__bytes_read.sum"]] == "Mbyte" and units[idx["gpu__time_duration.sum"]] in ("us", "usecond"), units[idx["dram__bytes_read.sum"]]
-fwd = [l for l in launch if "<16, 1, 0, 0>" in l["kernel"]]; bwd = [l for l in launch if "<16, 1, 1, 0>" in l["kernel"]]
+fwd = [l for l in launch if l["mode"] == "fwd"]; bwd = [l for l in launch if l["mode"] == "bwd"]
 avg = lambda ls: sum((l["dram_read_MB"] + l["dram_write_MB"]) for l in ls) / len(ls) * 1e6
 traffic = {"gowalla": {"fwd": avg(fwd), "bwd": avg(bwd), "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, cold-cache replay)",
                        "launches": launch}}
