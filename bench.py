@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--exchange", default="allgather", choices=["allgather", "alltoall", "none"],
                     help="multi-GPU hand-off of the outputs: all-gather (replicated consumer, north_star), "
                          "all-to-all of row blocks (row-sharded consumer) or none")
+    ap.add_argument("--layout", default="trd", choices=["trd", "rtd"],
+                    help="rtd: outputs / upstream gradients in the [R,T,d] layout of model.py:133-134 (fused transpose)")
     ap.add_argument("--no-calibrate", action="store_true", help="keep the static cost-model CTA split")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
     ap.add_argument("--cpu-steps", type=int, default=3)
@@ -234,7 +236,7 @@ def main():
     torch.cuda.synchronize()
     plan_ms = (time.perf_counter() - t0) * 1e3
 
-    step = PropagationStep(plan, L, d, 0.5)
+    step = PropagationStep(plan, L, d, 0.5, layout=args.layout)
     step.u_embed.copy_(torch.from_numpy(dh.xavier_embeddings(T, U, d, args.seed)))
     step.i_embed.copy_(torch.from_numpy(dh.xavier_embeddings(T, I, d, args.seed + 1)))
     gen = torch.Generator(device=dev).manual_seed(args.seed + rank)
@@ -443,6 +445,7 @@ def workload_config(args, g, L, d, world, stats=None, use_graph=None, gather=Non
         cfg["schedule"] = stats
     if use_graph is not None:
         cfg["cuda_graph"] = bool(use_graph)
+        cfg["layout"] = "[T,R,d] outputs (model.py:131-132)" if args.layout == "trd" else "[R,T,d] outputs / upstream (model.py:133-134, fused transpose)"
     if gather is not None:
         cfg["allgather_outputs"] = bool(gather) and args.exchange == "allgather"
         cfg["exchange"] = args.exchange if world > 1 else "none"

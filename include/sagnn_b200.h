@@ -145,6 +145,23 @@ int sagnn_propagate_bwd(const sagnn_plan* plan, const float* g_user_dev, const f
                         const void* masks_dev, void* workspace_dev, size_t workspace_bytes,
                         sagnn_stream_t stream);
 
+/* Layout flags of the _ex entry points.  SAGNN_LAYOUT_RTD: the tensors handed to / taken from the
+ * interval-fusion stage use the transposed layout of model.py:133-134 (tf.transpose(.., [1,0,2])):
+ * user_out [U,T,d], item_out [I,T,d] in the forward, g_user [U,T,d], g_item [I,T,d] in the
+ * backward.  The embedding tables and their gradients stay [T,U,d] / [T,I,d] (model.py:108-109).
+ * The transpose is fused into the epilogue (row stride T*d), so the two full-tensor copies of
+ * model.py:133-134 (and of their autodiff) disappear; results are bitwise those of the default
+ * layout, transposed. */
+enum { SAGNN_LAYOUT_TRD = 0, SAGNN_LAYOUT_RTD = 1 };
+int sagnn_propagate_fwd_ex(const sagnn_plan* plan, const float* u_embed_dev, const float* i_embed_dev,
+                           float* user_out_dev, float* item_out_dev, int n_layers, int d, float leaky,
+                           void* masks_dev, void* workspace_dev, size_t workspace_bytes, unsigned flags,
+                           sagnn_stream_t stream);
+int sagnn_propagate_bwd_ex(const sagnn_plan* plan, const float* g_user_dev, const float* g_item_dev,
+                           float* d_u_embed_dev, float* d_i_embed_dev, int n_layers, int d, float leaky,
+                           const void* masks_dev, void* workspace_dev, size_t workspace_bytes,
+                           unsigned flags, sagnn_stream_t stream);
+
 /* The same restricted to interval k (rows of the other intervals are not touched): all SMs work on
  * that interval's two CSRs, so a caller can pipeline per-interval copies with compute.  Tensors,
  * masks and workspace are the full [T, ...] buffers; calls must be stream-ordered. */

@@ -40,6 +40,10 @@ SIGNATURES = {
                                            vp, vp, ctypes.c_size_t, vp]),
     "sagnn_propagate_bwd": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                            vp, vp, ctypes.c_size_t, vp]),
+    "sagnn_propagate_fwd_ex": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                              vp, vp, ctypes.c_size_t, ctypes.c_uint, vp]),
+    "sagnn_propagate_bwd_ex": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                              vp, vp, ctypes.c_size_t, ctypes.c_uint, vp]),
     "sagnn_propagate_fwd_interval": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,
                                                     ctypes.c_float, vp, vp, ctypes.c_size_t, vp]),
     "sagnn_propagate_bwd_interval": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,

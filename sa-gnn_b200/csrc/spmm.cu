@@ -79,7 +79,7 @@ struct SpmmParams {
   int T;                     // number of intervals (row stride of the [R,T,d] layout)
   // layout flags (row-per-warp kernel only): 0 = [T,R,d] (default), 1 = [R,T,d], the transposed
   // hand-off of model.py:133-134
-  int a_rtd, o2_rtd, src_rtd;
+  int a_rtd, b_rtd, o2_rtd, src_rtd;
   // row-per-warp backward: sign masks one level down (of the rows being written); the pre-masked
   // copy sigma'(Z^{l-1}) (.) n goes to o2 and is the gather source of the next level
   const uint8_t* pmask_u;
@@ -736,15 +736,23 @@ namespace sagnn {
 // Backward, top level: the gather source is sigma'(Z^{L-1}) (.) G.  One streaming pass writes it
 // (both tables, 128-bit accesses, one mask byte per float4) so that the gather kernel reads plain
 // rows: cheaper than a mask load + selects per gathered edge (12 per row on the Gowalla shape).
+// rtd_T > 0: the upstream is laid out [R,T,d] (rtd_T = T, k0 = first interval of the range, rows_u /
+// rows_i = U / I); masks and output stay [T,R,d].
 __global__ void __launch_bounds__(256)
 premask_kernel(const float4* __restrict__ in_u, const float4* __restrict__ in_i, const uint8_t* __restrict__ m_u,
                const uint8_t* __restrict__ m_i, float4* __restrict__ out_u, float4* __restrict__ out_i, int64_t n4_u,
-               int64_t n4_i, float leaky) {
+               int64_t n4_i, float leaky, int rtd_T, int k0, int64_t rows_u, int64_t rows_i, int q) {
   const int64_t n = n4_u + n4_i, step = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
     const bool it = i >= n4_u;
     const int64_t j = it ? i - n4_u : i;
-    float4 x = it ? in_i[j] : in_u[j];
+    int64_t jin = j;
+    if (rtd_T > 0) {      // (k, r, c) of the [T,R,d/4] range -> ((r*T + k0 + k)*q + c) of the whole [R,T,d/4] tensor
+      const int64_t rows = it ? rows_i : rows_u, rq = rows * q;
+      const int64_t k = j / rq, rem = j - k * rq, r = rem / q, c = rem - r * q;
+      jin = (r * rtd_T + k0 + k) * q + c;
+    }
+    float4 x = it ? in_i[jin] : in_u[jin];
     const uint32_t b = it ? m_i[j] : m_u[j];
     x.x = (b & 1u) ? x.x : leaky * x.x;
     x.y = (b & 2u) ? x.y : leaky * x.y;
@@ -794,7 +802,7 @@ static int launch_rpw_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaSt
 
 template <int VPL, int MODE, bool WEIGHTED, bool MASKED>
 static int launch_rpw_l(const sagnn_plan* plan, const SpmmParams& prm, cudaStream_t st) {
-  if (MODE != MODE_MSG && (prm.a_rtd | prm.o2_rtd | prm.src_rtd))
+  if (MODE != MODE_MSG && (prm.a_rtd | prm.b_rtd | prm.o2_rtd | prm.src_rtd))
     return launch_rpw_t<VPL, MODE, WEIGHTED, MASKED, MODE != MODE_MSG>(plan, prm, st);
   return launch_rpw_t<VPL, MODE, WEIGHTED, MASKED, false>(plan, prm, st);
 }
@@ -867,7 +875,7 @@ static int launch(const sagnn_plan* plan, const SpmmParams& prm, int d, int mode
       default:       return launch_rpw_mode<MODE_MSG>(plan, prm, d, st);
     }
   }
-  SAGNN_REQUIRE(!(prm.a_rtd | prm.o2_rtd | prm.src_rtd), SAGNN_INVALID_ARG,
+  SAGNN_REQUIRE(!(prm.a_rtd | prm.b_rtd | prm.o2_rtd | prm.src_rtd), SAGNN_INVALID_ARG,
                 "the v7 kernel has no [R,T,d] layouts");
   switch (mode) {
     case MODE_FWD: return launch_mode<MODE_FWD>(plan, prm, d, st);
@@ -971,7 +979,9 @@ extern "C" int sagnn_workspace_bytes(const sagnn_plan* p, int n_layers, int d, s
 // segments (all 148 CTAs work on them) -- lets a caller pipeline copies with compute
 static int fwd_impl(const sagnn_plan* p, int interval, const float* uE, const float* iE, float* uOut,
                     float* iOut, int L, int d, float leaky, void* masks, void* ws, size_t ws_bytes,
-                    cudaStream_t st) {
+                    cudaStream_t st, unsigned flags = 0) {
+  SAGNN_REQUIRE(!(flags & ~(unsigned)SAGNN_LAYOUT_RTD), SAGNN_INVALID_ARG, "propagate_fwd: unknown flags 0x%x", flags);
+  SAGNN_REQUIRE(!flags || use_rpw(), SAGNN_INVALID_ARG, "propagate_fwd: [R,T,d] outputs need the row-per-warp kernel");
   if (int rc = check_common(p, L, d, "propagate_fwd")) return rc;
   SAGNN_REQUIRE(interval < p->T, SAGNN_INVALID_ARG, "propagate_fwd: interval %d outside [0,%d)", interval, p->T);
   SAGNN_REQUIRE(uE && iE && uOut && iOut && ws, SAGNN_INVALID_ARG, "propagate_fwd: NULL tensor");
@@ -1003,6 +1013,9 @@ static int fwd_impl(const sagnn_plan* p, int interval, const float* uE, const fl
     if (l == 0) { s.b_u = nullptr; s.b_i = nullptr; }
     else if (l == 1) { s.b_u = uE; s.b_i = iE; }
     else { s.b_u = uOut; s.b_i = iOut; }
+    // [R,T,d] hand-off (model.py:133-134): the layer-sum output (and its partial sums read back) are transposed
+    s.o2_rtd = (flags & SAGNN_LAYOUT_RTD) ? 1 : 0;
+    s.b_rtd = (l >= 2 && (flags & SAGNN_LAYOUT_RTD)) ? 1 : 0;
     const bool write_out = last || l >= 1;
     s.o2_u = write_out ? uOut : nullptr;
     s.o2_i = write_out ? iOut : nullptr;
@@ -1023,6 +1036,12 @@ extern "C" int sagnn_propagate_fwd(const sagnn_plan* p, const float* uE, const f
   return fwd_impl(p, -1, uE, iE, uOut, iOut, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+extern "C" int sagnn_propagate_fwd_ex(const sagnn_plan* p, const float* uE, const float* iE, float* uOut,
+                                      float* iOut, int L, int d, float leaky, void* masks, void* ws,
+                                      size_t ws_bytes, unsigned flags, sagnn_stream_t stream) {
+  return fwd_impl(p, -1, uE, iE, uOut, iOut, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream, flags);
+}
+
 extern "C" int sagnn_propagate_fwd_interval(const sagnn_plan* p, int k, const float* uE, const float* iE,
                                             float* uOut, float* iOut, int L, int d, float leaky, void* masks,
                                             void* ws, size_t ws_bytes, sagnn_stream_t stream) {
@@ -1031,7 +1050,10 @@ extern "C" int sagnn_propagate_fwd_interval(const sagnn_plan* p, int k, const fl
 }
 
 static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const float* gI, float* dU, float* dI,
-                    int L, int d, float leaky, const void* masks, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    int L, int d, float leaky, const void* masks, void* ws, size_t ws_bytes, cudaStream_t st,
+                    unsigned flags = 0) {
+  SAGNN_REQUIRE(!(flags & ~(unsigned)SAGNN_LAYOUT_RTD), SAGNN_INVALID_ARG, "propagate_bwd: unknown flags 0x%x", flags);
+  SAGNN_REQUIRE(!flags || use_rpw(), SAGNN_INVALID_ARG, "propagate_bwd: [R,T,d] upstream needs the row-per-warp kernel");
   if (int rc = check_common(p, L, d, "propagate_bwd")) return rc;
   SAGNN_REQUIRE(interval < p->T, SAGNN_INVALID_ARG, "propagate_bwd: interval %d outside [0,%d)", interval, p->T);
   SAGNN_REQUIRE(gU && gI && dU && dI && masks && ws, SAGNN_INVALID_ARG, "propagate_bwd: NULL tensor");
@@ -1068,9 +1090,11 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
         const int64_t ru = interval >= 0 ? p->U : (int64_t)p->T * p->U, ri = interval >= 0 ? p->I : (int64_t)p->T * p->I;
         const int64_t ou = interval >= 0 ? (int64_t)interval * p->U : 0, oi = interval >= 0 ? (int64_t)interval * p->I : 0;
         const int64_t q = d / 4;
+        const bool rtd = (flags & SAGNN_LAYOUT_RTD) != 0;   // whole-tensor base + interval offset inside the kernel
         premask_kernel<<<p->num_sms * 8, 256, 0, st>>>(
-            (const float4*)gU + ou * q, (const float4*)gI + oi * q, s.smask_u + ou * q, s.smask_i + oi * q,
-            (float4*)pu + ou * q, (float4*)pi + oi * q, ru * q, ri * q, leaky);
+            (const float4*)gU + (rtd ? 0 : ou * q), (const float4*)gI + (rtd ? 0 : oi * q), s.smask_u + ou * q,
+            s.smask_i + oi * q, (float4*)pu + ou * q, (float4*)pi + oi * q, ru * q, ri * q, leaky, rtd ? p->T : 0,
+            interval >= 0 ? interval : 0, p->U, p->I, (int)q);
         SAGNN_CUDA(cudaGetLastError());
         s.src_u = pu; s.src_i = pi;
         s.smask_u = nullptr; s.smask_i = nullptr;
@@ -1088,6 +1112,8 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
       }
     }
     s.a_u = gU; s.a_i = gI;
+    s.a_rtd = (flags & SAGNN_LAYOUT_RTD) ? 1 : 0;            // the dense upstream is read in the caller's layout
+    s.src_rtd = (s.a_rtd && s.src_u == gU) ? 1 : 0;          // ... also as the gather source when it is not pre-masked
     s.b_u = step == 0 ? nullptr : g_u;
     s.b_i = step == 0 ? nullptr : g_i;
     s.o1_u = l == 0 ? dU : buf[step & 1];
@@ -1104,6 +1130,12 @@ extern "C" int sagnn_propagate_bwd(const sagnn_plan* p, const float* gU, const f
                                    float* dI, int L, int d, float leaky, const void* masks, void* ws,
                                    size_t ws_bytes, sagnn_stream_t stream) {
   return bwd_impl(p, -1, gU, gI, dU, dI, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int sagnn_propagate_bwd_ex(const sagnn_plan* p, const float* gU, const float* gI, float* dU,
+                                      float* dI, int L, int d, float leaky, const void* masks, void* ws,
+                                      size_t ws_bytes, unsigned flags, sagnn_stream_t stream) {
+  return bwd_impl(p, -1, gU, gI, dU, dI, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream, flags);
 }
 
 extern "C" int sagnn_propagate_bwd_interval(const sagnn_plan* p, int k, const float* gU, const float* gI,

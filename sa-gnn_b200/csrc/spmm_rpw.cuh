@@ -213,7 +213,7 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
   const int64_t own0 = (int64_t)k * r_own;
   // [T,R,d]: interval k starts at row k*R, rows are D floats apart;
   // [R,T,d]: interval k starts at float k*D of row 0, rows are T*D floats apart (model.py:133-134)
-  const bool src_rtd = RTD && p.src_rtd, a_rtd = RTD && p.a_rtd, o2_rtd = RTD && p.o2_rtd;
+  const bool src_rtd = RTD && p.src_rtd, a_rtd = RTD && p.a_rtd, b_rtd = RTD && p.b_rtd, o2_rtd = RTD && p.o2_rtd;
   const char* src = reinterpret_cast<const char*>((item_side ? p.src_u : p.src_i) +
                                                   (src_rtd ? (int64_t)k * D : (int64_t)k * r_src * D));
   const uint32_t src_stride = (uint32_t)ROWB * (src_rtd ? p.T : 1);   // bytes between source rows
@@ -228,12 +228,13 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
   uint8_t* mk_f = item_side ? p.mask_i : p.mask_u;
   const uint8_t* pm_f = item_side ? p.pmask_i : p.pmask_u;
   const char* a_base = a_f ? reinterpret_cast<const char*>(a_f + (a_rtd ? (int64_t)k * D : own0 * D)) : nullptr;
-  const char* b_base = b_f ? reinterpret_cast<const char*>(b_f + own0 * D) : nullptr;   // internal tensor: always [T,R,d]
+  const char* b_base = b_f ? reinterpret_cast<const char*>(b_f + (b_rtd ? (int64_t)k * D : own0 * D)) : nullptr;
   char* o1_base = o1_f ? reinterpret_cast<char*>(o1_f + own0 * D) : nullptr;
   char* o2_base = o2_f ? reinterpret_cast<char*>(o2_f + (o2_rtd ? (int64_t)k * D : own0 * D)) : nullptr;
   uint8_t* mk_base = mk_f ? mk_f + own0 * MPR : nullptr;
   const uint8_t* pm_base = pm_f ? pm_f + own0 * MPR : nullptr;
   const uint32_t a_stride = (uint32_t)ROWB * (a_rtd ? p.T : 1);
+  const uint32_t b_stride = (uint32_t)ROWB * (b_rtd ? p.T : 1);
   const uint32_t o2_stride = (uint32_t)ROWB * (o2_rtd ? p.T : 1);
   // which optional tensors this launch has: one pinned register instead of pointer tests per task
   enum { F_B = 1, F_O1 = 2, F_O2 = 4, F_MK = 8, F_ADDNEXT = 16, F_PM = 32 };
@@ -298,7 +299,7 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
       if (MODE != MODE_MSG) {
         const uint32_t odst = own_lane + (uint32_t)slot * (2 * ROWB);
         const uint64_t ra = (uint64_t)(uint32_t)rq.x * a_stride + lane_off;
-        const uint64_t rb = RTD ? (uint64_t)(uint32_t)rq.x * ROWB + lane_off : ra;
+        const uint64_t rb = RTD ? (uint64_t)(uint32_t)rq.x * b_stride + lane_off : ra;
 #pragma unroll
         for (int v = 0; v < NV; ++v) cp_async_b<CW * 4>(odst + v * CHB, a_base + ra + v * CHB);
 #pragma unroll

@@ -235,9 +235,12 @@ def _check_tables(plan, u, i):
         raise ValueError("embeddings live on %s but the plan on %s" % (u.device, plan.device))
 
 
+_LAYOUTS = {"trd": 0, "rtd": 1}   # SAGNN_LAYOUT_TRD / SAGNN_LAYOUT_RTD
+
+
 class _Propagate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, u_embed, i_embed, plan, n_layers, leaky):
+    def forward(ctx, u_embed, i_embed, plan, n_layers, leaky, layout):
         _check_tables(plan, u_embed, i_embed)
         lib = _lib.load_library()
         u, i = u_embed.contiguous(), i_embed.contiguous()
@@ -245,12 +248,16 @@ class _Propagate(torch.autograd.Function):
         need_bwd = u_embed.requires_grad or i_embed.requires_grad
         with torch.cuda.device(plan.device):
             ws, mask_bytes = plan.scratch(n_layers, d)
-            u_out, i_out = torch.empty_like(u), torch.empty_like(i)
+            if layout:
+                u_out = torch.empty((plan.U, plan.T, d), dtype=torch.float32, device=plan.device)
+                i_out = torch.empty((plan.I, plan.T, d), dtype=torch.float32, device=plan.device)
+            else:
+                u_out, i_out = torch.empty_like(u), torch.empty_like(i)
             masks = torch.empty(mask_bytes, dtype=torch.uint8, device=plan.device) if need_bwd else None
-            _lib.check(lib.sagnn_propagate_fwd(plan.handle, _ptr(u), _ptr(i), _ptr(u_out), _ptr(i_out),
-                                               n_layers, d, float(leaky), _ptr(masks), _ptr(ws), ws.numel(),
-                                               _stream_ptr(plan.device)))
-        ctx.plan, ctx.n_layers, ctx.leaky, ctx.d = plan, n_layers, float(leaky), d
+            _lib.check(lib.sagnn_propagate_fwd_ex(plan.handle, _ptr(u), _ptr(i), _ptr(u_out), _ptr(i_out),
+                                                  n_layers, d, float(leaky), _ptr(masks), _ptr(ws), ws.numel(),
+                                                  layout, _stream_ptr(plan.device)))
+        ctx.plan, ctx.n_layers, ctx.leaky, ctx.d, ctx.layout = plan, n_layers, float(leaky), d, layout
         ctx.masks = masks
         return u_out, i_out
 
@@ -258,26 +265,35 @@ class _Propagate(torch.autograd.Function):
     def backward(ctx, g_user, g_item):
         plan, d = ctx.plan, ctx.d
         lib = _lib.load_library()
+        su, si = ((plan.U, plan.T, d), (plan.I, plan.T, d)) if ctx.layout else ((plan.T, plan.U, d), (plan.T, plan.I, d))
         with torch.cuda.device(plan.device):
             if g_user is None:
-                g_user = torch.zeros((plan.T, plan.U, d), dtype=torch.float32, device=plan.device)
+                g_user = torch.zeros(su, dtype=torch.float32, device=plan.device)
             if g_item is None:
-                g_item = torch.zeros((plan.T, plan.I, d), dtype=torch.float32, device=plan.device)
+                g_item = torch.zeros(si, dtype=torch.float32, device=plan.device)
             g_user, g_item = g_user.contiguous(), g_item.contiguous()
             ws, _ = plan.scratch(ctx.n_layers, d)
-            d_u, d_i = torch.empty_like(g_user), torch.empty_like(g_item)
-            _lib.check(lib.sagnn_propagate_bwd(plan.handle, _ptr(g_user), _ptr(g_item), _ptr(d_u), _ptr(d_i),
-                                               ctx.n_layers, d, ctx.leaky, _ptr(ctx.masks), _ptr(ws),
-                                               ws.numel(), _stream_ptr(plan.device)))
-        return d_u, d_i, None, None, None
+            d_u = torch.empty((plan.T, plan.U, d), dtype=torch.float32, device=plan.device)
+            d_i = torch.empty((plan.T, plan.I, d), dtype=torch.float32, device=plan.device)
+            _lib.check(lib.sagnn_propagate_bwd_ex(plan.handle, _ptr(g_user), _ptr(g_item), _ptr(d_u), _ptr(d_i),
+                                                  ctx.n_layers, d, ctx.leaky, _ptr(ctx.masks), _ptr(ws),
+                                                  ws.numel(), ctx.layout, _stream_ptr(plan.device)))
+        return d_u, d_i, None, None, None, None
 
 
-def propagate(plan, u_embed, i_embed, n_layers, leaky=0.5):
+def propagate(plan, u_embed, i_embed, n_layers, leaky=0.5, layout="trd"):
     """model.py:118-129 for all T intervals: returns (user_vector [T,U,d], item_vector [T,I,d]),
     i.e. the stacked ``tf.add_n(embs0)`` / ``tf.add_n(embs1)`` of model.py:126-132.  Differentiable
     w.r.t. both embedding tables (dense upstream gradients).  Edge dropout
-    (model.py:93-102) only rewrites the ignored edge values, so it has no counterpart here."""
-    return _Propagate.apply(u_embed, i_embed, plan, int(n_layers), float(leaky))
+    (model.py:93-102) only rewrites the ignored edge values, so it has no counterpart here.
+
+    layout="rtd" returns ``user_vector_tensor [U,T,d]`` / ``item_vector_tensor [I,T,d]`` instead,
+    the ``tf.transpose(.., perm=[1,0,2])`` of model.py:133-134 that feeds the LSTM: the transpose is
+    fused into the kernel epilogue (and the backward reads its upstream in that layout), values are
+    bitwise those of the default layout."""
+    if layout not in _LAYOUTS:
+        raise ValueError("layout must be 'trd' ([T,R,d], model.py:131-132) or 'rtd' ([R,T,d], model.py:133-134)")
+    return _Propagate.apply(u_embed, i_embed, plan, int(n_layers), float(leaky), _LAYOUTS[layout])
 
 
 def message_propagate(srclats, plan, k, type="user", leaky=0.5):
@@ -347,9 +363,9 @@ class IntervalPropagation(torch.nn.Module):
     module: owns ``uEmbed [T,U,d]`` / ``iEmbed [T,I,d]`` (xavier, model.py:108-109) and returns the
     stacked per-interval layer sums."""
 
-    def __init__(self, plan, latdim=64, gnn_layer=2, leaky=0.5):
+    def __init__(self, plan, latdim=64, gnn_layer=2, leaky=0.5, layout="trd"):
         super().__init__()
-        self.plan, self.gnn_layer, self.leaky = plan, gnn_layer, leaky
+        self.plan, self.gnn_layer, self.leaky, self.layout = plan, gnn_layer, leaky, layout
         self.uEmbed = torch.nn.Parameter(torch.empty(plan.T, plan.U, latdim, device=plan.device))
         self.iEmbed = torch.nn.Parameter(torch.empty(plan.T, plan.I, latdim, device=plan.device))
         # tf.contrib xavier on a 3-D shape: fan_in = T*rows, fan_out = T*d (Utils/NNLayers.py:47-50)
@@ -358,4 +374,4 @@ class IntervalPropagation(torch.nn.Module):
             torch.nn.init.uniform_(p_, -a, a)
 
     def forward(self):
-        return propagate(self.plan, self.uEmbed, self.iEmbed, self.gnn_layer, self.leaky)
+        return propagate(self.plan, self.uEmbed, self.iEmbed, self.gnn_layer, self.leaky, self.layout)

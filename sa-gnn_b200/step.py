@@ -16,8 +16,11 @@ from .propagate import _ptr, _stream_ptr
 
 
 class PropagationStep:
-    def __init__(self, plan, n_layers, d, leaky=0.5):
+    def __init__(self, plan, n_layers, d, leaky=0.5, layout="trd"):
+        """layout="rtd": outputs and upstream gradients are [R,T,d] (model.py:133-134, the LSTM's
+        input layout; SAGNN_LAYOUT_RTD), embeddings and their gradients stay [T,R,d]."""
         self.plan, self.L, self.d, self.leaky = plan, int(n_layers), int(d), float(leaky)
+        self.flags = {"trd": 0, "rtd": 1}[layout]
         dev = plan.device
         self.lib = _lib.load_library()
         with torch.cuda.device(dev):
@@ -26,8 +29,10 @@ class PropagationStep:
             self.masks = torch.empty(max(m, 1), dtype=torch.uint8, device=dev)
             mk = lambda rows: torch.empty((plan.T, rows, self.d), dtype=torch.float32, device=dev)
             self.u_embed, self.i_embed = mk(plan.U), mk(plan.I)
-            self.g_user, self.g_item = mk(plan.U), mk(plan.I)
-            self.user_out, self.item_out = mk(plan.U), mk(plan.I)
+            mo = mk if not self.flags else \
+                (lambda rows: torch.empty((rows, plan.T, self.d), dtype=torch.float32, device=dev))
+            self.g_user, self.g_item = mo(plan.U), mo(plan.I)
+            self.user_out, self.item_out = mo(plan.U), mo(plan.I)
             self.d_u, self.d_i = mk(plan.U), mk(plan.I)
         self.graph = None
         # L forward + L backward layer kernels + the streaming pre-mask of the upstream (row-per-warp kernel)
@@ -35,16 +40,17 @@ class PropagationStep:
 
     def forward(self):
         p = self.plan
-        _lib.check(self.lib.sagnn_propagate_fwd(p.handle, _ptr(self.u_embed), _ptr(self.i_embed),
-                                                _ptr(self.user_out), _ptr(self.item_out), self.L, self.d,
-                                                self.leaky, _ptr(self.masks), _ptr(self.ws), self.ws.numel(),
-                                                _stream_ptr(p.device)))
+        _lib.check(self.lib.sagnn_propagate_fwd_ex(p.handle, _ptr(self.u_embed), _ptr(self.i_embed),
+                                                   _ptr(self.user_out), _ptr(self.item_out), self.L, self.d,
+                                                   self.leaky, _ptr(self.masks), _ptr(self.ws), self.ws.numel(),
+                                                   self.flags, _stream_ptr(p.device)))
 
     def backward(self):
         p = self.plan
-        _lib.check(self.lib.sagnn_propagate_bwd(p.handle, _ptr(self.g_user), _ptr(self.g_item), _ptr(self.d_u),
-                                                _ptr(self.d_i), self.L, self.d, self.leaky, _ptr(self.masks),
-                                                _ptr(self.ws), self.ws.numel(), _stream_ptr(p.device)))
+        _lib.check(self.lib.sagnn_propagate_bwd_ex(p.handle, _ptr(self.g_user), _ptr(self.g_item), _ptr(self.d_u),
+                                                   _ptr(self.d_i), self.L, self.d, self.leaky, _ptr(self.masks),
+                                                   _ptr(self.ws), self.ws.numel(), self.flags,
+                                                   _stream_ptr(p.device)))
 
     def forward_interval(self, k):
         """Forward restricted to interval k (all SMs on its two CSRs); see sagnn_propagate_fwd_interval."""

@@ -354,6 +354,65 @@ def test_interval_launches_equal_full_launch_bitwise():
             assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("d,L", [(32, 1), (64, 2), (64, 3), (128, 3), (256, 2)])
+def test_rtd_layout_equals_transposed_default_bitwise(d, L):
+    """SAGNN_LAYOUT_RTD (the [R,T,d] hand-off of model.py:133-134 fused into the epilogue, and the
+    backward reading its upstream in that layout): same bits as the default layout, transposed;
+    and parity against the oracle's outputs transposed."""
+    g = dh.make_named("small", seed=21)
+    plan = sg.build_plan(g.sub_mat)
+    T, U, I = plan.T, g.n_user, g.n_item
+    uE, iE, gU, gI = random_tables(T, U, I, d, seed=31)
+    ref = run_gpu(plan, uE, iE, gU, gI, L)
+    u = torch.from_numpy(uE).cuda().requires_grad_(True)
+    i = torch.from_numpy(iE).cuda().requires_grad_(True)
+    uv, iv = sg.propagate(plan, u, i, L, 0.5, layout="rtd")
+    assert uv.shape == (U, T, d) and iv.shape == (I, T, d) and uv.is_contiguous() and iv.is_contiguous()
+    gUt = torch.from_numpy(gU).cuda().transpose(0, 1).contiguous()
+    gIt = torch.from_numpy(gI).cuda().transpose(0, 1).contiguous()
+    torch.autograd.backward([uv, iv], [gUt, gIt])
+    torch.cuda.synchronize()
+    assert torch.equal(uv.transpose(0, 1), ref[0]) and torch.equal(iv.transpose(0, 1), ref[1])
+    assert torch.equal(u.grad, ref[2]) and torch.equal(i.grad, ref[3])
+    adj, tp = adj_lists(g.sub_mat)
+    oref = po.propagate(adj, tp, uE, iE, gU, gI, L, 0.5, np.float64)
+    assert_parity(uv, np.transpose(oref[0], (1, 0, 2)), "user_vector_tensor [U,T,d]")
+    assert_parity(iv, np.transpose(oref[1], (1, 0, 2)), "item_vector_tensor [I,T,d]")
+
+
+def test_rtd_layout_step_graph_and_sliced_rows():
+    """PropagationStep(layout='rtd'): direct launches == CUDA-graph replay == default layout, on a
+    shape with sliced long rows; unknown flags are rejected."""
+    import ctypes
+    from sagnn_b200 import _lib
+    from sagnn_b200.step import PropagationStep
+    from sagnn_b200.propagate import _ptr, _stream_ptr
+    mats = random_interval_mats(2, 300, 40, 6000, seed=8)          # item rows of ~150 edges: slices
+    plan = sg.build_plan(mats)
+    a, b = PropagationStep(plan, 2, 64), PropagationStep(plan, 2, 64, layout="rtd")
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for t in (a.u_embed, a.i_embed, a.g_user, a.g_item):
+        t.normal_(generator=gen)
+    b.u_embed.copy_(a.u_embed); b.i_embed.copy_(a.i_embed)
+    b.g_user.copy_(a.g_user.transpose(0, 1)); b.g_item.copy_(a.g_item.transpose(0, 1))
+    a.run(); b.run()
+    torch.cuda.synchronize()
+    def same():
+        return (torch.equal(b.user_out.transpose(0, 1), a.user_out) and torch.equal(b.item_out.transpose(0, 1), a.item_out)
+                and torch.equal(b.d_u, a.d_u) and torch.equal(b.d_i, a.d_i))
+    assert same()
+    b.capture()
+    for t in (b.user_out, b.item_out, b.d_u, b.d_i):
+        t.zero_()
+    b.replay()
+    torch.cuda.synchronize()
+    assert same()
+    rc = _lib.load_library().sagnn_propagate_fwd_ex(
+        plan.handle, _ptr(b.u_embed), _ptr(b.i_embed), _ptr(b.user_out), _ptr(b.item_out), 2, 64, 0.5,
+        _ptr(b.masks), _ptr(b.ws), b.ws.numel(), 0x80, _stream_ptr(plan.device))
+    assert rc == 1   # SAGNN_INVALID_ARG
+
+
 # ---------------------------------------------------------------- BASELINE shape families
 @pytest.mark.parametrize("name,scale", [("gowalla", 0.05), ("amazon-book", 0.05), ("amazon-ref", 0.25), ("ml10m", 0.03)])
 def test_baseline_shapes_reduced_scale(name, scale):
