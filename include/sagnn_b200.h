@@ -77,6 +77,14 @@ int sagnn_plan_set_interval(sagnn_plan* plan, int k, const int32_t* row_dev, con
                             const int32_t* val_dev, const float* w_dev, int64_t nnz,
                             sagnn_stream_t stream);
 
+/* Optional, before finalize -- ROW SHARDING of the graphs over several GPUs (second way):
+ * this plan only schedules user rows [u_begin,u_end) of every A_k and item rows [i_begin,i_end) of
+ * every A_k^T (it still holds the complete adjacency, since the rows it owns gather from every row of
+ * the other side).  propagate_* then read whole tables and write only the owned rows; between layers
+ * the caller all-gathers the freshly written table (sagnn_propagate_fwd_layers / _bwd_levels /
+ * sagnn_workspace_table below).  Row-per-warp kernel only. */
+int sagnn_plan_set_row_block(sagnn_plan* plan, int u_begin, int u_end, int i_begin, int i_end);
+
 /* Optional, before finalize: the latdim the plan will mostly be run with (default 64).  It sizes
  * the hot-row set so that all of it fits the shared-memory staging area at that d; other d still
  * work (hot rows that do not fit are read through their ids). */
@@ -161,6 +169,30 @@ int sagnn_propagate_bwd_ex(const sagnn_plan* plan, const float* g_user_dev, cons
                            float* d_u_embed_dev, float* d_i_embed_dev, int n_layers, int d, float leaky,
                            const void* masks_dev, void* workspace_dev, size_t workspace_bytes,
                            unsigned flags, sagnn_stream_t stream);
+
+/* Row-sharded execution (plans with sagnn_plan_set_row_block): the L-layer forward / backward one
+ * stage at a time, so that the caller can all-gather the table each stage wrote (owned rows only)
+ * before the next stage gathers from it.  Same tensors, masks and workspace in every call of a step.
+ *   forward : layers [l_begin, l_end) of n_layers; after layer l < n_layers-1 exchange table
+ *             sagnn_workspace_table(which=0, index=l)  (E^{l+1}); u_embed / i_embed must be complete.
+ *   backward: phases [ph_begin, ph_end) of n_layers+1; phase 0 = sigma'(Z^{L-1}) (.) G of the owned rows
+ *             (g_user / g_item must be complete), phase j >= 1 = level kernel j-1; after phase
+ *             j < n_layers exchange table sagnn_workspace_table(which=1, index=j).
+ * user_out / item_out / d_u_embed / d_i_embed receive the owned rows only. */
+int sagnn_propagate_fwd_layers(const sagnn_plan* plan, int l_begin, int l_end, const float* u_embed_dev,
+                               const float* i_embed_dev, float* user_out_dev, float* item_out_dev,
+                               int n_layers, int d, float leaky, void* masks_dev, void* workspace_dev,
+                               size_t workspace_bytes, sagnn_stream_t stream);
+int sagnn_propagate_bwd_levels(const sagnn_plan* plan, int ph_begin, int ph_end, const float* g_user_dev,
+                               const float* g_item_dev, float* d_u_embed_dev, float* d_i_embed_dev,
+                               int n_layers, int d, float leaky, const void* masks_dev, void* workspace_dev,
+                               size_t workspace_bytes, sagnn_stream_t stream);
+/* Byte offset inside the workspace of the table to exchange (layout [T,U,d] then [T,I,d], fp32):
+ * which=0: written by forward layer `index` (0 <= index < n_layers-1);
+ * which=1: the gather source of backward level `index`, written by backward phase `index`
+ *          (0 <= index < n_layers). */
+int sagnn_workspace_table(const sagnn_plan* plan, int n_layers, int d, int which, int index,
+                          size_t* offset_bytes, size_t* user_bytes, size_t* item_bytes);
 
 /* The same restricted to interval k (rows of the other intervals are not touched): all SMs work on
  * that interval's two CSRs, so a caller can pipeline per-interval copies with compute.  Tensors,

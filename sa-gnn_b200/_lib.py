@@ -44,6 +44,13 @@ SIGNATURES = {
                                               vp, vp, ctypes.c_size_t, ctypes.c_uint, vp]),
     "sagnn_propagate_bwd_ex": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                               vp, vp, ctypes.c_size_t, ctypes.c_uint, vp]),
+    "sagnn_plan_set_row_block": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "sagnn_propagate_fwd_layers": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_float, vp, vp, ctypes.c_size_t, vp]),
+    "sagnn_propagate_bwd_levels": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_float, vp, vp, ctypes.c_size_t, vp]),
+    "sagnn_workspace_table": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_szp,
+                                             c_szp, c_szp]),
     "sagnn_propagate_fwd_interval": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,
                                                     ctypes.c_float, vp, vp, ctypes.c_size_t, vp]),
     "sagnn_propagate_bwd_interval": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,

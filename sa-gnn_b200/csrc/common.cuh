@@ -78,6 +78,10 @@ struct sagnn_plan {
   bool finalized = false;
   int weight_mode = 0;
   int hot_rows = sagnn::kHotRows; // hot slots actually used: min(kHotRows, kHotBytes / (4 * latdim hint))
+  // row sharding (sagnn_plan_set_row_block): only user rows [u_begin,u_end) and item rows [i_begin,i_end)
+  // of every interval get tasks; the others are some other rank's.  Default: all rows.
+  int u_begin = 0, u_end = 0, i_begin = 0, i_end = 0;
+  bool row_block = false;
 
   // canonical CSRs (what transToLsts / transpose produce; parity hooks read these)
   int32_t* deg = nullptr;         // [n_rows] structural degrees

@@ -149,7 +149,8 @@ __global__ void sched_key_kernel(const int32_t* __restrict__ deg, int64_t n_rows
 // hot slots = the kHotRows highest-degree rows of every table; per sorted position also the
 // number of tasks / slices / long rows it contributes (inputs of the three scans)
 __global__ void sched_slot_kernel(const uint32_t* __restrict__ srow, const int32_t* __restrict__ deg,
-                                  int64_t n_rows, int64_t N, int U, int K, int32_t* __restrict__ slot_of,
+                                  int64_t n_rows, int64_t N, int U, int K, int u_begin, int u_end, int i_begin,
+                                  int i_end, int32_t* __restrict__ slot_of,
                                   int32_t* __restrict__ hot_ids, int64_t* __restrict__ n_task,
                                   int64_t* __restrict__ n_chunk, int64_t* __restrict__ n_long) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,10 +163,13 @@ __global__ void sched_slot_kernel(const uint32_t* __restrict__ srow, const int32
   if (pos < K) hot_ids[(int64_t)t * kHotRows + pos] = (int32_t)(g - table_row0(t, N, U));
   const int d = deg[g];
   const bool lg = d > kChunk;
-  const int64_t nt = lg ? (d + kChunk - 1) / kChunk : 1;
+  // rows outside this rank's block (row sharding) contribute nothing to the schedule
+  const int64_t r = (int64_t)g - table_row0(t, N, U);
+  const bool own = (t & 1) ? (r >= i_begin && r < i_end) : (r >= u_begin && r < u_end);
+  const int64_t nt = !own ? 0 : (lg ? (d + kChunk - 1) / kChunk : 1);
   n_task[i] = nt;
   n_chunk[i] = lg ? nt : 0;
-  n_long[i] = lg ? 1 : 0;
+  n_long[i] = (lg && own) ? 1 : 0;
 }
 
 // kernel-side edge codes: one warp per row, stable partition hot-first (hot = slot, cold = id)
@@ -459,6 +463,18 @@ extern "C" int sagnn_plan_get_split(const sagnn_plan* p, int* ctas_per_segment) 
   return SAGNN_OK;
 }
 
+extern "C" int sagnn_plan_set_row_block(sagnn_plan* p, int u_begin, int u_end, int i_begin, int i_end) {
+  SAGNN_REQUIRE(p, SAGNN_INVALID_ARG, "set_row_block: NULL plan");
+  SAGNN_REQUIRE(!p->finalized, SAGNN_INVALID_ARG, "set_row_block: plan already finalized");
+  SAGNN_REQUIRE(0 <= u_begin && u_begin <= u_end && u_end <= p->U && 0 <= i_begin && i_begin <= i_end && i_end <= p->I,
+                SAGNN_INVALID_ARG, "set_row_block: need 0 <= u_begin <= u_end <= %d and 0 <= i_begin <= i_end <= %d "
+                "(got [%d,%d) [%d,%d))", p->U, p->I, u_begin, u_end, i_begin, i_end);
+  SAGNN_REQUIRE(sagnn::use_rpw(), SAGNN_INVALID_ARG, "set_row_block: row sharding needs the row-per-warp kernel");
+  p->u_begin = u_begin; p->u_end = u_end; p->i_begin = i_begin; p->i_end = i_end;
+  p->row_block = true;
+  return SAGNN_OK;
+}
+
 extern "C" int sagnn_plan_set_latdim_hint(sagnn_plan* p, int d) {
   SAGNN_REQUIRE(p && !p->finalized, SAGNN_INVALID_ARG, "set_latdim_hint: NULL or finalized plan");
   SAGNN_REQUIRE(d >= 4 && d % 4 == 0, SAGNN_INVALID_ARG, "set_latdim_hint: d=%d", d);
@@ -542,7 +558,9 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   }
   int64_t *n_task = cnt3.p, *n_chunk = cnt3.p + (R + 1), *n_long = cnt3.p + 2 * (R + 1);
   int64_t *task_off = off3.p, *chunk_off = off3.p + (R + 1), *long_off = off3.p + 2 * (R + 1);
-  sched_slot_kernel<<<blocks_for(R + 1), 256, 0, st>>>(srow, p->deg, R, N, U, p->hot_rows, slot_of, p->hot_ids, n_task,
+  if (!p->row_block) { p->u_begin = 0; p->u_end = p->U; p->i_begin = 0; p->i_end = p->I; }
+  sched_slot_kernel<<<blocks_for(R + 1), 256, 0, st>>>(srow, p->deg, R, N, U, p->hot_rows, p->u_begin, p->u_end,
+                                                       p->i_begin, p->i_end, slot_of, p->hot_ids, n_task,
                                                        n_chunk, n_long);
   {
     DevTmp<char> tmp; size_t tb = 0;
@@ -556,7 +574,7 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   SAGNN_CUDA(cudaMemcpy(&p->n_tasks, task_off + R, sizeof(int64_t), cudaMemcpyDeviceToHost));
   SAGNN_CUDA(cudaMemcpy(&p->n_chunks, chunk_off + R, sizeof(int64_t), cudaMemcpyDeviceToHost));
   SAGNN_CUDA(cudaMemcpy(&p->n_long, long_off + R, sizeof(int64_t), cudaMemcpyDeviceToHost));
-  p->n_short = R - p->n_long;
+  p->n_short = (p->row_block ? (int64_t)p->T * ((p->u_end - p->u_begin) + (p->i_end - p->i_begin)) : R) - p->n_long;
   {
     DevTmp<char> tmp; size_t tb = 0;
     DevTmp<int32_t> dmax;
@@ -622,9 +640,21 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
       std::vector<int64_t> hot(S);
       SAGNN_CUDA(cudaMemcpyAsync(hot.data(), hsum, sizeof(int64_t) * S, cudaMemcpyDeviceToHost, st));
       SAGNN_CUDA(cudaStreamSynchronize(st));
+      std::vector<int64_t> own_e(S);
+      for (int t = 0; t < S; ++t) {   // edges of the rows this rank owns (all of them without row sharding)
+        own_e[t] = p->nnz[t >> 1];
+        if (p->row_block) {
+          const int64_t row0 = (int64_t)(t >> 1) * N + ((t & 1) ? U : 0);
+          int64_t a = 0, b = 0;
+          SAGNN_CUDA(cudaMemcpy(&a, p->rowptr + row0 + ((t & 1) ? p->i_begin : p->u_begin), sizeof(int64_t), cudaMemcpyDeviceToHost));
+          SAGNN_CUDA(cudaMemcpy(&b, p->rowptr + row0 + ((t & 1) ? p->i_end : p->u_end), sizeof(int64_t), cudaMemcpyDeviceToHost));
+          own_e[t] = b - a;
+        }
+      }
       for (int t = 0; t < S; ++t) {
-        const double e = (double)p->nnz[t >> 1], h = (double)hot[t];
-        cost[t] = 4.0 * (e - h) + 0.9 * h + 30.0 * ((t & 1) ? p->I : p->U);
+        const double e = (double)own_e[t], h = p->row_block ? 0.0 : (double)hot[t];
+        const double rows = (t & 1) ? p->i_end - p->i_begin : p->u_end - p->u_begin;
+        cost[t] = 4.0 * (e - h) + 0.9 * h + 30.0 * rows + 1.0;
       }
     }
     p->seg_cost = cost;

@@ -979,7 +979,10 @@ extern "C" int sagnn_workspace_bytes(const sagnn_plan* p, int n_layers, int d, s
 // segments (all 148 CTAs work on them) -- lets a caller pipeline copies with compute
 static int fwd_impl(const sagnn_plan* p, int interval, const float* uE, const float* iE, float* uOut,
                     float* iOut, int L, int d, float leaky, void* masks, void* ws, size_t ws_bytes,
-                    cudaStream_t st, unsigned flags = 0) {
+                    cudaStream_t st, unsigned flags = 0, int l_begin = 0, int l_end = -1) {
+  if (l_end < 0) l_end = L;
+  SAGNN_REQUIRE(0 <= l_begin && l_begin <= l_end && l_end <= L, SAGNN_INVALID_ARG,
+                "propagate_fwd: layer range [%d,%d) outside [0,%d]", l_begin, l_end, L);
   SAGNN_REQUIRE(!(flags & ~(unsigned)SAGNN_LAYOUT_RTD), SAGNN_INVALID_ARG, "propagate_fwd: unknown flags 0x%x", flags);
   SAGNN_REQUIRE(!flags || use_rpw(), SAGNN_INVALID_ARG, "propagate_fwd: [R,T,d] outputs need the row-per-warp kernel");
   if (int rc = check_common(p, L, d, "propagate_fwd")) return rc;
@@ -1000,7 +1003,7 @@ static int fwd_impl(const sagnn_plan* p, int interval, const float* uE, const fl
   float* buf[2] = {(float*)(base + w.buf_off[0]), (float*)(base + w.buf_off[1])};
   const size_t mlw = mask_layer_bytes(p, d);
   const size_t mu = (size_t)p->T * p->U * (d / 4);
-  for (int l = 0; l < L; ++l) {
+  for (int l = l_begin; l < l_end; ++l) {
     s.ctrs = s.tickets + w.ticket_words + (size_t)l * 2 * p->T;
     const float* cur_u = l == 0 ? uE : buf[(l - 1) & 1];
     const float* cur_i = l == 0 ? iE : buf[(l - 1) & 1] + w.user_floats;
@@ -1051,7 +1054,13 @@ extern "C" int sagnn_propagate_fwd_interval(const sagnn_plan* p, int k, const fl
 
 static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const float* gI, float* dU, float* dI,
                     int L, int d, float leaky, const void* masks, void* ws, size_t ws_bytes, cudaStream_t st,
-                    unsigned flags = 0) {
+                    unsigned flags = 0, int ph_begin = 0, int ph_end = -1) {
+  // phases: 0 = streaming pre-mask of the upstream (row-per-warp kernel), j >= 1 = level kernel of step j-1
+  if (ph_end < 0) ph_end = L + 1;
+  SAGNN_REQUIRE(0 <= ph_begin && ph_begin <= ph_end && ph_end <= L + 1, SAGNN_INVALID_ARG,
+                "propagate_bwd: phase range [%d,%d) outside [0,%d]", ph_begin, ph_end, L + 1);
+  const int s_begin = ph_begin > 0 ? ph_begin - 1 : 0, s_end = ph_end - 1;
+  if (ph_begin == ph_end) return SAGNN_OK;
   SAGNN_REQUIRE(!(flags & ~(unsigned)SAGNN_LAYOUT_RTD), SAGNN_INVALID_ARG, "propagate_bwd: unknown flags 0x%x", flags);
   SAGNN_REQUIRE(!flags || use_rpw(), SAGNN_INVALID_ARG, "propagate_bwd: [R,T,d] upstream needs the row-per-warp kernel");
   if (int rc = check_common(p, L, d, "propagate_bwd")) return rc;
@@ -1074,7 +1083,7 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
   const size_t mu = (size_t)p->T * p->U * (d / 4);
   const bool rpw = use_rpw();
   if (interval >= 0) s.cta = p->cta_int_dev + (size_t)interval * p->num_sms;
-  for (int l = L - 1, step = 0; l >= 0; --l, ++step) {
+  for (int l = L - 1 - s_begin, step = s_begin; step < s_end || (step == 0 && ph_begin == 0); --l, ++step) {
     s.ctrs = s.tickets + w.ticket_words + (size_t)step * 2 * p->T;
     // g = total gradient w.r.t. E^{l+1}; at the top level it is the upstream itself
     const float* g_u = step == 0 ? gU : buf[(step - 1) & 1];
@@ -1091,11 +1100,13 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
         const int64_t ou = interval >= 0 ? (int64_t)interval * p->U : 0, oi = interval >= 0 ? (int64_t)interval * p->I : 0;
         const int64_t q = d / 4;
         const bool rtd = (flags & SAGNN_LAYOUT_RTD) != 0;   // whole-tensor base + interval offset inside the kernel
-        premask_kernel<<<p->num_sms * 8, 256, 0, st>>>(
-            (const float4*)gU + (rtd ? 0 : ou * q), (const float4*)gI + (rtd ? 0 : oi * q), s.smask_u + ou * q,
-            s.smask_i + oi * q, (float4*)pu + ou * q, (float4*)pi + oi * q, ru * q, ri * q, leaky, rtd ? p->T : 0,
-            interval >= 0 ? interval : 0, p->U, p->I, (int)q);
-        SAGNN_CUDA(cudaGetLastError());
+        if (ph_begin == 0) {
+          premask_kernel<<<p->num_sms * 8, 256, 0, st>>>(
+              (const float4*)gU + (rtd ? 0 : ou * q), (const float4*)gI + (rtd ? 0 : oi * q), s.smask_u + ou * q,
+              s.smask_i + oi * q, (float4*)pu + ou * q, (float4*)pi + oi * q, ru * q, ri * q, leaky, rtd ? p->T : 0,
+              interval >= 0 ? interval : 0, p->U, p->I, (int)q);
+          SAGNN_CUDA(cudaGetLastError());
+        }
         s.src_u = pu; s.src_i = pi;
         s.smask_u = nullptr; s.smask_i = nullptr;
       }
@@ -1118,6 +1129,7 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
     s.b_i = step == 0 ? nullptr : g_i;
     s.o1_u = l == 0 ? dU : buf[step & 1];
     s.o1_i = l == 0 ? dI : buf[step & 1] + w.user_floats;
+    if (step >= s_end) break;                                  // phase 0 only: just the pre-mask pass
     for (int wv = 0; wv < (interval >= 0 ? 1 : p->n_waves); ++wv) {
       if (interval < 0) s.cta = p->cta_dev + (size_t)wv * p->num_sms;
       if (int rc = launch(p, s, d, MODE_BWD, st)) return rc;
@@ -1136,6 +1148,39 @@ extern "C" int sagnn_propagate_bwd_ex(const sagnn_plan* p, const float* gU, cons
                                       float* dI, int L, int d, float leaky, const void* masks, void* ws,
                                       size_t ws_bytes, unsigned flags, sagnn_stream_t stream) {
   return bwd_impl(p, -1, gU, gI, dU, dI, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream, flags);
+}
+
+// ---- row sharding: one layer (level) at a time, the caller all-gathers the table in between ----
+extern "C" int sagnn_propagate_fwd_layers(const sagnn_plan* p, int l_begin, int l_end, const float* uE,
+                                          const float* iE, float* uOut, float* iOut, int L, int d, float leaky,
+                                          void* masks, void* ws, size_t ws_bytes, sagnn_stream_t stream) {
+  return fwd_impl(p, -1, uE, iE, uOut, iOut, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream, 0, l_begin,
+                  l_end);
+}
+
+extern "C" int sagnn_propagate_bwd_levels(const sagnn_plan* p, int ph_begin, int ph_end, const float* gU,
+                                          const float* gI, float* dU, float* dI, int L, int d, float leaky,
+                                          const void* masks, void* ws, size_t ws_bytes, sagnn_stream_t stream) {
+  SAGNN_REQUIRE(use_rpw() && use_premask(), SAGNN_INVALID_ARG,
+                "propagate_bwd_levels: needs the row-per-warp kernel with pre-masked sources");
+  return bwd_impl(p, -1, gU, gI, dU, dI, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream, 0, ph_begin, ph_end);
+}
+
+extern "C" int sagnn_workspace_table(const sagnn_plan* p, int L, int d, int which, int index, size_t* offset_bytes,
+                                     size_t* user_bytes, size_t* item_bytes) {
+  if (int rc = check_common(p, L, d, "workspace_table")) return rc;
+  SAGNN_REQUIRE(offset_bytes && (which == 0 || which == 1) && index >= 0 && index < (which ? L : L - 1),
+                SAGNN_INVALID_ARG, "workspace_table: which=%d index=%d (forward: 0 <= index < n_layers-1, "
+                "backward: 0 <= index < n_layers; n_layers=%d)", which, index, L);
+  SAGNN_REQUIRE(which == 0 || use_rpw(), SAGNN_INVALID_ARG, "workspace_table: the v7 kernel has no pre-masked tables");
+  WsLayout w = ws_layout(p, L, d);
+  // forward: E^{index+1}, written by layer `index`; backward: the pre-masked gather source of level
+  // step `index` (written by phase `index`: the pre-mask pass for 0, the level kernel of step index-1 after)
+  *offset_bytes = which == 0 ? w.buf_off[index & 1]
+                             : (index == 0 ? w.pm_off[L >= 2 ? 1 : 0] : w.pm_off[(index - 1) & 1]);
+  if (user_bytes) *user_bytes = sizeof(float) * w.user_floats;
+  if (item_bytes) *item_bytes = sizeof(float) * (w.table_floats - w.user_floats);
+  return SAGNN_OK;
 }
 
 extern "C" int sagnn_propagate_bwd_interval(const sagnn_plan* p, int k, const float* gU, const float* gI,

@@ -1,4 +1,5 @@
-"""Multi-GPU plumbing for the propagation path: interval sharding + output all-gather.
+"""Multi-GPU plumbing for the propagation path: interval sharding + output all-gather, and row
+sharding of the graphs (one table all-gather per layer) for when there are fewer intervals than GPUs.
 
 The T interval graphs share nothing -- separate adjacency, separate embedding slices
 ``uEmbed[k]`` / ``iEmbed[k]`` (model.py:108-109,119-120), separate outputs (model.py:128-129) --
@@ -124,3 +125,164 @@ class ShardedPropagation:
             iv = i_embed.new_zeros((0,) + tuple(i_embed.shape[1:]))
         return (gather_intervals(uv, self.owners, self.rank, self.group),
                 gather_intervals(iv, self.owners, self.rank, self.group))
+
+
+# ---------------------------------------------------------------------------------------------
+# Row sharding (second way): every rank holds all T graphs but computes only one block
+# of user rows of each A_k and one block of item rows of each A_k^T.  A row gathers from every
+# row of the other side, so each layer's freshly written table is all-gathered before the next
+# layer reads it: L-1 table all-gathers in the forward, L in the backward (the pre-masked
+# gradients), plus one for the outputs / parameter gradients when the consumer is replicated.
+# Both orientations are stored, so there is never a reduce-scatter or a float atomic.
+# ---------------------------------------------------------------------------------------------
+def padded_rows(n_rows, world):
+    """Rows rounded up so that every rank owns an equal block (pad rows are empty graph rows)."""
+    size, _ = row_blocks(n_rows, world)
+    return size * world
+
+
+def forward_stages(n_layers):
+    """[(layer, table index to exchange afterwards or None)] -- ``sagnn_propagate_fwd_layers``."""
+    return [(l, l if l < n_layers - 1 else None) for l in range(n_layers)]
+
+
+def backward_stages(n_layers):
+    """[(phase, table index to exchange afterwards or None)] -- ``sagnn_propagate_bwd_levels``:
+    phase 0 pre-masks the owned rows of the upstream, phase j >= 1 is level kernel j-1."""
+    return [(ph, ph if ph < n_layers else None) for ph in range(n_layers + 1)]
+
+
+def allgather_row_blocks(table, rank=None, group=None):
+    """In-place all-gather of equal row blocks: ``table [T, R, d]`` (R divisible by the world size)
+    holds this rank's rows ``[rank*b, (rank+1)*b)`` of every interval on entry and all rows on exit.
+    One collective per interval, sent straight from / received straight into the table (NCCL
+    all-gathers in place; other backends get a staged copy of the send block)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group) if rank is None else rank
+    T, R, d = table.shape
+    if R % world:
+        raise ValueError("rows (%d) must be a multiple of the world size (%d)" % (R, world))
+    if world == 1:
+        return table
+    b = R // world
+    in_place = table.is_cuda
+    for k in range(T):
+        mine = table[k, rank * b:(rank + 1) * b]
+        dist.all_gather_into_tensor(table[k], mine if in_place else mine.clone(), group=group)
+    return table
+
+
+class _RowShardedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u_embed, i_embed, rs):
+        be = rs._backend(u_embed.shape[2])
+        u, i = rs._pad(u_embed, rs.U, rs.U_pad), rs._pad(i_embed, rs.I, rs.I_pad)
+        need_bwd = u_embed.requires_grad or i_embed.requires_grad
+        u_out, i_out = torch.empty_like(u), torch.empty_like(i)
+        be.begin_forward(u, i, u_out, i_out, need_bwd)
+        for l, ex in forward_stages(rs.n_layers):
+            be.fwd_layers(l, l + 1)
+            if ex is not None:
+                for t in be.table(0, ex):
+                    allgather_row_blocks(t, rs.rank, rs.group)
+        allgather_row_blocks(u_out, rs.rank, rs.group)          # replicated consumer (model.py:131-155)
+        allgather_row_blocks(i_out, rs.rank, rs.group)
+        ctx.rs, ctx.be, ctx.masks = rs, be, be.masks
+        return u_out[:, :rs.U], i_out[:, :rs.I]
+
+    @staticmethod
+    def backward(ctx, g_user, g_item):
+        rs, be = ctx.rs, ctx.be
+        gu = rs._pad(g_user.contiguous(), rs.U, rs.U_pad)
+        gi = rs._pad(g_item.contiguous(), rs.I, rs.I_pad)
+        d_u, d_i = torch.empty_like(gu), torch.empty_like(gi)
+        be.masks = ctx.masks                                    # the masks of THIS forward
+        be.begin_backward(gu, gi, d_u, d_i)
+        for ph, ex in backward_stages(rs.n_layers):
+            be.bwd_levels(ph, ph + 1)
+            if ex is not None:
+                for t in be.table(1, ex):
+                    allgather_row_blocks(t, rs.rank, rs.group)
+        allgather_row_blocks(d_u, rs.rank, rs.group)            # replicated parameters
+        allgather_row_blocks(d_i, rs.rank, rs.group)
+        return d_u[:, :rs.U], d_i[:, :rs.I], None
+
+
+class _CudaRowBackend:
+    """The C-ABI calls of one row-sharded step (what the stages above drive)."""
+
+    def __init__(self, plan, n_layers, d, leaky):
+        from . import _lib
+        self.plan, self.L, self.d, self.leaky = plan, n_layers, d, float(leaky)
+        self.lib, self._lib = _lib.load_library(), _lib
+        self.ws, mask_bytes = plan.scratch(n_layers, d)
+        self.mask_bytes = mask_bytes
+
+    def begin_forward(self, u, i, u_out, i_out, need_bwd):
+        self.u, self.i, self.u_out, self.i_out = u, i, u_out, i_out
+        self.masks = torch.empty(max(self.mask_bytes, 1), dtype=torch.uint8, device=u.device) if need_bwd else None
+
+    def begin_backward(self, gu, gi, d_u, d_i):
+        self.gu, self.gi, self.d_u, self.d_i = gu, gi, d_u, d_i
+
+    def fwd_layers(self, a, b):
+        from .propagate import _ptr, _stream_ptr
+        p = self.plan
+        with torch.cuda.device(p.device):
+            self._lib.check(self.lib.sagnn_propagate_fwd_layers(
+                p.handle, a, b, _ptr(self.u), _ptr(self.i), _ptr(self.u_out), _ptr(self.i_out), self.L, self.d,
+                self.leaky, _ptr(self.masks), _ptr(self.ws), self.ws.numel(), _stream_ptr(p.device)))
+
+    def bwd_levels(self, a, b):
+        from .propagate import _ptr, _stream_ptr
+        p = self.plan
+        with torch.cuda.device(p.device):
+            self._lib.check(self.lib.sagnn_propagate_bwd_levels(
+                p.handle, a, b, _ptr(self.gu), _ptr(self.gi), _ptr(self.d_u), _ptr(self.d_i), self.L, self.d,
+                self.leaky, _ptr(self.masks), _ptr(self.ws), self.ws.numel(), _stream_ptr(p.device)))
+
+    def table(self, which, index):
+        return self.plan.workspace_table(self.ws, self.L, self.d, which, index)
+
+
+class RowShardedPropagation:
+    """Row-sharded drop-in for ``propagate`` over a process group: every rank passes the FULL
+    ``uEmbed [T,U,d]`` / ``iEmbed [T,I,d]`` (replicated parameters) and gets the full layer sums
+    back; each rank computes 1/world of the rows of every interval.  Use it when there are fewer
+    intervals than GPUs (or combine: interval-shard over groups of ranks, row-shard inside a group
+    by passing ``group``).  Results are bitwise those of the single-GPU ``propagate``."""
+
+    def __init__(self, sub_mats, U, I, n_layers=2, leaky=0.5, group=None, device=None, latdim=64,
+                 backend_factory=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.U, self.I, self.n_layers, self.leaky = int(U), int(I), int(n_layers), float(leaky)
+        self.U_pad, self.I_pad = padded_rows(self.U, self.world), padded_rows(self.I, self.world)
+        bu, bi = self.U_pad // self.world, self.I_pad // self.world
+        self.row_block = (self.rank * bu, (self.rank + 1) * bu, self.rank * bi, (self.rank + 1) * bi)
+        self._backends = {}
+        self._factory = backend_factory      # tests: a CPU stand-in for the C-ABI calls (gloo)
+        self.plan = None
+        if backend_factory is None:
+            from .propagate import build_plan
+            self.plan = build_plan(sub_mats, self.U, self.I, device=device, latdim=latdim,
+                                   row_block=self.row_block, padded_shape=(self.U_pad, self.I_pad))
+
+    def _backend(self, d):
+        if d not in self._backends:
+            self._backends[d] = (self._factory(self, d) if self._factory is not None
+                                 else _CudaRowBackend(self.plan, self.n_layers, d, self.leaky))
+        return self._backends[d]
+
+    @staticmethod
+    def _pad(t, rows, rows_pad):
+        t = t.contiguous()
+        if rows_pad == rows:
+            return t
+        out = t.new_zeros((t.shape[0], rows_pad, t.shape[2]))
+        out[:, :rows] = t
+        return out
+
+    def __call__(self, u_embed, i_embed):
+        return _RowShardedFn.apply(u_embed, i_embed, self)

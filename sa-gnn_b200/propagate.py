@@ -43,6 +43,7 @@ class Plan:
         self.device = device
         self.weight_mode = weight_mode
         self.has_val = has_val
+        self.row_block = None           # (u_begin, u_end, i_begin, i_end) of a row-sharded plan
         self._scratch = {}
 
     # -- lifetime ---------------------------------------------------------------------
@@ -122,6 +123,16 @@ class Plan:
                                                              ctypes.byref(m), ctypes.byref(b)))
         return f.value, m.value, b.value
 
+    def workspace_table(self, ws, n_layers, d, which, index):
+        """(user [T,U,d], item [T,I,d]) float32 views of the workspace table a row-sharded step
+        exchanges (``sagnn_workspace_table``): which=0 forward layer output, which=1 backward source."""
+        off, ub, ib = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(_lib.load_library().sagnn_workspace_table(self.handle, n_layers, d, which, index,
+                                                             ctypes.byref(off), ctypes.byref(ub), ctypes.byref(ib)))
+        o, nu, ni = off.value, ub.value, ib.value
+        return (ws[o:o + nu].view(torch.float32).view(self.T, self.U, d),
+                ws[o + nu:o + nu + ni].view(torch.float32).view(self.T, self.I, d))
+
     def scratch(self, n_layers, d):
         """Cached (workspace tensor, mask_bytes): fwd and bwd of one step run back to back on one
         stream and the backward needs nothing from the forward scratch, so they share it."""
@@ -157,7 +168,8 @@ def _split_interval(m):
     raise TypeError("unsupported interval description: %r" % type(m))
 
 
-def build_plan(sub_mats, U=None, I=None, *, device=None, edge_weight=None, strict_pad=False, latdim=64):
+def build_plan(sub_mats, U=None, I=None, *, device=None, edge_weight=None, strict_pad=False, latdim=64,
+               row_block=None, padded_shape=None):
     """Builds the device plan for ``T = len(sub_mats)`` interval graphs.
 
     sub_mats[k]: scipy sparse ``U x I`` matrix (``handler.subMat[k]``), or an ``[E,2]`` adjacency
@@ -167,6 +179,9 @@ def build_plan(sub_mats, U=None, I=None, *, device=None, edge_weight=None, stric
     latdim: the embedding width the plan will mostly run with (sizes the shared-memory hot-row set).
     strict_pad: raise like TF-CPU does when an interval's last populated row is more than 100
     rows before the end (model.py:87-91); by default such rows are simply zero (TF-GPU).
+    row_block: ``(u_begin, u_end, i_begin, i_end)`` -- row sharding (``sagnn_plan_set_row_block``): the
+    plan only computes those user / item rows of every interval (see ``dist.RowShardedPropagation``).
+    padded_shape: ``(U_pad, I_pad) >= (U, I)``: tables get extra empty rows (equal row blocks per rank).
     """
     if not torch.cuda.is_available():
         raise RuntimeError("sagnn_b200.build_plan needs a CUDA device (there is no CPU fallback)")
@@ -186,6 +201,10 @@ def build_plan(sub_mats, U=None, I=None, *, device=None, edge_weight=None, stric
                 raise ValueError("interval shape %s does not match (U, I) = (%d, %d)" % (shape, U, I))
     if U is None or I is None:
         raise ValueError("U and I are required when intervals are given as index arrays")
+    if padded_shape is not None:
+        if padded_shape[0] < U or padded_shape[1] < I:
+            raise ValueError("padded_shape %s is smaller than (U, I) = (%d, %d)" % (tuple(padded_shape), U, I))
+        U, I = int(padded_shape[0]), int(padded_shape[1])
     has_val = all(p[2] is not None for p in parts)
     custom = isinstance(edge_weight, (list, tuple))
     mode = 2 if custom else _WEIGHT_MODES[edge_weight]
@@ -217,6 +236,9 @@ def build_plan(sub_mats, U=None, I=None, *, device=None, edge_weight=None, stric
                     raise ValueError("interval %d: %d weights for %d edges" % (k, w_d.numel(), nnz[k]))
             _lib.check(lib.sagnn_plan_set_interval(handle, k, _ptr(row_d), _ptr(col_d), _ptr(val_d),
                                                    _ptr(w_d), nnz[k], st))
+        if row_block is not None:
+            _lib.check(lib.sagnn_plan_set_row_block(handle, *[int(x) for x in row_block]))
+            plan.row_block = tuple(int(x) for x in row_block)
         _lib.check(lib.sagnn_plan_set_latdim_hint(handle, int(latdim)))
         _lib.check(lib.sagnn_plan_finalize(handle, mode, st))
     return plan

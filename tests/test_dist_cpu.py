@@ -1,5 +1,6 @@
 """world_size-2 gloo tests (CPU) of the multi-GPU plumbing: interval assignment, the ordered
-all-gather of per-interval outputs and its backward.  The local compute is stood in for by the
+all-gather of per-interval outputs and its backward, and the row-sharded schedule (per-layer
+table all-gathers).  The local compute is stood in for by the
 oracle here (tests may use it); on GPUs it is the CUDA path (tests/test_gpu_parity.py)."""
 import os
 import socket
@@ -128,3 +129,57 @@ def test_interval_sharding_gloo_world2(T):
         assert ok_fwd and ok_bwd and ok_grad, (rank, ok_fwd, ok_bwd, ok_grad)
         covered += mine
     assert sorted(covered) == list(range(T))
+
+
+def _row_worker(rank, world, port, L, U, I, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from oracle import propagate_oracle as po
+        from helpers import DenseRowBackend, adj_lists, random_interval_mats, random_tables
+        T, d = 2, 8
+        mats = random_interval_mats(T, U, I, 260, seed=33)
+        adj, tp = adj_lists(mats)
+        uE, iE, gU, gI = [x.astype(np.float64) for x in random_tables(T, U, I, d, seed=6)]
+        rs = sd.RowShardedPropagation(mats, U, I, n_layers=L, leaky=0.5,
+                                      backend_factory=lambda rs_, d_: DenseRowBackend(rs_, d_, mats))
+        u = torch.from_numpy(uE).requires_grad_(True)
+        i = torch.from_numpy(iE).requires_grad_(True)
+        uv, iv = rs(u, i)
+        torch.autograd.backward([uv, iv], [torch.from_numpy(gU), torch.from_numpy(gI)])
+        ref = po.propagate(adj, tp, uE, iE, gU, gI, L, 0.5, np.float64)
+        got = [uv.detach().numpy(), iv.detach().numpy(), u.grad.numpy(), i.grad.numpy()]
+        err = [float(np.max(np.abs(g - r)) / np.max(np.abs(r))) for g, r in zip(got, ref)]
+        finite = all(np.isfinite(g).all() for g in got)
+        out_q.put((rank, rs.row_block, (rs.U_pad, rs.I_pad), err, finite))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("L,U,I", [(1, 40, 30), (2, 41, 29), (3, 40, 31)])
+def test_row_sharding_schedule_gloo_world2(L, U, I):
+    """The row-sharded schedule of sagnn_b200.dist (stage lists, in-place table all-gathers, padding
+    to equal row blocks, autograd wiring) reproduces the unsharded oracle on 2 ranks; the C-ABI calls
+    are stood in for by a dense CPU backend that, like the kernels, writes owned rows only (every
+    other row starts as NaN, so a missing exchange cannot go unnoticed)."""
+    assert sd.forward_stages(3) == [(0, 0), (1, 1), (2, None)]
+    assert sd.backward_stages(2) == [(0, 0), (1, 1), (2, None)]
+    assert sd.padded_rows(41, 2) == 42 and sd.padded_rows(40, 2) == 40
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_row_worker, args=(r, 2, port, L, U, I, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    blocks = sorted(r[1] for r in res)
+    assert blocks[0][0] == 0 and blocks[0][1] == blocks[1][0] and blocks[1][1] == res[0][2][0]
+    for rank, _, _, err, finite in res:
+        assert finite and max(err) < 1e-12, (rank, err)

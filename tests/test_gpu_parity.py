@@ -413,6 +413,104 @@ def test_rtd_layout_step_graph_and_sliced_rows():
     assert rc == 1   # SAGNN_INVALID_ARG
 
 
+# ---------------------------------------------------------------- row sharding (second way)
+@pytest.mark.parametrize("W,L,d,U,I", [(2, 2, 64, 300, 40), (3, 3, 128, 301, 41), (4, 1, 64, 120, 90)])
+def test_row_sharded_virtual_ranks_equal_single_plan_bitwise(W, L, d, U, I):
+    """W row-block plans on ONE GPU play the ranks of a row-sharded job: the real stage lists of
+    sagnn_b200.dist drive the real C-ABI calls (sagnn_propagate_fwd_layers / _bwd_levels), the table
+    all-gather is emulated by copying row blocks between the ranks' workspaces.  Every rank writes
+    only its own rows (the others stay NaN until exchanged) and the result is bitwise the
+    single-plan one, slices of long rows included."""
+    from sagnn_b200 import dist as sd
+    T = 2
+    mats = random_interval_mats(T, U, I, min(6000, U * I // 3), seed=8)     # item rows of ~150 edges: slices
+    ref_plan = sg.build_plan(mats)
+    uE, iE, gU, gI = random_tables(T, U, I, d, seed=13)
+    ref = run_gpu(ref_plan, uE, iE, gU, gI, L)
+    Up, Ip = sd.padded_rows(U, W), sd.padded_rows(I, W)
+    bu, bi = Up // W, Ip // W
+
+    def pad(x, rows):
+        out = torch.zeros((T, rows, d), dtype=torch.float32, device="cuda")
+        out[:, :x.shape[1]] = torch.from_numpy(x).cuda()
+        return out
+
+    def exchange(tables, b):                   # tables[r]: rank r's copy; rows [r*b, (r+1)*b) are its own
+        for r in range(W):
+            for q in range(W):
+                if q != r:
+                    tables[q][:, r * b:(r + 1) * b] = tables[r][:, r * b:(r + 1) * b]
+
+    nan = lambda rows: torch.full((T, rows, d), float("nan"), dtype=torch.float32, device="cuda")
+    bes, outs, grads = [], [], []
+    for r in range(W):
+        plan = sg.build_plan(mats, U, I, latdim=d, padded_shape=(Up, Ip),
+                             row_block=(r * bu, (r + 1) * bu, r * bi, (r + 1) * bi))
+        be = sd._CudaRowBackend(plan, L, d, 0.5)
+        outs.append((nan(Up), nan(Ip)))
+        grads.append((nan(Up), nan(Ip)))
+        be.begin_forward(pad(uE, Up), pad(iE, Ip), outs[r][0], outs[r][1], True)
+        be.begin_backward(pad(gU, Up), pad(gI, Ip), grads[r][0], grads[r][1])
+        bes.append(be)
+    for l, ex in sd.forward_stages(L):
+        for be in bes:
+            be.fwd_layers(l, l + 1)
+        if ex is not None:
+            exchange([be.table(0, ex)[0] for be in bes], bu)
+            exchange([be.table(0, ex)[1] for be in bes], bi)
+    torch.cuda.synchronize()
+    for r in range(W):                          # before the hand-off only the owned rows exist
+        own = torch.zeros(Up, dtype=torch.bool, device="cuda")
+        own[r * bu:(r + 1) * bu] = True
+        assert torch.isnan(outs[r][0][:, ~own]).all() and not torch.isnan(outs[r][0][:, own]).any()
+    exchange([o[0] for o in outs], bu)
+    exchange([o[1] for o in outs], bi)
+    for ph, ex in sd.backward_stages(L):
+        for be in bes:
+            be.bwd_levels(ph, ph + 1)
+        if ex is not None:
+            exchange([be.table(1, ex)[0] for be in bes], bu)
+            exchange([be.table(1, ex)[1] for be in bes], bi)
+    exchange([g[0] for g in grads], bu)
+    exchange([g[1] for g in grads], bi)
+    torch.cuda.synchronize()
+    for r in range(W):
+        assert torch.equal(outs[r][0][:, :U], ref[0]) and torch.equal(outs[r][1][:, :I], ref[1])
+        assert torch.equal(grads[r][0][:, :U], ref[2]) and torch.equal(grads[r][1][:, :I], ref[3])
+    st = bes[0].plan.stats()
+    assert st["short_rows"] + st["long_rows"] == T * (bu + bi)             # only the owned rows are scheduled
+
+
+def test_row_block_argument_checks():
+    mats = random_interval_mats(1, 30, 20, 100, seed=2)
+    with pytest.raises(sg.SagnnError):
+        sg.build_plan(mats, row_block=(10, 5, 0, 20))
+    with pytest.raises(sg.SagnnError):
+        sg.build_plan(mats, row_block=(0, 31, 0, 20))
+    with pytest.raises(ValueError):
+        sg.build_plan(mats, padded_shape=(29, 20))
+    plan = sg.build_plan(mats, row_block=(0, 30, 0, 20))                  # the whole graph as one block
+    uE, iE, gU, gI = random_tables(1, 30, 20, 64, seed=1)
+    a = run_gpu(plan, uE, iE, gU, gI, 2)
+    b = run_gpu(sg.build_plan(mats), uE, iE, gU, gI, 2)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_row_sharded_two_gpus_nccl():
+    """scripts/row_shard_check.py under torchrun: RowShardedPropagation over NCCL == single-GPU propagate."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731",
+                        os.path.join(root, "scripts", "row_shard_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ROW_SHARD_OK" in r.stdout
+
+
 # ---------------------------------------------------------------- BASELINE shape families
 @pytest.mark.parametrize("name,scale", [("gowalla", 0.05), ("amazon-book", 0.05), ("amazon-ref", 0.25), ("ml10m", 0.03)])
 def test_baseline_shapes_reduced_scale(name, scale):
