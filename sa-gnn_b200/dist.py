@@ -152,24 +152,32 @@ def backward_stages(n_layers):
     return [(ph, ph if ph < n_layers else None) for ph in range(n_layers + 1)]
 
 
-def allgather_row_blocks(table, rank=None, group=None):
-    """In-place all-gather of equal row blocks: ``table [T, R, d]`` (R divisible by the world size)
-    holds this rank's rows ``[rank*b, (rank+1)*b)`` of every interval on entry and all rows on exit.
-    One collective per interval, sent straight from / received straight into the table (NCCL
-    all-gathers in place; other backends get a staged copy of the send block)."""
+def allgather_row_blocks(tables, rank=None, group=None):
+    """In-place all-gather of equal row blocks of one table or a list of tables: each
+    ``table [T, R, d]`` (R divisible by the world size) holds this rank's rows
+    ``[rank*b, (rank+1)*b)`` of every interval on entry and all rows on exit.  One all-gather per
+    interval and table, sent straight from / received straight into the table; on NCCL all of them
+    are coalesced into ONE grouped launch (other backends: a loop with a staged send block)."""
+    single = isinstance(tables, torch.Tensor)
+    tabs = [tables] if single else list(tables)
     world = dist.get_world_size(group)
     rank = dist.get_rank(group) if rank is None else rank
-    T, R, d = table.shape
-    if R % world:
-        raise ValueError("rows (%d) must be a multiple of the world size (%d)" % (R, world))
-    if world == 1:
-        return table
-    b = R // world
-    in_place = table.is_cuda
-    for k in range(T):
-        mine = table[k, rank * b:(rank + 1) * b]
-        dist.all_gather_into_tensor(table[k], mine if in_place else mine.clone(), group=group)
-    return table
+    for t in tabs:
+        if t.shape[1] % world:
+            raise ValueError("rows (%d) must be a multiple of the world size (%d)" % (t.shape[1], world))
+    if world > 1:
+        pairs = []
+        for t in tabs:
+            b = t.shape[1] // world
+            pairs += [(t[k], t[k, rank * b:(rank + 1) * b]) for k in range(t.shape[0])]
+        if tabs[0].is_cuda:
+            with dist._coalescing_manager(group=group):
+                for out, mine in pairs:
+                    dist.all_gather_into_tensor(out, mine, group=group)
+        else:
+            for out, mine in pairs:
+                dist.all_gather_into_tensor(out, mine.clone(), group=group)
+    return tables
 
 
 class _RowShardedFn(torch.autograd.Function):
@@ -183,10 +191,8 @@ class _RowShardedFn(torch.autograd.Function):
         for l, ex in forward_stages(rs.n_layers):
             be.fwd_layers(l, l + 1)
             if ex is not None:
-                for t in be.table(0, ex):
-                    allgather_row_blocks(t, rs.rank, rs.group)
-        allgather_row_blocks(u_out, rs.rank, rs.group)          # replicated consumer (model.py:131-155)
-        allgather_row_blocks(i_out, rs.rank, rs.group)
+                allgather_row_blocks(be.table(0, ex), rs.rank, rs.group)
+        allgather_row_blocks([u_out, i_out], rs.rank, rs.group)  # replicated consumer (model.py:131-155)
         ctx.rs, ctx.be, ctx.masks = rs, be, be.masks
         return u_out[:, :rs.U], i_out[:, :rs.I]
 
@@ -201,10 +207,8 @@ class _RowShardedFn(torch.autograd.Function):
         for ph, ex in backward_stages(rs.n_layers):
             be.bwd_levels(ph, ph + 1)
             if ex is not None:
-                for t in be.table(1, ex):
-                    allgather_row_blocks(t, rs.rank, rs.group)
-        allgather_row_blocks(d_u, rs.rank, rs.group)            # replicated parameters
-        allgather_row_blocks(d_i, rs.rank, rs.group)
+                allgather_row_blocks(be.table(1, ex), rs.rank, rs.group)
+        allgather_row_blocks([d_u, d_i], rs.rank, rs.group)      # replicated parameters
         return d_u[:, :rs.U], d_i[:, :rs.I], None
 
 
