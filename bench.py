@@ -16,8 +16,10 @@ Reference arm (--impl reference): times that CPU restatement only (the reference
 TensorFlow 1.14, which cannot be installed here).
 Multi-GPU (torchrun, one rank per GPU): weak scaling -- every rank owns one full set of T
 interval graphs (interval sharding: intervals share nothing), no data-path collective in the
-propagation itself; the per-rank outputs are all-gathered over NCCL (north_star) on a side
-stream, overlapped with the backward, unless --no-allgather.
+propagation itself.  The hand-off of the per-rank outputs runs on a side stream overlapped with
+the backward: by default one NCCL all-to-all of row blocks to a row-sharded consumer, sent straight
+from the epilogue's [R,T,d] output (no pack copies); --exchange allgather = the all-gather to a
+replicated consumer that north_star names; --exchange none = compute only.
 """
 from __future__ import annotations
 
@@ -50,11 +52,13 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-allgather", action="store_true")
-    ap.add_argument("--exchange", default="allgather", choices=["allgather", "alltoall", "none"],
-                    help="multi-GPU hand-off of the outputs: all-gather (replicated consumer, north_star), "
-                         "all-to-all of row blocks (row-sharded consumer) or none")
-    ap.add_argument("--layout", default="trd", choices=["trd", "rtd"],
-                    help="rtd: outputs / upstream gradients in the [R,T,d] layout of model.py:133-134 (fused transpose)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "alltoall", "none"],
+                    help="multi-GPU hand-off of the outputs: all-to-all of row blocks (row-sharded consumer; the "
+                         "default for N > 1, sent straight from the [R,T,d] epilogue output), all-gather "
+                         "(replicated consumer, the collective north_star names) or none")
+    ap.add_argument("--layout", default=None, choices=["trd", "rtd"],
+                    help="rtd: outputs / upstream gradients in the [R,T,d] layout of model.py:133-134 (fused "
+                         "transpose); default trd, rtd with --exchange alltoall")
     ap.add_argument("--no-calibrate", action="store_true", help="keep the static cost-model CTA split")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
     ap.add_argument("--cpu-steps", type=int, default=3)
@@ -236,19 +240,28 @@ def main():
     torch.cuda.synchronize()
     plan_ms = (time.perf_counter() - t0) * 1e3
 
-    step = PropagationStep(plan, L, d, 0.5, layout=args.layout)
+    if args.no_allgather:
+        args.exchange = "none"
+    if args.exchange == "auto":
+        args.exchange = "alltoall" if world > 1 else "none"
+    if args.layout is None:
+        args.layout = "rtd" if (world > 1 and args.exchange == "alltoall") else "trd"
+    step = PropagationStep(plan, L, d, 0.5, layout=args.layout, row_multiple=world)
     step.u_embed.copy_(torch.from_numpy(dh.xavier_embeddings(T, U, d, args.seed)))
     step.i_embed.copy_(torch.from_numpy(dh.xavier_embeddings(T, I, d, args.seed + 1)))
     gen = torch.Generator(device=dev).manual_seed(args.seed + rank)
     step.g_user.normal_(generator=gen)
     step.g_item.normal_(generator=gen)
 
-    if args.no_allgather:
-        args.exchange = "none"
     do_gather = world > 1 and args.exchange != "none"
+    zero_copy = do_gather and args.exchange == "alltoall" and args.layout == "rtd"
     if do_gather:
-        gat_u = torch.empty((world,) + tuple(step.user_out.shape), dtype=torch.float32, device=dev)
-        gat_i = torch.empty((world,) + tuple(step.item_out.shape), dtype=torch.float32, device=dev)
+        if args.exchange == "allgather":
+            gat_u = torch.empty((world,) + tuple(step.user_out.shape), dtype=torch.float32, device=dev)
+            gat_i = torch.empty((world,) + tuple(step.item_out.shape), dtype=torch.float32, device=dev)
+        elif zero_copy:       # my row block of every rank's intervals: [world, block, T, d]
+            rcv_u = torch.empty((world, step.user_out_full.shape[0] // world, T, d), dtype=torch.float32, device=dev)
+            rcv_i = torch.empty((world, step.item_out_full.shape[0] // world, T, d), dtype=torch.float32, device=dev)
         side = torch.cuda.Stream()
 
     split = None
@@ -272,6 +285,10 @@ def main():
                 if args.exchange == "allgather":
                     dist.all_gather_into_tensor(gat_u, step.user_out)
                     dist.all_gather_into_tensor(gat_i, step.item_out)
+                elif zero_copy:
+                    from sagnn_b200.dist import exchange_rows_rtd
+                    exchange_rows_rtd(step.user_out_full, rcv_u)
+                    exchange_rows_rtd(step.item_out_full, rcv_i)
                 else:
                     from sagnn_b200.dist import exchange_rows
                     exchange_rows(step.user_out)
@@ -449,6 +466,14 @@ def workload_config(args, g, L, d, world, stats=None, use_graph=None, gather=Non
     if gather is not None:
         cfg["allgather_outputs"] = bool(gather) and args.exchange == "allgather"
         cfg["exchange"] = args.exchange if world > 1 else "none"
+        if world > 1:
+            cfg["exchange_detail"] = {
+                "alltoall": "one NCCL all-to-all per side: every rank receives its row block of all ranks' intervals "
+                            "(row-sharded consumer), sent straight from the [R,T,d] epilogue output, on a side "
+                            "stream overlapping the backward",
+                "allgather": "NCCL all-gather of the [T,R,d] outputs to every rank (replicated consumer), on a side "
+                             "stream overlapping the backward",
+                "none": "no hand-off collective (compute only)"}[args.exchange]
     return cfg
 
 

@@ -94,6 +94,24 @@ def exchange_rows(local, group=None):
     return recv.view(world * T, size, d)
 
 
+def exchange_rows_rtd(out_full, recv=None, group=None):
+    """The same hand-off with NO pack / pad copies, for outputs the epilogue already wrote in the
+    ``[R_pad, T_local, d]`` layout (``SAGNN_LAYOUT_RTD``; ``R_pad`` a multiple of the world size, pad
+    rows zero -- ``PropagationStep(layout="rtd", row_multiple=world).user_out_full``): the row block
+    of rank j is the contiguous slab ``out_full[j*b:(j+1)*b]``, so the output buffer IS the send
+    buffer of one all-to-all.  Returns ``[world, b, T_local, d]``: my row block of every rank's
+    intervals (``recv``: optional pre-allocated result)."""
+    world = dist.get_world_size(group)
+    Rp, T, d = out_full.shape
+    if Rp % world or not out_full.is_contiguous():
+        raise ValueError("need a contiguous [R_pad, T, d] tensor with R_pad (%d) a multiple of the world size" % Rp)
+    b = Rp // world
+    if recv is None:
+        recv = torch.empty((world, b, T, d), dtype=out_full.dtype, device=out_full.device)
+    dist.all_to_all_single(recv.view(world, -1), out_full.view(world, -1), group=group)
+    return recv
+
+
 class ShardedPropagation:
     """Interval-sharded drop-in for ``propagate``: every rank passes the FULL parameter tables
     (or just its own slices via ``local_only``) and gets the full ``[T,U,d]`` / ``[T,I,d]`` back."""

@@ -16,9 +16,13 @@ from .propagate import _ptr, _stream_ptr
 
 
 class PropagationStep:
-    def __init__(self, plan, n_layers, d, leaky=0.5, layout="trd"):
+    def __init__(self, plan, n_layers, d, leaky=0.5, layout="trd", row_multiple=1):
         """layout="rtd": outputs and upstream gradients are [R,T,d] (model.py:133-134, the LSTM's
-        input layout; SAGNN_LAYOUT_RTD), embeddings and their gradients stay [T,R,d]."""
+        input layout; SAGNN_LAYOUT_RTD), embeddings and their gradients stay [T,R,d].
+        row_multiple (rtd only): the output buffers ``user_out_full`` / ``item_out_full`` get zero rows
+        up to a multiple of it, so that equal row blocks can be sent to a row-sharded consumer straight
+        from the epilogue's output (``dist.exchange_rows_rtd``); ``user_out`` / ``item_out`` are the
+        [:R] prefixes the kernel writes."""
         self.plan, self.L, self.d, self.leaky = plan, int(n_layers), int(d), float(leaky)
         self.flags = {"trd": 0, "rtd": 1}[layout]
         dev = plan.device
@@ -32,7 +36,14 @@ class PropagationStep:
             mo = mk if not self.flags else \
                 (lambda rows: torch.empty((rows, plan.T, self.d), dtype=torch.float32, device=dev))
             self.g_user, self.g_item = mo(plan.U), mo(plan.I)
-            self.user_out, self.item_out = mo(plan.U), mo(plan.I)
+            if self.flags and row_multiple > 1:
+                pad = lambda rows: -(-rows // row_multiple) * row_multiple
+                self.user_out_full = torch.zeros((pad(plan.U), plan.T, self.d), dtype=torch.float32, device=dev)
+                self.item_out_full = torch.zeros((pad(plan.I), plan.T, self.d), dtype=torch.float32, device=dev)
+                self.user_out, self.item_out = self.user_out_full[:plan.U], self.item_out_full[:plan.I]
+            else:
+                self.user_out, self.item_out = mo(plan.U), mo(plan.I)
+                self.user_out_full, self.item_out_full = self.user_out, self.item_out
             self.d_u, self.d_i = mk(plan.U), mk(plan.I)
         self.graph = None
         # L forward + L backward layer kernels + the streaming pre-mask of the upstream (row-per-warp kernel)

@@ -1,7 +1,7 @@
-# usage: bash scripts/gpu_multi.sh N   -- N-GPU torchrun bench: all-gather (default), all-to-all, compute only
+# usage: bash scripts/gpu_multi.sh N [modes]  -- N-GPU torchrun bench: default (zero-copy row-block all-to-all), all-gather, compute only
 N=${1:-2}
 P=29517
-for X in allgather alltoall none; do
+for X in ${2:-auto allgather none}; do
   P=$((P+1))
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N --steps 20 --warmup 5 --exchange $X --no-e2e > gpurun_out/bench_n${N}_$X.json 2> gpurun_out/bench_n${N}_$X.err
   python - <<PY

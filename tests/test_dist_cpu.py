@@ -88,7 +88,15 @@ def _a2a_worker(rank, world, port, out_q):
         lo, hi = blocks[rank]
         want = torch.zeros(world * T, size, d)
         want[:, :hi - lo] = full[:, :, lo:hi].reshape(world * T, hi - lo, d)
-        out_q.put((rank, "ok" if torch.equal(got, want) else "mismatch", ""))
+        ok = torch.equal(got, want)
+        # zero-copy variant: the [R_pad, T, d] (rtd) output buffer is the send buffer
+        Rp = size * world
+        full_rtd = torch.zeros(world, Rp, T, d)
+        full_rtd[:, :R] = full.transpose(1, 2)
+        got2 = sd.exchange_rows_rtd(full_rtd[rank].clone())                     # [src, block, T, d]
+        want2 = full_rtd[:, rank * size:(rank + 1) * size]
+        ok = ok and torch.equal(got2, want2) and torch.equal(got2.transpose(1, 2).reshape(world * T, size, d), want)
+        out_q.put((rank, "ok" if ok else "mismatch", ""))
     finally:
         dist.destroy_process_group()
 
