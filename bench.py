@@ -52,10 +52,12 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-allgather", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "allgather", "alltoall", "none"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "allgather", "alltoall", "none"],
                     help="multi-GPU hand-off of the outputs: all-to-all of row blocks (row-sharded consumer; the "
                          "default for N > 1, sent straight from the [R,T,d] epilogue output), all-gather "
-                         "(replicated consumer, the collective north_star names) or none")
+                         "(replicated consumer, the collective north_star names), fused (the same row-block "
+                         "hand-off written by the epilogue itself into the peers' symmetric-memory receive buffers: "
+                         "peer stores over NVLink, no collective kernel) or none")
     ap.add_argument("--layout", default=None, choices=["trd", "rtd"],
                     help="rtd: outputs / upstream gradients in the [R,T,d] layout of model.py:133-134 (fused "
                          "transpose); default trd, rtd with --exchange alltoall")
@@ -242,10 +244,11 @@ def main():
 
     if args.no_allgather:
         args.exchange = "none"
-    if args.exchange == "auto":
-        args.exchange = "alltoall" if world > 1 else "none"
+    auto_exchange = args.exchange == "auto"
+    if auto_exchange:   # N > 1: the fused hand-off; falls back to the NCCL all-to-all if symmetric memory is unavailable
+        args.exchange = "fused" if world > 1 else "none"
     if args.layout is None:
-        args.layout = "rtd" if (world > 1 and args.exchange == "alltoall") else "trd"
+        args.layout = "rtd" if (world > 1 and args.exchange in ("alltoall", "fused")) else "trd"
     step = PropagationStep(plan, L, d, 0.5, layout=args.layout, row_multiple=world)
     step.u_embed.copy_(torch.from_numpy(dh.xavier_embeddings(T, U, d, args.seed)))
     step.i_embed.copy_(torch.from_numpy(dh.xavier_embeddings(T, I, d, args.seed + 1)))
@@ -263,6 +266,45 @@ def main():
             rcv_u = torch.empty((world, step.user_out_full.shape[0] // world, T, d), dtype=torch.float32, device=dev)
             rcv_i = torch.empty((world, step.item_out_full.shape[0] // world, T, d), dtype=torch.float32, device=dev)
         side = torch.cuda.Stream()
+    fused = do_gather and args.exchange == "fused"
+    fused_ok = None
+    if fused:
+        # receive buffers in symmetric memory: every rank maps every peer's buffer, the forward's
+        # epilogue stores each finished row straight into the consumer rank's buffer over NVLink
+        from sagnn_b200.dist import exchange_rows_rtd
+        bu, bi = step.user_out_full.shape[0] // world, step.item_out_full.shape[0] // world
+        try:
+            import torch.distributed._symmetric_memory as symm
+            rcv_u = symm.empty((world, bu, T, d), dtype=torch.float32, device=dev)
+            rcv_i = symm.empty((world, bi, T, d), dtype=torch.float32, device=dev)
+            rcv_u.zero_(); rcv_i.zero_()
+            hdl_u = symm.rendezvous(rcv_u, dist.group.WORLD)
+            hdl_i = symm.rendezvous(rcv_i, dist.group.WORLD)
+            have = 1
+        except Exception as e:   # no symmetric memory on this box
+            sys.stderr.write("[bench] rank %d: symmetric memory unavailable (%s)\n" % (rank, e))
+            have = 0
+        flag = torch.tensor([have], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not flag.item():
+            if not auto_exchange:
+                raise RuntimeError("--exchange fused needs torch symmetric memory on every rank")
+            fused, zero_copy, args.exchange = False, True, "alltoall"
+            rcv_u = torch.empty((world, bu, T, d), dtype=torch.float32, device=dev)
+            rcv_i = torch.empty((world, bi, T, d), dtype=torch.float32, device=dev)
+    if fused:
+        # one-time check against the NCCL hand-off of the plain forward: same bits in every slab
+        step.forward()
+        ref_u, ref_i = exchange_rows_rtd(step.user_out_full), exchange_rows_rtd(step.item_out_full)
+        step.set_scatter(world, rank, list(hdl_u.buffer_ptrs), list(hdl_i.buffer_ptrs))
+        step.forward()
+        hdl_u.barrier(channel=0)
+        torch.cuda.synchronize()
+        ok = torch.tensor([int(torch.equal(ref_u, rcv_u) and torch.equal(ref_i, rcv_i))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        fused_ok = bool(ok.item())
+        if not fused_ok:
+            raise RuntimeError("fused hand-off differs from the NCCL all-to-all of the same outputs")
 
     split = None
     if not args.no_calibrate:
@@ -278,7 +320,14 @@ def main():
         flush = _NoFlush()
 
     def one_step():
-        if do_gather:
+        if fused:
+            step.forward()                                          # rows land in the peers' buffers as they finish
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                hdl_u.barrier(channel=0)                            # every rank's forward is done: my slabs are complete
+            step.backward()
+            torch.cuda.current_stream().wait_stream(side)
+        elif do_gather:
             step.forward()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                           # overlaps the backward
@@ -441,6 +490,8 @@ def main():
             "gpu_launches": step.kernel_launches_per_step * args.steps,
             "clocks": clocks,
         }
+        if fused_ok is not None:
+            line["config"]["fused_handoff_bitwise_equal_to_nccl_alltoall"] = fused_ok
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -473,6 +524,10 @@ def workload_config(args, g, L, d, world, stats=None, use_graph=None, gather=Non
                             "stream overlapping the backward",
                 "allgather": "NCCL all-gather of the [T,R,d] outputs to every rank (replicated consumer), on a side "
                              "stream overlapping the backward",
+                "fused": "no collective kernel: the last forward layer's epilogue stores every finished row into the "
+                         "symmetric-memory receive buffer of the rank that owns its row block (peer stores over "
+                         "NVLink, sagnn_propagate_fwd_scatter), then one symmetric-memory barrier on a side stream; "
+                         "verified bitwise against the NCCL all-to-all before timing",
                 "none": "no hand-off collective (compute only)"}[args.exchange]
     return cfg
 

@@ -170,6 +170,22 @@ int sagnn_propagate_bwd_ex(const sagnn_plan* plan, const float* g_user_dev, cons
                            const void* masks_dev, void* workspace_dev, size_t workspace_bytes,
                            unsigned flags, sagnn_stream_t stream);
 
+/* Forward with the hand-off to a ROW-SHARDED consumer fused into the epilogue (interval sharding,
+ * `world` ranks, one process per GPU): the last layer writes row r of its layer sums not to
+ * user_out / item_out but straight into the receive buffer of rank r / blk (blk = ceil(rows / world)),
+ * at [rank][r % blk][k][:] of that rank's fp32 buffer [world, blk, T, d] -- peer-memory stores over
+ * NVLink / NVSwitch (buffers mapped on this device, e.g. CUDA IPC or torch symmetric memory; the
+ * tables user_recv_host[world] / item_recv_host[world] are HOST arrays of those device pointers, this
+ * rank's own buffer included).  No collective kernel, no pack copy: the transfer overlaps the math row
+ * by row.  The caller synchronises the ranks (any barrier after the call's stream work) before
+ * consumers read.  user_out / item_out ([U,T,d] / [I,T,d]) only hold the partial layer sums of
+ * n_layers >= 3.  Replaces model.py:131-134 + the exchange a data-parallel consumer needs. */
+int sagnn_propagate_fwd_scatter(const sagnn_plan* plan, const float* u_embed_dev, const float* i_embed_dev,
+                                float* user_out_dev, float* item_out_dev, int n_layers, int d, float leaky,
+                                void* masks_dev, void* workspace_dev, size_t workspace_bytes, int world,
+                                int rank, const void* const* user_recv_host, const void* const* item_recv_host,
+                                sagnn_stream_t stream);
+
 /* Row-sharded execution (plans with sagnn_plan_set_row_block): the L-layer forward / backward one
  * stage at a time, so that the caller can all-gather the table each stage wrote (owned rows only)
  * before the next stage gathers from it.  Same tensors, masks and workspace in every call of a step.

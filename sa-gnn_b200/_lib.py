@@ -44,6 +44,9 @@ SIGNATURES = {
                                               vp, vp, ctypes.c_size_t, ctypes.c_uint, vp]),
     "sagnn_propagate_bwd_ex": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                               vp, vp, ctypes.c_size_t, ctypes.c_uint, vp]),
+    "sagnn_propagate_fwd_scatter": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                                   vp, vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                                   ctypes.POINTER(vp), ctypes.POINTER(vp), vp]),
     "sagnn_plan_set_row_block": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "sagnn_propagate_fwd_layers": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int,
                                                   ctypes.c_int, ctypes.c_float, vp, vp, ctypes.c_size_t, vp]),

@@ -42,6 +42,8 @@ namespace sagnn {
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_MSG = 2 };
 constexpr int kThreads = SAGNN_THREADS;
 
+constexpr int kMaxPeers = 16;
+
 struct SpmmParams {
   const sagnn_task* tasks;
   const int32_t* enc;
@@ -85,6 +87,11 @@ struct SpmmParams {
   const uint8_t* pmask_u;
   const uint8_t* pmask_i;
   unsigned long long* trace; // diagnostics: per CTA {seg, t_start, t_staged, t_end} (ns) or NULL
+  // fused hand-off (sagnn_propagate_fwd_scatter): the last layer writes row r of its layer sum straight
+  // into the receive buffer of the rank that owns row block r / blk -- peer memory over NVLink
+  int peer_n, peer_rank, peer_blk_u, peer_blk_i;
+  float* peer_u[kMaxPeers];  // receive buffers [peer_n, blk_u, T, d] of every rank (this rank's own included)
+  float* peer_i[kMaxPeers];
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -975,11 +982,18 @@ extern "C" int sagnn_workspace_bytes(const sagnn_plan* p, int n_layers, int d, s
   return SAGNN_OK;
 }
 
+struct PeerScatter {   // host-side description of the fused hand-off
+  int world, rank;
+  const void* const* user_ptrs;
+  const void* const* item_ptrs;
+};
+
 // interval < 0: all T intervals in one launch per layer; otherwise only that interval's two
 // segments (all 148 CTAs work on them) -- lets a caller pipeline copies with compute
 static int fwd_impl(const sagnn_plan* p, int interval, const float* uE, const float* iE, float* uOut,
                     float* iOut, int L, int d, float leaky, void* masks, void* ws, size_t ws_bytes,
-                    cudaStream_t st, unsigned flags = 0, int l_begin = 0, int l_end = -1) {
+                    cudaStream_t st, unsigned flags = 0, int l_begin = 0, int l_end = -1,
+                    const PeerScatter* ps = nullptr) {
   if (l_end < 0) l_end = L;
   SAGNN_REQUIRE(0 <= l_begin && l_begin <= l_end && l_end <= L, SAGNN_INVALID_ARG,
                 "propagate_fwd: layer range [%d,%d) outside [0,%d]", l_begin, l_end, L);
@@ -1023,6 +1037,12 @@ static int fwd_impl(const sagnn_plan* p, int interval, const float* uE, const fl
     s.o2_u = write_out ? uOut : nullptr;
     s.o2_i = write_out ? iOut : nullptr;
     s.out_add_next = last ? 1 : 0;
+    if (ps && last) {   // the finished layer sums go straight to the ranks that own their row blocks
+      s.peer_n = ps->world; s.peer_rank = ps->rank;
+      s.peer_blk_u = (p->U + ps->world - 1) / ps->world;
+      s.peer_blk_i = (p->I + ps->world - 1) / ps->world;
+      for (int r = 0; r < ps->world; ++r) { s.peer_u[r] = (float*)ps->user_ptrs[r]; s.peer_i[r] = (float*)ps->item_ptrs[r]; }
+    }
     s.mask_u = masks ? (uint8_t*)masks + (size_t)l * mlw : nullptr;
     s.mask_i = masks ? (uint8_t*)masks + (size_t)l * mlw + mu : nullptr;
     for (int wv = 0; wv < (interval >= 0 ? 1 : p->n_waves); ++wv) {   // one launch unless 2T exceeds the SM count
@@ -1043,6 +1063,21 @@ extern "C" int sagnn_propagate_fwd_ex(const sagnn_plan* p, const float* uE, cons
                                       float* iOut, int L, int d, float leaky, void* masks, void* ws,
                                       size_t ws_bytes, unsigned flags, sagnn_stream_t stream) {
   return fwd_impl(p, -1, uE, iE, uOut, iOut, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream, flags);
+}
+
+extern "C" int sagnn_propagate_fwd_scatter(const sagnn_plan* p, const float* uE, const float* iE, float* uOut,
+                                           float* iOut, int L, int d, float leaky, void* masks, void* ws,
+                                           size_t ws_bytes, int world, int rank, const void* const* user_recv,
+                                           const void* const* item_recv, sagnn_stream_t stream) {
+  SAGNN_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, SAGNN_INVALID_ARG,
+                "propagate_fwd_scatter: world=%d rank=%d (need 1 <= world <= %d)", world, rank, kMaxPeers);
+  SAGNN_REQUIRE(user_recv && item_recv, SAGNN_INVALID_ARG, "propagate_fwd_scatter: NULL pointer table");
+  for (int r = 0; r < world; ++r)
+    SAGNN_REQUIRE(user_recv[r] && item_recv[r], SAGNN_INVALID_ARG, "propagate_fwd_scatter: NULL receive buffer of rank %d", r);
+  SAGNN_REQUIRE(use_rpw(), SAGNN_INVALID_ARG, "propagate_fwd_scatter: needs the row-per-warp kernel");
+  PeerScatter ps{world, rank, user_recv, item_recv};
+  return fwd_impl(p, -1, uE, iE, uOut, iOut, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream,
+                  SAGNN_LAYOUT_RTD, 0, -1, &ps);
 }
 
 extern "C" int sagnn_propagate_fwd_interval(const sagnn_plan* p, int k, const float* uE, const float* iE,

@@ -237,9 +237,10 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
   const uint32_t b_stride = (uint32_t)ROWB * (b_rtd ? p.T : 1);
   const uint32_t o2_stride = (uint32_t)ROWB * (o2_rtd ? p.T : 1);
   // which optional tensors this launch has: one pinned register instead of pointer tests per task
-  enum { F_B = 1, F_O1 = 2, F_O2 = 4, F_MK = 8, F_ADDNEXT = 16, F_PM = 32 };
+  enum { F_B = 1, F_O1 = 2, F_O2 = 4, F_MK = 8, F_ADDNEXT = 16, F_PM = 32, F_PEER = 64 };
   uint32_t flags = (b_base ? F_B : 0) | (o1_base ? F_O1 : 0) | (o2_base ? F_O2 : 0) | (mk_base ? F_MK : 0) |
-                   (p.out_add_next ? F_ADDNEXT : 0) | (pm_base ? F_PM : 0);
+                   (p.out_add_next ? F_ADDNEXT : 0) | (pm_base ? F_PM : 0) |
+                   ((RTD && MODE == MODE_FWD && p.peer_n > 0) ? F_PEER : 0);
   pin32(flags);
 
   // my bytes inside a chunk; my sign bits inside a row's mask bytes: byte (chunk v) = v*32 + mbyte
@@ -543,6 +544,18 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
               if (flags & F_ADDNEXT) o[i] += nxt_e[i];
             }
             char* dst = o2_base + (uint64_t)row * o2_stride + lane_off;
+            if constexpr (RTD && MODE == MODE_FWD) {
+              if (flags & F_PEER) {
+                // fused hand-off: row r belongs to the consumer rank r / blk; its receive buffer is
+                // [source rank, blk, T, d], so this row lands at [my rank][r % blk][k] -- a peer-memory
+                // store over NVLink (or a local one for my own block)
+                const uint32_t blk = item_side ? (uint32_t)p.peer_blk_i : (uint32_t)p.peer_blk_u;
+                const uint32_t pr = row / blk, lr = row - pr * blk;
+                float* pb = item_side ? p.peer_i[pr] : p.peer_u[pr];
+                dst = reinterpret_cast<char*>(pb) +
+                      (((uint64_t)p.peer_rank * blk + lr) * (uint32_t)p.T + (uint32_t)k) * ROWB + lane_off;
+              }
+            }
 #pragma unroll
             for (int v = 0; v < NV; ++v) stcs_chunk<CW>(dst + v * CHB, o + v * CW);
           }

@@ -49,8 +49,29 @@ class PropagationStep:
         # L forward + L backward layer kernels + the streaming pre-mask of the upstream (row-per-warp kernel)
         self.kernel_launches_per_step = 2 * self.L + (0 if os.environ.get("SAGNN_KERNEL", "").lower().startswith("v7") else 1)
 
+    def set_scatter(self, world, rank, user_ptrs, item_ptrs):
+        """Fused hand-off (``sagnn_propagate_fwd_scatter``, layout "rtd" only): from now on ``forward()``
+        writes the finished layer sums straight into the ranks' receive buffers ``[world, blk, T, d]``
+        (``user_ptrs`` / ``item_ptrs``: their device pointers as mapped on THIS device, own buffer
+        included) instead of ``user_out`` / ``item_out``.  ``set_scatter(0, 0, None, None)`` switches back."""
+        import ctypes
+        if not world:
+            self.scatter = None
+            return
+        if not self.flags:
+            raise ValueError("the fused hand-off needs layout='rtd'")
+        arr = lambda ptrs: (ctypes.c_void_p * world)(*[int(x) for x in ptrs])
+        self.scatter = (int(world), int(rank), arr(user_ptrs), arr(item_ptrs))
+
     def forward(self):
         p = self.plan
+        if getattr(self, "scatter", None):
+            w, r, up, ip = self.scatter
+            _lib.check(self.lib.sagnn_propagate_fwd_scatter(
+                p.handle, _ptr(self.u_embed), _ptr(self.i_embed), _ptr(self.user_out), _ptr(self.item_out), self.L,
+                self.d, self.leaky, _ptr(self.masks), _ptr(self.ws), self.ws.numel(), w, r, up, ip,
+                _stream_ptr(p.device)))
+            return
         _lib.check(self.lib.sagnn_propagate_fwd_ex(p.handle, _ptr(self.u_embed), _ptr(self.i_embed),
                                                    _ptr(self.user_out), _ptr(self.item_out), self.L, self.d,
                                                    self.leaky, _ptr(self.masks), _ptr(self.ws), self.ws.numel(),

@@ -413,6 +413,45 @@ def test_rtd_layout_step_graph_and_sliced_rows():
     assert rc == 1   # SAGNN_INVALID_ARG
 
 
+@pytest.mark.parametrize("W,L,d", [(1, 2, 64), (3, 2, 64), (4, 3, 128), (2, 1, 32)])
+def test_fused_scatter_to_row_sharded_consumer(W, L, d):
+    """sagnn_propagate_fwd_scatter: the last layer writes every row of the layer sums into the receive
+    buffer of the rank owning its row block ([source rank, blk, T, d]).  W receive buffers on ONE GPU
+    stand in for the peers' (peer memory is just another mapped pointer); this rank plays source
+    rank `me`.  Same bits as the plain forward; rows of other source ranks and pad rows untouched."""
+    from sagnn_b200.step import PropagationStep
+    g = dh.make_named("small", seed=23)
+    plan = sg.build_plan(g.sub_mat, latdim=d)
+    T, U, I = plan.T, g.n_user, g.n_item
+    a, b = PropagationStep(plan, L, d), PropagationStep(plan, L, d, layout="rtd")
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for t in (a.u_embed, a.i_embed):
+        t.normal_(generator=gen)
+    b.u_embed.copy_(a.u_embed); b.i_embed.copy_(a.i_embed)
+    a.forward()
+    me = W - 1
+    bu, bi = -(-U // W), -(-I // W)
+    rcv_u = [torch.full((W, bu, T, d), -7.0, device="cuda") for _ in range(W)]
+    rcv_i = [torch.full((W, bi, T, d), -7.0, device="cuda") for _ in range(W)]
+    b.set_scatter(W, me, [t.data_ptr() for t in rcv_u], [t.data_ptr() for t in rcv_i])
+    b.forward()
+    torch.cuda.synchronize()
+    for rcv, blk, rows, ref in ((rcv_u, bu, U, a.user_out), (rcv_i, bi, I, a.item_out)):
+        for r in range(W):
+            lo, hi = r * blk, min((r + 1) * blk, rows)
+            assert torch.equal(rcv[r][me, :hi - lo], ref[:, lo:hi].transpose(0, 1))      # [blk, T, d]
+            assert (rcv[r][me, hi - lo:] == -7.0).all()                                  # pad rows untouched
+            for other in range(W):
+                if other != me:
+                    assert (rcv[r][other] == -7.0).all()
+    b.set_scatter(0, 0, None, None)                      # and the backward is unaffected by the hand-off
+    b.g_user.normal_(generator=gen); b.g_item.normal_(generator=gen)
+    a.g_user.copy_(b.g_user.transpose(0, 1)); a.g_item.copy_(b.g_item.transpose(0, 1))
+    a.backward(); b.backward()
+    torch.cuda.synchronize()
+    assert torch.equal(a.d_u, b.d_u) and torch.equal(a.d_i, b.d_i)
+
+
 # ---------------------------------------------------------------- row sharding (SURVEY 8e, second way)
 @pytest.mark.parametrize("W,L,d,U,I", [(2, 2, 64, 300, 40), (3, 3, 128, 301, 41), (4, 1, 64, 120, 90)])
 def test_row_sharded_virtual_ranks_equal_single_plan_bitwise(W, L, d, U, I):
