@@ -124,6 +124,96 @@ def write_trn_mat_time(path, graphs: IntervalGraphs):
 
 
 # --------------------------------------------------------------------------
+# binary CSR container: the same content as trn_mat_time[1] (+ shape), but as raw
+# little-endian arrays that can be memory-mapped -- no unpickling of T scipy objects, O(1) open,
+# intervals can be read (or sharded over ranks) independently.  Layout, all offsets 64-byte aligned:
+#   0   8s  magic "SAGNNCSR"      8  u32 version (1)     12 u32 T      16 u64 U      24 u64 I
+#   32  u32 flags (bit 0: stored values present)          36 u32 reserved        40 u64 nnz[T]
+#   then per interval k: indptr int64 [U+1] | indices int32 [nnz_k] | data int32 [nnz_k] (if flag)
+# indptr / indices are the canonical CSR of subMat[k] (sorted column ids, no duplicates), data the
+# intc timestamps (preprocess_to_trnmat.ipynb:379) -- exactly what transToLsts consumes.
+# --------------------------------------------------------------------------
+_BIN_MAGIC = b"SAGNNCSR"
+_BIN_VERSION = 1
+
+
+def _align64(n):
+    return (n + 63) & ~63
+
+
+def write_trn_mat_bin(path, graphs, with_values=True):
+    """Writes ``graphs`` (IntervalGraphs or a list of U x I scipy matrices) as a binary CSR container."""
+    mats = graphs.sub_mat if isinstance(graphs, IntervalGraphs) else list(graphs)
+    if not mats:
+        raise ValueError("need at least one interval")
+    mats = [sp.csr_matrix(m) for m in mats]
+    for m in mats:
+        m.sum_duplicates()
+        m.sort_indices()
+    U, I = mats[0].shape
+    if any(m.shape != (U, I) for m in mats):
+        raise ValueError("all intervals must have the same shape")
+    T = len(mats)
+    with open(path, "wb") as f:
+        head = bytearray(_align64(40 + 8 * T))
+        head[0:8] = _BIN_MAGIC
+        head[8:40] = np.array([_BIN_VERSION, T], "<u4").tobytes() + np.array([U, I], "<u8").tobytes() + \
+            np.array([1 if with_values else 0, 0], "<u4").tobytes()
+        head[40:40 + 8 * T] = np.array([m.nnz for m in mats], "<u8").tobytes()
+        f.write(head)
+        for m in mats:
+            parts = [m.indptr.astype("<i8"), m.indices.astype("<i4")]
+            if with_values:
+                parts.append(m.data.astype("<i4"))
+            for a in parts:
+                b = a.tobytes()
+                f.write(b)
+                f.write(b"\0" * (_align64(len(b)) - len(b)))
+
+
+def load_trn_mat_bin(path, graph_num=None, mmap=True):
+    """Opens a binary CSR container: returns ``IntervalGraphs`` whose ``sub_mat`` are scipy CSR
+    matrices backed by the memory-mapped file (``mmap=False``: read into memory).  ``graph_num``
+    selects a prefix of the stored intervals like ``--graphNum`` (model.py:230-231)."""
+    raw = np.memmap(path, dtype=np.uint8, mode="r") if mmap else np.fromfile(path, dtype=np.uint8)
+    if raw.size < 40 or bytes(raw[0:8]) != _BIN_MAGIC:
+        raise ValueError("%s is not a SAGNNCSR container" % path)
+    version, T = (int(x) for x in raw[8:16].view("<u4"))
+    if version != _BIN_VERSION:
+        raise ValueError("unsupported SAGNNCSR version %d" % version)
+    U, I = (int(x) for x in raw[16:32].view("<u8"))
+    flags = int(raw[32:36].view("<u4")[0])
+    nnz = [int(x) for x in raw[40:40 + 8 * T].view("<u8")]
+    if graph_num is not None:
+        if graph_num > T:
+            raise IndexError("graphNum %d > %d stored intervals" % (graph_num, T))
+        T = graph_num
+    off = _align64(40 + 8 * len(nnz))
+    mats = []
+    for k in range(len(nnz)):
+        sizes = [8 * (U + 1), 4 * nnz[k]] + ([4 * nnz[k]] if flags & 1 else [])
+        if off + sum(_align64(x) for x in sizes) > raw.size:
+            raise ValueError("%s is truncated (interval %d)" % (path, k))
+        if k < T:
+            indptr = raw[off:off + sizes[0]].view("<i8")
+            indices = raw[off + _align64(sizes[0]):off + _align64(sizes[0]) + sizes[1]].view("<i4")
+            if flags & 1:
+                o2 = off + _align64(sizes[0]) + _align64(sizes[1])
+                data = raw[o2:o2 + sizes[2]].view("<i4")
+            else:
+                data = np.ones(nnz[k], dtype=np.intc)
+            if int(indptr[-1]) != nnz[k] or (nnz[k] and (int(indices.min()) < 0 or int(indices.max()) >= I)):
+                raise ValueError("%s: interval %d is corrupt" % (path, k))
+            m = sp.csr_matrix((U, I), dtype=np.intc)
+            # assign the arrays directly: no sort, no copy of the big arrays (they stay file-backed)
+            # (scipy wants one index dtype: the row pointers -- U+1 entries -- are narrowed, indices are not copied)
+            m.data, m.indices, m.indptr = data, indices, indptr.astype(np.int32)
+            mats.append(m)
+        off += sum(_align64(x) for x in sizes)
+    return IntervalGraphs(U, I, mats, meta={"container": "SAGNNCSR v1", "mmap": bool(mmap)})
+
+
+# --------------------------------------------------------------------------
 # synthetic power-law interval graphs  (SURVEY 8(d), appendix D)
 # --------------------------------------------------------------------------
 # name -> (U, I, T, total_edges or per-interval list, L, d, alpha_user, alpha_item)

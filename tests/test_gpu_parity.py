@@ -572,9 +572,15 @@ def test_config1_trn_mat_time_plumbing(tmp_path):
     check_against_oracle(h.sub_mat, 64, 2, leaky=0.5, seed=100, scale=0.05)
     # the plan built from adjacency lists equals the one built from the matrices
     plan2 = sg.build_plan(h.sub_mat)
+    # ... and so does the plan built from the memory-mapped binary container
+    bpath = str(tmp_path / "trn_mat_time.sagnncsr")
+    dh.write_trn_mat_bin(bpath, g)
+    plan3 = sg.build_plan(dh.load_trn_mat_bin(bpath, graph_num=3).sub_mat)
     for k in range(3):
         for side in (0, 1):
             assert torch.equal(plan.adjacency_list(k, side), plan2.adjacency_list(k, side))
+            assert torch.equal(plan.adjacency_list(k, side), plan3.adjacency_list(k, side))
+            assert torch.equal(plan2.degrees(k, side, value_sum=True)[1], plan3.degrees(k, side, value_sum=True)[1])
 
 
 @pytest.mark.parametrize("name", ["amazon-book", "ml10m"])

@@ -49,6 +49,48 @@ def test_trn_mat_time_round_trip(tmp_path):
         dh.load_trn_mat_time(str(p), graph_num=4)
 
 
+def test_binary_csr_container_round_trip(tmp_path):
+    """the mmap-able container holds exactly what trn_mat_time[1] holds -- same canonical
+    CSR, same intc values, same transToLsts / transpose outputs -- including an empty interval, the
+    --graphNum prefix, the value-less variant and rejection of foreign / truncated files."""
+    g = dh.make_named("tiny", seed=9)
+    g.sub_mat[1] = sp.csr_matrix(g.sub_mat[1].shape, dtype=np.intc)            # an empty interval
+    p = str(tmp_path / "trn_mat_time.sagnncsr")
+    dh.write_trn_mat_bin(p, g)
+    for mm in (True, False):
+        h = dh.load_trn_mat_bin(p, mmap=mm)
+        assert (h.n_user, h.n_item, h.graph_num, h.nnz) == (g.n_user, g.n_item, g.graph_num, g.nnz)
+        for a, b in zip(g.sub_mat, h.sub_mat):
+            assert b.dtype == np.intc and b.has_canonical_format
+            assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+            assert np.array_equal(a.data, b.data)
+            for x, y in zip(dh.transToLsts(a), dh.transToLsts(b)):
+                assert np.array_equal(np.asarray(x), np.asarray(y))
+            assert (dh.transpose(a) != dh.transpose(b)).nnz == 0
+    assert isinstance(dh.load_trn_mat_bin(p).sub_mat[0].indices, np.memmap)     # file-backed, not copied
+    assert dh.load_trn_mat_bin(p, graph_num=2).graph_num == 2
+    with pytest.raises(IndexError):
+        dh.load_trn_mat_bin(p, graph_num=4)
+    # same content as the pickle path
+    pk = str(tmp_path / "trn_mat_time")
+    dh.write_trn_mat_time(pk, g)
+    for a, b in zip(dh.load_trn_mat_time(pk).sub_mat, dh.load_trn_mat_bin(p).sub_mat):
+        assert (a != b).nnz == 0
+    # structure only
+    dh.write_trn_mat_bin(p, g.sub_mat, with_values=False)
+    h = dh.load_trn_mat_bin(p)
+    assert np.array_equal(h.sub_mat[0].indices, g.sub_mat[0].indices) and (h.sub_mat[0].data == 1).all()
+    # foreign and truncated files
+    bad = tmp_path / "bad"
+    bad.write_bytes(b"not a container" * 8)
+    with pytest.raises(ValueError):
+        dh.load_trn_mat_bin(str(bad))
+    whole = open(p, "rb").read()
+    bad.write_bytes(whole[:len(whole) // 2])
+    with pytest.raises(ValueError):
+        dh.load_trn_mat_bin(str(bad))
+
+
 def test_generator_properties():
     g = dh.make_named("small", seed=100)
     U, I = g.n_user, g.n_item
