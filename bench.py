@@ -426,10 +426,12 @@ def main():
     e2e = None
     if not args.no_e2e:
         host = {}
-        for name, src in (("uE", step.u_embed), ("iE", step.i_embed), ("gU", step.g_user), ("gI", step.g_item)):
-            host[name] = src.cpu().pin_memory()
-        for name, like in (("uO", step.user_out), ("iO", step.item_out), ("dU", step.d_u), ("dI", step.d_i)):
-            host[name] = torch.empty(like.shape, dtype=torch.float32).pin_memory()
+        # the host entry point speaks the reference's [T,R,d] layout whatever layout the device step uses
+        trd = lambda t: t if args.layout == "trd" else t.transpose(0, 1)
+        for name, src in (("uE", step.u_embed), ("iE", step.i_embed), ("gU", trd(step.g_user)), ("gI", trd(step.g_item))):
+            host[name] = src.contiguous().cpu().pin_memory()
+        for name, rows in (("uO", U), ("iO", I), ("dU", U), ("dI", I)):
+            host[name] = torch.empty((T, rows, d), dtype=torch.float32).pin_memory()
         h2d = sum(host[k].numel() * 4 for k in ("uE", "iE", "gU", "gI"))
         d2h = sum(host[k].numel() * 4 for k in ("uO", "iO", "dU", "dI"))
 
