@@ -167,6 +167,11 @@ def cpu_reference_run(g, L, d, steps, warmup, seed):
     import torch
     from oracle import propagate_oracle as po, tf1_mirror
     from sagnn_b200 import data_handler as dh
+    # all the host threads this process may use (torchrun presets OMP_NUM_THREADS=1 for its workers)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     T, U, I = g.graph_num, g.n_user, g.n_item
     adj = [torch.from_numpy(po.trans_to_lsts(m)[0].astype(np.int64)) for m in g.sub_mat]
     tp = [torch.from_numpy(po.trans_to_lsts(po.transpose(m))[0].astype(np.int64)) for m in g.sub_mat]
