@@ -124,6 +124,82 @@ def write_trn_mat_time(path, graphs: IntervalGraphs):
 
 
 # --------------------------------------------------------------------------
+# producer of trn_mat_time (preprocess_to_trnmat.ipynb cells 7, 13, 14): vectorised host
+# mirror of `trans` / `trans_sub`, pinned bit-exactly by tests/golden/trnmat_*.npz (made by exec'ing
+# the notebook's own cells).  The notebook walks list[user] -> {item: [timestamps]} in Python loops;
+# here the same events arrive as flat (user, item, timestamp) arrays in that iteration order.
+# --------------------------------------------------------------------------
+TS_MINN_INIT, TS_MAXX_INIT = 1647180684, 0      # the notebook's initial minn / maxx (cell 13)
+
+
+def interaction_to_triples(interaction):
+    """Flattens the notebook's ``trnInt`` (``list[U]`` of ``None | {item: [timestamps] | None}``) into
+    ``(users, items, times)`` int64 arrays in the order `trans` / `trans_sub` visit the events."""
+    us, its, ts = [], [], []
+    for usr, data in enumerate(interaction):
+        if data is None:
+            continue
+        for col in data:
+            if data[col] is not None:
+                for one in data[col]:
+                    us.append(usr)
+                    its.append(col)
+                    ts.append(one)
+    return np.array(us, np.int64), np.array(its, np.int64), np.array(ts, np.int64)
+
+
+def trans(users, items, times, n_user, n_item):
+    """`trans` (notebook cell 13): the global ``U x I`` float64 interaction-count matrix ``trnMat[0]``
+    plus the running ``(minn, maxx)`` timestamps that `trans_sub` buckets with."""
+    u, i, t = (np.asarray(x, np.int64) for x in (users, items, times))
+    minn = min(TS_MINN_INIT, int(t.min())) if t.size else TS_MINN_INIT
+    maxx = max(TS_MAXX_INIT, int(t.max())) if t.size else TS_MAXX_INIT
+    mat = sp.csr_matrix((np.ones(t.size, np.float64), (u, i)), shape=(n_user, n_item))   # duplicates are summed
+    return mat, minn, maxx
+
+
+def trans_sub(users, items, times, n_user, n_item, graph_num, minn, maxx):
+    """`trans_sub` (notebook cell 7): splits the events into ``graph_num`` equal time intervals,
+    ``interval id = int((t - minn) / ((maxx - minn) / graph_num))`` clamped to ``graph_num - 1``; interval
+    graph k holds, per ``(user, item)``, the timestamp of the pair's FIRST event (in visiting order)
+    that falls into interval k.  ``timeMat[user, item]`` = the interval id of the pair's last such
+    first-event, and -- the notebook fills a DOK matrix -- pairs whose value is 0 are not stored.
+    Returns ``(list of graph_num csr U x I intc, timeMat csr intc)``; ``trn_mat_time`` is
+    ``[trans(...)[0], sub_mats, time_mat]`` (cell 14)."""
+    u, i, t = (np.asarray(x, np.int64) for x in (users, items, times))
+    if maxx == minn:
+        raise ZeroDivisionError("all events share one timestamp: the notebook's interval width is 0")
+    interval = (maxx - minn) / graph_num                       # Python float, as in the notebook
+    g = np.minimum(((t - minn) / interval).astype(np.int64), graph_num - 1)
+    # first event of every (interval, user, item): np.unique returns first occurrences
+    key = (g * n_user + u) * n_item + i
+    _, first = np.unique(key, return_index=True)
+    first.sort()                                               # back to visiting order
+    gu, uu, ii, tt = g[first], u[first], i[first], t[first]
+    subs = []
+    for k in range(graph_num):
+        m = gu == k
+        subs.append(sp.csr_matrix((tt[m].astype(np.intc), (uu[m], ii[m])), shape=(n_user, n_item), dtype=np.intc))
+    # timeMat: the interval of the LAST appended event of each pair (later assignments overwrite)
+    pair = uu * n_item + ii
+    order = np.lexsort((first, pair))
+    last = np.ones(order.size, bool)
+    last[:-1] = pair[order][1:] != pair[order][:-1]
+    sel = order[last]
+    keep = gu[sel] != 0                                         # DOK drops explicit zeros
+    tm = sp.csr_matrix((gu[sel][keep].astype(np.intc), (uu[sel][keep], ii[sel][keep])),
+                       shape=(n_user, n_item), dtype=np.intc)
+    return subs, tm
+
+
+def make_trn_mat_time(users, items, times, n_user, n_item, graph_num):
+    """Cells 13-14 end to end: ``IntervalGraphs`` ready for `write_trn_mat_time` / `write_trn_mat_bin`."""
+    trn, minn, maxx = trans(users, items, times, n_user, n_item)
+    subs, tm = trans_sub(users, items, times, n_user, n_item, graph_num, minn, maxx)
+    return IntervalGraphs(int(n_user), int(n_item), subs, trn, tm, meta={"minn": minn, "maxx": maxx})
+
+
+# --------------------------------------------------------------------------
 # binary CSR container (SURVEY 8f N4): the same content as trn_mat_time[1] (+ shape), but as raw
 # little-endian arrays that can be memory-mapped -- no unpickling of T scipy objects, O(1) open,
 # intervals can be read (or sharded over ranks) independently.  Layout, all offsets 64-byte aligned:

@@ -49,6 +49,42 @@ def test_trn_mat_time_round_trip(tmp_path):
         dh.load_trn_mat_time(str(p), graph_num=4)
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "trnmat_*.npz"))))
+def test_trans_sub_matches_reference_notebook_fixtures(path):
+    """The producer of trn_mat_time: the vectorised `trans` / `trans_sub` mirror vs the
+    outputs of the reference notebook's own cells (tests/golden/make_golden_trnmat.py), bit-exact:
+    global count matrix, min / max timestamps, every interval graph (structure AND first-occurrence
+    timestamps), timeMat with its dropped zeros."""
+    z = np.load(path)
+    U, I, T = int(z["U"]), int(z["I"]), int(z["T"])
+    trn, minn, maxx = dh.trans(z["u"], z["i"], z["t"], U, I)
+    assert (minn, maxx) == (int(z["minn"]), int(z["maxx"]))
+    trn.sum_duplicates(); trn.sort_indices()
+    assert np.array_equal(trn.indptr, z["trn_indptr"]) and np.array_equal(trn.indices, z["trn_indices"])
+    assert np.array_equal(trn.data, z["trn_data"])
+    subs, tm = dh.trans_sub(z["u"], z["i"], z["t"], U, I, T, minn, maxx)
+    assert len(subs) == T
+    for k, m in enumerate(subs):
+        assert m.dtype == np.intc and m.has_canonical_format
+        assert np.array_equal(m.indptr, z["sub%d_indptr" % k]) and np.array_equal(m.indices, z["sub%d_indices" % k])
+        assert np.array_equal(m.data, z["sub%d_data" % k])
+    tm.sort_indices()
+    assert np.array_equal(tm.indptr, z["tm_indptr"]) and np.array_equal(tm.indices, z["tm_indices"])
+    assert np.array_equal(tm.data, z["tm_data"])
+    g = dh.make_trn_mat_time(z["u"], z["i"], z["t"], U, I, T)
+    assert g.graph_num == T and g.nnz == [int(z["sub%d_indptr" % k][-1]) for k in range(T)]
+    # each (user, item) pair can sit in several intervals, but at most once per interval
+    assert all(m.nnz == len(set(zip(*m.nonzero()))) for m in g.sub_mat)
+
+
+def test_interaction_to_triples_order():
+    inter = [None, {5: [30, 10], 2: [20]}, {}, {1: None, 7: [40]}]
+    u, i, t = dh.interaction_to_triples(inter)
+    assert u.tolist() == [1, 1, 1, 3] and i.tolist() == [5, 5, 2, 7] and t.tolist() == [30, 10, 20, 40]
+    with pytest.raises(ZeroDivisionError):
+        dh.trans_sub([0], [0], [5], 2, 2, 3, 5, 5)
+
+
 def test_binary_csr_container_round_trip(tmp_path):
     """the mmap-able container holds exactly what trn_mat_time[1] holds -- same canonical
     CSR, same intc values, same transToLsts / transpose outputs -- including an empty interval, the
