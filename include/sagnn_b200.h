@@ -228,6 +228,26 @@ int sagnn_message_propagate(const sagnn_plan* plan, int k, int side, const float
                             float* out_dev, int d, float leaky, void* workspace_dev,
                             size_t workspace_bytes, sagnn_stream_t stream);
 
+/* ---- sampled pair scores over the outputs ------------------------------------
+ * The second consumer of user_vector / item_vector and the producer of the sparse part of their
+ * upstream gradient:  scores[s] = sum_c act(u_rows[uids[s], c] * i_rows[iids[s], c]),
+ * activation 1 = lrelu (model.py:196-198, the SSL scores preds_one of interval k), 0 = none
+ * (model.py:171-173, the plain prediction dot product).  Replaces two tf.nn.embedding_lookup gathers,
+ * Mul, Maximum and reduce_sum.  A table is (base pointer, row stride in floats): interval k of a
+ * [T,R,d] tensor = (t + k*R*d, d), of a [R,T,d] tensor = (t + k*d, T*d).  ids are int32 device arrays
+ * and are not range-checked (like embedding_lookup on a GPU). */
+int sagnn_pair_scores_fwd(const float* u_rows_dev, int64_t u_stride, const float* i_rows_dev, int64_t i_stride,
+                          const int32_t* uids_dev, const int32_t* iids_dev, int64_t n, int d, int activation,
+                          float leaky, float* scores_dev, sagnn_stream_t stream);
+/* Backward: ADDS g_scores[s] * act'(x) * other_row into d_u_rows[uids[s]] / d_i_rows[iids[s]] (either
+ * may be NULL) -- i.e. accumulates the sparse gradient straight into the dense upstream tables that
+ * sagnn_propagate_bwd takes (TF: IndexedSlices -> unsorted_segment_sum -> AddN).  Uses float atomics
+ * (samples repeat rows), so the summation order, not the set of terms, may vary between runs. */
+int sagnn_pair_scores_bwd(const float* u_rows_dev, int64_t u_stride, const float* i_rows_dev, int64_t i_stride,
+                          const int32_t* uids_dev, const int32_t* iids_dev, int64_t n, int d, int activation,
+                          float leaky, const float* g_scores_dev, float* d_u_rows_dev, int64_t du_stride,
+                          float* d_i_rows_dev, int64_t di_stride, sagnn_stream_t stream);
+
 /* Host-buffer entry point (what a non-torch caller binds): copies the embeddings (and,
  * when g_*_host != NULL, the upstream gradients) to the device, runs forward (+ backward),
  * copies the results back and synchronises.  Device buffers are cached inside the plan.

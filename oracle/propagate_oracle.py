@@ -283,6 +283,29 @@ def propagate(adj, tp_adj, u_embed, i_embed, g_user, g_item, n_layers, leaky=0.5
     return uv, iv, du, di
 
 
+# --------------------------------------------------------------------------
+# sampled pair scores over the outputs  (model.py:171-173, 194-198)
+# --------------------------------------------------------------------------
+def pair_scores(u_rows, i_rows, uids, iids, leaky=0.5, activation=True):
+    """``pckUlat = embedding_lookup(user_vector[k], suids[k])``, ``pckIlat = embedding_lookup(item_vector[k],
+    siids[k])``, ``preds_one = reduce_sum(Activate(pckUlat * pckIlat, 'leakyRelu'), -1)`` (model.py:194-196);
+    ``activation=False``: the plain ``reduce_sum(pckUlat * pckIlat, -1)`` of model.py:171-173.  Returns
+    ``(scores [n], x [n, d])`` with ``x`` the products (the tape)."""
+    x = u_rows[np.asarray(uids)] * i_rows[np.asarray(iids)]
+    return (leaky_relu(x, leaky) if activation else x).sum(axis=-1), x
+
+
+def pair_scores_backward(u_rows, i_rows, uids, iids, g_scores, leaky=0.5, activation=True):
+    """TF autodiff of `pair_scores`: Sum -> broadcast, MaximumGrad (tie rule of `leaky_relu_grad`), Mul,
+    then the two embedding_lookup gradients (IndexedSlices, summed per row like unsorted_segment_sum).
+    Returns dense ``(d_u_rows, d_i_rows)``."""
+    uids, iids = np.asarray(uids), np.asarray(iids)
+    a, b = u_rows[uids], i_rows[iids]
+    g = np.broadcast_to(np.asarray(g_scores, dtype=u_rows.dtype)[:, None], a.shape)
+    gx = leaky_relu_grad(a * b, g, leaky) if activation else g
+    return (_unsorted_segment_sum(gx * b, uids, u_rows.shape[0]), _unsorted_segment_sum(gx * a, iids, i_rows.shape[0]))
+
+
 def pass_masks_from_tape(tape, leaky=0.5):
     """The MaximumGrad decisions of a forward tape: True where the gradient passes unscaled."""
     out = []

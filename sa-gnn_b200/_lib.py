@@ -60,6 +60,10 @@ SIGNATURES = {
                                                     ctypes.c_float, vp, vp, ctypes.c_size_t, vp]),
     "sagnn_message_propagate": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int,
                                                ctypes.c_float, vp, ctypes.c_size_t, vp]),
+    "sagnn_pair_scores_fwd": (ctypes.c_int, [vp, ctypes.c_int64, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_float, vp, vp]),
+    "sagnn_pair_scores_bwd": (ctypes.c_int, [vp, ctypes.c_int64, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_float, vp, vp, ctypes.c_int64, vp, ctypes.c_int64, vp]),
     "sagnn_host_forward": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int]),
     "sagnn_host_backward": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float]),
     "sagnn_propagate_host": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,

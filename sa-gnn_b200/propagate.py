@@ -339,6 +339,74 @@ def message_propagate(srclats, plan, k, type="user", leaky=0.5):
     return out
 
 
+class _PairScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, user_vec, item_vec, k, uids, iids, activation, leaky, layout):
+        lib = _lib.load_library()
+        u, i = user_vec.contiguous(), item_vec.contiguous()
+        T, d = (u.shape[1], u.shape[2]) if layout else (u.shape[0], u.shape[2])
+        n = int(uids.numel())
+        scores = torch.empty(n, dtype=torch.float32, device=u.device)
+        geo = _pair_geometry(u, i, k, layout)
+        with torch.cuda.device(u.device):
+            _lib.check(lib.sagnn_pair_scores_fwd(geo[0], geo[1], geo[2], geo[3], _ptr(uids), _ptr(iids), n, d,
+                                                 activation, leaky, _ptr(scores), _stream_ptr(u.device)))
+        ctx.save_for_backward(u, i, uids, iids)
+        ctx.args = (k, activation, leaky, layout, n, d)
+        return scores
+
+    @staticmethod
+    def backward(ctx, g):
+        u, i, uids, iids = ctx.saved_tensors
+        k, activation, leaky, layout, n, d = ctx.args
+        lib = _lib.load_library()
+        d_u = torch.zeros_like(u) if ctx.needs_input_grad[0] else None
+        d_i = torch.zeros_like(i) if ctx.needs_input_grad[1] else None
+        su = _pair_geometry(u, i, k, layout)                                  # the tables
+        gu = _pair_geometry(d_u if d_u is not None else u, d_i if d_i is not None else i, k, layout)   # their gradients
+        with torch.cuda.device(u.device):
+            _lib.check(lib.sagnn_pair_scores_bwd(su[0], su[1], su[2], su[3], _ptr(uids), _ptr(iids), n, d, activation,
+                                                 leaky, _ptr(g.contiguous()), gu[0] if d_u is not None else None, gu[1],
+                                                 gu[2] if d_i is not None else None, gu[3], _stream_ptr(u.device)))
+        return d_u, d_i, None, None, None, None, None, None
+
+
+def _pair_geometry(u, i, k, layout):
+    """(user base, user row stride, item base, item row stride) of interval k: [T,R,d] (layout 0) or [R,T,d]."""
+    d = u.shape[2]
+    if layout:      # [R,T,d]: interval k starts k*d floats in, rows are T*d apart
+        T = u.shape[1]
+        return (ctypes.c_void_p(u.data_ptr() + 4 * k * d), T * d, ctypes.c_void_p(i.data_ptr() + 4 * k * d), T * d)
+    return (ctypes.c_void_p(u.data_ptr() + 4 * k * u.shape[1] * d), d,
+            ctypes.c_void_p(i.data_ptr() + 4 * k * i.shape[1] * d), d)
+
+
+def pair_scores(user_vec, item_vec, k, uids, iids, activation="leakyRelu", leaky=0.5, layout="trd", check_ids=True):
+    """``sum_c act(user_vec[k][uids] * item_vec[k][iids])`` over the propagation's outputs: the SSL
+    scores ``preds_one`` of interval ``k`` (model.py:194-198; ``activation="leakyRelu"``) or a plain
+    prediction dot product (model.py:171-173; ``activation=None``).  ``user_vec`` / ``item_vec`` are
+    ``[T,U,d]`` / ``[T,I,d]`` (``layout="trd"``) or ``[U,T,d]`` / ``[I,T,d]`` (``"rtd"``); ``uids`` / ``iids`` int
+    CUDA tensors of equal length (``suids[k]`` / ``siids[k]``).  Differentiable w.r.t. both tables: the
+    backward scatters the sparse gradient with a hand-written kernel (``sagnn_pair_scores_bwd``)."""
+    if not (user_vec.is_cuda and item_vec.is_cuda and uids.is_cuda and iids.is_cuda):
+        raise RuntimeError("sagnn_b200.pair_scores: tensors must be CUDA tensors (no CPU fallback)")
+    if user_vec.dtype != torch.float32 or item_vec.dtype != torch.float32:
+        raise TypeError("tables must be float32")
+    if layout not in _LAYOUTS or activation not in (None, "none", "leakyRelu"):
+        raise ValueError("layout must be 'trd' or 'rtd', activation None or 'leakyRelu'")
+    lay = _LAYOUTS[layout]
+    T, U, I = (user_vec.shape[1], user_vec.shape[0], item_vec.shape[0]) if lay else \
+        (user_vec.shape[0], user_vec.shape[1], item_vec.shape[1])
+    if not 0 <= int(k) < T or uids.numel() != iids.numel() or user_vec.shape[2] != item_vec.shape[2]:
+        raise ValueError("bad interval / id arrays / latdim")
+    uids, iids = uids.to(torch.int32).contiguous(), iids.to(torch.int32).contiguous()
+    if check_ids and uids.numel():
+        if int(uids.min()) < 0 or int(uids.max()) >= U or int(iids.min()) < 0 or int(iids.max()) >= I:
+            raise IndexError("pair_scores: id out of range (tf.nn.embedding_lookup on CPU raises too)")
+    act = 1 if activation == "leakyRelu" else 0
+    return _PairScores.apply(user_vec, item_vec, int(k), uids, iids, act, float(leaky), lay)
+
+
 def _host_ptr(a):
     if a is None:
         return ctypes.c_void_p(0)

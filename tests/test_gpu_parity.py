@@ -452,6 +452,70 @@ def test_fused_scatter_to_row_sharded_consumer(W, L, d):
     assert torch.equal(a.d_u, b.d_u) and torch.equal(a.d_i, b.d_i)
 
 
+# ---------------------------------------------------------------- sampled pair scores
+@pytest.mark.parametrize("d,layout,act", [(64, "trd", "leakyRelu"), (64, "rtd", "leakyRelu"), (128, "trd", None),
+                                          (32, "rtd", None), (256, "trd", "leakyRelu")])
+def test_pair_scores_match_oracle(d, layout, act):
+    """sagnn_pair_scores_fwd / _bwd (model.py:171-173,194-198) vs the fp64 oracle, on the outputs'
+    two layouts; users repeat in the samples (like suids), so gradient rows collide."""
+    T, U, I, n, k = 3, 70, 50, 4000, 1
+    rng = np.random.default_rng(d)
+    uv, iv = rng.standard_normal((T, U, d)).astype(np.float32), rng.standard_normal((T, I, d)).astype(np.float32)
+    uids, iids = rng.integers(0, U, n).astype(np.int32), rng.integers(0, I, n).astype(np.int32)
+    g = rng.standard_normal(n).astype(np.float32)
+    tu, ti = torch.from_numpy(uv).cuda(), torch.from_numpy(iv).cuda()
+    if layout == "rtd":
+        tu, ti = tu.transpose(0, 1).contiguous(), ti.transpose(0, 1).contiguous()
+    tu.requires_grad_(True); ti.requires_grad_(True)
+    s = sg.pair_scores(tu, ti, k, torch.from_numpy(uids).cuda(), torch.from_numpy(iids).cuda(), activation=act,
+                       leaky=0.5, layout=layout)
+    s.backward(torch.from_numpy(g).cuda())
+    torch.cuda.synchronize()
+    ref_s, _ = po.pair_scores(uv[k].astype(np.float64), iv[k].astype(np.float64), uids, iids, 0.5, act is not None)
+    ref_du, ref_di = po.pair_scores_backward(uv[k].astype(np.float64), iv[k].astype(np.float64), uids, iids,
+                                             g.astype(np.float64), 0.5, act is not None)
+    assert_parity(s, ref_s, "scores")
+    du, di = (tu.grad.transpose(0, 1), ti.grad.transpose(0, 1)) if layout == "rtd" else (tu.grad, ti.grad)
+    assert_parity(du[k], ref_du, "d user_vector[k]")
+    assert_parity(di[k], ref_di, "d item_vector[k]")
+    for j in range(T):                                   # the other intervals get no gradient
+        if j != k:
+            assert not du[j].any() and not di[j].any()
+    with pytest.raises(IndexError):
+        sg.pair_scores(tu, ti, k, torch.tensor([U], device="cuda"), torch.tensor([0], device="cuda"), layout=layout)
+    empty = torch.empty(0, dtype=torch.int32, device="cuda")
+    assert sg.pair_scores(tu, ti, k, empty, empty, layout=layout).numel() == 0
+
+
+def test_pair_scores_feed_the_propagation_backward():
+    """End of the chain the reference builds (model.py:118-129 -> 194-198): the SSL scores of every
+    interval on top of `propagate`, gradients w.r.t. the embedding tables through both hand-written
+    backward kernels, vs the oracle chain."""
+    mats = random_interval_mats(2, 60, 45, 400, seed=17)
+    adj, tp = adj_lists(mats)
+    T, U, I, d, L, n = 2, 60, 45, 64, 2, 500
+    uE, iE, _, _ = random_tables(T, U, I, d, seed=19, scale=0.3)
+    rng = np.random.default_rng(23)
+    ids = [(rng.integers(0, U, n).astype(np.int32), rng.integers(0, I, n).astype(np.int32)) for _ in range(T)]
+    gs = [rng.standard_normal(n).astype(np.float32) for _ in range(T)]
+    plan = sg.build_plan(mats)
+    u = torch.from_numpy(uE).cuda().requires_grad_(True)
+    i = torch.from_numpy(iE).cuda().requires_grad_(True)
+    uv, iv = sg.propagate(plan, u, i, L, 0.5)
+    scores = [sg.pair_scores(uv, iv, k, torch.from_numpy(ids[k][0]).cuda(), torch.from_numpy(ids[k][1]).cuda())
+              for k in range(T)]
+    torch.autograd.backward(scores, [torch.from_numpy(x).cuda() for x in gs])
+    torch.cuda.synchronize()
+    ruv, riv, tape = po.propagate_forward(adj, tp, uE.astype(np.float64), iE.astype(np.float64), L, 0.5)
+    gU, gI = np.zeros_like(ruv), np.zeros_like(riv)
+    for k in range(T):
+        assert_parity(scores[k], po.pair_scores(ruv[k], riv[k], ids[k][0], ids[k][1], 0.5)[0], "scores[%d]" % k)
+        gU[k], gI[k] = po.pair_scores_backward(ruv[k], riv[k], ids[k][0], ids[k][1], gs[k].astype(np.float64), 0.5)
+    rdu, rdi = po.propagate_backward(adj, tp, tape, gU, gI, L, 0.5)
+    assert_parity(u.grad, rdu, "dU through pair scores")
+    assert_parity(i.grad, rdi, "dI through pair scores")
+
+
 # ---------------------------------------------------------------- row sharding (SURVEY 8e, second way)
 @pytest.mark.parametrize("W,L,d,U,I", [(2, 2, 64, 300, 40), (3, 3, 128, 301, 41), (4, 1, 64, 120, 90)])
 def test_row_sharded_virtual_ranks_equal_single_plan_bitwise(W, L, d, U, I):

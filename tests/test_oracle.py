@@ -220,3 +220,37 @@ def test_backward_matches_finite_differences_fp64():
             flat[pos] = old
             fd = (lp - lm) / (2 * eps)
             assert abs(fd - grad.reshape(-1)[pos]) < 1e-6 * max(1.0, abs(fd)), (which, pos)
+
+
+def test_pair_scores_oracle_closed_form_autograd_and_tie_rule():
+    """SURVEY 8f N2 oracle (model.py:171-173,194-198): closed form on a tiny case, agreement with torch
+    autograd of the same op graph away from ties, and TF's MaximumGrad tie rule at x == 0."""
+    import torch
+    U = np.array([[1.0, -2.0], [0.5, 4.0], [3.0, 0.0]])
+    I = np.array([[2.0, 1.0], [-1.0, 0.25]])
+    uids, iids = [0, 2, 1, 0], [0, 1, 1, 0]
+    s, x = po.pair_scores(U, I, uids, iids, leaky=0.5)
+    # sample 0: (2, -2) -> 2 + (-1) = 1; sample 1: (-3, 0) -> -1.5 + 0; sample 2: (-0.5, 1) -> -0.25 + 1
+    assert np.allclose(s, [1.0, -1.5, 0.75, 1.0])
+    s_lin, _ = po.pair_scores(U, I, uids, iids, activation=False)
+    assert np.allclose(s_lin, [0.0, -3.0, 0.5, 0.0])
+    g = np.array([1.0, 2.0, -1.0, 0.5])
+    dU, dI = po.pair_scores_backward(U, I, uids, iids, g, leaky=0.5)
+    # the x == 0 element (user 2, column 1) takes the leaky branch: d/du = leaky * g * i
+    assert dU[2, 1] == 0.5 * 2.0 * 0.25
+    # user 0 is sampled twice (g = 1 and 0.5): its gradient rows add up (unsorted_segment_sum)
+    assert np.allclose(dU[0], [(1.0 + 0.5) * 1.0 * 2.0, (1.0 + 0.5) * 0.5 * 1.0])
+    rng = np.random.default_rng(3)
+    Ur, Ir = rng.standard_normal((30, 16)), rng.standard_normal((20, 16))
+    uu, ii, gg = rng.integers(0, 30, 200), rng.integers(0, 20, 200), rng.standard_normal(200)
+    for act in (True, False):
+        tu = torch.from_numpy(Ur).requires_grad_(True)
+        ti = torch.from_numpy(Ir).requires_grad_(True)
+        xx = tu[torch.from_numpy(uu)] * ti[torch.from_numpy(ii)]
+        sc = (torch.maximum(0.3 * xx, xx) if act else xx).sum(-1)
+        sc.backward(torch.from_numpy(gg))
+        s2, _ = po.pair_scores(Ur, Ir, uu, ii, leaky=0.3, activation=act)
+        d2 = po.pair_scores_backward(Ur, Ir, uu, ii, gg, leaky=0.3, activation=act)
+        assert np.allclose(s2, sc.detach().numpy(), rtol=1e-13, atol=1e-13)
+        assert np.allclose(d2[0], tu.grad.numpy(), rtol=1e-12, atol=1e-12)
+        assert np.allclose(d2[1], ti.grad.numpy(), rtol=1e-12, atol=1e-12)
