@@ -63,6 +63,20 @@ const char* sagnn_version(void);
  * Replaces the 2T transToLsts() calls + tf.sparse.SparseTensor wrapping of
  * model.py:227-237 and the transpose() of DataHandler.py:9-11. */
 
+/* Producer of the interval graphs from raw events (preprocess_to_trnmat.ipynb cell 7, `trans_sub`):
+ * users_dev / items_dev int32 [n], times_dev int64 [n] in the notebook's visiting order (user
+ * ascending, then the user's items, then the pair's timestamps); minn / maxx as `trans` (cell 13)
+ * leaves them.  Event e goes to interval int((t - minn) / ((maxx - minn) / T)) clamped to T-1; per
+ * (interval, user, item) the FIRST event is kept.  Writes the adjacency lists of all intervals back
+ * to back, interval 0 first, each row-major sorted -- rows / cols / stored values (timestamps, intc) --
+ * into row_out / col_out / val_out (capacity n) and the T list lengths into nnz_host: interval k is
+ * the slice [sum_{j<k} nnz_j, +nnz_k), which is what sagnn_plan_set_interval takes.  An empty
+ * interval has nnz 0 (pass the reference's (0,0) fallback edge to the plan, DataHandler.py:66-68).
+ * Synchronises the stream.  (timeMat, which the model never reads, is not produced.) */
+int sagnn_bucket_events(const int32_t* users_dev, const int32_t* items_dev, const int64_t* times_dev, int64_t n,
+                        int U, int I, int T, int64_t minn, int64_t maxx, int32_t* row_out_dev, int32_t* col_out_dev,
+                        int32_t* val_out_dev, int64_t* nnz_host, sagnn_stream_t stream);
+
 /* nnz_host[T]: edge count of every interval (an empty interval must be passed as the
  * reference's single fallback edge (0,0), DataHandler.py:66-68 -- the Python shim does). */
 int sagnn_plan_create(int T, int U, int I, const int64_t* nnz_host, sagnn_plan** out);

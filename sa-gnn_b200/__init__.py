@@ -8,12 +8,12 @@ There is no CPU fallback: compute entry points raise if the CUDA library or a GP
 """
 from . import data_handler                                            # noqa: F401
 from .data_handler import transToLsts, trans_to_lsts, transpose       # noqa: F401
-from .propagate import (Plan, build_plan, propagate, message_propagate, pair_scores,  # noqa: F401
+from .propagate import (Plan, build_plan, bucket_events, propagate, message_propagate, pair_scores,  # noqa: F401
                         propagate_host, host_forward, host_backward, IntervalPropagation)
 from ._lib import lib_path, load_library, SagnnError                  # noqa: F401
 
 __all__ = [
-    "data_handler", "transToLsts", "trans_to_lsts", "transpose", "Plan", "build_plan", "propagate",
+    "data_handler", "transToLsts", "trans_to_lsts", "transpose", "Plan", "build_plan", "bucket_events", "propagate",
     "message_propagate", "pair_scores", "propagate_host", "host_forward", "host_backward", "IntervalPropagation", "lib_path", "load_library",
     "SagnnError",
 ]

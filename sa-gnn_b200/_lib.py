@@ -22,6 +22,8 @@ STATUS = {0: "OK", 1: "INVALID_ARG", 2: "UNSORTED_INPUT", 3: "CUDA_ERROR", 4: "W
 SIGNATURES = {
     "sagnn_last_error": (ctypes.c_char_p, []),
     "sagnn_version": (ctypes.c_char_p, []),
+    "sagnn_bucket_events": (ctypes.c_int, [vp, vp, vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int64, ctypes.c_int64, vp, vp, vp, c_i64p, vp]),
     "sagnn_plan_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p, ctypes.POINTER(vp)]),
     "sagnn_plan_set_interval": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int64, vp]),
     "sagnn_plan_set_latdim_hint": (ctypes.c_int, [vp, ctypes.c_int]),

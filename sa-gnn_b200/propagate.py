@@ -156,11 +156,12 @@ def _split_interval(m):
         idx, data, shape = transToLsts(m)         # includes the (0,0) fallback for empty matrices
         return idx[:, 0], idx[:, 1], data, shape
     if isinstance(m, (tuple, list)):
-        if len(m) == 2:
-            return m[0], m[1], None, None
-        if len(m) == 3:
-            return m[0], m[1], m[2], None
-        raise ValueError("interval tuple must be (row, col) or (row, col, val)")
+        if len(m) not in (2, 3):
+            raise ValueError("interval tuple must be (row, col) or (row, col, val)")
+        if len(m[0]) == 0:                                 # empty interval: the fallback edge of DataHandler.py:66-68
+            z = np.zeros(1, dtype=np.int32)
+            return z, z, (z if len(m) == 3 else None), None
+        return m[0], m[1], (m[2] if len(m) == 3 else None), None
     if getattr(m, "ndim", 0) == 2 and m.shape[1] == 2:     # transToLsts-style [E,2] list
         if m.shape[0] == 0:
             m = np.array([[0, 0]], dtype=np.int32)         # DataHandler.py:66-68
@@ -242,6 +243,41 @@ def build_plan(sub_mats, U=None, I=None, *, device=None, edge_weight=None, stric
         _lib.check(lib.sagnn_plan_set_latdim_hint(handle, int(latdim)))
         _lib.check(lib.sagnn_plan_finalize(handle, mode, st))
     return plan
+
+
+def bucket_events(users, items, times, U, I, graph_num, minn=None, maxx=None, device=None):
+    """Device-side ``trans_sub`` (preprocess_to_trnmat.ipynb cell 7; ``sagnn_bucket_events``): raw
+    ``(user, item, timestamp)`` events in the notebook's visiting order -> the ``graph_num`` interval
+    adjacency lists as ``[(row, col, val)]`` int32 CUDA tensors (row-major sorted, first-event
+    timestamps), ready for ``build_plan(lists, U, I)``.  ``minn`` / ``maxx`` default to what `trans`
+    (cell 13) computes.  Same result as ``data_handler.trans_sub``, bit for bit."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("sagnn_b200.bucket_events needs a CUDA device (there is no CPU fallback)")
+    from .data_handler import TS_MAXX_INIT, TS_MINN_INIT
+    lib = _lib.load_library()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    t = (times if isinstance(times, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(times, dtype=np.int64)))
+    t = t.to(device=device, dtype=torch.int64).contiguous()
+    u, i = _as_dev_i32(users, device), _as_dev_i32(items, device)
+    n = int(t.numel())
+    if u.numel() != n or i.numel() != n:
+        raise ValueError("users, items and times must have the same length")
+    if minn is None:
+        minn = min(TS_MINN_INIT, int(t.min())) if n else TS_MINN_INIT
+    if maxx is None:
+        maxx = max(TS_MAXX_INIT, int(t.max())) if n else TS_MAXX_INIT
+    T = int(graph_num)
+    with torch.cuda.device(device):
+        row = torch.empty(max(n, 1), dtype=torch.int32, device=device)
+        col, val = torch.empty_like(row), torch.empty_like(row)
+        nnz = (ctypes.c_int64 * T)()
+        _lib.check(lib.sagnn_bucket_events(_ptr(u), _ptr(i), _ptr(t), n, int(U), int(I), T, int(minn), int(maxx),
+                                           _ptr(row), _ptr(col), _ptr(val), nnz, _stream_ptr(device)))
+    out, off = [], 0
+    for k in range(T):
+        out.append((row[off:off + nnz[k]], col[off:off + nnz[k]], val[off:off + nnz[k]]))
+        off += nnz[k]
+    return out
 
 
 def _check_tables(plan, u, i):

@@ -452,6 +452,56 @@ def test_fused_scatter_to_row_sharded_consumer(W, L, d):
     assert torch.equal(a.d_u, b.d_u) and torch.equal(a.d_i, b.d_i)
 
 
+# ---------------------------------------------------------------- device-side trans_sub
+def _coo_of(m):
+    m = sp.csr_matrix(m)
+    m.sort_indices()
+    return np.repeat(np.arange(m.shape[0]), np.diff(m.indptr)), m.indices, m.data
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "trnmat_*.npz"))))
+def test_bucket_events_matches_reference_notebook_fixtures(path):
+    """sagnn_bucket_events vs the outputs of the reference notebook's own `trans_sub` cell
+    (tests/golden/make_golden_trnmat.py): every interval's adjacency list and stored timestamps, bit-exact."""
+    z = np.load(path)
+    U, I, T = int(z["U"]), int(z["I"]), int(z["T"])
+    lists = sg.bucket_events(z["u"], z["i"], z["t"], U, I, T)
+    assert len(lists) == T
+    for k, (row, col, val) in enumerate(lists):
+        ind = z["sub%d_indptr" % k]
+        assert np.array_equal(row.cpu().numpy(), np.repeat(np.arange(U), np.diff(ind)))
+        assert np.array_equal(col.cpu().numpy(), z["sub%d_indices" % k])
+        assert np.array_equal(val.cpu().numpy(), z["sub%d_data" % k])
+
+
+def test_bucket_events_large_random_equals_host_mirror_and_feeds_the_plan():
+    rng = np.random.default_rng(41)
+    U, I, T, n = 3000, 2000, 6, 300000
+    u = np.sort(rng.integers(0, U, n))                       # the notebook visits users in ascending order
+    i = rng.integers(0, 60, n) * 33 % I                      # few items per user: many repeated pairs
+    t = rng.integers(1388534400, 1406073600, n)
+    t[:50] = t[0]                                            # equal timestamps, and the maximum lands in the clamp
+    subs, _ = dh.trans_sub(u, i, t, U, I, T, *dh.trans(u, i, t, U, I)[1:])
+    lists = sg.bucket_events(u, i, t, U, I, T)
+    assert sum(len(l[0]) for l in lists) < n                 # duplicates were dropped
+    for k in range(T):
+        r, c, v = _coo_of(subs[k])
+        assert np.array_equal(lists[k][0].cpu().numpy(), r) and np.array_equal(lists[k][1].cpu().numpy(), c)
+        assert np.array_equal(lists[k][2].cpu().numpy(), v)
+    plan, ref = sg.build_plan(lists, U, I), sg.build_plan(subs)
+    for k in range(T):
+        for side in (0, 1):
+            assert torch.equal(plan.adjacency_list(k, side), ref.adjacency_list(k, side))
+            assert torch.equal(plan.degrees(k, side, value_sum=True)[1], ref.degrees(k, side, value_sum=True)[1])
+    # an interval nobody falls into (minn far below the data) becomes the reference's fallback edge
+    sparse = sg.bucket_events(u, i, t, U, I, 3, minn=int(t.min()) - 10 * int(t.max() - t.min()))
+    assert len(sparse[0][0]) == 0 and sg.build_plan(sparse, U, I).nnz[0] == 1
+    with pytest.raises(sg.SagnnError):
+        sg.bucket_events(np.array([U, 0]), np.array([0, 0]), np.array([1400000000, 1400000100]), U, I, T)   # id out of range
+    with pytest.raises(sg.SagnnError):
+        sg.bucket_events(np.array([0]), np.array([0]), np.array([5]), U, I, T, minn=5, maxx=5)
+
+
 # ---------------------------------------------------------------- sampled pair scores (SURVEY 8f N2)
 @pytest.mark.parametrize("d,layout,act", [(64, "trd", "leakyRelu"), (64, "rtd", "leakyRelu"), (128, "trd", None),
                                           (32, "rtd", None), (256, "trd", "leakyRelu")])
