@@ -262,6 +262,19 @@ int sagnn_pair_scores_bwd(const float* u_rows_dev, int64_t u_stride, const float
                           float leaky, const float* g_scores_dev, float* d_u_rows_dev, int64_t du_stride,
                           float* d_i_rows_dev, int64_t di_stride, sagnn_stream_t stream);
 
+/* ---- device-side sampleSslBatch (model.py:304-339) ---------------------------
+ * For interval k and the batch users bat_ids_dev int32 [batch]: posset(u) = the items of user u in
+ * A_k (read from the plan's CSR instead of densifying subMat[k][batIds].toarray()), s = min(ssl_num,
+ * |posset| / 2), all = 2*s uniform draws with replacement from posset; emits, users in batch order,
+ * i_locs[cur] = all[j], i_locs[cur+1] = all[s+j], u_locs[cur] = u_locs[cur+1] = u,
+ * u_locs_seq[cur] = u_locs_seq[cur+1] = batch position, cur += 2 (j < s) -- the reference's
+ * suids[k] / siids[k] / suLocs_seq[k] feed.  Output capacity batch*2*ssl_num int32 each; the number
+ * of entries written goes to *n_out_host.  Counter-based generator keyed by (seed, k, batch
+ * position, draw): same seed, same samples; the stream is not numpy's.  Synchronises the stream. */
+int sagnn_sample_ssl_batch(const sagnn_plan* plan, int k, const int32_t* bat_ids_dev, int batch, int ssl_num,
+                           uint64_t seed, int32_t* u_locs_dev, int32_t* i_locs_dev, int32_t* u_locs_seq_dev,
+                           int64_t* n_out_host, sagnn_stream_t stream);
+
 /* Host-buffer entry point (what a non-torch caller binds): copies the embeddings (and,
  * when g_*_host != NULL, the upstream gradients) to the device, runs forward (+ backward),
  * copies the results back and synchronises.  Device buffers are cached inside the plan.

@@ -1,0 +1,106 @@
+// Device-side sampleSslBatch (LIU-YUXI/SA-GNN model.py:304-339).  The reference, per train
+// step and per interval k, densifies `subMat[k][batIds].toarray()` (batch x item floats) only to read
+// each batch user's positive items back with argwhere, then draws `np.random.choice(posset, 2*sslNum)`
+// in a Python loop.  The plan already holds every A_k as CSR on the device, so the positives of user u
+// in interval k are simply idx[rowptr[g] .. rowptr[g+1]) with g = k*(U+I) + u: one scan for the output
+// offsets and one kernel that draws the samples with a counter-based generator.
+//
+// Same output contract as the reference: for batch position b (ascending) with
+// s = min(sslNum, |posset| / 2) > 0, `all = choice(posset, 2*s)` (uniform, with replacement), and for
+// j < s:  iLocs[cur] = all[j] (positive), iLocs[cur+1] = all[s+j] (negative),
+//         uLocs[cur] = uLocs[cur+1] = batIds[b], uLocs_seq[cur] = uLocs_seq[cur+1] = b, cur += 2.
+// Users with fewer than two positives in the interval emit nothing.  The random STREAM differs from
+// numpy's Mersenne Twister by construction; parity is on the contract above (tests check membership,
+// counts, layout, uniformity and seed determinism).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace sagnn {
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {     // splitmix64 finaliser
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+
+__global__ void ssl_count_kernel(const int32_t* __restrict__ deg, const int32_t* __restrict__ bat, int batch, int U,
+                                 int64_t row0, int ssl_num, int64_t* __restrict__ cnt, int* __restrict__ bad) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > batch) return;
+  if (b == batch) { cnt[b] = 0; return; }                   // slot of the total after the exclusive scan
+  const int u = bat[b];
+  if (u < 0 || u >= U) { atomicOr(bad, 1); cnt[b] = 0; return; }
+  const int half = deg[row0 + u] / 2;
+  cnt[b] = 2 * (int64_t)(half < ssl_num ? half : ssl_num);
+}
+
+__global__ void ssl_draw_kernel(const int32_t* __restrict__ deg, const int64_t* __restrict__ rowptr,
+                                const int32_t* __restrict__ idx, const int32_t* __restrict__ bat, int batch, int U,
+                                int64_t row0, int ssl_num, uint64_t seed, const int64_t* __restrict__ off,
+                                int32_t* __restrict__ u_locs, int32_t* __restrict__ i_locs, int32_t* __restrict__ u_seq) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(tid / (2 * ssl_num)), j = (int)(tid % (2 * ssl_num));   // j-th element of `all`
+  if (b >= batch) return;
+  const int u = bat[b];
+  if (u < 0 || u >= U) return;
+  const int d = deg[row0 + u];
+  const int s = d / 2 < ssl_num ? d / 2 : ssl_num;
+  if (j >= 2 * s) return;
+  const uint64_t r = mix64(mix64(seed ^ ((uint64_t)b << 32 | (uint32_t)j)) + (uint64_t)row0);
+  const int pick = (int)(((r >> 32) * (uint64_t)d) >> 32);                    // uniform in [0, d)
+  const int64_t o = off[b] + (j < s ? 2 * j : 2 * (j - s) + 1);               // positives even, negatives odd
+  i_locs[o] = idx[rowptr[row0 + u] + pick];
+  u_locs[o] = u;
+  u_seq[o] = b;
+}
+
+template <typename T>
+struct SmpTmp {
+  T* p = nullptr;
+  ~SmpTmp() { cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * (n ? n : 1)); }
+  operator T*() const { return p; }
+};
+
+}  // namespace sagnn
+
+using namespace sagnn;
+
+extern "C" int sagnn_sample_ssl_batch(const sagnn_plan* p, int k, const int32_t* bat_ids, int batch, int ssl_num,
+                                      uint64_t seed, int32_t* u_locs, int32_t* i_locs, int32_t* u_locs_seq,
+                                      int64_t* n_out_host, sagnn_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  SAGNN_REQUIRE(p && n_out_host, SAGNN_INVALID_ARG, "sample_ssl_batch: NULL plan / n_out_host");
+  SAGNN_REQUIRE(p->finalized, SAGNN_NOT_FINALIZED, "sample_ssl_batch: plan not finalized");
+  SAGNN_REQUIRE(k >= 0 && k < p->T, SAGNN_INVALID_ARG, "sample_ssl_batch: interval %d outside [0,%d)", k, p->T);
+  SAGNN_REQUIRE(batch >= 0 && ssl_num >= 1 && ssl_num <= (1 << 20), SAGNN_INVALID_ARG,
+                "sample_ssl_batch: batch=%d sslNum=%d", batch, ssl_num);
+  *n_out_host = 0;
+  if (batch == 0) return SAGNN_OK;
+  SAGNN_REQUIRE(bat_ids && u_locs && i_locs && u_locs_seq, SAGNN_INVALID_ARG, "sample_ssl_batch: NULL tensor");
+  const int64_t row0 = (int64_t)k * p->N;                   // user rows of A_k in the global row space
+  SmpTmp<int64_t> cnt, off;
+  SmpTmp<int> bad;
+  SmpTmp<char> tmp;
+  SAGNN_CUDA(cnt.alloc(batch + 1)); SAGNN_CUDA(off.alloc(batch + 1)); SAGNN_CUDA(bad.alloc(1));
+  SAGNN_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
+  ssl_count_kernel<<<(batch + 1 + 255) / 256, 256, 0, st>>>(p->deg, bat_ids, batch, p->U, row0, ssl_num, cnt, bad);
+  size_t tb = 0;
+  SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, batch + 1, st));
+  SAGNN_CUDA(tmp.alloc(tb));
+  SAGNN_CUDA(cub::DeviceScan::ExclusiveSum((void*)tmp.p, tb, cnt.p, off.p, batch + 1, st));
+  const int64_t threads = (int64_t)batch * 2 * ssl_num;
+  ssl_draw_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p->deg, p->rowptr, p->idx, bat_ids, batch, p->U, row0,
+                                                                    ssl_num, seed, off, u_locs, i_locs, u_locs_seq);
+  SAGNN_CUDA(cudaGetLastError());
+  int hbad = 0;
+  int64_t total = 0;
+  SAGNN_CUDA(cudaMemcpyAsync(&total, off.p + batch, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  SAGNN_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SAGNN_CUDA(cudaStreamSynchronize(st));
+  SAGNN_REQUIRE(!hbad, SAGNN_OUT_OF_RANGE, "sample_ssl_batch: a batch id is outside [0,%d)", p->U);
+  *n_out_host = total;
+  return SAGNN_OK;
+}

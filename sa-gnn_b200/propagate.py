@@ -116,6 +116,25 @@ class Plan:
         keys = ["rows", "short_rows", "long_rows", "chunks", "max_degree", "edges_both_sides", "_", "sms"]
         return {k: int(v) for k, v in zip(keys, out) if k != "_"}
 
+    # -- samplers ---------------------------------------------------------------------
+    def sample_ssl_batch(self, bat_ids, ssl_num, seed=0):
+        """``Recommender.sampleSslBatch(batIds, self.handler.subMat)`` (model.py:304-339) on the device,
+        straight from the plan's CSR: returns per interval ``(uLocs, iLocs, uLocs_seq)`` int32 CUDA tensors
+        (positives at even, negatives at odd positions; users with fewer than two items in the interval
+        emit nothing).  ``seed`` keys the counter-based generator (same seed, same samples)."""
+        lib = _lib.load_library()
+        bat = _as_dev_i32(bat_ids, self.device)
+        batch, cap = int(bat.numel()), max(1, int(bat.numel()) * 2 * int(ssl_num))
+        out = []
+        with torch.cuda.device(self.device):
+            for k in range(self.T):
+                u, i, s = (torch.empty(cap, dtype=torch.int32, device=self.device) for _ in range(3))
+                n = ctypes.c_int64()
+                _lib.check(lib.sagnn_sample_ssl_batch(self.handle, k, _ptr(bat), batch, int(ssl_num), int(seed) & (2**64 - 1),
+                                                      _ptr(u), _ptr(i), _ptr(s), ctypes.byref(n), _stream_ptr(self.device)))
+                out.append((u[:n.value], i[:n.value], s[:n.value]))
+        return out
+
     # -- scratch ----------------------------------------------------------------------
     def workspace_bytes(self, n_layers, d):
         f, m, b = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()

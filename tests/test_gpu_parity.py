@@ -502,6 +502,50 @@ def test_bucket_events_large_random_equals_host_mirror_and_feeds_the_plan():
         sg.bucket_events(np.array([0]), np.array([0]), np.array([5]), U, I, T, minn=5, maxx=5)
 
 
+# ---------------------------------------------------------------- device-side sampleSslBatch
+def test_sample_ssl_batch_contract():
+    """sagnn_sample_ssl_batch vs the contract of Recommender.sampleSslBatch (model.py:304-339): per
+    interval and batch user 2*min(sslNum, |posset|//2) samples, all of them items of that user in that
+    interval, positives / negatives interleaved, uLocs / uLocs_seq laid out like the reference's, users
+    with fewer than two items silent; seed-deterministic; draws uniform over posset."""
+    g = dh.make_named("small", seed=29)
+    plan = sg.build_plan(g.sub_mat)
+    U, T, ssl = g.n_user, plan.T, 5
+    rng = np.random.default_rng(1)
+    bat = rng.permutation(U)[:512].astype(np.int32)
+    out = plan.sample_ssl_batch(bat, ssl, seed=7)
+    again = plan.sample_ssl_batch(bat, ssl, seed=7)
+    other = plan.sample_ssl_batch(bat, ssl, seed=8)
+    assert len(out) == T
+    for k in range(T):
+        m = sp.csr_matrix(g.sub_mat[k])
+        deg = np.diff(m.indptr)[bat]
+        want = 2 * np.minimum(ssl, deg // 2)
+        u, i, sq = (np.array(x.cpu().numpy(), dtype=np.int64) for x in out[k])   # own, writeable copies (scipy indexing)
+        assert len(u) == len(i) == len(sq) == int(want.sum())
+        assert np.array_equal(sq, np.repeat(np.arange(len(bat)), want))          # batch order, 2*s entries each
+        assert np.array_equal(u, bat[sq])
+        assert np.asarray(m[u, i]).ravel().astype(bool).all()                    # every sample is an item of that user
+        for a, b in zip(out[k], again[k]):
+            assert torch.equal(a, b)
+        assert not torch.equal(out[k][1], other[k][1])
+    # uniformity: one user with many items, many draws -> every item drawn, counts within 5 sigma
+    k, m = 0, sp.csr_matrix(g.sub_mat[0])
+    hub = int(np.argmax(np.diff(m.indptr)))
+    d = int(np.diff(m.indptr)[hub])
+    assert d >= 8
+    draws = plan.sample_ssl_batch(np.full(4000, hub, dtype=np.int32), d // 2, seed=3)[0][1].cpu().numpy()
+    assert len(draws) == 4000 * 2 * (d // 2)
+    items, counts = np.unique(draws, return_counts=True)
+    assert np.array_equal(items, m.indices[m.indptr[hub]:m.indptr[hub + 1]])
+    mean = len(draws) / d
+    assert np.all(np.abs(counts - mean) < 5 * np.sqrt(mean))
+    empty = plan.sample_ssl_batch(np.empty(0, dtype=np.int32), ssl)
+    assert all(x[0].numel() == 0 for x in empty)
+    with pytest.raises(sg.SagnnError):
+        plan.sample_ssl_batch(np.array([U], dtype=np.int32), ssl)
+
+
 # ---------------------------------------------------------------- sampled pair scores (SURVEY 8f N2)
 @pytest.mark.parametrize("d,layout,act", [(64, "trd", "leakyRelu"), (64, "rtd", "leakyRelu"), (128, "trd", None),
                                           (32, "rtd", None), (256, "trd", "leakyRelu")])
