@@ -399,7 +399,7 @@ class _PairScores(torch.autograd.Function):
     def forward(ctx, user_vec, item_vec, k, uids, iids, activation, leaky, layout):
         lib = _lib.load_library()
         u, i = user_vec.contiguous(), item_vec.contiguous()
-        T, d = (u.shape[1], u.shape[2]) if layout else (u.shape[0], u.shape[2])
+        d = u.shape[2]
         n = int(uids.numel())
         scores = torch.empty(n, dtype=torch.float32, device=u.device)
         geo = _pair_geometry(u, i, k, layout)
