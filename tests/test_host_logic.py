@@ -193,6 +193,30 @@ def test_no_cpu_fallback_without_gpu():
     assert rc == 3 and b"no CPU fallback" in sg.load_library().sagnn_last_error()
 
 
+def test_argument_validation_needs_no_device():
+    """Size limits and malformed arguments are rejected by the C ABI before any CUDA call (status +
+    message, no exception across the boundary): the reference's maximum sizes (int32 row space), a
+    latdim that is not a multiple of 4, an empty time range, too many peers."""
+    lib = sg.load_library()
+    err = lambda: lib.sagnn_last_error().decode()
+    h = ctypes.c_void_p()
+    nnz = (ctypes.c_int64 * 4)(1, 1, 1, 1)
+    assert lib.sagnn_plan_create(4, 2 ** 29, 2 ** 29, nnz, ctypes.byref(h)) == 1 and "2^31" in err()   # T*(U+I) rows
+    assert lib.sagnn_plan_create(0, 3, 3, nnz, ctypes.byref(h)) == 1
+    assert lib.sagnn_pair_scores_fwd(None, 64, None, 64, None, None, 0, 66, 1, 0.5, None, None) == 1 and "multiple of 4" in err()
+    assert lib.sagnn_pair_scores_fwd(None, 64, None, 64, None, None, 0, 64, 7, 0.5, None, None) == 1 and "activation" in err()
+    assert lib.sagnn_pair_scores_fwd(None, 64, None, 64, None, None, 0, 64, 1, 0.5, None, None) == 0          # n = 0: nothing to do
+    out = (ctypes.c_int64 * 3)()
+    assert lib.sagnn_bucket_events(None, None, None, 5, 10, 10, 3, 100, 100, None, None, None, out, None) == 1 and "maxx" in err()
+    assert lib.sagnn_bucket_events(None, None, None, 0, 10, 10, 3, 0, 100, None, None, None, out, None) == 0 and list(out) == [0, 0, 0]
+    ptrs = (ctypes.c_void_p * 17)()
+    assert lib.sagnn_propagate_fwd_scatter(None, None, None, None, None, 2, 64, 0.5, None, None, 0, 17, 0, ptrs, ptrs, None) == 1
+    assert "world" in err()
+    assert lib.sagnn_plan_set_row_block(None, 0, 1, 0, 1) == 1
+    n_out = ctypes.c_int64()
+    assert lib.sagnn_sample_ssl_batch(None, 0, None, 4, 2, 0, None, None, None, ctypes.byref(n_out), None) == 1
+
+
 def test_product_never_imports_oracle():
     for path in glob.glob(os.path.join(ROOT, "sa-gnn_b200", "**", "*.py"), recursive=True) + \
             glob.glob(os.path.join(ROOT, "sa-gnn_b200", "csrc", "*")) + [os.path.join(ROOT, "sagnn_b200.py")]:
