@@ -203,6 +203,42 @@ def test_propagate_matches_golden_fixtures(path):
         assert_parity(g, z[name], name)
 
 
+MODELREF = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "modelref_*.npz"))
+                  if not p.endswith("modelref_errors.npz"))
+
+
+@pytest.mark.parametrize("path", MODELREF)
+@pytest.mark.parametrize("layout", ["trd", "rtd"])
+def test_propagate_matches_reference_model_py_executed(path, layout):
+    """CUDA path vs the outputs of the reference's own model.py text (tests/golden/make_golden_model.py):
+    forward <= 1e-5 against user_vector / item_vector (and the transposed tensors of model.py:133-134 in
+    the [R,T,d] layout), backward <= 1e-5 against fp64 finite differences of that forward -- no masks
+    shared with the checker.  The plan is built from the scipy matrices, like prepareModel does."""
+    z = np.load(path)
+    T, U, I, L, leaky = int(z["T"]), int(z["U"]), int(z["I"]), int(z["L"]), float(z["leaky"])
+    mats = [sp.csr_matrix((z[f"csr_data{k}"], z[f"csr_indices{k}"], z[f"csr_indptr{k}"]), shape=(U, I)) for k in range(T)]
+    plan = sg.build_plan(mats)
+    u = torch.from_numpy(z["uE"]).cuda().requires_grad_(True)
+    i = torch.from_numpy(z["iE"]).cuda().requires_grad_(True)
+    uv, iv = sg.propagate(plan, u, i, L, leaky, layout=layout)
+    gu, gi = torch.from_numpy(z["gU"]).cuda(), torch.from_numpy(z["gI"]).cuda()
+    if layout == "rtd":
+        assert_parity(uv, z["user_vector_tensor"], "user_vector_tensor [U,T,d]")
+        assert_parity(iv, z["item_vector_tensor"], "item_vector_tensor [I,T,d]")
+        gu, gi = gu.transpose(0, 1).contiguous(), gi.transpose(0, 1).contiguous()
+    else:
+        assert_parity(uv, z["user_vector"], "user_vector [T,U,d]")
+        assert_parity(iv, z["item_vector"], "item_vector [T,I,d]")
+    torch.autograd.backward([uv, iv], [gu, gi])
+    assert_parity(u.grad, z["dU"], "dU vs finite differences of the reference forward")
+    assert_parity(i.grad, z["dI"], "dI vs finite differences of the reference forward")
+    for k in range(T):   # adjacency lists: the reference's transToLsts / transpose outputs
+        ptr, idx = plan.csr(k, 0)
+        np.testing.assert_array_equal(idx.cpu().numpy(), z[f"adj{k}"][:, 1])
+        ptr, idx = plan.csr(k, 1)
+        np.testing.assert_array_equal(idx.cpu().numpy(), z[f"tp{k}"][:, 1])
+
+
 @pytest.mark.parametrize("d,L", [(32, 1), (64, 2), (64, 3), (128, 3), (128, 4), (256, 2)])
 def test_propagate_small_random(d, L):
     check_against_oracle(random_interval_mats(3, 120, 80, 900, seed=d + L), d, L, seed=L)

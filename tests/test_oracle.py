@@ -69,6 +69,62 @@ def test_oracle_frozen_outputs(path):
         np.testing.assert_allclose(got, z[name], rtol=1e-12, atol=1e-12)
 
 
+# ---------------------------------------------------------------- golden: the reference's model.py, executed
+MODELREF = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "modelref_*.npz"))
+                  if not p.endswith("modelref_errors.npz"))
+
+
+@pytest.mark.parametrize("path", MODELREF)
+def test_oracles_match_reference_model_py_executed(path):
+    """Float parity pinned to the reference: the fixtures hold what /root/reference/model.py:80-102,
+    118-134 computes when its own text is executed over numpy stand-ins for the TF ops
+    (tests/golden/make_golden_model.py + tf1_shim.py), with the adjacency lists built by the
+    reference's prepareModel lines 227-238; gradients are fp64 central differences of that forward.
+    All three restatements (numpy, C, torch mirror) must reproduce them."""
+    z = np.load(path)
+    T, L, leaky = int(z["T"]), int(z["L"]), float(z["leaky"])
+    adj = [z[f"adj{k}"] for k in range(T)]
+    tp = [z[f"tp{k}"] for k in range(T)]
+    # index construction of the fixture == the oracle's own (and therefore the device plan's, tested on GPU)
+    for k in range(T):
+        m = sp.csr_matrix((z[f"csr_data{k}"], z[f"csr_indices{k}"], z[f"csr_indptr{k}"]), shape=(int(z["U"]), int(z["I"])))
+        np.testing.assert_array_equal(po.trans_to_lsts(m)[0], adj[k])
+        np.testing.assert_array_equal(po.trans_to_lsts(po.transpose(m))[0], tp[k])
+        np.testing.assert_array_equal(po.trans_to_lsts(m, norm=True)[1], z[f"adj_values{k}"])   # all zeros: F3
+    for impl in (po.propagate, c_oracle.propagate):
+        uv, iv, du, di = impl(adj, tp, z["uE"], z["iE"], z["gU"], z["gI"], L, leaky, np.float64)[:4]
+        np.testing.assert_allclose(uv, z["user_vector"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(iv, z["item_vector"], rtol=1e-12, atol=1e-12)
+        # [R,T,d] hand-off of model.py:133-134
+        np.testing.assert_allclose(np.transpose(uv, (1, 0, 2)), z["user_vector_tensor"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(np.transpose(iv, (1, 0, 2)), z["item_vector_tensor"], rtol=1e-12, atol=1e-12)
+        # finite differences with h = 1e-8 carry ~1e-7 of rounding noise
+        assert po.relerr(du, z["dU"]) < 2e-6 and po.relerr(di, z["dI"]) < 2e-6
+    # the reference computes in fp32: the fp32 oracle agrees with its fp32 run to rounding
+    uv32, iv32 = po.propagate(adj, tp, z["uE"], z["iE"], z["gU"], z["gI"], L, leaky, np.float32)[:2]
+    assert po.relerr(uv32, z["user_vector_f32"]) < 1e-6 and po.relerr(iv32, z["item_vector_f32"]) < 1e-6
+    t64 = lambda x: torch.from_numpy(np.asarray(x, dtype=np.float64))
+    t = lambda x: torch.from_numpy(np.asarray(x, dtype=np.int64))
+    tu, ti, tdu, tdi = tf1_mirror.propagate([t(x) for x in adj], [t(x) for x in tp], t64(z["uE"]), t64(z["iE"]),
+                                            t64(z["gU"]), t64(z["gI"]), L, leaky)
+    assert po.relerr(tu.numpy(), z["user_vector"]) < 1e-12 and po.relerr(ti.numpy(), z["item_vector"]) < 1e-12
+    assert po.relerr(tdu.numpy(), z["dU"]) < 2e-6 and po.relerr(tdi.numpy(), z["dI"]) < 2e-6
+
+
+def test_inputs_the_reference_itself_rejects(golden_dir):
+    """modelref_errors.npz: executing model.py on a one-edge interval (also the (0,0) fallback of an
+    empty matrix, DataHandler.py:66-68) fails in segment_sum's shape inference (tf.squeeze made the
+    ids rank 0), and rows ending more than 100 before R fail in the identity lookup (model.py:87-91).
+    The oracle's strict mode raises on the second; both are inputs the reference cannot run, so the
+    product's natural result there (zero rows / the fallback edge contributing) has nothing to match."""
+    z = np.load(os.path.join(golden_dir, "modelref_errors.npz"))
+    assert "rank 0" in str(z["one_edge"]) and "rank 0" in str(z["empty"])
+    assert "is not in [0, 200)" in str(z["tail_gap_gt_100"])
+    for frag in ("self.messagePropagate(embs1[-1],self.edgeDropout(self.subAdj[k]),'user')", "tf.add_n(embs0)",
+                 "transToLsts(transpose(seqadj), norm=True)"):
+        assert frag in str(z["executed_text"])
+
+
 # ---------------------------------------------------------------- closed-form tiny cases
 def test_closed_form_3x3_two_layers():
     # A = [[1,1,0],[0,0,0],[0,1,1]]   user 1 has no edges; item 0 only user 0
