@@ -11,7 +11,8 @@
 
 namespace sagnn {
 
-constexpr int kChunk = 64;        // max edges one lane-group gathers for one task
+constexpr int kChunk = 64;        // max edges one warp gathers for one task
+constexpr int kPktTasks = 4;      // tasks per packet of the packed task stream (packet-stream kernel)
 constexpr int kHotRows = 768;     // max hot slots per source table (slot = degree rank); array stride
 constexpr int kHotBytes = 192 * 1024;   // shared memory the kernels give to staged hot rows
 
@@ -53,6 +54,8 @@ struct sagnn_seg {
   int64_t edge_base;    // first edge of the segment in idx / enc
   int64_t task_begin;   // its slice of the task list: long-row slices first (longest rows first),
   int64_t task_end;     //   then short rows in descending-degree order
+  int64_t pkt_begin;    // its slice of the packet directory (packet-stream kernel): packets of
+  int64_t pkt_end;      //   kPktTasks consecutive tasks, the last one padded with no-work records
 };
 
 struct sagnn_cta {      // persistent CTA -> segment binding (CTAs are dealt out by segment cost)
@@ -95,11 +98,19 @@ struct sagnn_plan {
   int32_t* enc = nullptr;         // [2 * e_total] edge codes, hot-first inside every row
   float* w_enc = nullptr;         // [2 * e_total] weights in enc order (optional)
   int32_t* hot_ids = nullptr;     // [2T, kHotRows] row ids (inside table t) of table t's hot slots
-  sagnn_task* tasks = nullptr;    // [n_tasks] grouped by segment
+  sagnn_task* tasks = nullptr;    // [n_tasks] grouped by segment (v8 kernel only; the packet stream replaces it)
+  // packed task stream (packet-stream kernel): what a warp needs for kPktTasks tasks in one contiguous,
+  // 16-byte aligned block = one TMA bulk copy: kPktTasks records {row, n | flags, slice id, code offset}
+  // then every task's edge codes (padded to 4) [each followed by its weights]
+  uint4* pkt_stream = nullptr;
+  uint32_t* pkt_dir = nullptr;    // [n_pkts + 1] packet offsets in 16-byte units
+  int64_t n_pkts = 0;
+  size_t pkt_stream_bytes = 0;
   sagnn_seg* seg_dev = nullptr;   // [2T]
   sagnn_cta* cta_dev = nullptr;   // [n_waves][num_sms] all intervals: one launch per wave (normally one wave)
   int n_waves = 1;
   sagnn_cta* cta_int_dev = nullptr;  // [T][num_sms] one interval per launch
+  std::vector<sagnn_cta> cta_host, cta_int_host;   // host copies: the packet-stream kernel takes its table by value
   int64_t* chunk_base = nullptr;  // [n_long + 1] first slice of each long row
   uint32_t* chunk_lr = nullptr;   // [n_chunks] long-row rank of each slice
   std::vector<sagnn_seg> seg_host;
@@ -130,5 +141,6 @@ struct sagnn_plan {
 namespace sagnn {
 void free_host_cache(sagnn_plan* p);
 int apply_cta_split(sagnn_plan* p, const std::vector<double>& cost, cudaStream_t st);
-bool use_rpw();   // row-per-warp kernel selected (default; SAGNN_KERNEL=v7 selects the half-warp kernel)
+bool use_rpw();   // always true since the half-warp kernel (v7) was retired; kept for the call sites
+bool use_pkt();   // packet-stream kernel (v9, default); SAGNN_KERNEL=v8 selects the cp.async-ring kernel
 }

@@ -250,6 +250,55 @@ __global__ void sched_task_kernel(const uint32_t* __restrict__ srow, const int32
   tasks[j] = k;
 }
 
+// ---- packed task stream (packet-stream kernel) ----------------------------------------------
+// bytes of edge codes (+ weights) task j contributes to its packet: n padded to a multiple of four
+__global__ void pkt_size_kernel(const sagnn_task* __restrict__ tasks, int64_t n_tasks, int wmul,
+                                int64_t* __restrict__ cbytes) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > n_tasks) return;
+  cbytes[j] = j == n_tasks ? 0 : (int64_t)(((tasks[j].meta & 0x7fu) + 3u) & ~3u) * 4 * wmul;
+}
+
+// one warp per task: its record, codes (and weights) into the packet; packet p of the whole plan starts
+// at byte 16*kPktTasks*p + coff[first task of p] (every packet opens with kPktTasks 16-byte records)
+__global__ void pkt_fill_kernel(const sagnn_task* __restrict__ tasks, int64_t n_tasks,
+                                const int64_t* __restrict__ coff, const sagnn_seg* __restrict__ seg, int S,
+                                const int32_t* __restrict__ idx, const float* __restrict__ w,
+                                unsigned char* __restrict__ stream, uint32_t* __restrict__ dir) {
+  const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= n_tasks) return;
+  int lo = 0, hi = S;                     // segment that owns task j: largest s with task_begin <= j
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (seg[mid].task_begin <= j) lo = mid; else hi = mid;
+  }
+  const sagnn_seg sg = seg[lo];
+  const int64_t local = j - sg.task_begin;
+  const int64_t pk = sg.pkt_begin + local / kPktTasks;
+  const int t = (int)(local % kPktTasks);
+  const int64_t f = j - t;                // first task of the packet
+  const int64_t pkt_off = (int64_t)16 * kPktTasks * pk + coff[f];
+  const uint32_t code_off = (uint32_t)(16 * kPktTasks + (coff[j] - coff[f]));
+  const sagnn_task k = tasks[j];
+  const uint32_t n = k.meta & 0x7fu, n4 = (n + 3u) & ~3u;
+  unsigned char* pkt = stream + pkt_off;
+  if (lane == 0) {
+    reinterpret_cast<uint4*>(pkt)[t] = make_uint4(k.row, n | (k.meta & 0x80000000u), k.aux, code_off);
+    if (t == 0) dir[pk] = (uint32_t)(pkt_off >> 4);
+    if (j == sg.task_end - 1)             // the segment's last packet: pad with no-work records
+      for (int q = t + 1; q < kPktTasks; ++q) reinterpret_cast<uint4*>(pkt)[q] = make_uint4(0u, 0x40000000u, 0u, 0u);
+  }
+  const int32_t* src = idx + sg.edge_base + k.e_off;
+  int32_t* dst = reinterpret_cast<int32_t*>(pkt + code_off);
+  for (uint32_t e = lane; e < n4; e += 32) dst[e] = e < n ? src[e] : 0;
+  if (w) {
+    const float* ws = w + sg.edge_base + k.e_off;
+    float* wd = reinterpret_cast<float*>(pkt + code_off) + n4;
+    for (uint32_t e = lane; e < n4; e += 32) wd[e] = e < n ? ws[e] : 0.f;
+  }
+}
+
 struct CastI64 {
   __host__ __device__ int64_t operator()(int32_t v) const { return (int64_t)v; }
 };
@@ -310,11 +359,13 @@ int apply_cta_split(sagnn_plan* p, const std::vector<double>& cost, cudaStream_t
   }
   if (!p->cta_dev) SAGNN_CUDA(cudaMalloc(&p->cta_dev, sizeof(sagnn_cta) * cta.size()));
   SAGNN_CUDA(cudaMemcpyAsync(p->cta_dev, cta.data(), sizeof(sagnn_cta) * cta.size(), cudaMemcpyHostToDevice, st));
+  p->cta_host = cta;
   std::vector<sagnn_cta> cta_int((size_t)p->T * sms);
   for (int k = 0; k < p->T; ++k) deal_ctas(cost, 2 * k, 2 * k + 2, sms, cta_int.data() + (size_t)k * sms, nullptr);
   if (!p->cta_int_dev) SAGNN_CUDA(cudaMalloc(&p->cta_int_dev, sizeof(sagnn_cta) * cta_int.size()));
   SAGNN_CUDA(cudaMemcpyAsync(p->cta_int_dev, cta_int.data(), sizeof(sagnn_cta) * cta_int.size(),
                              cudaMemcpyHostToDevice, st));
+  p->cta_int_host = cta_int;
   SAGNN_CUDA(cudaStreamSynchronize(st));
   return SAGNN_OK;
 }
@@ -359,8 +410,12 @@ extern "C" int sagnn_plan_create(int T, int U, int I, const int64_t* nnz_host, s
     p->e_total += nnz_host[k];
   }
   p->is_set.assign(T, 0);
-  SAGNN_CUDA(cudaGetDevice(&p->device));
-  SAGNN_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
+  cudaError_t e0 = cudaGetDevice(&p->device);
+  if (e0 == cudaSuccess) e0 = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device);
+  if (e0 != cudaSuccess) {
+    delete p;
+    return cuda_fail(e0, "cudaGetDevice / cudaDeviceGetAttribute", __FILE__, __LINE__);
+  }
   cudaError_t a1 = cudaMalloc(&p->deg, sizeof(int32_t) * p->n_rows);
   cudaError_t a2 = cudaMalloc(&p->rowptr, sizeof(int64_t) * (p->n_rows + 1));
   cudaError_t a3 = cudaMalloc(&p->idx, sizeof(int32_t) * 2 * p->e_total);
@@ -379,7 +434,7 @@ extern "C" int sagnn_plan_destroy(sagnn_plan* p) {
   sagnn::free_host_cache(p);
   cudaFree(p->deg); cudaFree(p->rowptr); cudaFree(p->idx); cudaFree(p->val); cudaFree(p->w);
   cudaFree(p->valsum); cudaFree(p->chunk_base); cudaFree(p->chunk_lr); cudaFree(p->tasks);
-  cudaFree(p->enc); cudaFree(p->w_enc); cudaFree(p->hot_ids); cudaFree(p->seg_dev); cudaFree(p->cta_dev); cudaFree(p->cta_int_dev);
+  cudaFree(p->enc); cudaFree(p->w_enc); cudaFree(p->pkt_stream); cudaFree(p->pkt_dir); cudaFree(p->hot_ids); cudaFree(p->seg_dev); cudaFree(p->cta_dev); cudaFree(p->cta_int_dev);
   delete p;
   return SAGNN_OK;
 }
@@ -469,7 +524,6 @@ extern "C" int sagnn_plan_set_row_block(sagnn_plan* p, int u_begin, int u_end, i
   SAGNN_REQUIRE(0 <= u_begin && u_begin <= u_end && u_end <= p->U && 0 <= i_begin && i_begin <= i_end && i_end <= p->I,
                 SAGNN_INVALID_ARG, "set_row_block: need 0 <= u_begin <= u_end <= %d and 0 <= i_begin <= i_end <= %d "
                 "(got [%d,%d) [%d,%d))", p->U, p->I, u_begin, u_end, i_begin, i_end);
-  SAGNN_REQUIRE(sagnn::use_rpw(), SAGNN_INVALID_ARG, "set_row_block: row sharding needs the row-per-warp kernel");
   p->u_begin = u_begin; p->u_end = u_end; p->i_begin = i_begin; p->i_end = i_end;
   p->row_block = true;
   return SAGNN_OK;
@@ -527,7 +581,7 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   }
 
   // ---- schedule: per-segment task lists, hot slots, hot-first edge codes ------------------
-  if (sagnn::use_rpw()) p->hot_rows = 0;   // the row-per-warp kernel stages no hot rows: every code is a source-row id
+  p->hot_rows = 0;   // no staged hot rows: every edge code is a source-row id
   SAGNN_REQUIRE(p->num_sms >= 2, SAGNN_INVALID_ARG, "finalize: need at least 2 SMs");
   SAGNN_REQUIRE(2 * p->e_total < ((int64_t)1 << 32), SAGNN_INVALID_ARG,
                 "finalize: %lld edge entries exceed 2^32", (long long)(2 * p->e_total));
@@ -587,17 +641,22 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
     
   }
 
-  SAGNN_CUDA(cudaMalloc(&p->enc, sizeof(int32_t) * 2 * p->e_total));
-  if (p->w) SAGNN_CUDA(cudaMalloc(&p->w_enc, sizeof(float) * 2 * p->e_total));
-  sched_encode_kernel<<<blocks_for(R * 32), 256, 0, st>>>(p->rowptr, p->idx, p->w, slot_of, R, N, U, p->enc,
-                                                          p->w_enc, nhot_row);
+  const bool pkt = sagnn::use_pkt();
+  if (!pkt) {   // v8 kernel: edge codes (and weights) in CSR order, copied next to the canonical arrays
+    SAGNN_CUDA(cudaMalloc(&p->enc, sizeof(int32_t) * 2 * p->e_total));
+    if (p->w) SAGNN_CUDA(cudaMalloc(&p->w_enc, sizeof(float) * 2 * p->e_total));
+    sched_encode_kernel<<<blocks_for(R * 32), 256, 0, st>>>(p->rowptr, p->idx, p->w, slot_of, R, N, U, p->enc,
+                                                            p->w_enc, nhot_row);
+  } else {      // packet stream: the codes are read straight from the canonical CSR when the packets are filled
+    SAGNN_CUDA(cudaMemsetAsync(nhot_row, 0, sizeof(int32_t) * R, st));
+  }
 
   SAGNN_CUDA(cudaMalloc(&p->tasks, sizeof(sagnn_task) * (p->n_tasks ? p->n_tasks : 1)));
   SAGNN_CUDA(cudaMalloc(&p->chunk_base, sizeof(int64_t) * (p->n_long + 1)));
   SAGNN_CUDA(cudaMalloc(&p->chunk_lr, sizeof(uint32_t) * (p->n_chunks ? p->n_chunks : 1)));
   SAGNN_CUDA(cudaMemcpyAsync(p->chunk_base + p->n_long, &p->n_chunks, sizeof(int64_t), cudaMemcpyHostToDevice, st));
   sched_task_kernel<<<blocks_for(p->n_tasks), 256, 0, st>>>(srow, p->deg, p->rowptr, nhot_row, task_off, chunk_off,
-                                                            long_off, p->enc, R, p->n_tasks, N, U, p->tasks, p->chunk_base,
+                                                            long_off, pkt ? p->idx : p->enc, R, p->n_tasks, N, U, p->tasks, p->chunk_base,
                                                             p->chunk_lr);
   SAGNN_CUDA(cudaGetLastError());
 
@@ -616,9 +675,46 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
       p->seg_host[t].task_begin = tb[t];
       p->seg_host[t].task_end = tb[t + 1];
     }
+    int64_t pk = 0;
+    for (int t = 0; t < S; ++t) {
+      p->seg_host[t].pkt_begin = pk;
+      pk += (tb[t + 1] - tb[t] + kPktTasks - 1) / kPktTasks;
+      p->seg_host[t].pkt_end = pk;
+    }
+    p->n_pkts = pk;
   }
   SAGNN_CUDA(cudaMalloc(&p->seg_dev, sizeof(sagnn_seg) * S));
   SAGNN_CUDA(cudaMemcpyAsync(p->seg_dev, p->seg_host.data(), sizeof(sagnn_seg) * S, cudaMemcpyHostToDevice, st));
+
+  if (pkt) {    // packed task stream: one scan over the tasks' code bytes places every packet
+    DevTmp<int64_t> cbytes, coff;
+    DevTmp<char> tmp; size_t tb = 0;
+    const int64_t nt = p->n_tasks;
+    SAGNN_CUDA(cbytes.alloc(nt + 1));
+    SAGNN_CUDA(coff.alloc(nt + 1));
+    pkt_size_kernel<<<blocks_for(nt + 1), 256, 0, st>>>(p->tasks, nt, p->w ? 2 : 1, cbytes);
+    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cbytes.p, coff.p, nt + 1, st));
+    SAGNN_CUDA(tmp.alloc(tb));
+    SAGNN_CUDA(cub::DeviceScan::ExclusiveSum((void*)tmp.p, tb, cbytes.p, coff.p, nt + 1, st));
+    int64_t code_bytes = 0;
+    SAGNN_CUDA(cudaMemcpyAsync(&code_bytes, coff.p + nt, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SAGNN_CUDA(cudaStreamSynchronize(st));
+    const int64_t total = (int64_t)16 * kPktTasks * p->n_pkts + code_bytes;
+    SAGNN_REQUIRE((total >> 4) < ((int64_t)1 << 32), SAGNN_INVALID_ARG, "finalize: packet stream of %lld bytes exceeds 2^36",
+                  (long long)total);
+    p->pkt_stream_bytes = (size_t)total;
+    SAGNN_CUDA(cudaMalloc(&p->pkt_stream, total ? total : 16));
+    SAGNN_CUDA(cudaMalloc(&p->pkt_dir, sizeof(uint32_t) * (p->n_pkts + 1)));
+    const uint32_t end16 = (uint32_t)(total >> 4);
+    SAGNN_CUDA(cudaMemcpyAsync(p->pkt_dir + p->n_pkts, &end16, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (nt)
+      pkt_fill_kernel<<<blocks_for(nt * 32), 256, 0, st>>>(p->tasks, nt, coff, p->seg_dev, S, p->idx, p->w,
+                                                           (unsigned char*)p->pkt_stream, p->pkt_dir);
+    SAGNN_CUDA(cudaGetLastError());
+    SAGNN_CUDA(cudaStreamSynchronize(st));
+    cudaFree(p->tasks);     // the stream carries the records from here on
+    p->tasks = nullptr;
+  }
 
   // persistent CTAs (one per SM) are dealt to segments in proportion to their cost.  Measured on
   // B200 (scripts/trace_cta.py): a cold (global) edge costs ~4 units, a hot (staged) edge ~0.9,

@@ -6,46 +6,40 @@
 // The backward is the same gather run on the same two CSRs with the sign-masked
 // upstream as the source -- no scatter, no float atomics, deterministic.
 //
-// Work decomposition: a "group" of LPR = d/4 lanes owns one task; each lane keeps a
-// float4 (128-bit loads) of the row.  A task is either a whole short row (deg <= 64)
-// or one <=64-edge chunk of a long row; chunk partial sums go through a workspace and
-// the group that finishes a row last (integer ticket) reduces them in fixed chunk
-// order, so results do not depend on scheduling.  Tasks are ordered longest-first and
-// dealt round-robin over a grid sized to the SM count x occupancy.
+// Work decomposition: ONE WARP OWNS ONE TASK (the 32 lanes span the latent dimension).  A task is
+// either a whole short row (deg <= 64) or one <=64-edge slice of a long row; slice sums go through
+// a workspace and the warp that finishes a group of 16 slices last (integer ticket) reduces them in
+// fixed slice order, so results do not depend on scheduling.  Two kernels share this contract:
+// spmm_pkt.cuh (v9, default: TMA-staged packed task stream, static packet interleave) and
+// spmm_rpw.cuh (v8, SAGNN_KERNEL=v8: cp.async rings + per-segment queues, kept for A/B runs).
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
 
-#ifndef SAGNN_THREADS
-#define SAGNN_THREADS 1024     // one persistent CTA per SM
-#endif
-#ifndef SAGNN_UNR
-#define SAGNN_UNR 4            // gather slots per pipeline block
-#endif
-#ifndef SAGNN_GRAB
-#define SAGNN_GRAB 2           // task rounds a warp takes per queue atomic
-#endif
-#ifndef SAGNN_HOT_BYTES
-#define SAGNN_HOT_BYTES kHotBytes      // shared memory given to staged hot rows
-#endif
-#ifndef SAGNN_D64_LPR8
-#define SAGNN_D64_LPR8 0
-#endif
-#ifndef SAGNN_HOP
-#define SAGNN_HOP 0            // 1: CTAs whose segment is drained help the other segments
-#endif
-
 namespace sagnn {
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_MSG = 2 };
-constexpr int kThreads = SAGNN_THREADS;
 
 constexpr int kMaxPeers = 16;
+constexpr int kMaxCtas = 160;     // persistent CTAs (one per SM) the by-value CTA table of the packet-stream kernel holds
+
+// what one persistent CTA of the packet-stream kernel works on, passed BY VALUE inside the kernel
+// parameters (constant bank): everything derived from it is provably warp-uniform, so the compiler
+// keeps segment bases, strides and stream positions in uniform registers
+struct PktCta {
+  uint32_t seg;        // segment (2*interval + side)
+  uint32_t q0;         // first packet of warp 0 inside the segment's packet list
+  uint32_t stride;     // packets between two consecutive packets of one warp (= 32 x CTAs of the segment)
+  uint32_t pkt_begin;  // the segment's slice of the packet directory
+  uint32_t n_pk;
+};
 
 struct SpmmParams {
-  const sagnn_task* tasks;
+  const uint32_t* pkt_dir;   // packet-stream kernel: packet offsets (16-byte units) ...
+  const uint4* pkt_stream;   // ... into the packed records + edge codes (+ weights)
+  const sagnn_task* tasks;   // v8 kernel: task records, edge codes, weights
   const int32_t* enc;
   const float* w;            // weights in enc order or NULL
   const int64_t* chunk_base;
@@ -53,6 +47,7 @@ struct SpmmParams {
   const int32_t* hot_ids;
   const sagnn_seg* seg;
   const sagnn_cta* cta;
+  const sagnn_cta* cta_host; // host copy of `cta` (launch code only)
   int hot_rows;              // hot slots per table used by the plan's edge codes
   int single_seg;            // >= 0: every CTA works on this segment (messagePropagate); -1: use cta[]
   int n_seg_total;           // 2T
@@ -92,6 +87,7 @@ struct SpmmParams {
   int peer_n, peer_rank, peer_blk_u, peer_blk_i;
   float* peer_u[kMaxPeers];  // receive buffers [peer_n, blk_u, T, d] of every rank (this rank's own included)
   float* peer_i[kMaxPeers];
+  PktCta ctad[kMaxCtas];     // packet-stream kernel: per-CTA work descriptor (filled per launch)
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -117,6 +113,12 @@ __device__ __forceinline__ float4 ld_strong(const float* p) {
 __device__ __forceinline__ unsigned ticket_release_add(unsigned* p) {
   unsigned old;
   asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
+  return old;
+}
+// same with acquire as well: the last arriver's later reads of the other slices' partials are ordered after it
+__device__ __forceinline__ unsigned ticket_acq_rel_add(unsigned* p) {
+  unsigned old;
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
   return old;
 }
 __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -185,559 +187,15 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-// One gather slot: hot edges come from the staged copy in shared memory, cold edges from global
-// memory through the read-only path; both loads target the same registers (no merge moves).
-__device__ __forceinline__ void gather_slot(float4& v, uint32_t hot_addr, const void* gaddr, int is_hot, int is_cold) {
-  asm volatile(
-      "{\n\t.reg .pred ph, pc;\n\t"
-      "setp.ne.s32 ph, %6, 0;\n\t"
-      "setp.ne.s32 pc, %7, 0;\n\t"
-      "@ph ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
-      "@pc ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5];\n\t}"
-      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-      : "r"(hot_addr), "l"(gaddr), "r"(is_hot), "r"(is_cold));
-}
-
-// same, deciding inside: slot U_ of the block is hot when U_ < nhb, cold when nhb <= U_ < nb
-template <int U_>
-__device__ __forceinline__ void gather_slot_u(float4& v, uint32_t hot_addr, const void* gaddr, int nhb, int nb) {
-  asm volatile(
-      "{\n\t.reg .pred ph, pc;\n\t"
-      "setp.gt.s32 ph, %6, %8;\n\t"
-      "setp.gt.s32 pc, %7, %8;\n\t"
-      "and.pred pc, pc, !ph;\n\t"
-      "@ph ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
-      "@pc ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5];\n\t}"
-      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-      : "r"(hot_addr), "l"(gaddr), "r"(nhb), "r"(nb), "n"(U_));
-}
-template <int UNR_, int U_ = 0>
-struct SlotDispatch {     // compile-time slot index for the in-asm compare
-  __device__ __forceinline__ static void run(int u, float4& v, uint32_t ha, const void* ga, int nhb, int nb) {
-    if (u == U_) gather_slot_u<U_>(v, ha, ga, nhb, nb);
-    else SlotDispatch<UNR_, U_ + 1>::run(u, v, ha, ga, nhb, nb);
-  }
-};
-template <int UNR_>
-struct SlotDispatch<UNR_, UNR_> {
-  __device__ __forceinline__ static void run(int, float4&, uint32_t, const void*, int, int) {}
-};
-
 // keep a CTA-lifetime value in a register: the compiler must not rematerialise it from the
 // kernel parameters inside the gather loop (it does, under the 64-register cap)
 template <typename T>
 __device__ __forceinline__ void pin64(T*& p) { asm volatile("" : "+l"(p)); }
 __device__ __forceinline__ void pin32(uint32_t& v) { asm volatile("" : "+r"(v)); }
 
-// ---- packed fp32x2 math (sm_100a FADD2 / FFMA2; same IEEE results as the scalar forms) ----
-struct f4p { float2 lo, hi; };
-__device__ __forceinline__ f4p f4p_zero() { return f4p{make_float2(0.f, 0.f), make_float2(0.f, 0.f)}; }
-__device__ __forceinline__ void acc_add(f4p& a, const float4& x) {
-  a.lo = __fadd2_rn(a.lo, make_float2(x.x, x.y));
-  a.hi = __fadd2_rn(a.hi, make_float2(x.z, x.w));
-}
-__device__ __forceinline__ float4 f4p_get(const f4p& a) { return make_float4(a.lo.x, a.lo.y, a.hi.x, a.hi.y); }
-
-// accumulate one gathered float4: plain, weighted, sign-masked (backward), or both
-template <bool WEIGHTED, bool MASKED>
-__device__ __forceinline__ void accumulate(f4p& a, const float4& x, float w, uint32_t bits, float leaky) {
-  if (!WEIGHTED && !MASKED) {
-    acc_add(a, x);
-  } else {
-    float s0 = WEIGHTED ? w : 1.f, s1 = s0, s2 = s0, s3 = s0;
-    if (MASKED) {   // source = sigma'(Z) (.) g : pass where the bit is set, else leaky
-      const float wl = s0 * leaky;
-      s0 = (bits & 1u) ? s0 : wl; s1 = (bits & 2u) ? s1 : wl;
-      s2 = (bits & 4u) ? s2 : wl; s3 = (bits & 8u) ? s3 : wl;
-    }
-    a.lo = __ffma2_rn(make_float2(x.x, x.y), make_float2(s0, s1), a.lo);
-    a.hi = __ffma2_rn(make_float2(x.z, x.w), make_float2(s2, s3), a.hi);
-  }
-}
-
-struct SegPtrs {               // segment-uniform table pointers, written once per segment to shared memory
-  const float* a;
-  const float* b;
-  float* o1;
-  float* o2;
-  uint8_t* mk;
-  uint32_t a_stride, b_stride, o2_stride, pad;   // bytes between consecutive rows of a / b / o2
-};
-
-// compile-time geometry shared by the kernel and its launcher
-template <int LPR, int V, int MODE, bool WEIGHTED>
-struct Geo {
-  static constexpr int D = LPR * V * 4;
-  static constexpr int MPR = D / 4;                           // mask bytes per row (4 sign bits per byte)
-  static constexpr int GPW = 32 / LPR;                        // lane groups per warp
-#ifdef SAGNN_UNR_V2
-  static constexpr int UNR = (V == 2) ? SAGNN_UNR_V2 : SAGNN_UNR;
-#else
-  static constexpr int UNR = (V == 2 && SAGNN_UNR > 1) ? SAGNN_UNR / 2 : SAGNN_UNR;
-#endif
-  static constexpr int KST = (SAGNN_HOT_BYTES / (4 * D)) < kHotRows ? (SAGNN_HOT_BYTES / (4 * D)) : kHotRows;
-  static constexpr size_t HOT = (size_t)KST * D * 4;
-  static constexpr size_t SMEM = HOT;
-};
-
-// One persistent CTA per SM, bound to one segment (interval, orientation).  It stages the
-// segment's hottest source rows in shared memory with TMA bulk copies, then drains the
-// segment's task queue (greedy, longest-first).  Each gather slot is one predicated pair of
-// loads into the same registers: from the staged copy when the edge is hot, from global
-// memory (read-only path, 128-bit) when it is cold.
-// The lane groups of a warp run in lock step (trip counts are warp maxima), so every
-// shuffle uses the full mask; tasks arrive sorted by degree, so the groups sharing a warp
-// have near-equal rows.
-template <int LPR, int V, int MODE, bool WEIGHTED>
-__global__ void __launch_bounds__(kThreads, 1)
-spmm_layer_kernel(const __grid_constant__ SpmmParams p) {
-  using G = Geo<LPR, V, MODE, WEIGHTED>;
-  constexpr int D = G::D, MPR = G::MPR, GPW = G::GPW, UNR = G::UNR, KST = G::KST;
-  constexpr int R = SAGNN_GRAB;
-  constexpr bool WARM = KST < kHotRows;               // this latdim may meet hot slots that do not fit
-  const bool warm = WARM && p.hot_rows > KST;         // ... and this plan has them: read those via their ids
-  constexpr bool BWD = MODE == MODE_BWD;
-  static_assert(LPR % UNR == 0, "unroll must divide the group width");
-  static_assert(SAGNN_GRAB >= 2, "the record pipeline looks two rounds ahead");
-  constexpr unsigned FULL = 0xffffffffu;
-
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* hot = reinterpret_cast<float*>(smem_raw);    // [KST][D]
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ SegPtrs sp;
-  __shared__ int skip_seg;
-  __shared__ int warm_ids[WARM ? kHotRows : 1];
-
-  const int lane = threadIdx.x & 31;
-
-  const int gl = lane % LPR;
-  const int gbase = lane - gl;                        // first lane of my group
-  const int grp = lane / LPR;
-  const float leaky = p.leaky;
-
-  const int n_hops = (SAGNN_HOP && p.single_seg < 0) ? p.n_seg_total : 1;
-  const int seg0 = p.single_seg >= 0 ? p.single_seg : p.cta[blockIdx.x].seg;
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
-  unsigned phase = 0;
-  if (p.trace && threadIdx.x == 0) {
-    p.trace[blockIdx.x * 4 + 0] = (unsigned long long)seg0;
-    p.trace[blockIdx.x * 4 + 1] = globaltimer_ns();
-  }
-
-  for (int hop = 0; hop < n_hops; ++hop) {
-    int seg = seg0 + hop;
-    if (seg >= p.n_seg_total) seg -= p.n_seg_total;
-    const sagnn_seg sg = p.seg[seg];
-    const unsigned n_seg_tasks = (unsigned)(sg.task_end - sg.task_begin);
-    unsigned* ctr = p.ctrs + seg;
-    if (hop > 0) {     // help another segment only if its queue still has work (CTA-uniform decision)
-      __syncthreads();
-      if (threadIdx.x == 0) skip_seg = (*(volatile unsigned*)ctr >= n_seg_tasks) ? 1 : 0;
-      __syncthreads();
-      if (skip_seg) continue;
-    }
-    const int k = seg >> 1;
-    const bool item_side = seg & 1;
-    const int r_own = item_side ? p.I : p.U, r_src = item_side ? p.U : p.I;
-    const float* src = (item_side ? p.src_u : p.src_i) + (int64_t)k * r_src * D;
-    const uint8_t* smask = BWD ? (item_side ? p.smask_u : p.smask_i) + (int64_t)k * r_src * MPR : nullptr;
-    const int32_t* enc = p.enc + sg.edge_base;
-    const float* wts = WEIGHTED ? p.w + sg.edge_base : nullptr;
-    const sagnn_task* tasks = p.tasks + sg.task_begin;
-
-    // ---- stage the hot rows of the source table (TMA bulk copies, one per row) -----------
-    {
-      __syncthreads();                                // everyone is done with the previous segment
-      const int32_t* ids = p.hot_ids + (int64_t)(seg ^ 1) * kHotRows;
-      const int n_stage = r_src < KST ? r_src : KST;
-      if (threadIdx.x == 0) {
-        const int64_t own0 = (int64_t)k * r_own;
-        const float* a = item_side ? p.a_i : p.a_u;
-        const float* b = item_side ? p.b_i : p.b_u;
-        float* o1 = item_side ? p.o1_i : p.o1_u;
-        float* o2 = item_side ? p.o2_i : p.o2_u;
-        uint8_t* mk = item_side ? p.mask_i : p.mask_u;
-        sp.a = a ? a + own0 * D : nullptr;
-        sp.b = b ? b + own0 * D : nullptr;
-        sp.o1 = o1 ? o1 + own0 * D : nullptr;
-        sp.o2 = o2 ? o2 + own0 * D : nullptr;
-        sp.mk = mk ? mk + own0 * MPR : nullptr;
-        mbar_expect_tx(&bar, (unsigned)(n_stage * D * 4));
-      }
-      __syncthreads();
-      for (int s = threadIdx.x; s < n_stage; s += kThreads)
-        tma_bulk_g2s(hot + (size_t)s * D, src + (int64_t)__ldg(ids + s) * D, D * 4, &bar);
-      if (WARM) {
-        if (warm) {
-          const int n_hot = r_src < p.hot_rows ? r_src : p.hot_rows;
-          for (int s = threadIdx.x; s < n_hot; s += kThreads) warm_ids[s] = __ldg(ids + s);
-        }
-      }
-      mbar_wait(&bar, phase);
-      phase ^= 1u;
-      if (BWD) {
-        // the backward gathers sigma'(Z) (.) g: mask the staged rows once instead of per edge
-        __syncthreads();
-        for (int s = threadIdx.x / LPR; s < n_stage; s += kThreads / LPR) {
-          const int id = __ldg(ids + s);
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            float4* q = reinterpret_cast<float4*>(hot + (size_t)s * D + (v * LPR + gl) * 4);
-            float4 x = *q;
-            const uint32_t b = __ldg(smask + (int64_t)id * MPR + v * LPR + gl);
-            x.x = (b & 1u) ? x.x : leaky * x.x;
-            x.y = (b & 2u) ? x.y : leaky * x.y;
-            x.z = (b & 4u) ? x.z : leaky * x.z;
-            x.w = (b & 8u) ? x.w : leaky * x.w;
-            *q = x;
-          }
-        }
-      }
-      __syncthreads();
-    }
-
-    if (p.trace && threadIdx.x == 0 && hop == 0) p.trace[blockIdx.x * 4 + 2] = globaltimer_ns();
-
-    // lane-specific bases of everything the gather loop touches, pinned in registers
-    const char* src_lane = reinterpret_cast<const char*>(src) + gl * 16;
-    uint32_t hot_lane = smem_u32(hot) + gl * 16;
-    pin64(src_lane);
-    pin32(hot_lane);
-    pin64(enc);
-    pin64(tasks);
-
-    // ---- task queue -----------------------------------------------------------------------
-    // The list is ordered longest-first, so greedy grabbing (R rounds of GPW tasks per atomic)
-    // balances the warps; the atomic for the next grab is always in flight.
-    auto issue = [&]() -> unsigned { return lane == 0 ? atomicAdd(ctr, (unsigned)(R * GPW)) : 0u; };
-    auto ld_task = [&](unsigned t) -> sagnn_task {
-      sagnn_task q;
-      if (t < n_seg_tasks) {
-        const int4 r0 = __ldg(reinterpret_cast<const int4*>(tasks + t));
-        const int4 r1 = __ldg(reinterpret_cast<const int4*>(tasks + t) + 1);
-        q.row = (uint32_t)r0.x; q.meta = (uint32_t)r0.y; q.e_off = (uint32_t)r0.z; q.aux = (uint32_t)r0.w;
-        q.c[0] = r1.x; q.c[1] = r1.y; q.c[2] = r1.z; q.c[3] = r1.w;
-      } else {
-        q.row = 0; q.meta = 0x40000000u; q.e_off = 0; q.aux = 0;   // bit 30: no work
-        q.c[0] = q.c[1] = q.c[2] = q.c[3] = 0;
-      }
-      return q;
-    };
-    unsigned b0 = __shfl_sync(FULL, issue(), 0);      // grab being processed
-    unsigned pend = issue();                          // next grab, still in flight
-    unsigned b1 = 0xffffffffu;                        // resolved lazily
-    int r = 0;
-
-    // software pipeline: the next task record (which carries its first four edge codes) is
-    // always in flight, so a short row's gathers depend on nothing but that record
-    sagnn_task nxt = ld_task(b0 + grp);
-    b1 = __shfl_sync(FULL, pend, 0);
-    pend = issue();
-    int nxt_c = 0;                                      // first code batch of `nxt` (rows with > 4 edges)
-    float nxt_w = 0.f;
-    auto request_codes = [&]() {                        // needs nxt's record: called late in the iteration
-      const int nn = (int)(nxt.meta & 0x7fu);
-      nxt_c = 0;
-      if (gl < nn && (WEIGHTED || nn > 4)) {
-        nxt_c = __ldg(enc + nxt.e_off + gl);
-        if (WEIGHTED) nxt_w = __ldg(wts + nxt.e_off + gl);
-      }
-    };
-    request_codes();
-
-#if defined(SAGNN_PHASES)
-    long long ph[4] = {0, 0, 0, 0}, pt = clock64();
-#define PHASE(i) do { long long _t = clock64(); ph[i] += _t - pt; pt = _t; } while (0)
-#else
-#define PHASE(i) do {} while (0)
-#endif
-    while (b0 < n_seg_tasks) {                          // warp-uniform
-      const sagnn_task cur = nxt;
-      nxt = ld_task((r + 1 < R ? b0 + (r + 1) * GPW : b1) + grp);   // r = position of cur in grab b0
-      if (++r == R) {                                   // rotate the grabs
-        r = 0;
-        b0 = b1;
-        b1 = __shfl_sync(FULL, pend, 0);
-        pend = issue();
-      }
-      // codes of the first batch beyond the four carried by the record: requested one task ahead
-      int myc = nxt_c;
-      float myw = nxt_w;
-
-      const bool valid = !(cur.meta & 0x40000000u);
-      const bool multi = (cur.meta >> 31) != 0;          // slice of a long row
-#if defined(SAGNN_X3)
-      const int n = 0;                                    // experiment: no gathers at all
-#else
-      const int n = (int)(cur.meta & 0x7fu);
-#endif
-      const uint32_t own_off = cur.row * (uint32_t)(D * 4) + gl * 16;   // byte offset inside my table (< 4 GB)
-
-      // the row's own dense operand is independent of the gather: issue it first
-      float4 own_a[V];
-      if (MODE != MODE_MSG) {
-        const char* a = reinterpret_cast<const char*>(sp.a);
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-          own_a[v] = valid ? ld_nc(reinterpret_cast<const float*>(a + own_off + v * LPR * 16)) : f4_zero();
-      }
-
-      f4p acc[V];
-#pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] = f4p_zero();
-      PHASE(0);
-
-      // ---- gather-reduce over this task's edges (lock step over the warp) -------------------
-#if defined(SAGNN_NOHOT)
-      const int nh = 0;                                   // experiment: every edge is gathered from global memory
-#else
-      const int nh = (int)((cur.meta >> 8) & 0x7fu);
-#endif
-      int nmax = n;
-#pragma unroll
-      for (int o = LPR; o < 32; o <<= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
-      for (int eb = 0; eb < nmax; eb += LPR) {
-        // prefetch the next batch of codes while this one is gathered
-        int c_next = 0;
-        float w_next = 0.f;
-        if (eb + LPR + gl < n) {
-          c_next = __ldg(enc + cur.e_off + eb + LPR + gl);
-          if (WEIGHTED) w_next = __ldg(wts + cur.e_off + eb + LPR + gl);
-        }
-        const int nbmax = min(LPR, nmax - eb);
-        for (int j = 0; j < nbmax; j += UNR) {
-          const int nb = n - eb - j;             // my group's edges left from slot j on (may be <= 0)
-          const int nhb = nh - eb - j;           // ... of which hot (staged in shared memory)
-          int cs[UNR];
-          float wv[UNR];
-#pragma unroll
-          for (int u = 0; u < UNR; ++u) {
-            int c;
-            if (UNR == 4) {
-              if (eb == 0 && j == 0) c = cur.c[u & 3];                     // carried by the task record
-              else c = __shfl_sync(FULL, myc, gbase + j + u);
-            } else {
-              const int e = j + u;                                         // first-batch edge index
-              const int rc = e == 0 ? cur.c[0] : e == 1 ? cur.c[1] : e == 2 ? cur.c[2] : cur.c[3];
-              const int sc = __shfl_sync(FULL, myc, gbase + j + u);
-              c = (eb == 0 && e < 4) ? rc : sc;
-            }
-#if defined(SAGNN_X1)
-            if (!(u < nhb)) c &= 1023;          // experiment: cold gathers confined to 1024 rows
-#elif defined(SAGNN_X2)
-            if (!(u < nhb)) c &= 511;           // experiment: every edge reads the staged copy
-#endif
-            cs[u] = c;
-            wv[u] = WEIGHTED ? __shfl_sync(FULL, myw, gbase + j + u) : 1.f;
-          }
-          if (!warm && __all_sync(FULL, nhb >= UNR)) {
-            // fast path: every group has a full block of staged rows (sign-masked already in bwd)
-            float4 val[UNR][V];
-#pragma unroll
-            for (int u = 0; u < UNR; ++u)
-#pragma unroll
-              for (int v = 0; v < V; ++v) val[u][v] = lds_f4(hot_lane + (uint32_t)cs[u] * (D * 4) + v * LPR * 16);
-#pragma unroll
-            for (int u = 0; u < UNR; ++u)
-#pragma unroll
-              for (int v = 0; v < V; ++v) accumulate<WEIGHTED, false>(acc[v], val[u][v], wv[u], 0u, leaky);
-          } else if (__all_sync(FULL, nhb <= 0 && nb >= UNR)) {
-            // fast path: every group has a full block of rows in global memory
-            float4 val[UNR][V];
-            uint32_t mb[UNR][V];
-#pragma unroll
-            for (int u = 0; u < UNR; ++u)
-#pragma unroll
-              for (int v = 0; v < V; ++v) {
-                val[u][v] = ld_nc(reinterpret_cast<const float*>(src_lane + (int64_t)cs[u] * (D * 4) + v * LPR * 16));
-                mb[u][v] = BWD ? __ldg(smask + (int64_t)cs[u] * MPR + v * LPR + gl) : 0u;
-              }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u)
-#pragma unroll
-              for (int v = 0; v < V; ++v) accumulate<WEIGHTED, BWD>(acc[v], val[u][v], wv[u], mb[u][v], leaky);
-          } else {
-            // general path: per-slot hot / cold / idle predicates
-            float4 val[UNR][V];
-            uint32_t mb[UNR][V];
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-              int c = cs[u];
-              if (WARM) {
-                int hotf = u < nhb, coldf = (u < nb) && !hotf;
-                // hot slot that is not staged at this latdim: fetch it like a cold row
-                if (warm && hotf && c >= KST) { c = warm_ids[c]; hotf = 0; coldf = 1; }
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                  val[u][v] = f4_zero();
-                  mb[u][v] = 0xfu;
-                  gather_slot(val[u][v], hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16,
-                              src_lane + (int64_t)c * (D * 4) + v * LPR * 16, hotf, coldf);
-                  if (BWD) {
-                    if (coldf) mb[u][v] = __ldg(smask + (int64_t)c * MPR + v * LPR + gl);
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                  val[u][v] = f4_zero();
-                  mb[u][v] = 0xfu;
-#if defined(SAGNN_X2)
-                  SlotDispatch<UNR>::run(u, val[u][v], hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16,
-                                         src_lane + (int64_t)c * (D * 4) + v * LPR * 16, nb, nb);
-#else
-                  SlotDispatch<UNR>::run(u, val[u][v], hot_lane + (uint32_t)c * (D * 4) + v * LPR * 16,
-                                         src_lane + (int64_t)c * (D * 4) + v * LPR * 16, nhb, nb);
-#endif
-                  if (BWD) {
-                    if (u >= nhb && u < nb) mb[u][v] = __ldg(smask + (int64_t)c * MPR + v * LPR + gl);
-                  }
-                }
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u)
-#pragma unroll
-              for (int v = 0; v < V; ++v) accumulate<WEIGHTED, BWD>(acc[v], val[u][v], wv[u], mb[u][v], leaky);
-          }
-        }
-        myc = c_next;
-        myw = w_next;
-      }
-
-#if defined(SAGNN_PHASES)
-      { volatile float sink = acc[0].lo.x; (void)sink; }   // force the gathers to complete here
-#endif
-      PHASE(1);
-      request_codes();                                    // the next task's record has arrived by now
-      // ---- long rows: publish the partial sum; reduce through a fan-in-16 tree ----------------
-      // The last arriver of every group of 16 slices (then of 16 groups, ...) sums them in
-      // slice order, so the result does not depend on scheduling and no reduction chain is
-      // longer than 16 loads per level.  Release-only tickets; the reducer reads with strong
-      // loads that bypass L1, so no acquire fence / L1 invalidate is needed.
-      bool finish = valid;
-      if (__any_sync(FULL, multi)) {
-        int64_t cb = 0;
-        int nch = 1;
-        if (multi) {
-          const uint32_t lr = __ldg(p.chunk_lr + cur.aux);
-          cb = __ldg(p.chunk_base + lr);
-          nch = (int)(__ldg(p.chunk_base + lr + 1) - cb);
-        }
-        int pos = multi ? (int)((int64_t)cur.aux - cb) : 0;   // my slice inside the row
-        bool active = multi;                                   // still climbing the tree
-        finish = valid && !multi;
-        unsigned* tk = p.tickets;                              // ticket region of the current level
-        for (int stride = 1; __any_sync(FULL, active); stride *= 16) {
-          // members of my group at this level: slots gs + j*stride, j < 16, below nch
-          const int gs = pos - pos % (16 * stride);
-          int members = (nch - gs + stride - 1) / stride;
-          members = members > 16 ? 16 : members;
-          if (active) {
-            float* mine = p.partials + (cb + pos) * D;
-#pragma unroll
-            for (int v = 0; v < V; ++v) st_f4(mine + (v * LPR + gl) * 4, f4p_get(acc[v]));
-          }
-          __syncwarp();
-          unsigned old = 0;
-          unsigned* my_tk = tk + (cb + gs);                    // one ticket per group, named by its first slot
-          if (active && gl == 0) old = ticket_release_add(my_tk);
-          old = __shfl_sync(FULL, old, gbase);
-          if (active) {
-            if (old != (unsigned)(members - 1)) {
-              active = false;                                  // someone else finishes this group
-            } else {
-              if (gl == 0) *my_tk = 0u;                        // ready for the next launch
-#pragma unroll
-              for (int v = 0; v < V; ++v) acc[v] = f4p_zero();
-              const float* part = p.partials + (cb + gs) * D;
-              for (int c0 = 0; c0 < members; c0 += 4) {
-                float4 val[4][V];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                  for (int v = 0; v < V; ++v)
-                    val[u][v] = (c0 + u < members)
-                                    ? ld_strong(part + (int64_t)(c0 + u) * stride * D + (v * LPR + gl) * 4)
-                                    : f4_zero();
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                  for (int v = 0; v < V; ++v) acc_add(acc[v], val[u][v]);
-              }
-              if (gs == 0 && 16 * stride >= nch) {             // that was the whole row
-                finish = true;
-                active = false;
-              } else {
-                pos = gs;                                      // my sum becomes slot gs of the next level
-              }
-            }
-          }
-          tk += p.n_chunks;
-        }
-        __syncwarp();
-      }
-
-      PHASE(2);
-      // ---- fused epilogue ------------------------------------------------------------------
-      if (finish) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const uint32_t off = own_off + v * LPR * 16;     // bytes
-          const float4 z = f4p_get(acc[v]);
-          if (BWD) {
-            // n = G + g + A (sigma' . g_other)      
-            const char* g = reinterpret_cast<const char*>(sp.b);
-            char* dst = reinterpret_cast<char*>(sp.o1);
-            const float4 gv = g ? ld_stream(reinterpret_cast<const float*>(g + off)) : own_a[v];
-            st_f4(reinterpret_cast<float*>(dst + off), f4_add(f4_add(own_a[v], gv), z));
-          } else {
-            const float lzx = leaky * z.x, lzy = leaky * z.y, lzz = leaky * z.z, lzw = leaky * z.w;
-            // LeakyReLU = max(leaky*z, z)  (Utils/NNLayers.py:135-136)
-            const float4 act = make_float4(fmaxf(lzx, z.x), fmaxf(lzy, z.y), fmaxf(lzz, z.z), fmaxf(lzw, z.w));
-            if (MODE == MODE_MSG) {
-              st_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(sp.o1) + off), act);
-            } else {
-              const char* b = reinterpret_cast<const char*>(sp.b);
-              char* o1 = reinterpret_cast<char*>(sp.o1);
-              char* o2 = reinterpret_cast<char*>(sp.o2);
-              uint8_t* mk = sp.mk;
-              const float4 nxt_e = f4_add(own_a[v], act);          // E^{l+1} = E^l + lrelu(Z^l)
-              if (o1) st_f4(reinterpret_cast<float*>(o1 + off), nxt_e);
-              if (o2) {
-                float4 o = own_a[v];
-                if (b) o = f4_add(ld_stream(reinterpret_cast<const float*>(b + off)), own_a[v]);
-                if (p.out_add_next) o = f4_add(o, nxt_e);
-                st_stream(reinterpret_cast<float*>(o2 + off), o);
-              }
-              if (mk) {
-                // TF MaximumGrad sends the gradient to leaky*z where leaky*z >= z: bit = pass-through.
-                // One byte (4 sign bits) per lane: no cross-lane packing needed.
-                const uint32_t bits = (!(lzx >= z.x) ? 1u : 0u) | (!(lzy >= z.y) ? 2u : 0u) |
-                                      (!(lzz >= z.z) ? 4u : 0u) | (!(lzw >= z.w) ? 8u : 0u);
-                mk[(size_t)cur.row * MPR + v * LPR + gl] = (uint8_t)bits;
-              }
-            }
-          }
-        }
-      }
-      PHASE(3);
-    }
-#if defined(SAGNN_PHASES)
-    if (p.trace && lane == 0) {
-      unsigned long long* o = p.trace + (size_t)gridDim.x * 4 + ((size_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32) * 4;
-      for (int i = 0; i < 4; ++i) o[i] = (unsigned long long)ph[i];
-    }
-#endif
-  }
-  if (p.trace) {
-    __syncthreads();
-    if (threadIdx.x == 0) p.trace[blockIdx.x * 4 + 3] = globaltimer_ns();
-  }
-}
-
 }  // namespace sagnn
 #include "spmm_rpw.cuh"
+#include "spmm_pkt.cuh"
 namespace sagnn {
 
 // Backward, top level: the gather source is sigma'(Z^{L-1}) (.) G.  One streaming pass writes it
@@ -772,19 +230,75 @@ premask_kernel(const float4* __restrict__ in_u, const float4* __restrict__ in_i,
 // SAGNN_BWD_PREMASK=0 keeps the per-edge masks of the top backward level (A/B runs)
 static bool use_premask() {
   static const bool v = [] { const char* e = getenv("SAGNN_BWD_PREMASK"); return !(e && e[0] == '0'); }();
-  return v;
+  return v || use_pkt();   // the packet-stream kernel has no per-edge mask path
 }
 
 // ---------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------
-// SAGNN_KERNEL=v7 selects the half-warp lock-step kernel (kept for A/B runs); default: row per warp
-bool use_rpw() {
+bool use_rpw() { return true; }
+// SAGNN_KERNEL=v8 selects the cp.async-ring kernel (A/B runs); default: packet-stream kernel.
+// Read once: the plan's schedule (task records + codes vs packed stream) is built for one of them.
+bool use_pkt() {
   static const bool v = [] {
     const char* e = getenv("SAGNN_KERNEL");
-    return !(e && (e[0] == 'v' || e[0] == 'V') && e[1] == '7');
+    return !(e && (e[0] == 'v' || e[0] == 'V') && e[1] == '8');
   }();
   return v;
+}
+
+template <int VPL, int MODE, bool WEIGHTED, bool RTD>
+static int launch_pkt_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaStream_t st) {
+  SpmmParams prm = prm_in;
+  if (plan->trace_dev && plan->trace_launch < plan->trace_capacity)   // diagnostics only
+    prm.trace = plan->trace_dev + (size_t)(plan->trace_launch++) * plan->num_sms * 4;
+  using G = PktGeo<VPL, WEIGHTED>;
+  static_assert(G::SMEM <= 225 * 1024, "shared-memory budget exceeded");
+  static std::atomic<uint64_t> configured{0};   // bit per device: the attribute is per device
+  auto kern = spmm_pkt_kernel<VPL, MODE, WEIGHTED, RTD>;
+  const uint64_t bit = 1ull << (plan->device & 63);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {
+    SAGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+    configured.fetch_or(bit, std::memory_order_release);
+  }
+  if (plan->n_tasks == 0) return SAGNN_OK;
+  SAGNN_REQUIRE(plan->num_sms <= kMaxCtas, SAGNN_INVALID_ARG, "device has %d SMs, the CTA table holds %d", plan->num_sms, kMaxCtas);
+  for (int c = 0; c < plan->num_sms; ++c) {
+    const int sgi = prm.single_seg >= 0 ? prm.single_seg : prm.cta_host[c].seg;
+    const int rank = prm.single_seg >= 0 ? c : prm.cta_host[c].rank;
+    const int count = prm.single_seg >= 0 ? plan->num_sms : prm.cta_host[c].count;
+    const sagnn_seg& sh = plan->seg_host[sgi];
+    prm.ctad[c] = PktCta{(uint32_t)sgi, (uint32_t)rank * kPktWarps, (uint32_t)count * kPktWarps,
+                         (uint32_t)sh.pkt_begin, (uint32_t)(sh.pkt_end - sh.pkt_begin)};
+  }
+  kern<<<plan->num_sms, kPktThreads, G::SMEM, st>>>(prm);
+  SAGNN_CUDA(cudaGetLastError());
+  return SAGNN_OK;
+}
+
+template <int VPL, int MODE>
+static int launch_pkt_v(const sagnn_plan* plan, const SpmmParams& prm, cudaStream_t st) {
+  const bool wt = prm.w != nullptr;
+  if (MODE != MODE_MSG && (prm.a_rtd | prm.b_rtd | prm.o2_rtd | prm.src_rtd))
+    return wt ? launch_pkt_t<VPL, MODE, true, MODE != MODE_MSG>(plan, prm, st)
+              : launch_pkt_t<VPL, MODE, false, MODE != MODE_MSG>(plan, prm, st);
+  return wt ? launch_pkt_t<VPL, MODE, true, false>(plan, prm, st) : launch_pkt_t<VPL, MODE, false, false>(plan, prm, st);
+}
+
+template <int MODE>
+static int launch_pkt_mode(const sagnn_plan* plan, const SpmmParams& prm, int d, cudaStream_t st) {
+  SAGNN_REQUIRE(plan->pkt_stream && !prm.smask_u, SAGNN_INVALID_ARG,
+                "the packet-stream kernel needs a packed plan and pre-masked backward sources");
+  switch (d) {
+#ifndef SAGNN_ONLY_D64   // development builds: -DSAGNN_ONLY_D64 instantiates d = 64 only (compile time)
+    case 32:  return launch_pkt_v<1, MODE>(plan, prm, st);
+    case 128: return launch_pkt_v<4, MODE>(plan, prm, st);
+    case 256: return launch_pkt_v<8, MODE>(plan, prm, st);
+#endif
+    case 64:  return launch_pkt_v<2, MODE>(plan, prm, st);
+  }
+  set_error("latdim d=%d unsupported (need 32, 64, 128 or 256)", d);
+  return SAGNN_INVALID_ARG;
 }
 
 template <int VPL, int MODE, bool WEIGHTED, bool MASKED, bool RTD>
@@ -828,66 +342,29 @@ template <int MODE>
 static int launch_rpw_mode(const sagnn_plan* plan, const SpmmParams& prm, int d, cudaStream_t st) {
   SAGNN_REQUIRE(plan->hot_rows == 0, SAGNN_INVALID_ARG, "the row-per-warp kernel needs a plan without hot slots");
   switch (d) {
+#ifndef SAGNN_ONLY_D64
     case 32:  return launch_rpw_v<1, MODE>(plan, prm, st);
-    case 64:  return launch_rpw_v<2, MODE>(plan, prm, st);
     case 128: return launch_rpw_v<4, MODE>(plan, prm, st);
     case 256: return launch_rpw_v<8, MODE>(plan, prm, st);
-  }
-  set_error("latdim d=%d unsupported (need 32, 64, 128 or 256)", d);
-  return SAGNN_INVALID_ARG;
-}
-
-template <int LPR, int V, int MODE, bool WEIGHTED>
-static int launch_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaStream_t st) {
-  SpmmParams prm = prm_in;
-  if (plan->trace_dev && plan->trace_launch < plan->trace_capacity)   // diagnostics only
-    prm.trace = plan->trace_dev + (size_t)(plan->trace_launch++) * plan->num_sms * 4;
-  using G = Geo<LPR, V, MODE, WEIGHTED>;
-  static_assert(G::SMEM <= 227 * 1024 - 4096, "shared-memory budget exceeded");
-  static std::atomic<uint64_t> configured{0};   // bit per device: the attribute is per device
-  auto kern = spmm_layer_kernel<LPR, V, MODE, WEIGHTED>;
-  const uint64_t bit = 1ull << (plan->device & 63);
-  if (!(configured.load(std::memory_order_acquire) & bit)) {
-    SAGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
-    configured.fetch_or(bit, std::memory_order_release);
-  }
-  if (plan->n_tasks == 0) return SAGNN_OK;
-  kern<<<plan->num_sms, kThreads, G::SMEM, st>>>(prm);
-  SAGNN_CUDA(cudaGetLastError());
-  return SAGNN_OK;
-}
-
-template <int MODE>
-static int launch_mode(const sagnn_plan* plan, const SpmmParams& prm, int d, cudaStream_t st) {
-  const bool wt = prm.w != nullptr;
-  switch (d) {
-    case 32:  return wt ? launch_t<8, 1, MODE, true>(plan, prm, st)  : launch_t<8, 1, MODE, false>(plan, prm, st);
-#if SAGNN_D64_LPR8   // 8 lanes x 2 float4 per row: four rows per warp
-    case 64:  return wt ? launch_t<8, 2, MODE, true>(plan, prm, st) : launch_t<8, 2, MODE, false>(plan, prm, st);
-#else
-    case 64:  return wt ? launch_t<16, 1, MODE, true>(plan, prm, st) : launch_t<16, 1, MODE, false>(plan, prm, st);
 #endif
-    case 128: return wt ? launch_t<32, 1, MODE, true>(plan, prm, st) : launch_t<32, 1, MODE, false>(plan, prm, st);
-    case 256: return wt ? launch_t<32, 2, MODE, true>(plan, prm, st) : launch_t<32, 2, MODE, false>(plan, prm, st);
+    case 64:  return launch_rpw_v<2, MODE>(plan, prm, st);
   }
   set_error("latdim d=%d unsupported (need 32, 64, 128 or 256)", d);
   return SAGNN_INVALID_ARG;
 }
 
 static int launch(const sagnn_plan* plan, const SpmmParams& prm, int d, int mode, cudaStream_t st) {
-  if (use_rpw()) {
+  if (use_pkt()) {
     switch (mode) {
-      case MODE_FWD: return launch_rpw_mode<MODE_FWD>(plan, prm, d, st);
-      case MODE_BWD: return launch_rpw_mode<MODE_BWD>(plan, prm, d, st);
-      default:       return launch_rpw_mode<MODE_MSG>(plan, prm, d, st);
+      case MODE_FWD: return launch_pkt_mode<MODE_FWD>(plan, prm, d, st);
+      case MODE_BWD: return launch_pkt_mode<MODE_BWD>(plan, prm, d, st);
+      default:       return launch_pkt_mode<MODE_MSG>(plan, prm, d, st);
     }
   }
-  SAGNN_REQUIRE(!(prm.a_rtd | prm.b_rtd | prm.o2_rtd | prm.src_rtd), SAGNN_INVALID_ARG,
-                "the v7 kernel has no [R,T,d] layouts");
   switch (mode) {
-    case MODE_FWD: return launch_mode<MODE_FWD>(plan, prm, d, st);
-    case MODE_BWD: return launch_mode<MODE_BWD>(plan, prm, d, st);
-    default:       return launch_mode<MODE_MSG>(plan, prm, d, st);
+    case MODE_FWD: return launch_rpw_mode<MODE_FWD>(plan, prm, d, st);
+    case MODE_BWD: return launch_rpw_mode<MODE_BWD>(plan, prm, d, st);
+    default:       return launch_rpw_mode<MODE_MSG>(plan, prm, d, st);
   }
 }
 
@@ -933,9 +410,11 @@ static size_t mask_layer_bytes(const sagnn_plan* p, int d) { return (size_t)p->n
 
 static void base_params(const sagnn_plan* p, SpmmParams& s) {
   s = SpmmParams{};
-  s.tasks = p->tasks; s.enc = p->enc; s.w = p->w_enc;
+  s.pkt_dir = p->pkt_dir; s.pkt_stream = p->pkt_stream;
+  s.tasks = p->tasks; s.enc = p->enc;
+  s.w = use_pkt() ? p->w : p->w_enc;   // packet stream: weights travel inside the packets, this is only the flag
   s.chunk_base = p->chunk_base; s.chunk_lr = p->chunk_lr;
-  s.hot_ids = p->hot_ids; s.seg = p->seg_dev; s.cta = p->cta_dev; s.single_seg = -1;
+  s.hot_ids = p->hot_ids; s.seg = p->seg_dev; s.cta = p->cta_dev; s.cta_host = p->cta_host.data(); s.single_seg = -1;
   s.hot_rows = p->hot_rows;
   s.T = p->T;
   s.n_chunks = p->n_chunks;
@@ -1011,7 +490,7 @@ static int fwd_impl(const sagnn_plan* p, int interval, const float* uE, const fl
   s.tickets = (uint32_t*)(base + w.tickets_off);
   s.partials = (float*)(base + w.partials_off);
   s.leaky = leaky;
-  if (interval >= 0) s.cta = p->cta_int_dev + (size_t)interval * p->num_sms;
+  if (interval >= 0) { s.cta = p->cta_int_dev + (size_t)interval * p->num_sms; s.cta_host = p->cta_int_host.data() + (size_t)interval * p->num_sms; }
   SAGNN_CUDA(cudaMemsetAsync(s.tickets, 0, w.zero_bytes, st));
   s.ctrs = s.tickets + w.ticket_words;
   float* buf[2] = {(float*)(base + w.buf_off[0]), (float*)(base + w.buf_off[1])};
@@ -1046,7 +525,7 @@ static int fwd_impl(const sagnn_plan* p, int interval, const float* uE, const fl
     s.mask_u = masks ? (uint8_t*)masks + (size_t)l * mlw : nullptr;
     s.mask_i = masks ? (uint8_t*)masks + (size_t)l * mlw + mu : nullptr;
     for (int wv = 0; wv < (interval >= 0 ? 1 : p->n_waves); ++wv) {   // one launch unless 2T exceeds the SM count
-      if (interval < 0) s.cta = p->cta_dev + (size_t)wv * p->num_sms;
+      if (interval < 0) { s.cta = p->cta_dev + (size_t)wv * p->num_sms; s.cta_host = p->cta_host.data() + (size_t)wv * p->num_sms; }
       if (int rc = launch(p, s, d, MODE_FWD, st)) return rc;
     }
   }
@@ -1117,7 +596,7 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
   const size_t mlw = mask_layer_bytes(p, d);
   const size_t mu = (size_t)p->T * p->U * (d / 4);
   const bool rpw = use_rpw();
-  if (interval >= 0) s.cta = p->cta_int_dev + (size_t)interval * p->num_sms;
+  if (interval >= 0) { s.cta = p->cta_int_dev + (size_t)interval * p->num_sms; s.cta_host = p->cta_int_host.data() + (size_t)interval * p->num_sms; }
   for (int l = L - 1 - s_begin, step = s_begin; step < s_end || (step == 0 && ph_begin == 0); --l, ++step) {
     s.ctrs = s.tickets + w.ticket_words + (size_t)step * 2 * p->T;
     // g = total gradient w.r.t. E^{l+1}; at the top level it is the upstream itself
@@ -1166,7 +645,7 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
     s.o1_i = l == 0 ? dI : buf[step & 1] + w.user_floats;
     if (step >= s_end) break;                                  // phase 0 only: just the pre-mask pass
     for (int wv = 0; wv < (interval >= 0 ? 1 : p->n_waves); ++wv) {
-      if (interval < 0) s.cta = p->cta_dev + (size_t)wv * p->num_sms;
+      if (interval < 0) { s.cta = p->cta_dev + (size_t)wv * p->num_sms; s.cta_host = p->cta_host.data() + (size_t)wv * p->num_sms; }
       if (int rc = launch(p, s, d, MODE_BWD, st)) return rc;
     }
   }

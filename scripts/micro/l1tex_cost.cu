@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
+#include <cmath>
 #include <type_traits>
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -178,6 +179,43 @@ __global__ void __launch_bounds__(1024, 1) k_lsu(const float* __restrict__ tab, 
   if (acc.x + acc4.x == 123.456f) out[0] = acc.y + acc4.y + acc4.z + acc4.w;
 }
 
+
+// "task mix": what one task of the layer kernel moves, with no bookkeeping at all -- 12 gathered rows
+// (Zipf ids), NLD own rows loaded and NST rows stored at unique, streaming addresses (row = task id).
+template <int NLD, int NST>
+__global__ void __launch_bounds__(1024, 1) k_task(const float* __restrict__ tab, const int* __restrict__ ids, int iters,
+                                                  const float* __restrict__ own, float* __restrict__ dst, float* out) {
+  __shared__ __align__(16) int codes[32][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int* my = ids + ((size_t)blockIdx.x * 32 + warp) * iters * 16;
+  for (int i = lane; i < 256; i += 32) codes[warp][i] = my[i];
+  __syncthreads();
+  const char* tl = reinterpret_cast<const char*>(tab) + lane * 8;
+  float2 acc = make_float2(0, 0);
+  const size_t nwarps = (size_t)gridDim.x * 32;
+  for (int it = 0; it < iters; ++it) {
+    const size_t task = (size_t)it * nwarps + (size_t)blockIdx.x * 32 + warp;     // unique row per task
+    const int4* cp = reinterpret_cast<const int4*>(&codes[warp][(it & 15) * 16]);
+    int c[12];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) { const int4 t = cp[g]; c[4 * g] = t.x; c[4 * g + 1] = t.y; c[4 * g + 2] = t.z; c[4 * g + 3] = t.w; }
+    float2 v[12], o[NLD > 0 ? NLD : 1];
+#pragma unroll
+    for (int u = 0; u < 12; ++u) v[u] = __ldg(reinterpret_cast<const float2*>(tl + (size_t)(uint32_t)c[u] * 256));
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) o[q] = __ldg(reinterpret_cast<const float2*>(own + ((size_t)q * iters * nwarps + task) * 64) + lane);
+    float2 a = make_float2(0, 0);
+#pragma unroll
+    for (int u = 0; u < 12; ++u) { a.x += v[u].x; a.y += v[u].y; }
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) { a.x += o[q].x; a.y += o[q].y; }
+#pragma unroll
+    for (int q = 0; q < NST; ++q) *(reinterpret_cast<float2*>(dst + ((size_t)q * iters * nwarps + task) * 64) + lane) = a;
+    acc.x += a.x; acc.y += a.y;
+  }
+  if (acc.x == 123.456f) out[0] = acc.y;
+}
+
 // TMA variants: per-warp ring of S stages x B rows.  MODE 0: per-row bulk copies issued by lanes 0..B-1;
 // MODE 1: gather4 issued by lanes 0..B/4-1; MODE 2: bulk for the first B/2 rows, LDG.64 for the rest.
 template <int MODE, int W, int S, int B>
@@ -280,6 +318,29 @@ int main() {
   int* h = new int[n]; int* h_small = new int[n];
   uint64_t s = 88172645463325252ull;
   for (size_t i = 0; i < n; ++i) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; h[i] = (int)(s % rows); h_small[i] = h[i] % 384; }
+  // Zipf-distributed ids over the table (popularity rank scattered by a fixed permutation), like the item / user
+  // popularity of the synthetic interval graphs (alpha 1.0 / 0.8): do popular rows serialise at their L2 slice?
+  auto zipf_ids = [&](double alpha, int nrows) {
+    double* cdf = new double[nrows]; double acc = 0;
+    for (int r = 0; r < nrows; ++r) { acc += pow(r + 1.0, -alpha); cdf[r] = acc; }
+    int* perm = new int[nrows];
+    for (int r = 0; r < nrows; ++r) perm[r] = r;
+    uint64_t t = 0x9E3779B97F4A7C15ull;
+    for (int r = nrows - 1; r > 0; --r) { t ^= t << 13; t ^= t >> 7; t ^= t << 17; int q = (int)(t % (r + 1)); int x = perm[r]; perm[r] = perm[q]; perm[q] = x; }
+    int* out = new int[n];
+    for (size_t i = 0; i < n; ++i) {
+      t ^= t << 13; t ^= t >> 7; t ^= t << 17;
+      const double u = (t >> 11) * (1.0 / 9007199254740992.0) * acc;
+      int lo = 0, hi = nrows - 1;
+      while (lo < hi) { int mid = (lo + hi) / 2; if (cdf[mid] < u) lo = mid + 1; else hi = mid; }
+      out[i] = perm[lo];
+    }
+    int* d; CK(cudaMalloc(&d, n * 4)); CK(cudaMemcpy(d, out, n * 4, cudaMemcpyHostToDevice));
+    delete[] cdf; delete[] perm; delete[] out;
+    return d;
+  };
+  int* ids_z10 = zipf_ids(1.0, 52621);
+  int* ids_z08 = zipf_ids(0.8, 48653);
   int* ids; int* ids_small;
   CK(cudaMalloc(&ids, n * 4)); CK(cudaMemcpy(ids, h, n * 4, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&ids_small, n * 4)); CK(cudaMemcpy(ids_small, h_small, n * 4, cudaMemcpyHostToDevice));
@@ -306,6 +367,12 @@ int main() {
   report("nosh codes only", best_of([&] { k_nosh<6, 0><<<sms, 1024>>>(tab, ids, iters, out, 512); }), n);
   report("nosh ldg64 (L2)", best_of([&] { k_nosh<0, 0><<<sms, 1024>>>(tab, ids, iters, out, 512); }), n);
   report("nosh ldg64 (L1: 96 KB)", best_of([&] { k_nosh<0, 0><<<sms, 1024>>>(tab, ids_small, iters, out, 512); }), n);
+  CK(cudaFuncSetAttribute(k_nosh<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(100 * 1024)));
+  report("nosh ldg64 zipf1.0 (L1 190K)", best_of([&] { k_nosh<0, 0><<<sms, 1024>>>(tab, ids_z10, iters, out, 512); }), n);
+  report("nosh ldg64 zipf0.8 (L1 190K)", best_of([&] { k_nosh<0, 0><<<sms, 1024>>>(tab, ids_z08, iters, out, 512); }), n);
+  report("nosh ldg64 uniform (L1 90K)", best_of([&] { k_nosh<0, 0><<<sms, 1024, 100 * 1024>>>(tab, ids, iters, out, 512); }), n);
+  report("nosh ldg64 zipf1.0 (L1 90K)", best_of([&] { k_nosh<0, 0><<<sms, 1024, 100 * 1024>>>(tab, ids_z10, iters, out, 512); }), n);
+  report("nosh ldg64 zipf0.8 (L1 90K)", best_of([&] { k_nosh<0, 0><<<sms, 1024, 100 * 1024>>>(tab, ids_z08, iters, out, 512); }), n);
   report("nosh lds64 (512 staged)", best_of([&] { k_nosh<3, 0><<<sms, 1024, 512 * 256>>>(tab, ids, iters, out, 512); }), n);
   report("nosh mix 4 lds + 12 ldg", best_of([&] { k_nosh<4, 4><<<sms, 1024, 512 * 256>>>(tab, ids, iters, out, 512); }), n);
   report("nosh mix 8 lds + 8 ldg", best_of([&] { k_nosh<4, 8><<<sms, 1024, 512 * 256>>>(tab, ids, iters, out, 512); }), n);
@@ -313,6 +380,29 @@ int main() {
   report("stg64 (random rows)", best_of([&] { k_lsu<V_STG64, 0><<<sms, 1024>>>(tab, ids, iters, out, hot_rows); }), n);
   CK(cudaMemset(tab, 0, (size_t)rows * 256));
 
+  {
+    const int it_t = 64;                                   // 148 x 32 x 64 = 303,104 tasks: one layer launch of the Gowalla shape
+    const size_t ntask = (size_t)sms * 32 * it_t;
+    float* own; float* dst;
+    CK(cudaMalloc(&own, ntask * 256 * 2)); CK(cudaMemset(own, 0, ntask * 256 * 2));
+    CK(cudaMalloc(&dst, ntask * 256 * 2));
+    float* flush; CK(cudaMalloc(&flush, 256u << 20));
+    auto run = [&](const char* nm, auto f) {
+      float best = 1e9;
+      for (int r = 0; r < 4; ++r) {
+        CK(cudaMemset(flush, r, 256u << 20));                // L2 flush, like bench.py
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a); f(); cudaEventRecord(b); CK(cudaEventSynchronize(b));
+        float ms; cudaEventElapsedTime(&ms, a, b); if (ms < best) best = ms;
+      }
+      printf("%-34s %8.3f ms  = %6.1f SM-cycles/task (12 gathers + own loads + stores)\n", nm, best, best * 1e-3 * g_clk_ghz * 1e9 * 148 / ntask);
+    };
+    run("task mix: gathers only", [&] { k_task<0, 0><<<sms, 1024>>>(tab, ids_z10, it_t, own, dst, out); });
+    run("task mix: + 1 own load", [&] { k_task<1, 0><<<sms, 1024>>>(tab, ids_z10, it_t, own, dst, out); });
+    run("task mix: + 1 own load + 1 store", [&] { k_task<1, 1><<<sms, 1024>>>(tab, ids_z10, it_t, own, dst, out); });
+    run("task mix: + 2 own loads + 2 stores", [&] { k_task<2, 2><<<sms, 1024>>>(tab, ids_z10, it_t, own, dst, out); });
+    run("task mix: + 0 own loads + 2 stores", [&] { k_task<0, 2><<<sms, 1024>>>(tab, ids_z10, it_t, own, dst, out); });
+  }
   // tensor map for gather4: 2-D [rows, 64] fp32, box {64, 1}
   EncodeFn encode = nullptr;
   cudaDriverEntryPointQueryResult qres;
