@@ -64,6 +64,11 @@ def parse_args():
     ap.add_argument("--no-calibrate", action="store_true", help="keep the static cost-model CTA split")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--extras", default="auto", choices=["auto", "on", "off"],
+                    help="N > 1 (auto) / on: also measure BASELINE configs 3 and 5 the multi-GPU way north_star names "
+                         "(bench_multi.py) and run the row-sharding bitwise check; results go into line['extras']")
+    ap.add_argument("--extras-scale", type=float, default=1.0, help="size factor of the config-5 interval (tests)")
+    ap.add_argument("--extras-amazon-scale", type=float, default=1.0)
     ap.add_argument("--seed", type=int, default=100)
     return ap.parse_args()
 
@@ -210,7 +215,7 @@ def main():
             "value": val, "unit": "edge_traversals/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, g, L, d, world=1),
+            "config": workload_config(args, g, L, d, world),
             "cpu_baseline": {"value": val, "unit": "edge_traversals/s", "cores": threads, "kind": "port",
                              "sample": "full %s workload, %d timed fwd+bwd steps of oracle/tf1_mirror.py "
                                        "(torch-CPU op-by-op restatement of the TF1 graph; TF 1.14 itself is "
@@ -234,8 +239,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # a rank that dies must not leave the others waiting in a collective for the default 10 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     g, L, d = make_workload(args, rank)
     T, U, I = g.graph_num, g.n_user, g.n_item
@@ -314,7 +321,9 @@ def main():
     split = None
     if not args.no_calibrate:
         split = step.calibrate(rounds=2)        # measured load balance (setup, like the plan build)
-    use_graph = not args.no_graph and not do_gather
+    # one CUDA graph per rank: the plain step, or forward-with-fused-hand-off + backward (peer pointers are
+    # ordinary kernel arguments); the NCCL hand-offs keep direct launches
+    use_graph = not args.no_graph and (not do_gather or fused)
     if use_graph:
         step.capture()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -325,11 +334,14 @@ def main():
         flush = _NoFlush()
 
     def one_step():
-        if fused:
-            step.forward()                                          # rows land in the peers' buffers as they finish
+        if fused and use_graph:
+            step.replay()                                           # rows land in the peers' buffers as they finish
+            hdl_u.barrier(channel=0)                                # every rank is through: my receive slabs are complete
+        elif fused:
+            step.forward()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                hdl_u.barrier(channel=0)                            # every rank's forward is done: my slabs are complete
+                hdl_u.barrier(channel=0)
             step.backward()
             torch.cuda.current_stream().wait_stream(side)
         elif do_gather:
@@ -417,9 +429,11 @@ def main():
             traffic = None
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src,
-        "kernel": "spmm_rpw_kernel<%s> (one GNN layer, all T intervals, both orientations)"
-                  % ("FWD" if dom_is_fwd else "BWD"),
+        "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture of this command, not this run)"
+        if traffic is not None else None, "peak_source": peak_src,
+        "kernel": "%s<%s> (one GNN layer, all T intervals, both orientations)"
+                  % ("spmm_rpw_kernel" if os.environ.get("SAGNN_KERNEL", "").lower().startswith("v8") else "spmm_pkt_kernel",
+                     "FWD" if dom_is_fwd else "BWD"),
         "alg_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
         "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
         "step": {"alg_bytes": b_step, "achieved": b_step / (ms_per_step * 1e-3) / 1e9,
@@ -483,22 +497,40 @@ def main():
         except Exception as e:   # the C port is optional colour, never fatal
             cpu["fused_c_port"] = {"error": str(e)}
 
+    # ---- the configurations north_star names for N GPUs (results only; the headline above is untouched)
+    extras = None
+    launches = step.kernel_launches_per_step * args.steps
+    stats = plan.stats()
+    if args.extras == "on" or (args.extras == "auto" and world > 1):
+        import bench_multi
+        del flush
+        step = None
+        torch.cuda.empty_cache()
+        extras = bench_multi.run_extras(args, rank, world, dev, dist, peak)
+
     if rank == 0:
         line = {
             "metric": "fwd+bwd interval-graph SpMM edge traversals/s", "value": value,
             "unit": "edge_traversals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args, g, L, d, world, plan.stats(), use_graph, do_gather),
-                           cta_split=split),
+            "config": workload_config(args, g, L, d, world),
+            "run": dict(run_config(args, world, stats, use_graph, do_gather), cta_split=split),
             "graph_edges_per_s": edges_all / (ms_per_step * 1e-3),
             "plan_build_ms": plan_ms, "wall_s_timed_region": wall,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": step.kernel_launches_per_step * args.steps,
+            "gpu_launches": launches,
             "clocks": clocks,
         }
         if fused_ok is not None:
-            line["config"]["fused_handoff_bitwise_equal_to_nccl_alltoall"] = fused_ok
+            line["run"]["fused_handoff_bitwise_equal_to_nccl_alltoall"] = fused_ok
+        if cpu is not None and "fused_c_port" in cpu and "value" in cpu["fused_c_port"]:
+            # both CPU arms next to each other: the stated baseline (TF1-graph restatement) and the fused C port
+            cpu["ratios"] = {"device_resident_vs_tf1_mirror": value / cpu["value"],
+                             "device_resident_vs_fused_c_port": value / cpu["fused_c_port"]["value"],
+                             "e2e_vs_tf1_mirror": (e2e["value"] / cpu["value"]) if e2e else None,
+                             "e2e_vs_fused_c_port": (e2e["value"] / cpu["fused_c_port"]["value"]) if e2e else None}
+        line["extras"] = extras
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -506,36 +538,38 @@ def main():
     return 0
 
 
-def workload_config(args, g, L, d, world, stats=None, use_graph=None, gather=None):
-    cfg = {
+def workload_config(args, g, L, d, world):
+    """What is measured (identical for both arms); how it was run goes into ``run``."""
+    return {
         "workload": "%s-shaped synthetic power-law interval graphs (SURVEY app. D)" % args.workload,
         "T": g.graph_num, "U": g.n_user, "I": g.n_item, "interval_edges": g.nnz, "edges": sum(g.nnz),
         "layers": L, "latdim": d, "leaky": 0.5, "scale": args.scale, "seed": args.seed,
         "edge_traversals_per_step": 4 * L * sum(g.nnz),
         "per_gpu": "every rank owns one full set of T interval graphs (interval sharding, weak scaling)"
                    if world > 1 else "single GPU",
-        "l2": "256 MB buffer written between timed steps (L2 flush), outside the event pairs",
     }
-    if stats is not None:
-        cfg["schedule"] = stats
-    if use_graph is not None:
-        cfg["cuda_graph"] = bool(use_graph)
-        cfg["layout"] = "[T,R,d] outputs (model.py:131-132)" if args.layout == "trd" else "[R,T,d] outputs / upstream (model.py:133-134, fused transpose)"
-    if gather is not None:
-        cfg["allgather_outputs"] = bool(gather) and args.exchange == "allgather"
-        cfg["exchange"] = args.exchange if world > 1 else "none"
-        if world > 1:
-            cfg["exchange_detail"] = {
-                "alltoall": "one NCCL all-to-all per side: every rank receives its row block of all ranks' intervals "
-                            "(row-sharded consumer), sent straight from the [R,T,d] epilogue output, on a side "
-                            "stream overlapping the backward",
-                "allgather": "NCCL all-gather of the [T,R,d] outputs to every rank (replicated consumer), on a side "
-                             "stream overlapping the backward",
-                "fused": "no collective kernel: the last forward layer's epilogue stores every finished row into the "
-                         "symmetric-memory receive buffer of the rank that owns its row block (peer stores over "
-                         "NVLink, sagnn_propagate_fwd_scatter), then one symmetric-memory barrier on a side stream; "
-                         "verified bitwise against the NCCL all-to-all before timing",
-                "none": "no hand-off collective (compute only)"}[args.exchange]
+
+
+def run_config(args, world, stats, use_graph, gather):
+    cfg = {"l2": "256 MB buffer written between timed steps (L2 flush), outside the event pairs",
+           "schedule": stats, "cuda_graph": bool(use_graph),
+           "kernel": os.environ.get("SAGNN_KERNEL", "v10 packet stream (default)"),
+           "layout": "[T,R,d] outputs (model.py:131-132)" if args.layout == "trd"
+                     else "[R,T,d] outputs / upstream (model.py:133-134, fused transpose)",
+           "allgather_outputs": bool(gather) and args.exchange == "allgather",
+           "exchange": args.exchange if world > 1 else "none"}
+    if world > 1:
+        cfg["exchange_detail"] = {
+            "alltoall": "one NCCL all-to-all per side: every rank receives its row block of all ranks' intervals "
+                        "(row-sharded consumer), sent straight from the [R,T,d] epilogue output, on a side "
+                        "stream overlapping the backward",
+            "allgather": "NCCL all-gather of the [T,R,d] outputs to every rank (replicated consumer), on a side "
+                         "stream overlapping the backward",
+            "fused": "no collective kernel: the last forward layer's epilogue stores every finished row into the "
+                     "symmetric-memory receive buffer of the rank that owns its row block (peer stores over "
+                     "NVLink, sagnn_propagate_fwd_scatter); forward + backward replay from one CUDA graph, then one "
+                     "symmetric-memory barrier; verified bitwise against the NCCL all-to-all before timing",
+            "none": "no hand-off collective (compute only)"}[args.exchange]
     return cfg
 
 

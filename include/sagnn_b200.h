@@ -78,7 +78,15 @@ int sagnn_bucket_events(const int32_t* users_dev, const int32_t* items_dev, cons
                         int32_t* val_out_dev, int64_t* nnz_host, sagnn_stream_t stream);
 
 /* nnz_host[T]: edge count of every interval (an empty interval must be passed as the
- * reference's single fallback edge (0,0), DataHandler.py:66-68 -- the Python shim does). */
+ * reference's single fallback edge (0,0), DataHandler.py:66-68 -- the Python shim does).
+ * Size limits (checked, SAGNN_INVALID_ARG otherwise; all far above BASELINE's largest config, 10 M x 2 M rows,
+ * 1 B edges over 8 intervals, which is split over 8 plans anyway):
+ *   1 <= nnz[k] < 2^31                 per interval (edge ids inside a segment are 32-bit);
+ *   T * (U + I) < 2^31                 global row ids are 32-bit (checked here);
+ *   2 * sum_k nnz[k] < 2^32            edge entries of both orientations of all intervals (checked by finalize);
+ *   packed task stream < 2^36 bytes    its directory addresses 16-byte units with 32 bits (checked by finalize);
+ *   device SM count <= 160             size of the by-value CTA table of the packet-stream kernel (checked at launch);
+ *   latdim d in {32, 64, 128, 256}     at every propagate / message_propagate call. */
 int sagnn_plan_create(int T, int U, int I, const int64_t* nnz_host, sagnn_plan** out);
 
 /* Adjacency list of interval k in the order transToLsts emits it (row-major COO of the

@@ -14,7 +14,8 @@ namespace sagnn {
 constexpr int kChunk = 64;        // max edges one warp gathers for one task
 constexpr int kPktTasks = 4;      // tasks per packet of the packed task stream (packet-stream kernel)
 constexpr int kHotRows = 768;     // max hot slots per source table (slot = degree rank); array stride
-constexpr int kHotBytes = 192 * 1024;   // shared memory the kernels give to staged hot rows
+constexpr int kHotBytes = 192 * 1024;   // (v7 legacy) shared memory given to staged hot rows
+constexpr int kSmemBudget = 226 * 1024; // dynamic shared memory a persistent CTA of the packet-stream kernel may use
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
@@ -34,6 +35,29 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
   } while (0)
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- packet-stream kernel geometry shared by the plan builder and the kernel ----
+#ifndef SAGNN_PKT_HOT
+#define SAGNN_PKT_HOT 0         // 1: build the hot-row staging path (shared-memory copies of popular source rows); measured slower, off
+#endif
+#ifndef SAGNN_PKT_THREADS
+#define SAGNN_PKT_THREADS 1024
+#endif
+#ifndef SAGNN_PKT_SLOTS
+#define SAGNN_PKT_SLOTS 3       // packets resident / in flight per warp
+#endif
+constexpr int kPktThreads = SAGNN_PKT_THREADS;
+constexpr int kPktWarps = kPktThreads / 32;
+
+// hot slots a plan may hand out for latdim d (what fits next to the packet ring)
+inline int pkt_hot_capacity(int d, bool weighted) {
+  const int ns = weighted ? 2 : SAGNN_PKT_SLOTS;
+  const size_t pkt = (size_t)kPktWarps * ns * (kPktTasks * 16 + kPktTasks * (kChunk + 4) * 4 * (weighted ? 2 : 1));
+  const long cap = ((long)kSmemBudget - (long)pkt) / (4L * d);
+  return (int)(cap < 0 ? 0 : (cap > kHotRows ? kHotRows : cap));
+}
+
+
 
 }  // namespace sagnn
 
@@ -80,7 +104,8 @@ struct sagnn_plan {
   bool has_custom_w = false;
   bool finalized = false;
   int weight_mode = 0;
-  int hot_rows = sagnn::kHotRows; // hot slots actually used: min(kHotRows, kHotBytes / (4 * latdim hint))
+  int hot_rows = 0;               // hot slots per source table the edge codes use (packet-stream kernel: what fits at latdim_hint)
+  int latdim_hint = 64;
   // row sharding (sagnn_plan_set_row_block): only user rows [u_begin,u_end) and item rows [i_begin,i_end)
   // of every interval get tasks; the others are some other rank's.  Default: all rows.
   int u_begin = 0, u_end = 0, i_begin = 0, i_end = 0;

@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sagnn {
@@ -137,12 +139,19 @@ __device__ __forceinline__ int64_t table_row0(uint32_t t, int64_t N, int U) {
   return (int64_t)(t >> 1) * N + ((t & 1) ? U : 0);
 }
 
-// sort key: rows grouped by table, descending degree inside a table (stable => ascending id on ties)
-__global__ void sched_key_kernel(const int32_t* __restrict__ deg, int64_t n_rows, int64_t N, int U,
+// sort key: rows grouped by table, long rows (deg > kChunk) first by descending degree, then the short
+// rows by descending degree CLASS = number of `bucket`-edge gather blocks (stable => ascending row id
+// inside a class).  Lock-step lane groups only need equal block counts, and a class that keeps its rows
+// in id order reads its own rows and writes its outputs as a forward-moving window over the tables
+// instead of scattered 256-byte rows (scripts/micro/l1tex_cost.cu "task mix": +20-30 % for scattered).
+__global__ void sched_key_kernel(const int32_t* __restrict__ deg, int64_t n_rows, int64_t N, int U, int bucket,
                                  uint64_t* __restrict__ key, uint32_t* __restrict__ row) {
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_rows) return;
-  key[g] = ((uint64_t)table_of(g, N, U) << 32) | (uint32_t)(0x7fffffff - deg[g]);
+  const int d = deg[g];
+  const int cls = d > kChunk ? d : (d + bucket - 1) / bucket;   // long rows keep their exact order and stay in front
+  const uint32_t sub = d > kChunk ? (uint32_t)(0x7fffffff - d) : (uint32_t)(0x7fffffff - cls) ;
+  key[g] = ((uint64_t)table_of(g, N, U) << 32) | sub;
   row[g] = (uint32_t)g;
 }
 
@@ -256,14 +265,16 @@ __global__ void pkt_size_kernel(const sagnn_task* __restrict__ tasks, int64_t n_
                                 int64_t* __restrict__ cbytes) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j > n_tasks) return;
-  cbytes[j] = j == n_tasks ? 0 : (int64_t)(((tasks[j].meta & 0x7fu) + 3u) & ~3u) * 4 * wmul;
+  if (j == n_tasks) { cbytes[j] = 0; return; }
+  const uint32_t n = tasks[j].meta & 0x7fu, nh = (tasks[j].meta >> 8) & 0x7fu;
+  cbytes[j] = (int64_t)(((nh + 3u) & ~3u) + ((n - nh + 3u) & ~3u)) * 4 * wmul;   // [hot slots | row ids], each padded to 4
 }
 
 // one warp per task: its record, codes (and weights) into the packet; packet p of the whole plan starts
 // at byte 16*kPktTasks*p + coff[first task of p] (every packet opens with kPktTasks 16-byte records)
 __global__ void pkt_fill_kernel(const sagnn_task* __restrict__ tasks, int64_t n_tasks,
                                 const int64_t* __restrict__ coff, const sagnn_seg* __restrict__ seg, int S,
-                                const int32_t* __restrict__ idx, const float* __restrict__ w,
+                                const int32_t* __restrict__ codes, const float* __restrict__ w,
                                 unsigned char* __restrict__ stream, uint32_t* __restrict__ dir) {
   const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -281,21 +292,25 @@ __global__ void pkt_fill_kernel(const sagnn_task* __restrict__ tasks, int64_t n_
   const int64_t pkt_off = (int64_t)16 * kPktTasks * pk + coff[f];
   const uint32_t code_off = (uint32_t)(16 * kPktTasks + (coff[j] - coff[f]));
   const sagnn_task k = tasks[j];
-  const uint32_t n = k.meta & 0x7fu, n4 = (n + 3u) & ~3u;
+  const uint32_t n = k.meta & 0x7fu, nh = (k.meta >> 8) & 0x7fu, nc = n - nh;
+  const uint32_t nh4 = (nh + 3u) & ~3u, nc4 = (nc + 3u) & ~3u;
   unsigned char* pkt = stream + pkt_off;
   if (lane == 0) {
-    reinterpret_cast<uint4*>(pkt)[t] = make_uint4(k.row, n | (k.meta & 0x80000000u), k.aux, code_off);
+    reinterpret_cast<uint4*>(pkt)[t] = make_uint4(k.row, n | (nh << 8) | (k.meta & 0x80000000u), k.aux, code_off);
     if (t == 0) dir[pk] = (uint32_t)(pkt_off >> 4);
     if (j == sg.task_end - 1)             // the segment's last packet: pad with no-work records
       for (int q = t + 1; q < kPktTasks; ++q) reinterpret_cast<uint4*>(pkt)[q] = make_uint4(0u, 0x40000000u, 0u, 0u);
   }
-  const int32_t* src = idx + sg.edge_base + k.e_off;
+  // the task's codes are hot-first: [hot slots, padded to 4][source-row ids, padded to 4][weights, same split]
+  const int32_t* src = codes + sg.edge_base + k.e_off;
   int32_t* dst = reinterpret_cast<int32_t*>(pkt + code_off);
-  for (uint32_t e = lane; e < n4; e += 32) dst[e] = e < n ? src[e] : 0;
+  for (uint32_t e = lane; e < nh4; e += 32) dst[e] = e < nh ? src[e] : 0;
+  for (uint32_t e = lane; e < nc4; e += 32) dst[nh4 + e] = e < nc ? src[nh + e] : 0;
   if (w) {
     const float* ws = w + sg.edge_base + k.e_off;
-    float* wd = reinterpret_cast<float*>(pkt + code_off) + n4;
-    for (uint32_t e = lane; e < n4; e += 32) wd[e] = e < n ? ws[e] : 0.f;
+    float* wd = reinterpret_cast<float*>(pkt + code_off) + nh4 + nc4;
+    for (uint32_t e = lane; e < nh4; e += 32) wd[e] = e < nh ? ws[e] : 0.f;
+    for (uint32_t e = lane; e < nc4; e += 32) wd[nh4 + e] = e < nc ? ws[nh + e] : 0.f;
   }
 }
 
@@ -532,8 +547,7 @@ extern "C" int sagnn_plan_set_row_block(sagnn_plan* p, int u_begin, int u_end, i
 extern "C" int sagnn_plan_set_latdim_hint(sagnn_plan* p, int d) {
   SAGNN_REQUIRE(p && !p->finalized, SAGNN_INVALID_ARG, "set_latdim_hint: NULL or finalized plan");
   SAGNN_REQUIRE(d >= 4 && d % 4 == 0, SAGNN_INVALID_ARG, "set_latdim_hint: d=%d", d);
-  const int k = kHotBytes / (4 * d);
-  p->hot_rows = k < kHotRows ? (k < 1 ? 1 : k) : kHotRows;
+  p->latdim_hint = d;
   return SAGNN_OK;
 }
 
@@ -581,7 +595,16 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   }
 
   // ---- schedule: per-segment task lists, hot slots, hot-first edge codes ------------------
-  p->hot_rows = 0;   // no staged hot rows: every edge code is a source-row id
+  // hot slots: the highest-degree rows of every table, as many as fit the kernel's staging area at the hinted
+  // latdim (SAGNN_HOT_ROWS overrides, 0 = none); the v8 kernel stages nothing
+  // OFF by default: measured on B200 (Gowalla shape, 472 staged rows) 0.61 vs 0.47 ms per step -- the staged
+  // copy takes the shared memory the L1 cache would otherwise use for exactly those rows, and the extra
+  // lock-step phase costs more than the L2 round trips it saves.  Builds with -DSAGNN_PKT_HOT=1 honour SAGNN_HOT_ROWS=N.
+  p->hot_rows = 0;
+  if (const char* e = getenv("SAGNN_HOT_ROWS")) {
+    const int v = atoi(e), cap = (SAGNN_PKT_HOT && sagnn::use_pkt()) ? sagnn::pkt_hot_capacity(p->latdim_hint, p->w != nullptr) : 0;
+    p->hot_rows = v < 0 ? 0 : (v > cap ? cap : v);
+  }
   SAGNN_REQUIRE(p->num_sms >= 2, SAGNN_INVALID_ARG, "finalize: need at least 2 SMs");
   SAGNN_REQUIRE(2 * p->e_total < ((int64_t)1 << 32), SAGNN_INVALID_ARG,
                 "finalize: %lld edge entries exceed 2^32", (long long)(2 * p->e_total));
@@ -601,7 +624,9 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   SAGNN_CUDA(off3.alloc(3 * (R + 1)));
   SAGNN_CUDA(cudaMalloc(&p->hot_ids, sizeof(int32_t) * 2 * p->T * kHotRows));
   SAGNN_CUDA(cudaMemsetAsync(p->hot_ids, 0, sizeof(int32_t) * 2 * p->T * kHotRows, st));
-  sched_key_kernel<<<blocks_for(R), 256, 0, st>>>(p->deg, R, N, U, key_in, row_in);
+  int bucket = sagnn::use_pkt() ? 4 : 1;   // the packet kernel gathers in blocks of four slots
+  if (const char* e = getenv("SAGNN_SORT_BUCKET")) bucket = atoi(e) > 0 ? atoi(e) : bucket;
+  sched_key_kernel<<<blocks_for(R), 256, 0, st>>>(p->deg, R, N, U, bucket, key_in, row_in);
   {
     DevTmp<char> tmp; size_t tb = 0;
     const int end_bit = 32 + bits_for(2 * p->T);
@@ -642,12 +667,12 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   }
 
   const bool pkt = sagnn::use_pkt();
-  if (!pkt) {   // v8 kernel: edge codes (and weights) in CSR order, copied next to the canonical arrays
+  if (!pkt || p->hot_rows > 0) {   // hot-first edge codes (and weights) per row; without hot slots a plain copy (v8)
     SAGNN_CUDA(cudaMalloc(&p->enc, sizeof(int32_t) * 2 * p->e_total));
     if (p->w) SAGNN_CUDA(cudaMalloc(&p->w_enc, sizeof(float) * 2 * p->e_total));
     sched_encode_kernel<<<blocks_for(R * 32), 256, 0, st>>>(p->rowptr, p->idx, p->w, slot_of, R, N, U, p->enc,
                                                             p->w_enc, nhot_row);
-  } else {      // packet stream: the codes are read straight from the canonical CSR when the packets are filled
+  } else {      // packet stream without hot slots: the codes are read straight from the canonical CSR
     SAGNN_CUDA(cudaMemsetAsync(nhot_row, 0, sizeof(int32_t) * R, st));
   }
 
@@ -656,7 +681,7 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   SAGNN_CUDA(cudaMalloc(&p->chunk_lr, sizeof(uint32_t) * (p->n_chunks ? p->n_chunks : 1)));
   SAGNN_CUDA(cudaMemcpyAsync(p->chunk_base + p->n_long, &p->n_chunks, sizeof(int64_t), cudaMemcpyHostToDevice, st));
   sched_task_kernel<<<blocks_for(p->n_tasks), 256, 0, st>>>(srow, p->deg, p->rowptr, nhot_row, task_off, chunk_off,
-                                                            long_off, pkt ? p->idx : p->enc, R, p->n_tasks, N, U, p->tasks, p->chunk_base,
+                                                            long_off, p->enc ? p->enc : p->idx, R, p->n_tasks, N, U, p->tasks, p->chunk_base,
                                                             p->chunk_lr);
   SAGNN_CUDA(cudaGetLastError());
 
@@ -708,12 +733,14 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
     const uint32_t end16 = (uint32_t)(total >> 4);
     SAGNN_CUDA(cudaMemcpyAsync(p->pkt_dir + p->n_pkts, &end16, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     if (nt)
-      pkt_fill_kernel<<<blocks_for(nt * 32), 256, 0, st>>>(p->tasks, nt, coff, p->seg_dev, S, p->idx, p->w,
-                                                           (unsigned char*)p->pkt_stream, p->pkt_dir);
+      pkt_fill_kernel<<<blocks_for(nt * 32), 256, 0, st>>>(p->tasks, nt, coff, p->seg_dev, S, p->enc ? p->enc : p->idx,
+                                                           p->enc ? p->w_enc : p->w, (unsigned char*)p->pkt_stream, p->pkt_dir);
     SAGNN_CUDA(cudaGetLastError());
     SAGNN_CUDA(cudaStreamSynchronize(st));
-    cudaFree(p->tasks);     // the stream carries the records from here on
+    cudaFree(p->tasks);     // the stream carries the records, codes and weights from here on
     p->tasks = nullptr;
+    cudaFree(p->enc); p->enc = nullptr;
+    cudaFree(p->w_enc); p->w_enc = nullptr;
   }
 
   // persistent CTAs (one per SM) are dealt to segments in proportion to their cost.  Measured on

@@ -247,15 +247,15 @@ bool use_pkt() {
   return v;
 }
 
-template <int VPL, int MODE, bool WEIGHTED, bool RTD>
+template <int D, int MODE, bool WEIGHTED, bool RTD>
 static int launch_pkt_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaStream_t st) {
   SpmmParams prm = prm_in;
   if (plan->trace_dev && plan->trace_launch < plan->trace_capacity)   // diagnostics only
     prm.trace = plan->trace_dev + (size_t)(plan->trace_launch++) * plan->num_sms * 4;
-  using G = PktGeo<VPL, WEIGHTED>;
-  static_assert(G::SMEM <= 225 * 1024, "shared-memory budget exceeded");
+  using G = PktGeo<D, WEIGHTED>;
+  static_assert(G::SMEM <= (size_t)kSmemBudget, "shared-memory budget exceeded");
   static std::atomic<uint64_t> configured{0};   // bit per device: the attribute is per device
-  auto kern = spmm_pkt_kernel<VPL, MODE, WEIGHTED, RTD>;
+  auto kern = spmm_pkt_kernel<D, MODE, WEIGHTED, RTD>;
   const uint64_t bit = 1ull << (plan->device & 63);
   if (!(configured.load(std::memory_order_acquire) & bit)) {
     SAGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
@@ -271,18 +271,20 @@ static int launch_pkt_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaSt
     prm.ctad[c] = PktCta{(uint32_t)sgi, (uint32_t)rank * kPktWarps, (uint32_t)count * kPktWarps,
                          (uint32_t)sh.pkt_begin, (uint32_t)(sh.pkt_end - sh.pkt_begin)};
   }
-  kern<<<plan->num_sms, kPktThreads, G::SMEM, st>>>(prm);
+  // the staging area is only allocated when the plan has hot slots: without them the L1 keeps that capacity
+  const int staged = plan->hot_rows < G::HOT_CAP ? plan->hot_rows : G::HOT_CAP;
+  kern<<<plan->num_sms, kPktThreads, G::PKT_SMEM + (size_t)staged * G::ROWB, st>>>(prm);
   SAGNN_CUDA(cudaGetLastError());
   return SAGNN_OK;
 }
 
-template <int VPL, int MODE>
+template <int D, int MODE>
 static int launch_pkt_v(const sagnn_plan* plan, const SpmmParams& prm, cudaStream_t st) {
   const bool wt = prm.w != nullptr;
   if (MODE != MODE_MSG && (prm.a_rtd | prm.b_rtd | prm.o2_rtd | prm.src_rtd))
-    return wt ? launch_pkt_t<VPL, MODE, true, MODE != MODE_MSG>(plan, prm, st)
-              : launch_pkt_t<VPL, MODE, false, MODE != MODE_MSG>(plan, prm, st);
-  return wt ? launch_pkt_t<VPL, MODE, true, false>(plan, prm, st) : launch_pkt_t<VPL, MODE, false, false>(plan, prm, st);
+    return wt ? launch_pkt_t<D, MODE, true, MODE != MODE_MSG>(plan, prm, st)
+              : launch_pkt_t<D, MODE, false, MODE != MODE_MSG>(plan, prm, st);
+  return wt ? launch_pkt_t<D, MODE, true, false>(plan, prm, st) : launch_pkt_t<D, MODE, false, false>(plan, prm, st);
 }
 
 template <int MODE>
@@ -291,11 +293,11 @@ static int launch_pkt_mode(const sagnn_plan* plan, const SpmmParams& prm, int d,
                 "the packet-stream kernel needs a packed plan and pre-masked backward sources");
   switch (d) {
 #ifndef SAGNN_ONLY_D64   // development builds: -DSAGNN_ONLY_D64 instantiates d = 64 only (compile time)
-    case 32:  return launch_pkt_v<1, MODE>(plan, prm, st);
-    case 128: return launch_pkt_v<4, MODE>(plan, prm, st);
-    case 256: return launch_pkt_v<8, MODE>(plan, prm, st);
+    case 32:  return launch_pkt_v<32, MODE>(plan, prm, st);
+    case 128: return launch_pkt_v<128, MODE>(plan, prm, st);
+    case 256: return launch_pkt_v<256, MODE>(plan, prm, st);
 #endif
-    case 64:  return launch_pkt_v<2, MODE>(plan, prm, st);
+    case 64:  return launch_pkt_v<64, MODE>(plan, prm, st);
   }
   set_error("latdim d=%d unsupported (need 32, 64, 128 or 256)", d);
   return SAGNN_INVALID_ARG;

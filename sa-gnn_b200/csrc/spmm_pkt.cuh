@@ -1,65 +1,64 @@
-// Packet-stream layer kernel (v9, the default).  Included by spmm.cu after spmm_rpw.cuh (shares its
+// Packet-stream layer kernel (v10, the default).  Included by spmm.cu after spmm_rpw.cuh (shares its
 // per-lane load / store / accumulate helpers).
 //
 // Same contract as the v8 kernel (one launch = one GNN layer over all T intervals and both
-// orientations: LIU-YUXI/SA-GNN model.py:118-127; backward = SURVEY A.2), same row-per-warp mapping
-// (32 lanes span the latent dimension, every control decision warp-uniform), but built around what
-// the round-2 microbenchmark (scripts/micro/l1tex_cost.cu, profiles/r2_micro_l1tex_cost.txt) says
-// bounds a gather kernel on B200: the SM's L1TEX / LSU pipe.  A 256-byte row costs that pipe
-// 3.8 cycles as an LDG from L2 and 8+ as a cp.async, so everything that is not a gathered row must
-// stay out of it:
+// orientations: LIU-YUXI/SA-GNN model.py:118-127; backward = SURVEY A.2).  What round 2 measured
+// (profiles/r2_micro_l1tex_cost.txt, profiles/r2_ncu_*.md) and what this kernel does about it:
 //
+//   * A bookkeeping-free loop that moves exactly what a layer moves (12 gathered 256-byte rows, the
+//     task's own rows, its stores) runs at 63-77 SM cycles per task; v8 and the first packet kernel
+//     both sat at ~115 with the issue slots ~57 % busy on ~200 warp instructions per task, three
+//     quarters of the tasks having <= 7 edges.  The cost is per TASK, not per edge.
+//   * So a task is owned by a LANE GROUP of d/4 lanes (one float4 per lane: 128-bit loads), and a warp
+//     runs G = 128/d tasks in lock step (4 at d=32, 2 at d=64, 1 at d>=128): every instruction of the
+//     bookkeeping, the gathers and the epilogue serves G tasks.  Tasks arrive sorted by degree, so
+//     the tasks of one iteration have (nearly) the same length; control flow follows the longest,
+//     shorter ones predicate their loads off.
 //   * The schedule is a PACKED TASK STREAM built by the plan: packets of 4 tasks = 4 records
 //     {row, n | flags, slice id, code offset} followed by the tasks' edge codes (and weights), in
 //     schedule order.  A warp brings its next packets into shared memory with ONE TMA bulk copy
 //     each (cp.async.bulk + mbarrier, issued by one lane, SLOTS-1 packets ahead): no per-task
-//     record / code requests, no LSU work besides the warp-uniform LDS.128 that read them back.
+//     record / code requests, no LSU work besides the LDS.128 that read them back.
 //   * Packets are dealt statically (packet q of a segment belongs to warp q mod (32 x CTAs of the
-//     segment)); tasks are sorted by descending degree, so the interleave balances itself and the
-//     queue atomics of v8 are gone.
-//   * TWO TASKS IN FLIGHT PER WARP (512 threads x 128 registers): the gathers and own-row loads of
-//     task t+1 are issued before task t is reduced, so a warp always has a task's worth of rows in
-//     flight while it adds, runs the epilogue and stores (ncu on the one-task form: issue slots 57 %
-//     busy, the rest long-scoreboard stalls on the gathers; SAGNN_PKT_BANKS=1 builds that form).
-//   * The task's own dense rows (E^l row, layer-sum row / G and g rows) are plain 64/128-bit loads
-//     into registers, issued together with the task's gathers.
-//   * Gather: as v8 -- all loads of a row issued before the first add (blocks of 16, 8, 4, 2, 1
-//     unpredicated ld.global.nc), packed FADD2 / FFMA2 accumulation.
-//   * Long rows (deg > 64): <= 64-edge slices, fan-in-16 ticket tree, deterministic (as v8).
+//     segment)): the degree-sorted interleave balances itself, no queue atomics.  The CTA's work
+//     descriptor comes by value through the kernel parameters, so everything derived from it lives in
+//     uniform registers.
+//   * Gather: all loads of a (remainder) block are issued before the first add; full blocks of 8
+//     slots, then one straight-line case per remainder length; packed FADD2 / FFMA2 accumulation.
+//     The task's own dense rows (E^l row, layer-sum row / G and g rows) are loaded with its gathers.
+//   * Long rows (deg > 64): <= 64-edge slices, fan-in-16 ticket tree, deterministic (as v8), run per
+//     lane group.
 #pragma once
 
 namespace sagnn {
 
-#ifndef SAGNN_PKT_BANKS
-#define SAGNN_PKT_BANKS 1       // tasks in flight per warp: 1 = one at a time (1024 threads, default); 2 = software-pipelined (512 threads x 128 registers: measured 0.78 vs 0.50 ms, half the warps cost more than the overlap gains)
-#endif
-#ifndef SAGNN_PKT_THREADS
-#define SAGNN_PKT_THREADS (SAGNN_PKT_BANKS == 2 ? 512 : 1024)
-#endif
-#ifndef SAGNN_PKT_SLOTS
-#define SAGNN_PKT_SLOTS 3       // packets resident / in flight per warp
-#endif
-constexpr int kPktThreads = SAGNN_PKT_THREADS;
-constexpr int kPktWarps = kPktThreads / 32;
 constexpr uint32_t kPktNoWork = 0x40000000u;   // record meta bit 30: padding record (end of the segment)
 
-template <int VPL, bool WEIGHTED>
+template <int D_, bool WEIGHTED>
 struct PktGeo {
-  static constexpr int D = 32 * VPL;
+  static constexpr int D = D_;
   static constexpr int ROWB = D * 4;
-  static constexpr int CW = VPL < 4 ? VPL : 4;        // floats per lane per chunk (one load instruction)
-  static constexpr int NV = VPL / CW;                 // chunks per lane (2 at d=256)
-  static constexpr int CHB = 32 * CW * 4;             // bytes one chunk spans across the warp
-  static constexpr int MPR = D / 4;                   // mask bytes per row
-  // half of the gather super-block (2*HB-1 rows in flight per lane below a full block, 2*HB in one)
-#ifdef SAGNN_PKT_HB
-  static constexpr int HB = SAGNN_PKT_HB;
+  static constexpr int LPT = D >= 128 ? 32 : D / 4;   // lanes per task: one float4 per lane and chunk
+  static constexpr int G = 32 / LPT;                  // tasks a warp runs in lock step
+  static constexpr int NV = D / (LPT * 4);            // float4 chunks per lane (2 at d=256)
+  static constexpr int VPL = 4 * NV;                  // floats per lane
+  static constexpr int CHB = LPT * 16;                // bytes one chunk spans across the lane group
+  static constexpr int MPR = D / 4;                   // mask bytes per row: byte q = float4 q, bit i = element 4q+i
+#ifdef SAGNN_PKT_GS
+  static constexpr int GS = SAGNN_PKT_GS;
 #else
-  static constexpr int HB = (15 * VPL <= 36) ? 8 : (7 * VPL <= 36) ? 4 : (3 * VPL <= 36) ? 2 : 1;
+  // gather slots per block: 4 at d <= 64 (16 value registers: 8 spills under the 64-register cap and measured
+  // slower), 8 at d = 128 (one task per warp, 32 value registers, no spills: ML-10M shape 5.5 -> see DESIGN), 2 at d = 256
+  static constexpr int GS = NV == 2 ? 2 : (G == 1 ? 8 : 4);
 #endif
   static constexpr int NS = WEIGHTED ? 2 : SAGNN_PKT_SLOTS;    // packets resident / in flight per warp
-  static constexpr int SLOT_BYTES = kPktTasks * 16 + kPktTasks * kChunk * 4 * (WEIGHTED ? 2 : 1);
-  static constexpr size_t SMEM = (size_t)kPktWarps * NS * SLOT_BYTES;
+  // a task's codes: [hot slots, padded to 4][source-row ids, padded to 4] (<= kChunk + 4 words) [+ its weights, same split]
+  static constexpr int SLOT_BYTES = kPktTasks * 16 + kPktTasks * (kChunk + 4) * 4 * (WEIGHTED ? 2 : 1);
+  static constexpr size_t PKT_SMEM = (size_t)kPktWarps * NS * SLOT_BYTES;
+  // the rest of the CTA's shared memory holds staged copies of the source table's most popular rows
+  static constexpr int HOT_CAP = (int)((kSmemBudget - PKT_SMEM) / ROWB);
+  static constexpr size_t SMEM = PKT_SMEM + (size_t)HOT_CAP * ROWB;
+  static_assert(kPktTasks % G == 0, "a packet holds whole lock-step groups");
 };
 
 __device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, unsigned bytes) {
@@ -81,22 +80,27 @@ __device__ __forceinline__ void tma_bulk_g2s_u32(uint32_t dst_smem, const void* 
                : "memory");
 }
 
-template <int VPL, int MODE, bool WEIGHTED, bool RTD>
+template <int D_, int MODE, bool WEIGHTED, bool RTD>
 __global__ void __launch_bounds__(kPktThreads, 1)
 spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
-  using G = PktGeo<VPL, WEIGHTED>;
-  constexpr int D = G::D, ROWB = G::ROWB, CW = G::CW, NV = G::NV, CHB = G::CHB, MPR = G::MPR, HB = G::HB;
-  constexpr int NS = G::NS;
+  using Geo = PktGeo<D_, WEIGHTED>;
+  constexpr int D = Geo::D, ROWB = Geo::ROWB, LPT = Geo::LPT, G = Geo::G, NV = Geo::NV, VPL = Geo::VPL, CHB = Geo::CHB,
+                MPR = Geo::MPR, GS = Geo::GS, NS = Geo::NS;
   constexpr bool BWD = MODE == MODE_BWD;
   constexpr bool OWN = MODE != MODE_MSG;              // the task has dense rows of its own
-  constexpr int BANKS = SAGNN_PKT_BANKS;
+  constexpr bool HOT = SAGNN_PKT_HOT != 0;            // hot-row staging compiled in (experiment)
   constexpr unsigned FULL = 0xffffffffu;
 
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];      // [packet rings of all warps | staged hot rows]
   __shared__ __align__(8) uint64_t bars[kPktWarps * NS];
+  __shared__ __align__(8) uint64_t hot_bar;
   const int lane = threadIdx.x & 31;
   // shuffled: tells the compiler the value is warp-uniform (uniform registers for everything derived from it)
   const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
+  const int grp = lane / LPT;                          // my task inside the lock-step group
+  const int piece = lane % LPT;                        // my float4 inside a row chunk
+  const unsigned gmask = G == 1 ? FULL : (((1u << LPT) - 1u) << (grp * LPT));   // the lanes of my lane group
+  const int leader = grp * LPT;
   const float leaky = p.leaky;
   // the CTA's work descriptor comes by value through the kernel parameters: warp-uniform by construction
   const PktCta cd = p.ctad[blockIdx.x];
@@ -132,38 +136,58 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
   const uint32_t a_stride = (uint32_t)ROWB * (a_rtd ? p.T : 1);
   const uint32_t b_stride = (uint32_t)ROWB * (b_rtd ? p.T : 1);
   const uint32_t o2_stride = (uint32_t)ROWB * (o2_rtd ? p.T : 1);
-  // which optional tensors this launch has: one pinned register instead of pointer tests per task
+  // which optional tensors this launch has (uniform)
   enum { F_B = 1, F_O1 = 2, F_O2 = 4, F_MK = 8, F_ADDNEXT = 16, F_PM = 32, F_PEER = 64 };
-  uint32_t flags = (b_base ? F_B : 0) | (o1_base ? F_O1 : 0) | (o2_base ? F_O2 : 0) | (mk_base ? F_MK : 0) |
-                   (p.out_add_next ? F_ADDNEXT : 0) | (pm_base ? F_PM : 0) |
-                   ((RTD && MODE == MODE_FWD && p.peer_n > 0) ? F_PEER : 0);
+  const uint32_t flags = (b_base ? F_B : 0) | (o1_base ? F_O1 : 0) | (o2_base ? F_O2 : 0) | (mk_base ? F_MK : 0) |
+                         (p.out_add_next ? F_ADDNEXT : 0) | (pm_base ? F_PM : 0) |
+                         ((RTD && MODE == MODE_FWD && p.peer_n > 0) ? F_PEER : 0);
 
-  // my bytes inside a chunk; my sign bits inside a row's mask bytes: byte (chunk v) = v*32 + mbyte
-  uint32_t lane_off = (uint32_t)lane * (CW * 4);
+  uint32_t lane_off = (uint32_t)piece * 16;            // my bytes inside a chunk
   pin32(lane_off);
-  const int mbyte = CW == 4 ? lane : (CW == 2 ? lane >> 1 : lane >> 2);
-  const int mshift = CW == 4 ? 0 : (CW == 2 ? (lane & 1) * 2 : (lane & 3));
   auto mask_bits = [&](const uint8_t* base, uint32_t c) -> uint32_t {   // sign bits of row c that belong to my elements
     uint32_t bits = 0;
 #pragma unroll
-    for (int v = 0; v < NV; ++v)
-      bits |= (((uint32_t)__ldg(base + (uint64_t)c * MPR + v * 32 + mbyte)) >> mshift) << (v * 4);
+    for (int v = 0; v < NV; ++v) bits |= ((uint32_t)__ldg(base + (uint64_t)c * MPR + v * LPT + piece)) << (v * 4);
     return bits;
   };
-
   const char* src_lane = src + lane_off;
-  uint32_t src_stride_r = src_stride;
   pin64(src_lane);
 
-  // ---- my packets: q0, q0 + stride, ... of the segment's packet list -------------------------
+  // ---- hot rows: the plan's first `hot_rows` slots of my source table, staged by TMA bulk copies -------
+  // Edge codes are hot-first inside every task: the first nh codes are slot numbers, the rest row ids.  Slots
+  // that do not fit at this latdim (plan built for a smaller d) are read through their row ids.
+  const int n_hot = !HOT ? 0 : (p.hot_rows < Geo::HOT_CAP ? p.hot_rows : Geo::HOT_CAP);   // slots staged in shared memory
+  const int32_t* hot_ids = p.hot_ids + (size_t)(seg ^ 1) * kHotRows;
+  const uint32_t hot0 = smem_u32(smem_raw) + (uint32_t)Geo::PKT_SMEM;
+  if (HOT && n_hot > 0) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&hot_bar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx_u32(smem_u32(&hot_bar), (unsigned)n_hot * ROWB);
+    }
+    __syncthreads();
+    for (int sl = threadIdx.x; sl < n_hot; sl += kPktThreads)
+      tma_bulk_g2s_u32(hot0 + (uint32_t)sl * ROWB, src + (uint64_t)(uint32_t)__ldg(hot_ids + sl) * src_stride, ROWB,
+                       smem_u32(&hot_bar));
+  }
+  const uint32_t hot_lane = hot0 + lane_off;
+  const bool all_fit = p.hot_rows <= Geo::HOT_CAP;     // (uniform) every hot slot of the plan is staged
+
+  // ---- my packets -----------------------------------------------------------------------------
+  // The first NS packets of every warp are dealt statically (packet q0 + s*stride of the segment's
+  // list), the rest come from the segment's queue head, one atomic per packet, fetched two refills
+  // ahead (queue head -> directory entry -> bulk copy are three dependent round trips, each hidden
+  // behind a packet's worth of work).  SMs do not run at the same speed (GPC size, die of the L2
+  // slice): with a purely static deal the slowest CTA of a segment finished 15-20 % after the mean.
   const unsigned n_pk = cd.n_pk;
   const uint32_t* dir = p.pkt_dir + cd.pkt_begin;     // packet offsets, 16-byte units into the stream
   const unsigned q0 = cd.q0 + (unsigned)warp;
   const unsigned stride = cd.stride;
-  const unsigned n_my = q0 < n_pk ? (n_pk - q0 + stride - 1) / stride : 0u;
+  const unsigned q_dyn0 = (unsigned)NS * stride;       // packets below this index are dealt statically
+  unsigned* qhead = p.ctrs + seg;
 
-  uint32_t slot0 = smem_u32(smem_raw) + (uint32_t)warp * (NS * G::SLOT_BYTES);
-  uint32_t bar0 = smem_u32(&bars[warp * NS]);
+  const uint32_t slot0 = smem_u32(smem_raw) + (uint32_t)warp * (NS * Geo::SLOT_BYTES);
+  const uint32_t bar0 = smem_u32(&bars[warp * NS]);
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < NS; ++s)
@@ -172,153 +196,209 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
   }
   __syncwarp();
 
-  auto load_dir = [&](unsigned j) -> uint2 {          // {first, end} 16-byte unit of my j-th packet
-    const uint32_t* d = dir + (q0 + j * stride);
-    return make_uint2(__ldg(d), __ldg(d + 1));
+  auto load_dir = [&](unsigned q) -> uint2 {          // {first, end} 16-byte unit of packet q (0,0 past the end)
+    if (q >= n_pk) return make_uint2(0u, 0u);
+    const uint32_t* dp = dir + q;
+    return make_uint2(__ldg(dp), __ldg(dp + 1));
   };
+  // next packet of the segment's queue: the atomic is issued now, its result (lane 0's register) is only
+  // broadcast when the packet index is needed, one refill later -- nobody waits for the round trip
+  auto grab_issue = [&]() -> unsigned { return lane == 0 ? atomicAdd(qhead, 1u) : 0u; };
+  auto grab_value = [&](unsigned raw) -> unsigned { return __shfl_sync(FULL, raw, 0) + q_dyn0; };
   auto issue_pkt = [&](unsigned slot, uint2 dv) {      // one lane, one bulk copy: records + codes (+ weights)
     if (lane == 0) {
       const unsigned bytes = (dv.y - dv.x) * 16u;
       mbar_expect_tx_u32(bar0 + 8 * slot, bytes);
-      tma_bulk_g2s_u32(slot0 + slot * G::SLOT_BYTES, reinterpret_cast<const char*>(p.pkt_stream) + (uint64_t)dv.x * 16u,
+      tma_bulk_g2s_u32(slot0 + slot * Geo::SLOT_BYTES, reinterpret_cast<const char*>(p.pkt_stream) + (uint64_t)dv.x * 16u,
                        bytes, bar0 + 8 * slot);
     }
   };
-
-  if (n_my > 0) {
+  unsigned n_issued = 0;                               // packets of mine brought in (or on their way)
 #pragma unroll
-    for (int s = 0; s < NS; ++s)
-      if ((unsigned)s < n_my) issue_pkt(s, load_dir(s));
+  for (int s = 0; s < NS; ++s) {
+    const uint2 dv = load_dir(q0 + (unsigned)s * stride);
+    if (dv.y != 0u) { issue_pkt(s, dv); ++n_issued; }
   }
+  // two-deep look-ahead of the dynamic part: dir_next belongs to the packet of the next refill, q_next to the one after
   uint2 dir_next = make_uint2(0u, 0u);
-  if (n_my > (unsigned)NS) dir_next = load_dir(NS);
+  unsigned q_raw = 0;                                  // lane 0: ticket of the packet after dir_next's
+  bool more = n_issued == (unsigned)NS;                // the queue may still have packets for me
+  if (more) {
+    const unsigned r0 = grab_issue();
+    q_raw = grab_issue();
+    dir_next = load_dir(grab_value(r0));
+  }
 
-  // own rows of a task (row r): a = E^l / G row, b = layer-sum / running-gradient row, pm = sign bits one level down
-  struct Own { float a[VPL]; float b[VPL]; uint32_t pbits; };
-  auto load_own = [&](Own& o, uint32_t row) {
-    if (!OWN) return;
-    const char* pa = a_base + (uint64_t)row * a_stride + lane_off;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) ldg_chunk<CW>(o.a + v * CW, pa + v * CHB);
-    if (flags & F_B) {
-      const char* pb = b_base + (uint64_t)row * (RTD ? b_stride : a_stride) + lane_off;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) ldg_chunk<CW>(o.b + v * CW, pb + v * CHB);
-    }
-    if (BWD && (flags & F_PM)) o.pbits = mask_bits(pm_base, row);
-  };
-
-  // ---- task stream ----------------------------------------------------------------------------
-  // A bank = the registers of one task in flight: gathered rows, own rows, record fields.  With two
-  // banks (the default) the gathers of task t+1 are issued before task t is reduced, so a warp always
-  // has a task's worth of rows in flight while it adds, runs the epilogue and stores.
-  struct Bank {
-    float val[2 * HB][VPL];
-    float acc[VPL];
-    Own own;
-    uint32_t row, aux, cb;     // row id, slice id, shared-memory address of the task's edge codes
-    int meta;                  // n | long-row-slice flag (bit 31)
-    int jl;                    // first edge of the blocks still in flight
-    unsigned refill;           // ring slot this task frees when it is done (NS: none)
-  };
-  unsigned j = 0;                                      // packet the cursor is in
+  bool hot_ready = n_hot == 0;                         // the staged rows have landed (waited for on first use)
+  unsigned j = 0;                                      // packet the cursor is in (count of mine)
   int t = 0;                                           // next record inside it
   unsigned slot = 0, parity = 0;                       // ring slot of packet j and its mbarrier phase
-  unsigned j_issue = NS;                               // next packet to bring in
 
-  auto gather = [&](Bank& b, auto kc, int jj, int s0) {   // K loads of the codes at position jj, all unpredicated
-    constexpr int K = decltype(kc)::value;
-    int c[K];
-    if constexpr (K >= 4) {
-#pragma unroll
-      for (int g = 0; g < K / 4; ++g) {
-        const int4 c4 = lds_i4(b.cb + (uint32_t)(jj + 4 * g) * 4);
-        c[4 * g] = c4.x; c[4 * g + 1] = c4.y; c[4 * g + 2] = c4.z; c[4 * g + 3] = c4.w;
-      }
-    } else if constexpr (K == 2) {
-      const int2 c2 = lds_i2(b.cb + (uint32_t)jj * 4);
-      c[0] = c2.x; c[1] = c2.y;
-    } else {
-      c[0] = lds_i1(b.cb + (uint32_t)jj * 4);
+  while (j < n_issued) {
+    if (t == 0) {
+      mbar_wait_u32(bar0 + 8 * slot, parity);                                  // first touch of packet j
     }
-#pragma unroll
-    for (int u = 0; u < K; ++u)
-#pragma unroll
-      for (int v = 0; v < NV; ++v)
-        ldg_chunk<CW>(b.val[s0 + u] + v * CW, src_lane + (uint64_t)(uint32_t)c[u] * src_stride_r + v * CHB);
-  };
-  auto reduce = [&](Bank& b, auto kc, int jj, int s0) {
-    constexpr int K = decltype(kc)::value;
-    const uint32_t wb = b.cb + (uint32_t)(((b.meta & 0x7f) + 3) & ~3) * 4;   // the task's weights follow its codes
-#pragma unroll
-    for (int u = 0; u < K; ++u) {
-      float w = 1.f;
-      if constexpr (WEIGHTED) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(wb + (uint32_t)(jj + u) * 4) : "memory");
-      rpw_accumulate<VPL, WEIGHTED, false>(b.acc, b.val[s0 + u], w, 0u, leaky);
-    }
-  };
-  constexpr int S8 = 0, S4 = HB >= 8 ? 8 : 0, S2 = S4 + (HB >= 4 ? 4 : 0), S1 = S2 + (HB >= 2 ? 2 : 0);
-
-  // next record of my stream -> bank; false at the end of the stream
-  auto fetch = [&](Bank& b) -> bool {
-    if (j >= n_my) return false;
-    if (t == 0) mbar_wait_u32(bar0 + 8 * slot, parity);              // first touch of packet j
-    const uint32_t sbase = slot0 + slot * G::SLOT_BYTES;
-    const int4 rec = lds_i4(sbase + (uint32_t)t * 16);               // {row, meta, slice id, code offset}
-    if (rec.y & (int)kPktNoWork) { j = n_my; return false; }         // padding: the segment's last packet ends here
-    b.row = (uint32_t)rec.x; b.meta = rec.y; b.aux = (uint32_t)rec.z; b.cb = sbase + (uint32_t)rec.w;
-    b.refill = NS;
-    if (++t == kPktTasks) {
-      b.refill = slot;
+    const uint32_t sbase = slot0 + slot * Geo::SLOT_BYTES;
+    const int4 rec = lds_i4(sbase + (uint32_t)(t + grp) * 16);                // my task: {row, meta, slice id, code offset}
+    if (__shfl_sync(FULL, rec.y, 0) & (int)kPktNoWork) break;                 // padding: the segment's last packet ends here
+    const bool valid = !(rec.y & (int)kPktNoWork);
+    const uint32_t row = (uint32_t)rec.x;
+    const int n = valid ? (rec.y & 0x7f) : 0;
+    const bool multi = valid && rec.y < 0;                                     // bit 31: slice of a long row
+    const int nh = (HOT && valid) ? ((rec.y >> 8) & 0x7f) : 0;                 // my task's leading codes that are hot slots
+    const int nc = n - nh;                                                     // ... the rest are source-row ids
+    const uint32_t hb = sbase + (uint32_t)rec.w;                               // my task's hot slots ...
+    const uint32_t cb = hb + (uint32_t)((nh + 3) & ~3) * 4;                    // ... its source-row ids ...
+    const uint32_t hwb = cb + (uint32_t)((nc + 3) & ~3) * 4;                   // ... and the weights, same split
+    const uint32_t wb = hwb + (uint32_t)((nh + 3) & ~3) * 4;
+    // the lock-step group follows its longest task: cold edges (global gathers) and hot edges (shared memory)
+    int nmax = n - nh, hmax = nh;
+    if constexpr (G >= 2) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, LPT));
+    if constexpr (G >= 4) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, 2 * LPT));
+    if constexpr (HOT && G >= 2) hmax = max(hmax, __shfl_xor_sync(FULL, hmax, LPT));
+    if constexpr (HOT && G >= 4) hmax = max(hmax, __shfl_xor_sync(FULL, hmax, 2 * LPT));
+    unsigned refill = NS;                                                      // ring slot these tasks free (NS: none)
+    t += G;
+    if (t == kPktTasks) {
+      refill = slot;
       t = 0;
       ++j;
       slot = slot + 1 == (unsigned)NS ? 0u : slot + 1;
       parity ^= (slot == 0u);
     }
-    return true;
-  };
-  // issue everything the task loads: full blocks are gathered and added on the spot, the last (partial)
-  // block and the own rows stay in flight
-  auto start = [&](Bank& b) {
-    const int n = b.meta & 0x7f;
+
+    float acc[VPL];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) b.acc[i] = 0.f;
+    for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
+    float val[GS][VPL];
+
+    // K slots starting at edge jj: loads of the lanes whose task is that long (all lanes when G == 1)
+    auto gather = [&](auto kc, int jj) {
+      constexpr int K = decltype(kc)::value;
+      int c[K];
+      if constexpr (K >= 4) {
+#pragma unroll
+        for (int g = 0; g < K / 4; ++g) {
+          const int4 c4 = lds_i4(cb + (uint32_t)(jj + 4 * g) * 4);
+          c[4 * g] = c4.x; c[4 * g + 1] = c4.y; c[4 * g + 2] = c4.z; c[4 * g + 3] = c4.w;
+        }
+        if constexpr (K % 4 >= 2) { const int2 c2 = lds_i2(cb + (uint32_t)(jj + (K & ~3)) * 4); c[K & ~3] = c2.x; c[(K & ~3) + 1] = c2.y; }
+        if constexpr (K % 2 == 1) c[K - 1] = lds_i1(cb + (uint32_t)(jj + K - 1) * 4);
+      } else if constexpr (K == 3) {
+        const int2 c2 = lds_i2(cb + (uint32_t)jj * 4);
+        c[0] = c2.x; c[1] = c2.y; c[2] = lds_i1(cb + (uint32_t)(jj + 2) * 4);
+      } else if constexpr (K == 2) {
+        const int2 c2 = lds_i2(cb + (uint32_t)jj * 4);
+        c[0] = c2.x; c[1] = c2.y;
+      } else {
+        c[0] = lds_i1(cb + (uint32_t)jj * 4);
+      }
+      const int left = nc - jj;                         // my task's cold edges from jj on (<= 0: none)
+#pragma unroll
+      for (int u = 0; u < K; ++u) {
+        if (G == 1 || u < left) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+            ldg_chunk<4>(val[u] + v * 4, src_lane + (uint64_t)(uint32_t)c[u] * src_stride + v * CHB);
+        }
+      }
+    };
+    auto reduce = [&](auto kc, int jj) {
+      constexpr int K = decltype(kc)::value;
+      const int left = nc - jj;
+#pragma unroll
+      for (int u = 0; u < K; ++u) {
+        if (G == 1 || u < left) {
+          float w = 1.f;
+          if constexpr (WEIGHTED) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(wb + (uint32_t)(jj + u) * 4) : "memory");
+          rpw_accumulate<VPL, WEIGHTED, false>(acc, val[u], w, 0u, leaky);
+        }
+      }
+    };
+
+    // ---- gather-reduce: full blocks on the spot, the remainder stays in flight under the own-row loads ----
     int jl = 0;
-    for (; jl + 2 * HB <= n; jl += 2 * HB) {           // long tasks: 2*HB rows in flight per lane
-      gather(b, std::integral_constant<int, 2 * HB>(), jl, 0);
-      reduce(b, std::integral_constant<int, 2 * HB>(), jl, 0);
+    for (; jl + GS <= nmax; jl += GS) {
+      gather(std::integral_constant<int, GS>(), jl);
+      reduce(std::integral_constant<int, GS>(), jl);
     }
-    b.jl = jl;
-    const int rem = n - jl;                            // < 2*HB: one block per set bit, all issued before the first add
-    int jj = jl;
-    if constexpr (HB >= 8) { if (rem & 8) { gather(b, std::integral_constant<int, 8>(), jj, S8); jj += 8; } }
-    if constexpr (HB >= 4) { if (rem & 4) { gather(b, std::integral_constant<int, 4>(), jj, S4); jj += 4; } }
-    if constexpr (HB >= 2) { if (rem & 2) { gather(b, std::integral_constant<int, 2>(), jj, S2); jj += 2; } }
-    if (rem & 1) gather(b, std::integral_constant<int, 1>(), jj, S1);
-    if (b.meta >= 0) load_own(b.own, b.row);           // slices of long rows: only the finisher needs the own rows
-  };
-  auto finish = [&](Bank& b) {
-    {
-      const int rem = (b.meta & 0x7f) - b.jl;
-      int jj = b.jl;
-      if constexpr (HB >= 8) { if (rem & 8) { reduce(b, std::integral_constant<int, 8>(), jj, S8); jj += 8; } }
-      if constexpr (HB >= 4) { if (rem & 4) { reduce(b, std::integral_constant<int, 4>(), jj, S4); jj += 4; } }
-      if constexpr (HB >= 2) { if (rem & 2) { reduce(b, std::integral_constant<int, 2>(), jj, S2); jj += 2; } }
-      if (rem & 1) reduce(b, std::integral_constant<int, 1>(), jj, S1);
+    const int rem = nmax - jl;                          // < GS, warp-uniform: one straight-line case per length
+    switch (rem) {
+      case 1: gather(std::integral_constant<int, 1>(), jl); break;
+      case 2: gather(std::integral_constant<int, 2>(), jl); break;
+      case 3: gather(std::integral_constant<int, 3>(), jl); break;
+      case 4: if constexpr (GS > 4) gather(std::integral_constant<int, 4>(), jl); break;
+      case 5: if constexpr (GS > 4) gather(std::integral_constant<int, 5>(), jl); break;
+      case 6: if constexpr (GS > 4) gather(std::integral_constant<int, 6>(), jl); break;
+      case 7: if constexpr (GS > 4) gather(std::integral_constant<int, 7>(), jl); break;
+      default: break;
     }
-    // the last task of a packet: its codes and weights (and those of the tasks before it) are consumed
-    if (b.refill < (unsigned)NS) {
-      __syncwarp();
-      if (j_issue < n_my) {
-        issue_pkt(b.refill, dir_next);
-        ++j_issue;
-        if (j_issue < n_my) dir_next = load_dir(j_issue);
+    // own rows: a = E^l / G row, b = layer-sum / running-gradient row, pbits = sign bits one level down
+    float own_a[VPL], own_b[VPL];                       // always loaded before the epilogue reads them
+    uint32_t pbits = 0;
+    auto load_own = [&]() {
+      if (!OWN) return;
+      const char* pa = a_base + (uint64_t)row * a_stride + lane_off;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) ldg_chunk<4>(own_a + v * 4, pa + v * CHB);
+      if (flags & F_B) {
+        const char* pb = b_base + (uint64_t)row * (RTD ? b_stride : a_stride) + lane_off;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) ldg_chunk<4>(own_b + v * 4, pb + v * CHB);
+      }
+      if (BWD && (flags & F_PM)) pbits = mask_bits(pm_base, row);
+    };
+    if (valid && !multi) load_own();                    // slices of long rows: only the finisher needs the own rows
+
+    // ---- hot edges: staged rows out of shared memory, added while the cold remainder and the own rows fly ----
+    if (HOT && hmax > 0) {
+      if (!hot_ready) { mbar_wait_u32(smem_u32(&hot_bar), 0); hot_ready = true; }
+      for (int hj = 0; hj < hmax; hj += 4) {
+        const int4 hc = lds_i4(hb + (uint32_t)hj * 4);
+        const int sl[4] = {hc.x, hc.y, hc.z, hc.w};
+        const int left = nh - hj;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (u < left) {
+            float hv[VPL];
+            if (all_fit || sl[u] < n_hot) {
+#pragma unroll
+              for (int v = 0; v < NV; ++v) lds_chunk<4>(hv + v * 4, hot_lane + (uint32_t)sl[u] * ROWB + v * CHB);
+            } else {                                    // slot beyond what fits at this latdim: through its row id
+              const uint32_t r = (uint32_t)__ldg(hot_ids + sl[u]);
+#pragma unroll
+              for (int v = 0; v < NV; ++v) ldg_chunk<4>(hv + v * 4, src_lane + (uint64_t)r * src_stride + v * CHB);
+            }
+            float w = 1.f;
+            if constexpr (WEIGHTED) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(hwb + (uint32_t)(hj + u) * 4) : "memory");
+            rpw_accumulate<VPL, WEIGHTED, false>(acc, hv, w, 0u, leaky);
+          }
+        }
       }
     }
-    const uint32_t row = b.row;
-    const bool multi = b.meta < 0;                     // bit 31: slice of a long row
-    float (&acc)[VPL] = b.acc;
-    Own& own = b.own;
+    switch (rem) {
+      case 1: reduce(std::integral_constant<int, 1>(), jl); break;
+      case 2: reduce(std::integral_constant<int, 2>(), jl); break;
+      case 3: reduce(std::integral_constant<int, 3>(), jl); break;
+      case 4: if constexpr (GS > 4) reduce(std::integral_constant<int, 4>(), jl); break;
+      case 5: if constexpr (GS > 4) reduce(std::integral_constant<int, 5>(), jl); break;
+      case 6: if constexpr (GS > 4) reduce(std::integral_constant<int, 6>(), jl); break;
+      case 7: if constexpr (GS > 4) reduce(std::integral_constant<int, 7>(), jl); break;
+      default: break;
+    }
+
+    // the last tasks of a packet: its codes and weights are consumed, bring the next packet into its slot
+    if (refill < (unsigned)NS) {
+      __syncwarp();
+      if (dir_next.y != 0u) {                            // the queue had a packet left for me
+        issue_pkt(refill, dir_next);
+        ++n_issued;
+        const unsigned q_next = more ? grab_value(q_raw) : n_pk;
+        more = q_next < n_pk;
+        dir_next = load_dir(q_next);
+        if (more) q_raw = grab_issue();
+      }
+    }
 
     // ---- long rows: publish the slice sum; reduce through a fan-in-16 ticket tree -------------
     // The last arriver of every group of 16 slices (then of 16 groups, ...) sums them in slice
@@ -326,10 +406,10 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
     // L1-bypassing GPU-scope loads that depend on the ticket value.  (An acq_rel ticket or an acquire
     // fence in the last arriver would be the formally complete pattern, but ptxas implements GPU-scope
     // acquire as CCTL.IVALL: one invalidation of the SM's whole L1 per slice, which the gathers of
-    // high-degree graphs pay for.)
-    bool whole_row = true;
+    // high-degree graphs pay for.)  Lane groups run this independently (group-masked shuffles).
+    bool whole_row = valid;
     if (multi) {
-      const uint32_t aux = b.aux;                      // global slice id
+      const uint32_t aux = (uint32_t)rec.z;            // global slice id
       const uint32_t lr = __ldg(p.chunk_lr + aux);
       const int64_t cbase = __ldg(p.chunk_base + lr);
       const int nch = (int)(__ldg(p.chunk_base + lr + 1) - cbase);
@@ -344,16 +424,16 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
         members = members > 16 ? 16 : members;
         char* mine = reinterpret_cast<char*>(p.partials + (cbase + pos) * D) + lane_off;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) st_chunk<CW>(mine + v * CHB, acc + v * CW);
-        __syncwarp();
+        for (int v = 0; v < NV; ++v) st_chunk<4>(mine + v * CHB, acc + v * 4);
+        __syncwarp(gmask);
         unsigned* my_tk = tk + (cbase + gs);           // one ticket per group, named by its first slot
         unsigned old = 0;
-        if (lane == 0) old = ticket_release_add(my_tk);
-        old = __shfl_sync(FULL, old, 0);
+        if (lane == leader) old = ticket_release_add(my_tk);
+        old = __shfl_sync(gmask, old, leader);
         if (old != (unsigned)(members - 1)) {
           active = false;                              // someone else finishes this group
         } else {
-          if (lane == 0) *my_tk = 0u;                  // ready for the next launch
+          if (lane == leader) *my_tk = 0u;             // ready for the next launch
 #pragma unroll
           for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
           const char* part = reinterpret_cast<const char*>(p.partials + (cbase + gs) * D) + lane_off;
@@ -364,10 +444,10 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
 #pragma unroll
               for (int v = 0; v < NV; ++v) {
                 if (c0 + u < members) {
-                  ld_strong_chunk<CW>(pv[u] + v * CW, part + (int64_t)(c0 + u) * lstride * ROWB + v * CHB);
+                  ld_strong_chunk<4>(pv[u] + v * 4, part + (int64_t)(c0 + u) * lstride * ROWB + v * CHB);
                 } else {
 #pragma unroll
-                  for (int i = 0; i < CW; ++i) pv[u][v * CW + i] = 0.f;
+                  for (int i = 0; i < 4; ++i) pv[u][v * 4 + i] = 0.f;
                 }
               }
 #pragma unroll
@@ -382,8 +462,8 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
         }
         tk += p.n_chunks;
       }
-      __syncwarp();
-      if (whole_row) load_own(own, row);               // slices do not prefetch: only the finisher needs the own rows
+      __syncwarp(gmask);
+      if (whole_row) load_own();
     }
 
     // ---- fused epilogue ------------------------------------------------------------------------
@@ -393,15 +473,15 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
         // n = G + g + A (sigma' . g_other)      (SURVEY A.2); at the top level g == G
         float o[VPL];
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) o[i] = own.a[i] + ((flags & F_B) ? own.b[i] : own.a[i]) + acc[i];
+        for (int i = 0; i < VPL; ++i) o[i] = own_a[i] + ((flags & F_B) ? own_b[i] : own_a[i]) + acc[i];
 #pragma unroll
-        for (int v = 0; v < NV; ++v) st_chunk<CW>(o1_base + off + v * CHB, o + v * CW);
+        for (int v = 0; v < NV; ++v) st_chunk<4>(o1_base + off + v * CHB, o + v * 4);
         if (flags & F_O2) {                                        // the source of the next level down: sigma'(Z^{l-1}) (.) n
           float om[VPL];
 #pragma unroll
-          for (int i = 0; i < VPL; ++i) om[i] = ((own.pbits >> i) & 1u) ? o[i] : leaky * o[i];
+          for (int i = 0; i < VPL; ++i) om[i] = ((pbits >> i) & 1u) ? o[i] : leaky * o[i];
 #pragma unroll
-          for (int v = 0; v < NV; ++v) st_chunk<CW>(o2_base + off + v * CHB, om + v * CW);
+          for (int v = 0; v < NV; ++v) st_chunk<4>(o2_base + off + v * CHB, om + v * 4);
         }
       } else {
         // LeakyReLU = max(leaky*z, z)  (Utils/NNLayers.py:135-136)
@@ -416,20 +496,20 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
         }
         if (MODE == MODE_MSG) {
 #pragma unroll
-          for (int v = 0; v < NV; ++v) st_chunk<CW>(o1_base + off + v * CHB, act + v * CW);
+          for (int v = 0; v < NV; ++v) st_chunk<4>(o1_base + off + v * CHB, act + v * 4);
         } else {
           float nxt_e[VPL];                                         // E^{l+1} = E^l + lrelu(Z^l)
 #pragma unroll
-          for (int i = 0; i < VPL; ++i) nxt_e[i] = own.a[i] + act[i];
+          for (int i = 0; i < VPL; ++i) nxt_e[i] = own_a[i] + act[i];
           if (flags & F_O1) {
 #pragma unroll
-            for (int v = 0; v < NV; ++v) st_chunk<CW>(o1_base + off + v * CHB, nxt_e + v * CW);
+            for (int v = 0; v < NV; ++v) st_chunk<4>(o1_base + off + v * CHB, nxt_e + v * 4);
           }
           if (flags & F_O2) {
             float o[VPL];
 #pragma unroll
             for (int i = 0; i < VPL; ++i) {
-              o[i] = (flags & F_B) ? own.b[i] + own.a[i] : own.a[i];
+              o[i] = (flags & F_B) ? own_b[i] + own_a[i] : own_a[i];
               if (flags & F_ADDNEXT) o[i] += nxt_e[i];
             }
             char* dst = o2_base + (uint64_t)row * o2_stride + lane_off;
@@ -446,47 +526,18 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
               }
             }
 #pragma unroll
-            for (int v = 0; v < NV; ++v) stcs_chunk<CW>(dst + v * CHB, o + v * CW);
+            for (int v = 0; v < NV; ++v) stcs_chunk<4>(dst + v * CHB, o + v * 4);
           }
-          if (flags & F_MK) {
+          if (flags & F_MK) {                                       // one mask byte per float4: no shuffles
             uint8_t* mrow = mk_base + (uint64_t)row * MPR;
-            if constexpr (CW == 4) {
 #pragma unroll
-              for (int v = 0; v < NV; ++v) mrow[v * 32 + lane] = (uint8_t)((bits >> (v * 4)) & 0xfu);
-            } else if constexpr (CW == 2) {
-              const uint32_t hi = __shfl_down_sync(FULL, bits, 1);
-              if (!(lane & 1)) mrow[lane >> 1] = (uint8_t)(bits | (hi << 2));
-            } else {
-              const uint32_t b1_ = __shfl_down_sync(FULL, bits, 1), b2_ = __shfl_down_sync(FULL, bits, 2),
-                             b3_ = __shfl_down_sync(FULL, bits, 3);
-              if (!(lane & 3)) mrow[lane >> 2] = (uint8_t)(bits | (b1_ << 1) | (b2_ << 2) | (b3_ << 3));
-            }
+            for (int v = 0; v < NV; ++v) mrow[v * LPT + piece] = (uint8_t)((bits >> (v * 4)) & 0xfu);
           }
         }
       }
     }
-  };
-
-  if constexpr (BANKS == 1) {
-    Bank A;
-    while (fetch(A)) {
-      start(A);
-      finish(A);
-    }
-  } else {
-    Bank A, B;
-    bool more = fetch(A);
-    if (more) start(A);
-    while (more) {
-      const bool more_b = fetch(B);
-      if (more_b) start(B);
-      finish(A);
-      if (!more_b) break;
-      more = fetch(A);
-      if (more) start(A);
-      finish(B);
-    }
   }
+  if (HOT && !hot_ready) mbar_wait_u32(smem_u32(&hot_bar), 0);   // never leave while the staging copies are still landing
   if (p.trace) {
     __syncthreads();
     if (threadIdx.x == 0) p.trace[blockIdx.x * 4 + 3] = globaltimer_ns();

@@ -113,8 +113,15 @@ def exchange_rows_rtd(out_full, recv=None, group=None):
 
 
 class ShardedPropagation:
-    """Interval-sharded drop-in for ``propagate``: every rank passes the FULL parameter tables
-    (or just its own slices via ``local_only``) and gets the full ``[T,U,d]`` / ``[T,I,d]`` back."""
+    """Interval-sharded drop-in for ``propagate``: every rank passes the FULL parameter tables and gets
+    the full ``[T,U,d]`` / ``[T,I,d]`` back.
+
+    Gradient contract: the backward returns parameter gradients that are non-zero only in the intervals
+    THIS rank owns (the consumer is replicated, so every rank already holds the full upstream and no
+    collective runs in the backward).  With replicated ``uEmbed`` / ``iEmbed`` the caller must
+    SUM-all-reduce those gradients across the group before the optimizer step (intervals are disjoint, so
+    the sum just assembles them; DDP's mean would scale them by 1/world) -- or keep the parameters sharded
+    by interval like the plan.  ``tests/test_dist_cpu.py`` pins this contract."""
 
     def __init__(self, sub_mats, U=None, I=None, n_layers=2, leaky=0.5, group=None, device=None,
                  edge_weight=None):
@@ -274,8 +281,7 @@ class RowShardedPropagation:
     intervals than GPUs (or combine: interval-shard over groups of ranks, row-shard inside a group
     by passing ``group``).  Results are bitwise those of the single-GPU ``propagate``."""
 
-    def __init__(self, sub_mats, U, I, n_layers=2, leaky=0.5, group=None, device=None, latdim=64,
-                 backend_factory=None):
+    def __init__(self, sub_mats, U, I, n_layers=2, leaky=0.5, group=None, device=None, latdim=64):
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -284,17 +290,22 @@ class RowShardedPropagation:
         bu, bi = self.U_pad // self.world, self.I_pad // self.world
         self.row_block = (self.rank * bu, (self.rank + 1) * bu, self.rank * bi, (self.rank + 1) * bi)
         self._backends = {}
-        self._factory = backend_factory      # tests: a CPU stand-in for the C-ABI calls (gloo)
-        self.plan = None
-        if backend_factory is None:
-            from .propagate import build_plan
-            self.plan = build_plan(sub_mats, self.U, self.I, device=device, latdim=latdim,
-                                   row_block=self.row_block, padded_shape=(self.U_pad, self.I_pad))
+        self.plan = self._build_plan(sub_mats, device, latdim)
+
+    # The two hooks below are the only places that touch the CUDA library; there is no CPU path in the product.
+    # (tests/test_dist_cpu.py subclasses this class and overrides them with a dense stand-in to drive the
+    # exchange schedule over gloo.)
+    def _build_plan(self, sub_mats, device, latdim):
+        from .propagate import build_plan
+        return build_plan(sub_mats, self.U, self.I, device=device, latdim=latdim,
+                          row_block=self.row_block, padded_shape=(self.U_pad, self.I_pad))
+
+    def _make_backend(self, d):
+        return _CudaRowBackend(self.plan, self.n_layers, d, self.leaky)
 
     def _backend(self, d):
         if d not in self._backends:
-            self._backends[d] = (self._factory(self, d) if self._factory is not None
-                                 else _CudaRowBackend(self.plan, self.n_layers, d, self.leaky))
+            self._backends[d] = self._make_backend(d)
         return self._backends[d]
 
     @staticmethod

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(1024, 1) k_lsu(const float* __restrict__ tab, 
 
 // "task mix": what one task of the layer kernel moves, with no bookkeeping at all -- 12 gathered rows
 // (Zipf ids), NLD own rows loaded and NST rows stored at unique, streaming addresses (row = task id).
-template <int NLD, int NST>
+template <int NLD, int NST, bool SCATTER = false>
 __global__ void __launch_bounds__(1024, 1) k_task(const float* __restrict__ tab, const int* __restrict__ ids, int iters,
                                                   const float* __restrict__ own, float* __restrict__ dst, float* out) {
   __shared__ __align__(16) int codes[32][256];
@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(1024, 1) k_task(const float* __restrict__ tab,
   float2 acc = make_float2(0, 0);
   const size_t nwarps = (size_t)gridDim.x * 32;
   for (int it = 0; it < iters; ++it) {
-    const size_t task = (size_t)it * nwarps + (size_t)blockIdx.x * 32 + warp;     // unique row per task
+    size_t task = (size_t)it * nwarps + (size_t)blockIdx.x * 32 + warp;           // unique row per task
+    if (SCATTER) task = (task * 100003ull) % ((size_t)iters * nwarps);            // ... in scattered order (degree-sorted schedule)
     const int4* cp = reinterpret_cast<const int4*>(&codes[warp][(it & 15) * 16]);
     int c[12];
 #pragma unroll
@@ -401,6 +402,8 @@ int main() {
     run("task mix: + 1 own load", [&] { k_task<1, 0><<<sms, 1024>>>(tab, ids_z10, it_t, own, dst, out); });
     run("task mix: + 1 own load + 1 store", [&] { k_task<1, 1><<<sms, 1024>>>(tab, ids_z10, it_t, own, dst, out); });
     run("task mix: + 2 own loads + 2 stores", [&] { k_task<2, 2><<<sms, 1024>>>(tab, ids_z10, it_t, own, dst, out); });
+    run("task mix scattered rows: 1 own + 1 store", [&] { k_task<1, 1, true><<<sms, 1024>>>(tab, ids_z10, it_t, own, dst, out); });
+    run("task mix scattered rows: 2 own + 2 stores", [&] { k_task<2, 2, true><<<sms, 1024>>>(tab, ids_z10, it_t, own, dst, out); });
     run("task mix: + 0 own loads + 2 stores", [&] { k_task<0, 2><<<sms, 1024>>>(tab, ids_z10, it_t, own, dst, out); });
   }
   // tensor map for gather4: 2-D [rows, 64] fp32, box {64, 1}

@@ -153,8 +153,14 @@ def _row_worker(rank, world, port, L, U, I, out_q):
         mats = random_interval_mats(T, U, I, 260, seed=33)
         adj, tp = adj_lists(mats)
         uE, iE, gU, gI = [x.astype(np.float64) for x in random_tables(T, U, I, d, seed=6)]
-        rs = sd.RowShardedPropagation(mats, U, I, n_layers=L, leaky=0.5,
-                                      backend_factory=lambda rs_, d_: DenseRowBackend(rs_, d_, mats))
+        class _CpuRowSharded(sd.RowShardedPropagation):      # test-only stand-in for the two CUDA hooks
+            def _build_plan(self, sub_mats, device, latdim):
+                return None
+
+            def _make_backend(self, d_):
+                return DenseRowBackend(self, d_, mats)
+
+        rs = _CpuRowSharded(mats, U, I, n_layers=L, leaky=0.5)
         u = torch.from_numpy(uE).requires_grad_(True)
         i = torch.from_numpy(iE).requires_grad_(True)
         uv, iv = rs(u, i)
