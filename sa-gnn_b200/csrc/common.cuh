@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -106,6 +107,7 @@ struct sagnn_plan {
   int weight_mode = 0;
   int hot_rows = 0;               // hot slots per source table the edge codes use (packet-stream kernel: what fits at latdim_hint)
   int latdim_hint = 64;
+  bool pkt = true;                // schedule built for the packet-stream kernel (else: v8 task records + edge codes)
   // row sharding (sagnn_plan_set_row_block): only user rows [u_begin,u_end) and item rows [i_begin,i_end)
   // of every interval get tasks; the others are some other rank's.  Default: all rows.
   int u_begin = 0, u_end = 0, i_begin = 0, i_end = 0;
@@ -167,5 +169,12 @@ namespace sagnn {
 void free_host_cache(sagnn_plan* p);
 int apply_cta_split(sagnn_plan* p, const std::vector<double>& cost, cudaStream_t st);
 bool use_rpw();   // always true since the half-warp kernel (v7) was retired; kept for the call sites
-bool use_pkt();   // packet-stream kernel (v9, default); SAGNN_KERNEL=v8 selects the cp.async-ring kernel
+bool use_pkt();   // packet-stream kernel allowed (default); SAGNN_KERNEL=v8 forces the cp.async-ring kernel for every plan
+// which kernel a plan's schedule is built for: packet stream (v10) up to latdim 64, cp.async rings (v8) from 128 on --
+// measured on the ML-10M shape (d=128, mean user degree 143): v8 4.6 ms, v10 5.5-6.4 ms per step
+inline bool plan_uses_pkt(int latdim_hint) {
+  const char* e = getenv("SAGNN_KERNEL");
+  if (e && (e[0] == 'v' || e[0] == 'V') && e[1] == '1' && e[2] == '0') return true;   // SAGNN_KERNEL=v10: always
+  return use_pkt() && latdim_hint < 128;
+}
 }

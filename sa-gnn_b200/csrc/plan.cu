@@ -595,6 +595,7 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   }
 
   // ---- schedule: per-segment task lists, hot slots, hot-first edge codes ------------------
+  p->pkt = sagnn::plan_uses_pkt(p->latdim_hint);
   // hot slots: the highest-degree rows of every table, as many as fit the kernel's staging area at the hinted
   // latdim (SAGNN_HOT_ROWS overrides, 0 = none); the v8 kernel stages nothing
   // OFF by default: measured on B200 (Gowalla shape, 472 staged rows) 0.61 vs 0.47 ms per step -- the staged
@@ -602,7 +603,7 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   // lock-step phase costs more than the L2 round trips it saves.  Builds with -DSAGNN_PKT_HOT=1 honour SAGNN_HOT_ROWS=N.
   p->hot_rows = 0;
   if (const char* e = getenv("SAGNN_HOT_ROWS")) {
-    const int v = atoi(e), cap = (SAGNN_PKT_HOT && sagnn::use_pkt()) ? sagnn::pkt_hot_capacity(p->latdim_hint, p->w != nullptr) : 0;
+    const int v = atoi(e), cap = (SAGNN_PKT_HOT && p->pkt) ? sagnn::pkt_hot_capacity(p->latdim_hint, p->w != nullptr) : 0;
     p->hot_rows = v < 0 ? 0 : (v > cap ? cap : v);
   }
   SAGNN_REQUIRE(p->num_sms >= 2, SAGNN_INVALID_ARG, "finalize: need at least 2 SMs");
@@ -624,7 +625,7 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   SAGNN_CUDA(off3.alloc(3 * (R + 1)));
   SAGNN_CUDA(cudaMalloc(&p->hot_ids, sizeof(int32_t) * 2 * p->T * kHotRows));
   SAGNN_CUDA(cudaMemsetAsync(p->hot_ids, 0, sizeof(int32_t) * 2 * p->T * kHotRows, st));
-  int bucket = sagnn::use_pkt() ? 4 : 1;   // the packet kernel gathers in blocks of four slots
+  int bucket = p->pkt ? 4 : 1;   // the packet kernel gathers in blocks of four slots
   if (const char* e = getenv("SAGNN_SORT_BUCKET")) bucket = atoi(e) > 0 ? atoi(e) : bucket;
   sched_key_kernel<<<blocks_for(R), 256, 0, st>>>(p->deg, R, N, U, bucket, key_in, row_in);
   {
@@ -666,7 +667,7 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
     
   }
 
-  const bool pkt = sagnn::use_pkt();
+  const bool pkt = p->pkt;
   if (!pkt || p->hot_rows > 0) {   // hot-first edge codes (and weights) per row; without hot slots a plain copy (v8)
     SAGNN_CUDA(cudaMalloc(&p->enc, sizeof(int32_t) * 2 * p->e_total));
     if (p->w) SAGNN_CUDA(cudaMalloc(&p->w_enc, sizeof(float) * 2 * p->e_total));

@@ -228,9 +228,9 @@ premask_kernel(const float4* __restrict__ in_u, const float4* __restrict__ in_i,
 }
 
 // SAGNN_BWD_PREMASK=0 keeps the per-edge masks of the top backward level (A/B runs)
-static bool use_premask() {
+static bool use_premask(const sagnn_plan* p) {
   static const bool v = [] { const char* e = getenv("SAGNN_BWD_PREMASK"); return !(e && e[0] == '0'); }();
-  return v || use_pkt();   // the packet-stream kernel has no per-edge mask path
+  return v || p->pkt;   // the packet-stream kernel has no per-edge mask path
 }
 
 // ---------------------------------------------------------------------------------------
@@ -356,7 +356,7 @@ static int launch_rpw_mode(const sagnn_plan* plan, const SpmmParams& prm, int d,
 }
 
 static int launch(const sagnn_plan* plan, const SpmmParams& prm, int d, int mode, cudaStream_t st) {
-  if (use_pkt()) {
+  if (plan->pkt) {
     switch (mode) {
       case MODE_FWD: return launch_pkt_mode<MODE_FWD>(plan, prm, d, st);
       case MODE_BWD: return launch_pkt_mode<MODE_BWD>(plan, prm, d, st);
@@ -414,7 +414,7 @@ static void base_params(const sagnn_plan* p, SpmmParams& s) {
   s = SpmmParams{};
   s.pkt_dir = p->pkt_dir; s.pkt_stream = p->pkt_stream;
   s.tasks = p->tasks; s.enc = p->enc;
-  s.w = use_pkt() ? p->w : p->w_enc;   // packet stream: weights travel inside the packets, this is only the flag
+  s.w = p->pkt ? p->w : p->w_enc;   // packet stream: weights travel inside the packets, this is only the flag
   s.chunk_base = p->chunk_base; s.chunk_lr = p->chunk_lr;
   s.hot_ids = p->hot_ids; s.seg = p->seg_dev; s.cta = p->cta_dev; s.cta_host = p->cta_host.data(); s.single_seg = -1;
   s.hot_rows = p->hot_rows;
@@ -610,7 +610,7 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
     if (rpw) {
       // below the top level the source is the copy the level above already multiplied by sigma'(Z^l);
       // at the top level one streaming pass makes that copy of the upstream
-      if (step == 0 && use_premask()) {
+      if (step == 0 && use_premask(p)) {
         float* pu = pmb[L >= 2 ? 1 : 0]; float* pi = pu + w.user_floats;
         const int64_t ru = interval >= 0 ? p->U : (int64_t)p->T * p->U, ri = interval >= 0 ? p->I : (int64_t)p->T * p->I;
         const int64_t ou = interval >= 0 ? (int64_t)interval * p->U : 0, oi = interval >= 0 ? (int64_t)interval * p->I : 0;
@@ -677,7 +677,7 @@ extern "C" int sagnn_propagate_fwd_layers(const sagnn_plan* p, int l_begin, int 
 extern "C" int sagnn_propagate_bwd_levels(const sagnn_plan* p, int ph_begin, int ph_end, const float* gU,
                                           const float* gI, float* dU, float* dI, int L, int d, float leaky,
                                           const void* masks, void* ws, size_t ws_bytes, sagnn_stream_t stream) {
-  SAGNN_REQUIRE(use_rpw() && use_premask(), SAGNN_INVALID_ARG,
+  SAGNN_REQUIRE(use_rpw() && use_premask(p), SAGNN_INVALID_ARG,
                 "propagate_bwd_levels: needs the row-per-warp kernel with pre-masked sources");
   return bwd_impl(p, -1, gU, gI, dU, dI, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream, 0, ph_begin, ph_end);
 }

@@ -47,9 +47,9 @@ struct PktGeo {
 #ifdef SAGNN_PKT_GS
   static constexpr int GS = SAGNN_PKT_GS;
 #else
-  // gather slots per block: 4 at d <= 64 (16 value registers: 8 spills under the 64-register cap and measured
-  // slower), 8 at d = 128 (one task per warp, 32 value registers, no spills: ML-10M shape 5.5 -> see DESIGN), 2 at d = 256
-  static constexpr int GS = NV == 2 ? 2 : (G == 1 ? 8 : 4);
+  // gather slots per block: 4 (16 value registers; 8 spills at d = 64 under the 64-register cap and measured slower,
+  // and at d = 128 it measured 6.4 vs 5.5 ms on the ML-10M shape), 2 at d = 256
+  static constexpr int GS = NV == 2 ? 2 : 4;
 #endif
   static constexpr int NS = WEIGHTED ? 2 : SAGNN_PKT_SLOTS;    // packets resident / in flight per warp
   // a task's codes: [hot slots, padded to 4][source-row ids, padded to 4] (<= kChunk + 4 words) [+ its weights, same split]
@@ -175,9 +175,10 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
 
   // ---- my packets -----------------------------------------------------------------------------
   // The first NS packets of every warp are dealt statically (packet q0 + s*stride of the segment's
-  // list), the rest come from the segment's queue head, one atomic per packet, fetched two refills
-  // ahead (queue head -> directory entry -> bulk copy are three dependent round trips, each hidden
-  // behind a packet's worth of work).  SMs do not run at the same speed (GPC size, die of the L2
+  // list), the rest come from the segment's queue head in batches of qb packets per atomic (1 for small
+  // segments, up to 8 when a warp has hundreds of packets: all warps of a segment hit ONE counter, and
+  // millions of single-packet grabs serialise in its L2 slice), fetched ahead: queue head -> directory
+  // entry -> bulk copy are three dependent round trips, each hidden behind a packet's worth of work.  SMs do not run at the same speed (GPC size, die of the L2
   // slice): with a purely static deal the slowest CTA of a segment finished 15-20 % after the mean.
   const unsigned n_pk = cd.n_pk;
   const uint32_t* dir = p.pkt_dir + cd.pkt_begin;     // packet offsets, 16-byte units into the stream
@@ -203,7 +204,9 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
   };
   // next packet of the segment's queue: the atomic is issued now, its result (lane 0's register) is only
   // broadcast when the packet index is needed, one refill later -- nobody waits for the round trip
-  auto grab_issue = [&]() -> unsigned { return lane == 0 ? atomicAdd(qhead, 1u) : 0u; };
+  unsigned qb = n_pk / (stride * 8u);                  // >= 8 grabs per warp before batches grow
+  qb = qb < 1u ? 1u : (qb > 8u ? 8u : qb);
+  auto grab_issue = [&]() -> unsigned { return lane == 0 ? atomicAdd(qhead, qb) : 0u; };
   auto grab_value = [&](unsigned raw) -> unsigned { return __shfl_sync(FULL, raw, 0) + q_dyn0; };
   auto issue_pkt = [&](unsigned slot, uint2 dv) {      // one lane, one bulk copy: records + codes (+ weights)
     if (lane == 0) {
@@ -221,12 +224,21 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
   }
   // two-deep look-ahead of the dynamic part: dir_next belongs to the packet of the next refill, q_next to the one after
   uint2 dir_next = make_uint2(0u, 0u);
-  unsigned q_raw = 0;                                  // lane 0: ticket of the packet after dir_next's
+  unsigned q_raw = 0;                                  // lane 0: ticket of the batch after the current one
+  unsigned q_cur = n_pk, q_end = n_pk;                 // current batch: packets [q_cur, q_end) still to fetch
   bool more = n_issued == (unsigned)NS;                // the queue may still have packets for me
+  auto next_packet = [&]() -> unsigned {               // warp-uniform; n_pk or more when the queue is drained
+    if (q_cur == q_end && more) {                      // batch used up: move to the one grabbed a batch ago
+      q_cur = grab_value(q_raw);
+      q_end = q_cur + qb;
+      more = q_cur < n_pk;
+      if (more) q_raw = grab_issue();
+    }
+    return q_cur < q_end ? q_cur++ : n_pk;
+  };
   if (more) {
-    const unsigned r0 = grab_issue();
     q_raw = grab_issue();
-    dir_next = load_dir(grab_value(r0));
+    dir_next = load_dir(next_packet());
   }
 
   bool hot_ready = n_hot == 0;                         // the staged rows have landed (waited for on first use)
@@ -393,10 +405,7 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
       if (dir_next.y != 0u) {                            // the queue had a packet left for me
         issue_pkt(refill, dir_next);
         ++n_issued;
-        const unsigned q_next = more ? grab_value(q_raw) : n_pk;
-        more = q_next < n_pk;
-        dir_next = load_dir(q_next);
-        if (more) q_raw = grab_issue();
+        dir_next = load_dir(next_packet());
       }
     }
 

@@ -45,7 +45,7 @@ def run_gpu(plan, uE, iE, gU, gI, L, leaky=0.5, want_masks=False):
 
 
 def check_against_oracle(mats, d, L, leaky=0.5, seed=0, edge_weight=None, scale=1.0, tables=None,
-                         max_ties=8):
+                         max_ties=8, latdim=None, report=None):
     """Three-part parity (the derivative of LeakyReLU jumps at 0, so a pre-activation that is
     zero to within fp32 rounding may legitimately take the other branch):
       A. forward outputs vs the fp64 oracle                         <= 1e-5;
@@ -59,7 +59,8 @@ def check_against_oracle(mats, d, L, leaky=0.5, seed=0, edge_weight=None, scale=
     if edge_weight == "lightgcn":
         ew = [po.lightgcn_edge_weights(a, U, I) for a in adj]
         tew = [po.lightgcn_edge_weights(a, I, U) for a in tp]
-    plan = sg.build_plan(mats, edge_weight=edge_weight)
+    # latdim hint = d by default: plans hinted >= 128 run the v8 kernel, below that the packet-stream kernel
+    plan = sg.build_plan(mats, edge_weight=edge_weight, latdim=latdim or d)
     uv, iv, du, di, gm = run_gpu(plan, uE, iE, gU, gI, L, leaky, want_masks=True)
     ref = c_oracle.propagate(adj, tp, uE, iE, gU, gI, L, leaky, np.float64, ew, tew,
                              mask_in=gm, mask_cmp=gm, tie_tol=1e-5)
@@ -70,6 +71,18 @@ def check_against_oracle(mats, d, L, leaky=0.5, seed=0, edge_weight=None, scale=
     assert mism <= max_ties, "%d near-tie sign flips" % mism
     assert_parity(du, ref[2], "dU")
     assert_parity(di, ref[3], "dI")
+    if report is not None:
+        # also the UNCONDITIONAL backward error (oracle with its own masks) and the number of near-tie flips
+        free = c_oracle.propagate(adj, tp, uE, iE, gU, gI, L, leaky, np.float64, ew, tew)
+        line = ("%s: near-tie sign flips %d (far from ties %d); fwd relerr %.2e / %.2e; bwd relerr given the GPU's masks "
+                "%.2e / %.2e, against the oracle's own masks %.2e / %.2e" % (
+                    report, mism, far, po.relerr(uv.detach().cpu().numpy(), ref[0]), po.relerr(iv.detach().cpu().numpy(), ref[1]),
+                    po.relerr(du.cpu().numpy(), ref[2]), po.relerr(di.cpu().numpy(), ref[3]),
+                    po.relerr(du.cpu().numpy(), free[2]), po.relerr(di.cpu().numpy(), free[3])))
+        print("\n[parity] " + line)
+        os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
+        with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.txt"), "a") as f:
+            f.write(line + "\n")
     return plan
 
 
@@ -242,6 +255,13 @@ def test_propagate_matches_reference_model_py_executed(path, layout):
 @pytest.mark.parametrize("d,L", [(32, 1), (64, 2), (64, 3), (128, 3), (128, 4), (256, 2)])
 def test_propagate_small_random(d, L):
     check_against_oracle(random_interval_mats(3, 120, 80, 900, seed=d + L), d, L, seed=L)
+
+
+@pytest.mark.parametrize("d,L,hint", [(128, 3, 64), (256, 2, 64), (64, 2, 128), (32, 1, 128)])
+def test_propagate_other_kernel_than_the_hint_would_pick(d, L, hint):
+    """A plan hinted below 128 carries the packed task stream (v10 kernel), from 128 on the v8 task records:
+    both kernels must serve every latdim."""
+    check_against_oracle(random_interval_mats(3, 120, 80, 900, seed=d + L), d, L, seed=L, latdim=hint)
 
 
 def test_propagate_long_rows_chunked_reduction():
@@ -788,7 +808,7 @@ def test_other_baseline_shapes_full_size(name):
     rng = np.random.default_rng(100)
     gU = rng.standard_normal((T, U, d), dtype=np.float32)
     gI = rng.standard_normal((T, I, d), dtype=np.float32)
-    check_against_oracle(g.sub_mat, d, L, tables=(uE, iE, gU, gI), max_ties=256)
+    check_against_oracle(g.sub_mat, d, L, tables=(uE, iE, gU, gI), max_ties=256, report="%s full size (L=%d, d=%d)" % (name, L, d))
 
 
 def test_monster_rows_three_level_slice_tree():
@@ -822,7 +842,7 @@ def test_gowalla_full_size_parity_and_properties():
     rng = np.random.default_rng(100)
     gU = rng.standard_normal((T, U, d)).astype(np.float32)
     gI = rng.standard_normal((T, I, d)).astype(np.float32)
-    plan = check_against_oracle(g.sub_mat, d, L, tables=(uE, iE, gU, gI), max_ties=64)
+    plan = check_against_oracle(g.sub_mat, d, L, tables=(uE, iE, gU, gI), max_ties=64, report="gowalla full size (L=%d, d=%d)" % (L, d))
     got = run_gpu(plan, uE, iE, gU, gI, L)
     deg = plan.degrees(0, 0).cpu().numpy()
     lonely = np.flatnonzero(deg == 0)[:50]
