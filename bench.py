@@ -52,12 +52,13 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-allgather", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "allgather", "alltoall", "none"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "ce", "allgather", "alltoall", "none"],
                     help="multi-GPU hand-off of the outputs: all-to-all of row blocks (row-sharded consumer; the "
                          "default for N > 1, sent straight from the [R,T,d] epilogue output), all-gather "
                          "(replicated consumer, the collective north_star names), fused (the same row-block "
                          "hand-off written by the epilogue itself into the peers' symmetric-memory receive buffers: "
-                         "peer stores over NVLink, no collective kernel) or none")
+                         "peer stores over NVLink, no collective kernel), ce (the same receive buffers filled by the "
+                         "copy engines: one peer memcpy per row block on a side stream while the SMs run the backward) or none")
     ap.add_argument("--layout", default=None, choices=["trd", "rtd"],
                     help="rtd: outputs / upstream gradients in the [R,T,d] layout of model.py:133-134 (fused "
                          "transpose); default trd, rtd with --exchange alltoall")
@@ -257,10 +258,13 @@ def main():
     if args.no_allgather:
         args.exchange = "none"
     auto_exchange = args.exchange == "auto"
-    if auto_exchange:   # N > 1: the fused hand-off; falls back to the NCCL all-to-all if symmetric memory is unavailable
-        args.exchange = "fused" if world > 1 else "none"
+    if auto_exchange:
+        # N > 1: hand-off into symmetric-memory receive buffers -- written by the epilogue itself (peer stores) up to
+        # 3 ranks, by the copy engines during the backward from 4 on (measured on 8 x B200: 0.550 vs 0.584 ms at N=8,
+        # 0.563 vs 0.536 ms at N=2); falls back to the NCCL all-to-all if symmetric memory is unavailable
+        args.exchange = "none" if world == 1 else ("fused" if world < 4 else "ce")
     if args.layout is None:
-        args.layout = "rtd" if (world > 1 and args.exchange in ("alltoall", "fused")) else "trd"
+        args.layout = "rtd" if (world > 1 and args.exchange in ("alltoall", "fused", "ce")) else "trd"
     step = PropagationStep(plan, L, d, 0.5, layout=args.layout, row_multiple=world)
     step.u_embed.copy_(torch.from_numpy(dh.xavier_embeddings(T, U, d, args.seed)))
     step.i_embed.copy_(torch.from_numpy(dh.xavier_embeddings(T, I, d, args.seed + 1)))
@@ -278,7 +282,8 @@ def main():
             rcv_u = torch.empty((world, step.user_out_full.shape[0] // world, T, d), dtype=torch.float32, device=dev)
             rcv_i = torch.empty((world, step.item_out_full.shape[0] // world, T, d), dtype=torch.float32, device=dev)
         side = torch.cuda.Stream()
-    fused = do_gather and args.exchange == "fused"
+    ce = do_gather and args.exchange == "ce"
+    fused = do_gather and args.exchange in ("fused", "ce")      # both fill symmetric-memory receive buffers
     fused_ok = None
     if fused:
         # receive buffers in symmetric memory: every rank maps every peer's buffer, the forward's
@@ -317,6 +322,34 @@ def main():
         fused_ok = bool(ok.item())
         if not fused_ok:
             raise RuntimeError("fused hand-off differs from the NCCL all-to-all of the same outputs")
+        if ce:
+            # copy-engine variant: the forward writes its [R,T,d] output locally, then one peer memcpy per row
+            # block (DMA over NVLink, no SM) puts block j into rank j's receive buffer while the backward runs
+            step.set_scatter(0, 0, None, None)
+            peer_u = [hdl_u.get_buffer(r, (world, bu, T, d), torch.float32) for r in range(world)]
+            peer_i = [hdl_i.get_buffer(r, (world, bi, T, d), torch.float32) for r in range(world)]
+            rcv_u.zero_(); rcv_i.zero_()
+            hdl_u.barrier(channel=0)
+
+            def ce_step():
+                step.forward()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for j in range(world):
+                        r = (rank + j) % world               # start with my own block, then round the ring
+                        peer_u[r][rank].copy_(step.user_out_full[r * bu:(r + 1) * bu], non_blocking=True)
+                        peer_i[r][rank].copy_(step.item_out_full[r * bi:(r + 1) * bi], non_blocking=True)
+                step.backward()
+                torch.cuda.current_stream().wait_stream(side)
+
+            ce_step()
+            hdl_u.barrier(channel=0)
+            torch.cuda.synchronize()
+            ok = torch.tensor([int(torch.equal(ref_u, rcv_u) and torch.equal(ref_i, rcv_i))], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            fused_ok = bool(ok.item())
+            if not fused_ok:
+                raise RuntimeError("copy-engine hand-off differs from the NCCL all-to-all of the same outputs")
 
     split = None
     if not args.no_calibrate:
@@ -324,7 +357,18 @@ def main():
     # one CUDA graph per rank: the plain step, or forward-with-fused-hand-off + backward (peer pointers are
     # ordinary kernel arguments); the NCCL hand-offs keep direct launches
     use_graph = not args.no_graph and (not do_gather or fused)
-    if use_graph:
+    ce_graph = None
+    if use_graph and ce:
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            ce_step()
+        torch.cuda.current_stream().wait_stream(cap)
+        torch.cuda.synchronize()
+        ce_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ce_graph):
+            ce_step()
+    elif use_graph:
         step.capture()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     if args.no_flush:
@@ -334,7 +378,13 @@ def main():
         flush = _NoFlush()
 
     def one_step():
-        if fused and use_graph:
+        if ce:
+            if ce_graph is not None:
+                ce_graph.replay()
+            else:
+                ce_step()
+            hdl_u.barrier(channel=0)
+        elif fused and use_graph:
             step.replay()                                           # rows land in the peers' buffers as they finish
             hdl_u.barrier(channel=0)                                # every rank is through: my receive slabs are complete
         elif fused:
@@ -569,6 +619,10 @@ def run_config(args, world, stats, use_graph, gather):
                      "symmetric-memory receive buffer of the rank that owns its row block (peer stores over "
                      "NVLink, sagnn_propagate_fwd_scatter); forward + backward replay from one CUDA graph, then one "
                      "symmetric-memory barrier; verified bitwise against the NCCL all-to-all before timing",
+            "ce": "no collective kernel and no SM: after the forward, one peer memcpy per row block (copy engines over "
+                  "NVLink) fills the consumers' symmetric-memory receive buffers on a side stream while the backward runs; "
+                  "forward + copies + backward replay from one CUDA graph, then one symmetric-memory barrier; verified "
+                  "bitwise against the NCCL all-to-all before timing",
             "none": "no hand-off collective (compute only)"}[args.exchange]
     return cfg
 

@@ -7,8 +7,9 @@ deliberately *un*-fused: it materialises the ``[E, d]`` gather, the padded
 segment-sum, etc.  It is the checker for the CUDA path, never the product.
 
 parity status: index construction pinned to the reference's own functions
-(tests/golden/); propagation fwd/bwd PARITY UNPINNED (no reference-owned
-vectors exist, TF1 not importable) -- see oracle/__init__.py.
+(tests/golden/index_*.npz); propagation fwd/bwd pinned to the reference's own
+model.py text executed over a numpy TF shim (tests/golden/modelref_*.npz) --
+see oracle/__init__.py.
 """
 from __future__ import annotations
 
