@@ -266,14 +266,90 @@ def rowshard_check(args, rank, world, dev, dist):
             "note": "RowShardedPropagation over NCCL (per-layer in-place table all-gathers) vs sagnn_b200.propagate on one GPU"}
 
 
+def fusion_chain_check(args, rank, world, dev, dist):
+    """The data-parallel chain the fused hand-off exists for, over real peer memory: every rank owns two
+    interval graphs, runs its forward with sagnn_propagate_fwd_scatter (peer stores into the symmetric-memory
+    receive buffers), assembles ITS row block of all intervals from the slabs, runs the interval fusion
+    (model.py:135-155) and a loss, sends the dense upstream back to the interval owners (one all-to-all) and
+    runs sagnn_propagate_bwd_ex; outputs and gradients are compared with the single-GPU chain."""
+    import torch.distributed._symmetric_memory as symm
+    import sagnn_b200 as sg
+    from sagnn_b200 import data_handler as dh
+    from sagnn_b200.fusion import IntervalFusion, slabs_to_rtd
+    from sagnn_b200.step import PropagationStep
+    tl, U, I, d, L = 2, 3000, 2000, 64, 2
+    T = tl * world
+    g = dh.make_interval_graphs(U, I, T, [20000] * T, seed=5)                  # same graphs on every rank
+    owners = [k // tl for k in range(T)]
+    mine = [k for k in range(T) if owners[k] == rank]
+    gen = torch.Generator(device=dev).manual_seed(11)                          # same tables on every rank
+    uE = torch.randn((T, U, d), device=dev, generator=gen) * 0.3
+    iE = torch.randn((T, I, d), device=dev, generator=gen) * 0.3
+    wu = torch.randn((U, d), device=dev, generator=gen)
+    wi = torch.randn((I, d), device=dev, generator=gen)
+    fusion = IntervalFusion(d, heads=16, device=dev, seed=5)
+    # single-GPU chain
+    plan = sg.build_plan(g.sub_mat, device=dev, latdim=d)
+    u, i = uE.clone().requires_grad_(True), iE.clone().requires_grad_(True)
+    uv, iv = sg.propagate(plan, u, i, L, 0.5, layout="rtd")
+    fu, fi = fusion(uv, iv)
+    ((fu * wu).sum() + (fi * wi).sum()).backward()
+    ref = [fu.detach(), fi.detach(), u.grad, i.grad]
+    fusion.zero_grad()
+    # sharded chain
+    st = PropagationStep(sg.build_plan([g.sub_mat[k] for k in mine], device=dev, latdim=d), L, d, layout="rtd",
+                         row_multiple=world)
+    st.u_embed.copy_(uE[mine]); st.i_embed.copy_(iE[mine])
+    bu, bi = st.user_out_full.shape[0] // world, st.item_out_full.shape[0] // world
+    rcv_u = symm.empty((world, bu, tl, d), dtype=torch.float32, device=dev)
+    rcv_i = symm.empty((world, bi, tl, d), dtype=torch.float32, device=dev)
+    rcv_u.zero_(); rcv_i.zero_()
+    hu, hi = symm.rendezvous(rcv_u, dist.group.WORLD), symm.rendezvous(rcv_i, dist.group.WORLD)
+    hu.barrier(channel=0)
+    st.set_scatter(world, rank, list(hu.buffer_ptrs), list(hi.buffer_ptrs))
+    st.forward()
+    hu.barrier(channel=0)
+    torch.cuda.synchronize(dev)
+    lo_u, hi_u, lo_i, hi_i = rank * bu, min((rank + 1) * bu, U), rank * bi, min((rank + 1) * bi, I)
+    xu = slabs_to_rtd(rcv_u, owners, max(hi_u - lo_u, 0)).clone().requires_grad_(True)
+    xi = slabs_to_rtd(rcv_i, owners, max(hi_i - lo_i, 0)).clone().requires_grad_(True)
+    fu, fi = fusion(xu, xi)
+    relerr = lambda a, b: float(((a.detach() - b.detach()).abs().max() / b.detach().abs().max().clamp_min(1e-30)).item())
+    e_f = max(relerr(fu, ref[0][lo_u:hi_u]), relerr(fi, ref[1][lo_i:hi_i]))
+    ((fu * wu[lo_u:hi_u]).sum() + (fi * wi[lo_i:hi_i]).sum()).backward()
+    # reverse hand-off: my block's upstream of rank r's intervals -> rank r
+    send_u = torch.zeros((world, bu, tl, d), device=dev); send_i = torch.zeros((world, bi, tl, d), device=dev)
+    for r in range(world):
+        ks = [k for k in range(T) if owners[k] == r]
+        send_u[r, :hi_u - lo_u] = xu.grad[:, ks]
+        send_i[r, :hi_i - lo_i] = xi.grad[:, ks]
+    back_u, back_i = torch.empty_like(send_u), torch.empty_like(send_i)
+    dist.all_to_all_single(back_u.view(world, -1), send_u.view(world, -1))
+    dist.all_to_all_single(back_i.view(world, -1), send_i.view(world, -1))
+    st.set_scatter(0, 0, None, None)
+    st.g_user.copy_(back_u.reshape(world * bu, tl, d)[:U]); st.g_item.copy_(back_i.reshape(world * bi, tl, d)[:I])
+    st.backward()
+    torch.cuda.synchronize(dev)
+    e_g = max(relerr(st.d_u, ref[2][mine]), relerr(st.d_i, ref[3][mine]))
+    t = torch.tensor([e_f, e_g], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e_f, e_g = float(t[0]), float(t[1])
+    return {"chain_matches_single_gpu": bool(e_f <= 1e-5 and e_g <= 1e-5), "max_relerr_fused_vectors": e_f,
+            "max_relerr_embedding_grads": e_g,
+            "graph": "T=%d intervals of 20 K edges (2 per rank), U=%d, I=%d, L=%d, d=%d" % (T, U, I, L, d),
+            "note": "propagate (fwd_scatter, peer stores) -> slabs -> LSTM/LN/MHSA/mean per row block -> loss -> all-to-all "
+                    "of the [blk,T,d] upstream -> sagnn_propagate_bwd_ex; vs propagate(layout=rtd) -> fusion -> autograd on one GPU"}
+
+
 def run_extras(args, rank, world, dev, dist, peak_gbs):
     """Every part is independent and failure-tolerant: an exception becomes an ``error`` entry."""
     res = {}
     parts = [("rowshard", lambda: rowshard_check(args, rank, world, dev, dist)),
+             ("fusion_chain", lambda: fusion_chain_check(args, rank, world, dev, dist)),
              ("amazon_book_strong_scaling", lambda: amazon_strong(args, rank, world, dev, dist)),
              ("scaled_config5", lambda: scaled_config(args, rank, world, dev, dist, peak_gbs))]
     for name, fn in parts:
-        if world == 1 and name == "rowshard":
+        if world == 1 and name in ("rowshard", "fusion_chain"):
             continue
         t0 = time.perf_counter()
         try:

@@ -1,0 +1,96 @@
+"""Interval fusion: the CONSUMER of the propagation path (LIU-YUXI/SA-GNN
+``model.py:135-155``, ``Utils/attention.py:31-78``), so that the hand-off layouts the path writes have a reader:
+
+  * ``IntervalFusion``: BasicLSTMCell over the T intervals -> layer norm -> multi-head self-attention ->
+    mean over T, on the ``[R,T,d]`` tensors ``propagate(..., layout="rtd")`` returns
+    (``user_vector_tensor`` / ``item_vector_tensor``, model.py:133-134).  Dense framework-side work (GEMMs and
+    pointwise ops through torch / cuBLAS), NOT part of the sparse hot path and not hand-written kernels;
+    its autograd produces the dense ``[R,T,d]`` upstream that ``sagnn_propagate_bwd_ex`` consumes.
+  * ``slabs_to_rtd``: assembles a row-sharded consumer's input from the receive slabs
+    ``[source rank, row block, T_local, d]`` that ``sagnn_propagate_fwd_scatter`` (peer stores from the epilogue)
+    or the copy-engine hand-off fill: rank j holds row block j of EVERY interval, which is all an LSTM over T needs.
+
+Same semantics as TF 1.14 for the ops involved (gate order i, j, f, o with forget_bias 1.0; layer norm over
+(T, d) with epsilon 1e-12; exp-normalised attention with 1e-8 in the denominator); checked against
+``oracle/fusion_oracle.py`` (the builder's restatement: parity unpinned for this consumer).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+class IntervalFusion(torch.nn.Module):
+    def __init__(self, d, heads=16, dtype=torch.float32, device=None, seed=0):
+        super().__init__()
+        if d % heads:
+            raise ValueError("latdim must be a multiple of the number of attention heads (attention.py:49)")
+        self.d, self.heads = d, heads
+        g = torch.Generator().manual_seed(seed)
+
+        def xavier(rows, cols):
+            a = math.sqrt(6.0 / (rows + cols))
+            return torch.nn.Parameter(((torch.rand((rows, cols), generator=g, dtype=torch.float64) * 2 - 1) * a).to(dtype=dtype, device=device))
+
+        zeros = lambda n: torch.nn.Parameter(torch.zeros(n, dtype=dtype, device=device))
+        self.lstm_kernel, self.lstm_bias = xavier(2 * d, 4 * d), zeros(4 * d)    # one cell for both sides (model.py:141-146)
+        for side in ("user", "item"):
+            setattr(self, side + "_ln_gamma", torch.nn.Parameter(torch.ones(d, dtype=dtype, device=device)))
+            setattr(self, side + "_ln_beta", zeros(d))
+            for n in ("q", "k", "v"):
+                setattr(self, "%s_w%s" % (side, n), xavier(d, d))
+                setattr(self, "%s_b%s" % (side, n), zeros(d))
+
+    def side_params(self, side):
+        names = {"lstm_kernel": "lstm_kernel", "lstm_bias": "lstm_bias", "ln_gamma": side + "_ln_gamma",
+                 "ln_beta": side + "_ln_beta"}
+        names.update({k + n: "%s_%s%s" % (side, k, n) for n in ("q", "k", "v") for k in ("w", "b")})
+        return {k: getattr(self, v) for k, v in names.items()}
+
+    def lstm(self, x):
+        R, T, d = x.shape
+        h = x.new_zeros((R, d))
+        c = x.new_zeros((R, d))
+        outs = []
+        for t in range(T):
+            g = torch.cat([x[:, t], h], dim=1) @ self.lstm_kernel + self.lstm_bias
+            i, j, f, o = g.split(d, dim=1)
+            c = c * torch.sigmoid(f + 1.0) + torch.sigmoid(i) * torch.tanh(j)
+            h = torch.tanh(c) * torch.sigmoid(o)
+            outs.append(h)
+        return torch.stack(outs, dim=1)
+
+    def fuse(self, x, side):
+        """x [R,T,d] -> [R,d]   (model.py:146-155 for one side)."""
+        p = self.side_params(side)
+        R, T, d = x.shape
+        h = self.lstm(x)
+        mean = h.mean(dim=(1, 2), keepdim=True)
+        var = h.var(dim=(1, 2), unbiased=False, keepdim=True)
+        n = (h - mean) / torch.sqrt(var + 1e-12) * p["ln_gamma"] + p["ln_beta"]
+        dk = d // self.heads
+        split = lambda y: y.reshape(R, T, self.heads, dk).permute(0, 2, 1, 3)
+        q, k, v = split(n @ p["wq"] + p["bq"]), split(n @ p["wk"] + p["bk"]), split(n @ p["wv"] + p["bv"])
+        scores = torch.exp(q @ k.transpose(-1, -2) / math.sqrt(dk))
+        attn = scores / (scores.sum(dim=-1, keepdim=True) + 1e-8)
+        ctx = (attn @ v).permute(0, 2, 1, 3).reshape(R, T, d)
+        return ctx.mean(dim=1)
+
+    def forward(self, user_rtd, item_rtd):
+        return self.fuse(user_rtd, "user"), self.fuse(item_rtd, "item")
+
+
+def slabs_to_rtd(slabs, owners, rank_rows=None):
+    """Receive slabs ``[world, blk, T_local, d]`` (slab r = my row block of source rank r's intervals, in that
+    rank's local interval order) -> ``[blk, T, d]`` in true interval order.  ``owners[k]`` = rank that owns
+    interval k (``dist.assign_intervals``).  ``rank_rows``: keep only the first rows of the (padded) block."""
+    world = slabs.shape[0]
+    local = [[k for k, r in enumerate(owners) if r == src] for src in range(world)]
+    T = len(owners)
+    cols = [None] * T
+    for src in range(world):
+        for j, k in enumerate(local[src]):
+            cols[k] = slabs[src, :, j]
+    x = torch.stack(cols, dim=1)
+    return x if rank_rows is None else x[:rank_rows]

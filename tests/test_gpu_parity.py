@@ -508,6 +508,82 @@ def test_fused_scatter_to_row_sharded_consumer(W, L, d):
     assert torch.equal(a.d_u, b.d_u) and torch.equal(a.d_i, b.d_i)
 
 
+@pytest.mark.parametrize("W,L,d", [(2, 2, 64), (3, 2, 64), (2, 1, 32)])
+def test_chain_propagation_scatter_fusion_backward_on_virtual_ranks(W, L, d):
+    """The whole data-parallel chain the fused hand-off is designed for, with W ranks played on
+    one GPU: rank r owns the intervals LPT gives it and runs its forward with sagnn_propagate_fwd_scatter into
+    the W receive buffers ([source rank, blk, T_local, d]); consumer rank j assembles row block j of ALL
+    intervals from its slabs (slabs_to_rtd), runs the interval fusion (LSTM over T -> layer norm -> MHSA -> mean,
+    model.py:135-155) and back-propagates a loss; the dense [blk, T, d] upstream goes back to the interval owners,
+    whose sagnn_propagate_bwd_ex ([R,T,d] upstream) yields the embedding gradients.  Must equal the single-GPU
+    chain propagate(layout="rtd") -> fusion -> autograd."""
+    from sagnn_b200.step import PropagationStep
+    from sagnn_b200.fusion import IntervalFusion, slabs_to_rtd
+    from sagnn_b200.dist import assign_intervals
+    mats = random_interval_mats(4, 210, 130, 1800, seed=41)
+    T, U, I = 4, 210, 130
+    uE, iE, _, _ = random_tables(T, U, I, d, seed=42, scale=0.3)
+    fusion = IntervalFusion(d, heads=16 if d % 16 == 0 else 8, device="cuda", seed=5)
+    wu = torch.randn((U, d), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    wi = torch.randn((I, d), device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    # ---- single GPU
+    plan = sg.build_plan(mats, latdim=d)
+    u = torch.from_numpy(uE).cuda().requires_grad_(True)
+    i = torch.from_numpy(iE).cuda().requires_grad_(True)
+    uv, iv = sg.propagate(plan, u, i, L, 0.5, layout="rtd")
+    fu, fi = fusion(uv, iv)
+    ((fu * wu).sum() + (fi * wi).sum()).backward()
+    ref_fu, ref_fi, ref_du, ref_di = fu.detach(), fi.detach(), u.grad.clone(), i.grad.clone()
+    fusion.zero_grad()
+    # ---- W ranks: interval owners (propagation) x row-block owners (fusion)
+    owners = assign_intervals([m.nnz for m in mats], W)
+    mine = [[k for k in range(T) if owners[k] == r] for r in range(W)]
+    tl = max(len(x) for x in mine)
+    bu, bi = -(-U // W), -(-I // W)
+    rcv_u = [torch.zeros((W, bu, tl, d), device="cuda") for _ in range(W)]
+    rcv_i = [torch.zeros((W, bi, tl, d), device="cuda") for _ in range(W)]
+    steps = []
+    for r in range(W):
+        st = None
+        if mine[r]:
+            st = PropagationStep(sg.build_plan([mats[k] for k in mine[r]], latdim=d), L, d, layout="rtd")
+            st.u_embed.copy_(torch.from_numpy(uE[mine[r]])); st.i_embed.copy_(torch.from_numpy(iE[mine[r]]))
+            # this rank's slabs have T_local = len(mine[r]) intervals: point the scatter at views of that depth
+            vu = [t[:, :, :len(mine[r])].contiguous() for t in rcv_u]
+            vi = [t[:, :, :len(mine[r])].contiguous() for t in rcv_i]
+            st.set_scatter(W, r, [t.data_ptr() for t in vu], [t.data_ptr() for t in vi])
+            st.forward()
+            torch.cuda.synchronize()
+            for j in range(W):
+                rcv_u[j][r, :, :len(mine[r])] = vu[j][r]
+                rcv_i[j][r, :, :len(mine[r])] = vi[j][r]
+        steps.append(st)
+    g_back_u = [torch.zeros((U, len(mine[r]), d), device="cuda") for r in range(W)]
+    g_back_i = [torch.zeros((I, len(mine[r]), d), device="cuda") for r in range(W)]
+    for j in range(W):                                    # consumer rank j: row block j of every interval
+        lo_u, hi_u, lo_i, hi_i = j * bu, min((j + 1) * bu, U), j * bi, min((j + 1) * bi, I)
+        xu = slabs_to_rtd(rcv_u[j], owners, hi_u - lo_u).clone().requires_grad_(True)
+        xi = slabs_to_rtd(rcv_i[j], owners, hi_i - lo_i).clone().requires_grad_(True)
+        fu, fi = fusion(xu, xi)
+        assert_parity(fu, ref_fu[lo_u:hi_u].cpu().numpy(), "fused user vector, row block %d" % j)
+        assert_parity(fi, ref_fi[lo_i:hi_i].cpu().numpy(), "fused item vector, row block %d" % j)
+        ((fu * wu[lo_u:hi_u]).sum() + (fi * wi[lo_i:hi_i]).sum()).backward()
+        for r in range(W):                                # reverse hand-off: upstream of interval k goes to its owner
+            for jj, k in enumerate(mine[r]):
+                g_back_u[r][lo_u:hi_u, jj] = xu.grad[:, k]
+                g_back_i[r][lo_i:hi_i, jj] = xi.grad[:, k]
+    for r in range(W):
+        if steps[r] is None:
+            continue
+        st = steps[r]
+        st.set_scatter(0, 0, None, None)
+        st.g_user.copy_(g_back_u[r]); st.g_item.copy_(g_back_i[r])
+        st.backward()
+        torch.cuda.synchronize()
+        assert_parity(st.d_u, ref_du[mine[r]].cpu().numpy(), "dU of rank %d's intervals" % r)
+        assert_parity(st.d_i, ref_di[mine[r]].cpu().numpy(), "dI of rank %d's intervals" % r)
+
+
 # ---------------------------------------------------------------- device-side trans_sub (SURVEY 8f N4)
 def _coo_of(m):
     m = sp.csr_matrix(m)
