@@ -392,7 +392,7 @@ using namespace sagnn;
 // C ABI
 // ---------------------------------------------------------------------------------------
 extern "C" const char* sagnn_last_error(void) { return sagnn::last_error(); }
-extern "C" const char* sagnn_version(void) { return "sagnn_b200 0.1 (sm_100a)"; }
+extern "C" const char* sagnn_version(void) { return "sagnn_b200 0.2 (sm_100a; packet-stream kernel v10)"; }
 
 extern "C" int sagnn_plan_create(int T, int U, int I, const int64_t* nnz_host, sagnn_plan** out) {
   SAGNN_REQUIRE(out != nullptr, SAGNN_INVALID_ARG, "plan_create: out is NULL");

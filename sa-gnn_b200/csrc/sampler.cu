@@ -68,6 +68,10 @@ struct SmpTmp {
 
 using namespace sagnn;
 
+// Difference to the reference worth knowing: posset there is `temLabel != 0` (model.py:317), i.e. stored explicit
+// zeros would not be sampled; here every stored edge of the interval counts.  The reference's interval matrices
+// store raw timestamps (preprocess_to_trnmat.ipynb:379), never zeros, so the sets are the same on its data.
+// The draws come from a counter-based generator: same output contract, not numpy's MT19937 stream.
 extern "C" int sagnn_sample_ssl_batch(const sagnn_plan* p, int k, const int32_t* bat_ids, int batch, int ssl_num,
                                       uint64_t seed, int32_t* u_locs, int32_t* i_locs, int32_t* u_locs_seq,
                                       int64_t* n_out_host, sagnn_stream_t stream_) {

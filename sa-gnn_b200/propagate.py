@@ -154,8 +154,10 @@ class Plan:
 
     def scratch(self, n_layers, d):
         """Cached (workspace tensor, mask_bytes): fwd and bwd of one step run back to back on one
-        stream and the backward needs nothing from the forward scratch, so they share it."""
-        key = (n_layers, d)
+        stream and the backward needs nothing from the forward scratch, so they share it.  The workspace
+        holds tickets, queue heads, slice partials and the ping-pong tables of a call in flight, so it is
+        cached PER CUDA STREAM: calls issued on different streams never share one."""
+        key = (n_layers, d, torch.cuda.current_stream(self.device).cuda_stream)
         if key not in self._scratch:
             f, m, b = self.workspace_bytes(n_layers, d)
             ws = torch.empty(max(f, b, 1), dtype=torch.uint8, device=self.device)

@@ -887,6 +887,17 @@ def test_other_baseline_shapes_full_size(name):
     check_against_oracle(g.sub_mat, d, L, tables=(uE, iE, gU, gI), max_ties=256, report="%s full size (L=%d, d=%d)" % (name, L, d))
 
 
+def test_many_tiny_rows_batched_packet_queue():
+    """Hundreds of thousands of 1-2 edge rows (the scaled-s10 regime): a warp has hundreds of packets, so the
+    packet queue hands them out in batches of several per atomic; packets of partly empty rows, long tails of
+    zero-degree rows, the last partial packet of every segment."""
+    rng = np.random.default_rng(77)
+    U, I, E = 300_000, 120_000, 380_000
+    keys = np.unique(rng.integers(0, U * I, size=E, dtype=np.int64))
+    m = sp.csr_matrix((np.ones(keys.size, np.intc), (keys // I, keys % I)), shape=(U, I))
+    check_against_oracle([m], 64, 2, seed=5, scale=0.5, max_ties=64)
+
+
 def test_monster_rows_three_level_slice_tree():
     """Rows far beyond 16*16*64 edges (as in BASELINE config 5, where head items collect millions
     of users) are reduced through a three-level ticket tree: a hub item linked to 90 % of 120 K
