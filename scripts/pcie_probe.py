@@ -1,0 +1,26 @@
+"""PCIe probe: H2D alone, D2H alone, both at once (pinned memory, 156 MB each: one step's worth of the host entry point)."""
+import time, torch
+n = 155_556_864
+h_in = torch.empty(n, dtype=torch.uint8).pin_memory(); h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+d_in = torch.empty(n, dtype=torch.uint8, device="cuda"); d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+def run(h2d, d2h, reps=10):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(reps):
+        if h2d:
+            with torch.cuda.stream(s1): d_in.copy_(h_in, non_blocking=True)
+        if d2h:
+            with torch.cuda.stream(s2): h_out.copy_(d_out, non_blocking=True)
+    torch.cuda.synchronize(); return (time.perf_counter() - t0) / reps
+for name, a, b in (("H2D alone", 1, 0), ("D2H alone", 0, 1), ("both at once", 1, 1)):
+    run(a, b, 2); t = run(a, b)
+    print("%-13s %.2f ms  %.1f GB/s per direction" % (name, t * 1e3, n / t / 1e9))
+c = n // 6
+def chunked(reps=10):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(reps):
+        for k in range(6):
+            with torch.cuda.stream(s1): d_in[k*c:(k+1)*c].copy_(h_in[k*c:(k+1)*c], non_blocking=True)
+            with torch.cuda.stream(s2): h_out[k*c:(k+1)*c].copy_(d_out[k*c:(k+1)*c], non_blocking=True)
+    torch.cuda.synchronize(); return (time.perf_counter() - t0) / reps
+chunked(2); t = chunked(); print("%-13s %.2f ms  %.1f GB/s per direction" % ("both, 6 chunks", t * 1e3, n / t / 1e9))
