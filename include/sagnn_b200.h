@@ -283,6 +283,25 @@ int sagnn_sample_ssl_batch(const sagnn_plan* plan, int k, const int32_t* bat_ids
                            uint64_t seed, int32_t* u_locs_dev, int32_t* i_locs_dev, int32_t* u_locs_seq_dev,
                            int64_t* n_out_host, sagnn_stream_t stream);
 
+/* ---- device-side sampleTrainBatch + negSamp (model.py:252-302, DataHandler.py:28-41) ----------
+ * seq_ptr_dev int64 [U+1] / seq_items_dev int32: handler.sequence as CSR (a user's interactions in time order);
+ * tst_int_dev int32 [U] (held-out item, -1 = None; may be NULL); bat_ids_dev int32 [batch].  Per batch position b,
+ * u = bat_ids[b], seq = sequence[u], posset = seq[:-1], sampNum = min(train_sample_num, len(posset)) (0: nothing
+ * emitted), choose = randint(1, max(min(pred_num + 1, len(posset) - 3), 1)): the positive posset[-choose], sampNum
+ * times, and sampNum negatives = uniform items without a training interaction of u in ANY interval of the plan (the
+ * reference tests the dense row of trnMat; here a binary search in the plan's CSR rows) and different from seq[-1]
+ * and tst_int[u].  Outputs: u_locs / i_locs / u_locs_seq int32 (capacity 2*batch*train_sample_num): the positives of
+ * all users in batch order, then their negatives in the same order (*n_out_host = entries written);
+ * sequence int32 / mask float [batch_pad, pos_length]: the last pos_length items of posset[:-choose], right-aligned,
+ * mask 1 on them, rows >= batch zero (the reference pads to args.batch); choose_out int32 [batch] (nullable).
+ * Counter-based generator keyed by (seed, batch position, draw): same seed, same samples; not numpy's stream.
+ * Synchronises the stream. */
+int sagnn_sample_train_batch(const sagnn_plan* plan, const int64_t* seq_ptr_dev, const int32_t* seq_items_dev,
+                             const int32_t* tst_int_dev, const int32_t* bat_ids_dev, int batch, int batch_pad,
+                             int train_sample_num, int pred_num, int pos_length, uint64_t seed, int32_t* u_locs_dev,
+                             int32_t* i_locs_dev, int32_t* u_locs_seq_dev, int32_t* sequence_dev, float* mask_dev,
+                             int32_t* choose_out_dev, int64_t* n_out_host, sagnn_stream_t stream);
+
 /* Host-buffer entry point (what a non-torch caller binds): copies the embeddings (and,
  * when g_*_host != NULL, the upstream gradients) to the device, runs forward (+ backward),
  * copies the results back and synchronises.  Device buffers are cached inside the plan.

@@ -68,6 +68,8 @@ SIGNATURES = {
                                              ctypes.c_int, ctypes.c_float, vp, vp, ctypes.c_int64, vp, ctypes.c_int64, vp]),
     "sagnn_sample_ssl_batch": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, vp, vp, vp,
                                               c_i64p, vp]),
+    "sagnn_sample_train_batch": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_uint64, vp, vp, vp, vp, vp, vp, c_i64p, vp]),
     "sagnn_host_forward": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int]),
     "sagnn_host_backward": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float]),
     "sagnn_propagate_host": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,

@@ -375,6 +375,7 @@ static bool d_ok(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
 // workspace layout: [tickets | partials | table buffer 0 | table buffer 1]
 struct WsLayout {
   size_t tickets_off, partials_off, buf_off[2], pm_off[2], total;
+  size_t fwd_total;      // what a forward / messagePropagate call touches (no pre-masked backward tables)
   size_t ticket_words;   // slice-reduction tickets of all tree levels
   size_t zero_bytes;     // tickets + one set of per-segment queue heads per layer launch, zeroed per call
   size_t table_floats;   // T*(U+I)*d
@@ -399,8 +400,9 @@ static WsLayout ws_layout(const sagnn_plan* p, int n_layers, int d) {
     w.buf_off[b] = off;
     if (b < nbuf) off = align_up(off + sizeof(float) * w.table_floats, 256);
   }
+  w.fwd_total = off;
   const int npm = n_layers < 2 ? n_layers : 2;
-  for (int b = 0; b < 2; ++b) {   // row-per-warp backward: pre-masked copies of the upstream / running gradient
+  for (int b = 0; b < 2; ++b) {   // backward: pre-masked copies of the upstream / running gradient
     w.pm_off[b] = off;
     if (b < npm && use_rpw()) off = align_up(off + sizeof(float) * w.table_floats, 256);
   }
@@ -457,7 +459,7 @@ extern "C" int sagnn_workspace_bytes(const sagnn_plan* p, int n_layers, int d, s
                                      size_t* mask_bytes, size_t* bwd_bytes) {
   if (int rc = check_common(p, n_layers, d, "workspace_bytes")) return rc;
   WsLayout w = ws_layout(p, n_layers, d);
-  if (fwd_bytes) *fwd_bytes = w.total;
+  if (fwd_bytes) *fwd_bytes = w.fwd_total;
   if (bwd_bytes) *bwd_bytes = w.total;
   if (mask_bytes) *mask_bytes = mask_layer_bytes(p, d) * n_layers;
   return SAGNN_OK;
@@ -484,8 +486,8 @@ static int fwd_impl(const sagnn_plan* p, int interval, const float* uE, const fl
   SAGNN_REQUIRE(interval < p->T, SAGNN_INVALID_ARG, "propagate_fwd: interval %d outside [0,%d)", interval, p->T);
   SAGNN_REQUIRE(uE && iE && uOut && iOut && ws, SAGNN_INVALID_ARG, "propagate_fwd: NULL tensor");
   WsLayout w = ws_layout(p, L, d);
-  SAGNN_REQUIRE(ws_bytes >= w.total, SAGNN_WORKSPACE_TOO_SMALL,
-                "propagate_fwd: workspace %zu < %zu bytes", ws_bytes, w.total);
+  SAGNN_REQUIRE(ws_bytes >= w.fwd_total, SAGNN_WORKSPACE_TOO_SMALL,
+                "propagate_fwd: workspace %zu < %zu bytes", ws_bytes, w.fwd_total);
   char* base = (char*)ws;
   SpmmParams s;
   base_params(p, s);
@@ -715,8 +717,8 @@ extern "C" int sagnn_message_propagate(const sagnn_plan* p, int k, int side, con
                 "message_propagate: bad interval %d / side %d", k, side);
   SAGNN_REQUIRE(src && out && ws, SAGNN_INVALID_ARG, "message_propagate: NULL tensor");
   WsLayout w = ws_layout(p, 1, d);
-  SAGNN_REQUIRE(ws_bytes >= w.total, SAGNN_WORKSPACE_TOO_SMALL,
-                "message_propagate: workspace %zu < %zu bytes", ws_bytes, w.total);
+  SAGNN_REQUIRE(ws_bytes >= w.fwd_total, SAGNN_WORKSPACE_TOO_SMALL,
+                "message_propagate: workspace %zu < %zu bytes", ws_bytes, w.fwd_total);
   char* base = (char*)ws;
   SpmmParams s;
   base_params(p, s);

@@ -196,7 +196,14 @@ def allgather_row_blocks(tables, rank=None, group=None):
             b = t.shape[1] // world
             pairs += [(t[k], t[k, rank * b:(rank + 1) * b]) for k in range(t.shape[0])]
         if tabs[0].is_cuda:
-            with dist._coalescing_manager(group=group):
+            # one NCCL launch for all (interval, side) pairs when torch offers its (private) coalescing manager;
+            # otherwise the same in-place all-gathers one by one
+            cm = getattr(dist, "_coalescing_manager", None)
+            if cm is not None:
+                with cm(group=group):
+                    for out, mine in pairs:
+                        dist.all_gather_into_tensor(out, mine, group=group)
+            else:
                 for out, mine in pairs:
                     dist.all_gather_into_tensor(out, mine, group=group)
         else:

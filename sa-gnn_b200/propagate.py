@@ -135,6 +135,45 @@ class Plan:
                 out.append((u[:n.value], i[:n.value], s[:n.value]))
         return out
 
+    def sample_train_batch(self, bat_ids, sequences, tst_int=None, train_sample_num=40, pred_num=5, pos_length=200,
+                           batch_pad=None, seed=0):
+        """``Recommender.sampleTrainBatch(batIds, handler.trnMat, ...)`` + ``negSamp`` (model.py:252-302,
+        DataHandler.py:28-41) on the device.  ``sequences``: ``handler.sequence`` (list of per-user item lists) or a
+        ``(seq_ptr int64 [U+1], seq_items int32)`` pair of tensors; ``tst_int``: ``handler.tstInt`` (None entries = no
+        held-out item).  Returns ``(uLocs, iLocs, sequence [batch_pad, pos_length], mask, uLocs_seq, choose)`` CUDA
+        tensors laid out like the reference's lists (positives first, then the negatives).  The label test of the
+        negative sampler reads the plan's interval CSRs (trnMat = their union); ``seed`` keys the generator."""
+        lib = _lib.load_library()
+        dev = self.device
+        if isinstance(sequences, (tuple, list)) and len(sequences) == 2 and isinstance(sequences[0], torch.Tensor):
+            seq_ptr, seq_items = sequences[0].to(dev, torch.int64).contiguous(), sequences[1].to(dev, torch.int32).contiguous()
+        else:
+            lens = np.fromiter((len(x) for x in sequences), dtype=np.int64, count=len(sequences))
+            ptr = np.zeros(len(sequences) + 1, dtype=np.int64)
+            np.cumsum(lens, out=ptr[1:])
+            flat = np.concatenate([np.asarray(x, dtype=np.int32) for x in sequences]) if ptr[-1] else np.zeros(0, np.int32)
+            seq_ptr, seq_items = torch.from_numpy(ptr).to(dev), torch.from_numpy(flat).to(dev)
+        if seq_ptr.numel() != self.U + 1:
+            raise ValueError("need one sequence per user (%d), got %d" % (self.U, seq_ptr.numel() - 1))
+        tst = None
+        if tst_int is not None:
+            tst = _as_dev_i32(np.array([-1 if x is None else int(x) for x in tst_int], dtype=np.int32), dev)
+        bat = _as_dev_i32(bat_ids, dev)
+        batch = int(bat.numel())
+        batch_pad = batch if batch_pad is None else int(batch_pad)
+        cap = max(1, 2 * batch * int(train_sample_num))
+        with torch.cuda.device(dev):
+            u, i, s = (torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(3))
+            seq = torch.empty((batch_pad, int(pos_length)), dtype=torch.int32, device=dev)
+            mask = torch.empty((batch_pad, int(pos_length)), dtype=torch.float32, device=dev)
+            choose = torch.empty(max(batch, 1), dtype=torch.int32, device=dev)
+            n = ctypes.c_int64()
+            _lib.check(lib.sagnn_sample_train_batch(
+                self.handle, _ptr(seq_ptr), _ptr(seq_items), _ptr(tst), _ptr(bat), batch, batch_pad, int(train_sample_num),
+                int(pred_num), int(pos_length), int(seed) & (2**64 - 1), _ptr(u), _ptr(i), _ptr(s), _ptr(seq), _ptr(mask),
+                _ptr(choose), ctypes.byref(n), _stream_ptr(dev)))
+        return u[:n.value], i[:n.value], seq, mask, s[:n.value], choose[:batch]
+
     # -- scratch ----------------------------------------------------------------------
     def workspace_bytes(self, n_layers, d):
         f, m, b = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()

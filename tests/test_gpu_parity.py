@@ -679,6 +679,60 @@ def test_sample_ssl_batch_contract():
 
 
 # ---------------------------------------------------------------- sampled pair scores
+def test_sample_train_batch_contract():
+    """sagnn_sample_train_batch = Recommender.sampleTrainBatch + negSamp (model.py:252-302, DataHandler.py:28-41) on the
+    device: layout (positives first, then negatives), counts min(train_sample_num, len(seq)-1), the positive
+    posset[-choose] with choose in the reference's randint range, negatives without any training interaction and
+    different from the user's last and held-out item, right-aligned history / mask, zero padding rows, determinism."""
+    rng = np.random.default_rng(12)
+    U, I, T = 400, 300, 3
+    mats = random_interval_mats(T, U, I, 2500, seed=13)
+    plan = sg.build_plan(mats)
+    label = sum((m != 0).astype(np.int8) for m in mats).toarray() > 0            # trnMat structure = union of the intervals
+    seqs = []
+    for u in range(U):
+        n = int(rng.integers(0, 30)) if u % 17 else 0                            # some users with empty / tiny sequences
+        seqs.append([int(x) for x in rng.integers(0, I, size=n)])
+    seqs[5] = [int(x) for x in rng.integers(0, I, size=260)]                     # longer than pos_length
+    tst = [None if u % 5 == 0 else int(rng.integers(0, I)) for u in range(U)]
+    bat = rng.permutation(U)[:96].astype(np.int32)
+    bat[0] = 5
+    tsn, pred, plen, pad = 7, 5, 200, 128
+    out = plan.sample_train_batch(bat, seqs, tst, tsn, pred, plen, batch_pad=pad, seed=99)
+    uL, iL, seq, mask, uS, choose = [t.cpu().numpy() for t in out]
+    again = [t.cpu().numpy() for t in plan.sample_train_batch(bat, seqs, tst, tsn, pred, plen, batch_pad=pad, seed=99)]
+    assert all(np.array_equal(a, b) for a, b in zip((uL, iL, seq, mask, uS, choose), again))
+    other = plan.sample_train_batch(bat, seqs, tst, tsn, pred, plen, batch_pad=pad, seed=100)[1].cpu().numpy()
+    assert not np.array_equal(other, iL)
+    counts = [min(tsn, max(len(seqs[u]) - 1, 0)) for u in bat]
+    half = sum(counts)
+    assert len(uL) == len(iL) == len(uS) == 2 * half
+    assert seq.shape == (pad, plen) and mask.shape == (pad, plen)
+    cur = 0
+    for b, u in enumerate(bat):
+        s_, n = seqs[u], counts[b]
+        posset = s_[:-1]
+        hi = max(min(pred + 1, len(posset) - 3), 1)
+        assert 1 <= choose[b] <= hi
+        for j in range(n):
+            for o in (cur + j, half + cur + j):
+                assert uL[o] == u and uS[o] == b
+            assert iL[cur + j] == posset[-choose[b]]
+            neg = iL[half + cur + j]
+            assert 0 <= neg < I and not label[u, neg] and neg != s_[-1] and neg != (tst[u] if tst[u] is not None else -1)
+        cur += n
+        hist = posset[:len(posset) - choose[b]] if n else posset[:max(len(posset) - 1, 0)]
+        keep = hist[-plen:]
+        want = np.zeros(plen, np.int64); wm = np.zeros(plen)
+        if keep:
+            want[-len(keep):] = keep; wm[-len(keep):] = 1
+        np.testing.assert_array_equal(seq[b], want)
+        np.testing.assert_array_equal(mask[b], wm)
+    assert not seq[len(bat):].any() and not mask[len(bat):].any()
+    negs = iL[half:]
+    assert len(np.unique(negs)) > I // 3                                           # spread over the item range
+
+
 @pytest.mark.parametrize("d,layout,act", [(64, "trd", "leakyRelu"), (64, "rtd", "leakyRelu"), (128, "trd", None),
                                           (32, "rtd", None), (256, "trd", "leakyRelu")])
 def test_pair_scores_match_oracle(d, layout, act):
