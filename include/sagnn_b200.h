@@ -104,12 +104,12 @@ int sagnn_plan_set_interval(sagnn_plan* plan, int k, const int32_t* row_dev, con
  * every A_k^T (it still holds the complete adjacency, since the rows it owns gather from every row of
  * the other side).  propagate_* then read whole tables and write only the owned rows; between layers
  * the caller all-gathers the freshly written table (sagnn_propagate_fwd_layers / _bwd_levels /
- * sagnn_workspace_table below).  Row-per-warp kernel only. */
+ * sagnn_workspace_table below). */
 int sagnn_plan_set_row_block(sagnn_plan* plan, int u_begin, int u_end, int i_begin, int i_end);
 
-/* Optional, before finalize: the latdim the plan will mostly be run with (default 64).  It sizes
- * the hot-row set so that all of it fits the shared-memory staging area at that d; other d still
- * work (hot rows that do not fit are read through their ids). */
+/* Optional, before finalize: the latdim the plan will mostly be run with (default 64).  It picks the
+ * schedule the plan carries: the packed task stream of the packet-stream kernel below 128, the task records of
+ * the round-1 kernel from 128 on (measured faster there); every latdim in {32, 64, 128, 256} works with either. */
 int sagnn_plan_set_latdim_hint(sagnn_plan* plan, int d);
 
 /* Row pointers over all intervals, optional edge weights, degree-binned schedule.

@@ -41,6 +41,12 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 #ifndef SAGNN_PKT_HOT
 #define SAGNN_PKT_HOT 0         // 1: build the hot-row staging path (shared-memory copies of popular source rows); measured slower, off
 #endif
+#ifndef SAGNN_PKT_X
+#define SAGNN_PKT_X 0           // timing experiments (wrong results): 1 = no gathers, 2 = no own rows / epilogue
+#endif
+#ifndef SAGNN_PKT_PF
+#define SAGNN_PKT_PF 0          // 1: L1 prefetch of a task's next gather block while the current one is in flight
+#endif
 #ifndef SAGNN_PKT_THREADS
 #define SAGNN_PKT_THREADS 1024
 #endif

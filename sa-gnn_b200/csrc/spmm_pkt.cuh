@@ -264,7 +264,11 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
     const uint32_t hwb = cb + (uint32_t)((nc + 3) & ~3) * 4;                   // ... and the weights, same split
     const uint32_t wb = hwb + (uint32_t)((nh + 3) & ~3) * 4;
     // the lock-step group follows its longest task: cold edges (global gathers) and hot edges (shared memory)
+#if SAGNN_PKT_X == 1 || SAGNN_PKT_X >= 3   // timing experiments: no gathers at all
+    int nmax = 0, hmax = 0;
+#else
     int nmax = n - nh, hmax = nh;
+#endif
     if constexpr (G >= 2) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, LPT));
     if constexpr (G >= 4) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, 2 * LPT));
     if constexpr (HOT && G >= 2) hmax = max(hmax, __shfl_xor_sync(FULL, hmax, LPT));
@@ -329,9 +333,26 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
     };
 
     // ---- gather-reduce: full blocks on the spot, the remainder stays in flight under the own-row loads ----
+#if SAGNN_PKT_PF
+    // While a block's loads fly, the NEXT block's rows are pulled into L1 (no registers, no scoreboard): its loads
+    // then find them next to the SM instead of paying another L2 round trip.  Lane 2*slot + line fetches one 128-byte line.
+    auto prefetch_block = [&](int jj) {
+      constexpr int LINES = ROWB / 128 > 0 ? ROWB / 128 : 1;
+      if (piece < GS * LINES) {
+        const int e = jj + piece / LINES;
+        if (e < nc) {
+          const uint32_t code = (uint32_t)lds_i1(cb + (uint32_t)e * 4);
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(src + (uint64_t)code * src_stride + (uint32_t)(piece % LINES) * 128));
+        }
+      }
+    };
+#endif
     int jl = 0;
     for (; jl + GS <= nmax; jl += GS) {
       gather(std::integral_constant<int, GS>(), jl);
+#if SAGNN_PKT_PF
+      if (jl + GS < nmax) prefetch_block(jl + GS);
+#endif
       reduce(std::integral_constant<int, GS>(), jl);
     }
     const int rem = nmax - jl;                          // < GS, warp-uniform: one straight-line case per length
@@ -360,7 +381,9 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
       }
       if (BWD && (flags & F_PM)) pbits = mask_bits(pm_base, row);
     };
+#if SAGNN_PKT_X != 2 && SAGNN_PKT_X != 4   // (2, 4 = timing experiments without own-row loads)
     if (valid && !multi) load_own();                    // slices of long rows: only the finisher needs the own rows
+#endif
 
     // ---- hot edges: staged rows out of shared memory, added while the cold remainder and the own rows fly ----
     if (HOT && hmax > 0) {
@@ -417,7 +440,12 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
     // acquire as CCTL.IVALL: one invalidation of the SM's whole L1 per slice, which the gathers of
     // high-degree graphs pay for.)  Lane groups run this independently (group-masked shuffles).
     bool whole_row = valid;
+#if SAGNN_PKT_X == 3        // timing experiment: no slice publication / ticket tree
+    if (multi) whole_row = false;
+    if (false) {
+#else
     if (multi) {
+#endif
       const uint32_t aux = (uint32_t)rec.z;            // global slice id
       const uint32_t lr = __ldg(p.chunk_lr + aux);
       const int64_t cbase = __ldg(p.chunk_base + lr);
@@ -476,7 +504,14 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
     }
 
     // ---- fused epilogue ------------------------------------------------------------------------
+#if SAGNN_PKT_X == 4
+    own_a[0] = own_a[1] = own_a[2] = own_a[3] = 1.f; own_b[0] = own_b[1] = own_b[2] = own_b[3] = 1.f;
+#endif
+#if SAGNN_PKT_X == 2 || SAGNN_PKT_X == 5
+    if (whole_row && acc[0] + own_a[0] + own_b[0] == 123.456f) {   // keeps the loads alive, never true
+#else
     if (whole_row) {
+#endif
       const uint64_t off = (uint64_t)row * ROWB + lane_off;       // bytes inside a contiguous [rows, d] table
       if (BWD) {
         // n = G + g + A (sigma' . g_other)      (SURVEY A.2); at the top level g == G

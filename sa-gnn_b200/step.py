@@ -46,8 +46,8 @@ class PropagationStep:
                 self.user_out_full, self.item_out_full = self.user_out, self.item_out
             self.d_u, self.d_i = mk(plan.U), mk(plan.I)
         self.graph = None
-        # L forward + L backward layer kernels + the streaming pre-mask of the upstream (row-per-warp kernel)
-        self.kernel_launches_per_step = 2 * self.L + (0 if os.environ.get("SAGNN_KERNEL", "").lower().startswith("v7") else 1)
+        # L forward + L backward layer kernels + the streaming pre-mask of the upstream
+        self.kernel_launches_per_step = 2 * self.L + 1
 
     def set_scatter(self, world, rank, user_ptrs, item_ptrs):
         """Fused hand-off (``sagnn_propagate_fwd_scatter``, layout "rtd" only): from now on ``forward()``

@@ -6,7 +6,7 @@ import sagnn_b200 as sg
 from sagnn_b200 import data_handler as dh, _lib
 from sagnn_b200.step import PropagationStep
 
-name = sys.argv[1] if len(sys.argv) > 1 else "gowalla"
+name = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "gowalla"
 g = dh.make_named(name, seed=100)
 L, d = g.meta["L"], g.meta["d"]
 plan = sg.build_plan(g.sub_mat)
@@ -14,6 +14,8 @@ step = PropagationStep(plan, L, d)
 step.u_embed.copy_(torch.from_numpy(dh.xavier_embeddings(g.graph_num, g.n_user, d, 100)))
 step.i_embed.copy_(torch.from_numpy(dh.xavier_embeddings(g.graph_num, g.n_item, d, 101)))
 step.g_user.normal_(); step.g_item.normal_()
+if '--calibrate' in sys.argv:
+    print('calibrated split', step.calibrate(rounds=2))
 for _ in range(3):
     step.run()
 torch.cuda.synchronize()
