@@ -174,7 +174,7 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
   const bool all_fit = p.hot_rows <= Geo::HOT_CAP;     // (uniform) every hot slot of the plan is staged
 
   // ---- my packets -----------------------------------------------------------------------------
-  // The first NS packets of every warp are dealt statically (packet q0 + s*stride of the segment's
+  // The first NS + 1 packets of every warp are dealt statically (packet q0 + s*stride of the segment's
   // list), the rest come from the segment's queue head in batches of qb packets per atomic (1 for small
   // segments, up to 8 when a warp has hundreds of packets: all warps of a segment hit ONE counter, and
   // millions of single-packet grabs serialise in its L2 slice), fetched ahead: queue head -> directory
@@ -184,7 +184,7 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
   const uint32_t* dir = p.pkt_dir + cd.pkt_begin;     // packet offsets, 16-byte units into the stream
   const unsigned q0 = cd.q0 + (unsigned)warp;
   const unsigned stride = cd.stride;
-  const unsigned q_dyn0 = (unsigned)NS * stride;       // packets below this index are dealt statically
+  const unsigned q_dyn0 = (unsigned)(NS + 1) * stride; // packets below this index are dealt statically
   unsigned* qhead = p.ctrs + seg;
 
   const uint32_t slot0 = smem_u32(smem_raw) + (uint32_t)warp * (NS * Geo::SLOT_BYTES);
@@ -216,17 +216,20 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
                        bytes, bar0 + 8 * slot);
     }
   };
+  // start-up: the directory entries of my NS + 1 static packets are loaded together (independent loads, one DRAM
+  // round trip), NS bulk copies go out at once, the (NS+1)-th entry waits for the first free slot; the queue's first
+  // ticket is requested now and only read at that first refill -- nothing in the prologue waits for an atomic
   unsigned n_issued = 0;                               // packets of mine brought in (or on their way)
+  uint2 dv0[NS + 1];
 #pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    const uint2 dv = load_dir(q0 + (unsigned)s * stride);
-    if (dv.y != 0u) { issue_pkt(s, dv); ++n_issued; }
-  }
-  // two-deep look-ahead of the dynamic part: dir_next belongs to the packet of the next refill, q_next to the one after
-  uint2 dir_next = make_uint2(0u, 0u);
+  for (int s = 0; s <= NS; ++s) dv0[s] = load_dir(q0 + (unsigned)s * stride);
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+    if (dv0[s].y != 0u) { issue_pkt(s, dv0[s]); ++n_issued; }
+  uint2 dir_next = dv0[NS];                            // packet of the next refill ((0,0): none)
   unsigned q_raw = 0;                                  // lane 0: ticket of the batch after the current one
   unsigned q_cur = n_pk, q_end = n_pk;                 // current batch: packets [q_cur, q_end) still to fetch
-  bool more = n_issued == (unsigned)NS;                // the queue may still have packets for me
+  bool more = dir_next.y != 0u;                        // the queue may still have packets for me
   auto next_packet = [&]() -> unsigned {               // warp-uniform; n_pk or more when the queue is drained
     if (q_cur == q_end && more) {                      // batch used up: move to the one grabbed a batch ago
       q_cur = grab_value(q_raw);
@@ -236,10 +239,7 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
     }
     return q_cur < q_end ? q_cur++ : n_pk;
   };
-  if (more) {
-    q_raw = grab_issue();
-    dir_next = load_dir(next_packet());
-  }
+  if (more) q_raw = grab_issue();
 
   bool hot_ready = n_hot == 0;                         // the staged rows have landed (waited for on first use)
   unsigned j = 0;                                      // packet the cursor is in (count of mine)
