@@ -112,6 +112,17 @@ int sagnn_plan_set_row_block(sagnn_plan* plan, int u_begin, int u_end, int i_beg
  * the round-1 kernel from 128 on (measured faster there); every latdim in {32, 64, 128, 256} works with either. */
 int sagnn_plan_set_latdim_hint(sagnn_plan* plan, int d);
 
+/* Optional, before finalize: stage the n highest-degree rows of every source table in shared memory (TMA bulk
+ * copies at kernel start; every task's edge codes list its hot edges first, so the staged rows are read in a
+ * loop of their own without a per-edge test).  Default 0: on B200 an L1 hit costs the same L1TEX cycles as a
+ * shared-memory read and the staged copy takes the L1's capacity, so the measured step is slower with it
+ * (DESIGN.md section 4); kept for tables whose hot set does not stay in L1.  n is capped by what fits next to the
+ * packet rings at the hinted latdim (sagnn_plan_stats reports the number used); plans hinted latdim >= 128 ignore
+ * it.  The hot-first order changes the summation order inside a row, so results differ in the last bits between
+ * plans with different hot sets (still deterministic, still within 1e-5 of the reference).
+ * (north_star "TMA/shared-memory staging of hot item rows"; the reference has no counterpart.) */
+int sagnn_plan_set_hot_rows(sagnn_plan* plan, int n);
+
 /* Row pointers over all intervals, optional edge weights, degree-binned schedule.
  * Must be called once after every interval has been set. */
 int sagnn_plan_finalize(sagnn_plan* plan, int weight_mode, sagnn_stream_t stream);
@@ -134,7 +145,7 @@ int sagnn_plan_get_weights(const sagnn_plan* plan, int k, int side, float* w_dev
                            sagnn_stream_t stream);
 
 /* schedule statistics: out[0]=rows, out[1]=short rows, out[2]=long rows, out[3]=chunks,
- * out[4]=max degree, out[5]=sum of edges over both sides, out[6]=grid blocks, out[7]=SMs */
+ * out[4]=max degree, out[5]=sum of edges over both sides, out[6]=hot slots per table in use, out[7]=SMs */
 int sagnn_plan_stats(const sagnn_plan* plan, int64_t* out8);
 
 /* Load balance.  Persistent CTAs are dealt to the 2T segments (seg = 2k + side) from a static cost

@@ -27,6 +27,7 @@ SIGNATURES = {
     "sagnn_plan_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_i64p, ctypes.POINTER(vp)]),
     "sagnn_plan_set_interval": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int64, vp]),
     "sagnn_plan_set_latdim_hint": (ctypes.c_int, [vp, ctypes.c_int]),
+    "sagnn_plan_set_hot_rows": (ctypes.c_int, [vp, ctypes.c_int]),
     "sagnn_plan_finalize": (ctypes.c_int, [vp, ctypes.c_int, vp]),
     "sagnn_plan_get_csr": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
     "sagnn_plan_get_degrees": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]),

@@ -8,12 +8,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SOURCES = ["csrc/plan.cu", "csrc/spmm.cu", "csrc/pairs.cu", "csrc/events.cu", "csrc/sampler.cu"]
-HEADERS = ["csrc/common.cuh", "csrc/spmm_rpw.cuh", "../include/sagnn_b200.h"]
+HEADERS = ["csrc/common.cuh", "csrc/spmm_rpw.cuh", "csrc/spmm_pkt.cuh", "../include/sagnn_b200.h"]
 LIB = os.path.join(HERE, "lib", "libsagnn_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17", "--threads", "4",
     "-Xcompiler", "-fPIC", "-shared",
     "-Xcompiler", "-Wno-deprecated-declarations",
 ]

@@ -38,9 +38,6 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- packet-stream kernel geometry shared by the plan builder and the kernel ----
-#ifndef SAGNN_PKT_HOT
-#define SAGNN_PKT_HOT 0         // 1: build the hot-row staging path (shared-memory copies of popular source rows); measured slower, off
-#endif
 #ifndef SAGNN_PKT_X
 #define SAGNN_PKT_X 0           // timing experiments (wrong results): 1 = no gathers, 2 = no own rows / epilogue
 #endif
@@ -111,6 +108,7 @@ struct sagnn_plan {
   bool has_custom_w = false;
   bool finalized = false;
   int weight_mode = 0;
+  int hot_rows_wanted = 0;        // sagnn_plan_set_hot_rows (before finalize)
   int hot_rows = 0;               // hot slots per source table the edge codes use (packet-stream kernel: what fits at latdim_hint)
   int latdim_hint = 64;
   bool pkt = true;                // schedule built for the packet-stream kernel (else: v8 task records + edge codes)

@@ -551,6 +551,13 @@ extern "C" int sagnn_plan_set_latdim_hint(sagnn_plan* p, int d) {
   return SAGNN_OK;
 }
 
+extern "C" int sagnn_plan_set_hot_rows(sagnn_plan* p, int n) {
+  SAGNN_REQUIRE(p && !p->finalized, SAGNN_INVALID_ARG, "set_hot_rows: NULL or finalized plan");
+  SAGNN_REQUIRE(n >= 0, SAGNN_INVALID_ARG, "set_hot_rows: n=%d", n);
+  p->hot_rows_wanted = n;
+  return SAGNN_OK;
+}
+
 extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   SAGNN_REQUIRE(p, SAGNN_INVALID_ARG, "finalize: NULL plan");
@@ -596,15 +603,18 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
 
   // ---- schedule: per-segment task lists, hot slots, hot-first edge codes ------------------
   p->pkt = sagnn::plan_uses_pkt(p->latdim_hint);
-  // hot slots: the highest-degree rows of every table, as many as fit the kernel's staging area at the hinted
-  // latdim (SAGNN_HOT_ROWS overrides, 0 = none); the v8 kernel stages nothing
-  // OFF by default: measured on B200 (Gowalla shape, 472 staged rows) 0.61 vs 0.47 ms per step -- the staged
-  // copy takes the shared memory the L1 cache would otherwise use for exactly those rows, and the extra
-  // lock-step phase costs more than the L2 round trips it saves.  Builds with -DSAGNN_PKT_HOT=1 honour SAGNN_HOT_ROWS=N.
-  p->hot_rows = 0;
-  if (const char* e = getenv("SAGNN_HOT_ROWS")) {
-    const int v = atoi(e), cap = (SAGNN_PKT_HOT && p->pkt) ? sagnn::pkt_hot_capacity(p->latdim_hint, p->w != nullptr) : 0;
-    p->hot_rows = v < 0 ? 0 : (v > cap ? cap : v);
+  // hot slots (sagnn_plan_set_hot_rows, or SAGNN_HOT_ROWS=N for A/B runs): the N highest-degree rows of every
+  // table get slot numbers, every task's edge codes list its hot edges first, and the packet-stream kernel
+  // stages those rows in shared memory by TMA bulk copies (capped by what fits next to the packet rings at the
+  // hinted latdim; the round-1 kernel stages nothing).  OFF unless asked for: measured on B200 (Gowalla shape,
+  // 472 staged rows) 0.61 vs 0.47 ms per step -- the staged copy takes the shared memory the L1 cache would
+  // otherwise use for exactly those rows, an L1 hit costs the same L1TEX cycles as a shared-memory read, and the
+  // extra lock-step phase costs more than the L2 round trips it saves.
+  {
+    int want = p->hot_rows_wanted;
+    if (const char* e = getenv("SAGNN_HOT_ROWS")) want = atoi(e);
+    const int cap = p->pkt ? sagnn::pkt_hot_capacity(p->latdim_hint, p->w != nullptr) : 0;
+    p->hot_rows = want < 0 ? 0 : (want > cap ? cap : want);
   }
   SAGNN_REQUIRE(p->num_sms >= 2, SAGNN_INVALID_ARG, "finalize: need at least 2 SMs");
   SAGNN_REQUIRE(2 * p->e_total < ((int64_t)1 << 32), SAGNN_INVALID_ARG,

@@ -49,6 +49,7 @@ struct SpmmParams {
   const sagnn_cta* cta;
   const sagnn_cta* cta_host; // host copy of `cta` (launch code only)
   int hot_rows;              // hot slots per table used by the plan's edge codes
+  int pdl;                   // host only: launch as a programmatic dependent of the kernel before it on the stream
   int single_seg;            // >= 0: every CTA works on this segment (messagePropagate); -1: use cta[]
   int n_seg_total;           // 2T
   int U, I;
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(256)
 premask_kernel(const float4* __restrict__ in_u, const float4* __restrict__ in_i, const uint8_t* __restrict__ m_u,
                const uint8_t* __restrict__ m_i, float4* __restrict__ out_u, float4* __restrict__ out_i, int64_t n4_u,
                int64_t n4_i, float leaky, int rtd_T, int k0, int64_t rows_u, int64_t rows_i, int q) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the level kernel after me starts up under my tail
   const int64_t n = n4_u + n4_i, step = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
     const bool it = i >= n4_u;
@@ -247,15 +249,21 @@ bool use_pkt() {
   return v;
 }
 
-template <int D, int MODE, bool WEIGHTED, bool RTD>
-static int launch_pkt_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaStream_t st) {
+// SAGNN_PDL=0: plain stream order between the launches of a chain (A/B runs)
+static bool use_pdl() {
+  static const bool v = [] { const char* e = getenv("SAGNN_PDL"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
+template <int D, int MODE, bool WEIGHTED, bool RTD, bool HOT>
+static int launch_pkt_h(const sagnn_plan* plan, const SpmmParams& prm_in, cudaStream_t st) {
   SpmmParams prm = prm_in;
   if (plan->trace_dev && plan->trace_launch < plan->trace_capacity)   // diagnostics only
     prm.trace = plan->trace_dev + (size_t)(plan->trace_launch++) * plan->num_sms * 4;
   using G = PktGeo<D, WEIGHTED>;
   static_assert(G::SMEM <= (size_t)kSmemBudget, "shared-memory budget exceeded");
   static std::atomic<uint64_t> configured{0};   // bit per device: the attribute is per device
-  auto kern = spmm_pkt_kernel<D, MODE, WEIGHTED, RTD>;
+  auto kern = spmm_pkt_kernel<D, MODE, WEIGHTED, RTD, HOT>;
   const uint64_t bit = 1ull << (plan->device & 63);
   if (!(configured.load(std::memory_order_acquire) & bit)) {
     SAGNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
@@ -273,9 +281,22 @@ static int launch_pkt_t(const sagnn_plan* plan, const SpmmParams& prm_in, cudaSt
   }
   // the staging area is only allocated when the plan has hot slots: without them the L1 keeps that capacity
   const int staged = plan->hot_rows < G::HOT_CAP ? plan->hot_rows : G::HOT_CAP;
-  kern<<<plan->num_sms, kPktThreads, G::PKT_SMEM + (size_t)staged * G::ROWB, st>>>(prm);
-  SAGNN_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan->num_sms); cfg.blockDim = dim3(kPktThreads);
+  cfg.dynamicSmemBytes = G::PKT_SMEM + (size_t)staged * G::ROWB; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (prm.pdl && use_pdl()) ? 1 : 0;
+  SAGNN_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
   return SAGNN_OK;
+}
+
+// plans with hot slots (SAGNN_HOT_ROWS at plan build) run the instance with the shared-memory staging path
+template <int D, int MODE, bool WEIGHTED, bool RTD>
+static int launch_pkt_t(const sagnn_plan* plan, const SpmmParams& prm, cudaStream_t st) {
+  return plan->hot_rows > 0 ? launch_pkt_h<D, MODE, WEIGHTED, RTD, true>(plan, prm, st)
+                            : launch_pkt_h<D, MODE, WEIGHTED, RTD, false>(plan, prm, st);
 }
 
 template <int D, int MODE>
@@ -451,7 +472,7 @@ extern "C" int sagnn_plan_stats(const sagnn_plan* p, int64_t* out8) {
   SAGNN_REQUIRE(p && out8, SAGNN_INVALID_ARG, "plan_stats: NULL argument");
   SAGNN_REQUIRE(p->finalized, SAGNN_NOT_FINALIZED, "plan_stats: plan not finalized");
   out8[0] = p->n_rows; out8[1] = p->n_short; out8[2] = p->n_long; out8[3] = p->n_chunks;
-  out8[4] = p->max_deg; out8[5] = 2 * p->e_total; out8[6] = 0; out8[7] = p->num_sms;
+  out8[4] = p->max_deg; out8[5] = 2 * p->e_total; out8[6] = p->hot_rows; out8[7] = p->num_sms;
   return SAGNN_OK;
 }
 
@@ -530,6 +551,7 @@ static int fwd_impl(const sagnn_plan* p, int interval, const float* uE, const fl
     s.mask_i = masks ? (uint8_t*)masks + (size_t)l * mlw + mu : nullptr;
     for (int wv = 0; wv < (interval >= 0 ? 1 : p->n_waves); ++wv) {   // one launch unless 2T exceeds the SM count
       if (interval < 0) { s.cta = p->cta_dev + (size_t)wv * p->num_sms; s.cta_host = p->cta_host.data() + (size_t)wv * p->num_sms; }
+      s.pdl = (l > l_begin || wv > 0) ? 1 : 0;   // the launch before it on the stream is a kernel of this call
       if (int rc = launch(p, s, d, MODE_FWD, st)) return rc;
     }
   }
@@ -600,6 +622,7 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
   const size_t mlw = mask_layer_bytes(p, d);
   const size_t mu = (size_t)p->T * p->U * (d / 4);
   const bool rpw = use_rpw();
+  bool premasked = false;   // the pre-mask pass was launched by this call
   if (interval >= 0) { s.cta = p->cta_int_dev + (size_t)interval * p->num_sms; s.cta_host = p->cta_int_host.data() + (size_t)interval * p->num_sms; }
   for (int l = L - 1 - s_begin, step = s_begin; step < s_end || (step == 0 && ph_begin == 0); --l, ++step) {
     s.ctrs = s.tickets + w.ticket_words + (size_t)step * 2 * p->T;
@@ -624,6 +647,7 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
               s.smask_i + oi * q, (float4*)pu + ou * q, (float4*)pi + oi * q, ru * q, ri * q, leaky, rtd ? p->T : 0,
               interval >= 0 ? interval : 0, p->U, p->I, (int)q);
           SAGNN_CUDA(cudaGetLastError());
+          premasked = true;
         }
         s.src_u = pu; s.src_i = pi;
         s.smask_u = nullptr; s.smask_i = nullptr;
@@ -650,6 +674,7 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
     if (step >= s_end) break;                                  // phase 0 only: just the pre-mask pass
     for (int wv = 0; wv < (interval >= 0 ? 1 : p->n_waves); ++wv) {
       if (interval < 0) { s.cta = p->cta_dev + (size_t)wv * p->num_sms; s.cta_host = p->cta_host.data() + (size_t)wv * p->num_sms; }
+      s.pdl = (step > s_begin || wv > 0 || premasked) ? 1 : 0;
       if (int rc = launch(p, s, d, MODE_BWD, st)) return rc;
     }
   }

@@ -80,7 +80,7 @@ __device__ __forceinline__ void tma_bulk_g2s_u32(uint32_t dst_smem, const void* 
                : "memory");
 }
 
-template <int D_, int MODE, bool WEIGHTED, bool RTD>
+template <int D_, int MODE, bool WEIGHTED, bool RTD, bool HOT_>
 __global__ void __launch_bounds__(kPktThreads, 1)
 spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
   using Geo = PktGeo<D_, WEIGHTED>;
@@ -88,12 +88,15 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
                 MPR = Geo::MPR, GS = Geo::GS, NS = Geo::NS;
   constexpr bool BWD = MODE == MODE_BWD;
   constexpr bool OWN = MODE != MODE_MSG;              // the task has dense rows of its own
-  constexpr bool HOT = SAGNN_PKT_HOT != 0;            // hot-row staging compiled in (experiment)
+  constexpr bool HOT = HOT_;                          // plan with hot slots: popular source rows staged in shared memory
   constexpr unsigned FULL = 0xffffffffu;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];      // [packet rings of all warps | staged hot rows]
   __shared__ __align__(8) uint64_t bars[kPktWarps * NS];
   __shared__ __align__(8) uint64_t hot_bar;
+  // programmatic dependent launch: the next launch of the chain may take my SM as soon as I leave it and run its
+  // own start-up (plan data only) under the tail of this grid; no-ops when launched without the attribute
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x & 31;
   // shuffled: tells the compiler the value is warp-uniform (uniform registers for everything derived from it)
   const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
@@ -160,6 +163,7 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
   const int32_t* hot_ids = p.hot_ids + (size_t)(seg ^ 1) * kHotRows;
   const uint32_t hot0 = smem_u32(smem_raw) + (uint32_t)Geo::PKT_SMEM;
   if (HOT && n_hot > 0) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // staged rows are table data of the launch before
     if (threadIdx.x == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&hot_bar)) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -240,6 +244,9 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
     return q_cur < q_end ? q_cur++ : n_pk;
   };
   if (more) q_raw = grab_issue();
+  // everything above read the plan (packet stream, directory, this launch's own queue head); everything below
+  // reads or writes tables of the launch before: wait until that grid has completed and its stores are visible
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   bool hot_ready = n_hot == 0;                         // the staged rows have landed (waited for on first use)
   unsigned j = 0;                                      // packet the cursor is in (count of mine)

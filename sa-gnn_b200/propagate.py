@@ -113,7 +113,7 @@ class Plan:
     def stats(self):
         out = (ctypes.c_int64 * 8)()
         _lib.check(_lib.load_library().sagnn_plan_stats(self.handle, out))
-        keys = ["rows", "short_rows", "long_rows", "chunks", "max_degree", "edges_both_sides", "_", "sms"]
+        keys = ["rows", "short_rows", "long_rows", "chunks", "max_degree", "edges_both_sides", "hot_rows", "sms"]
         return {k: int(v) for k, v in zip(keys, out) if k != "_"}
 
     # -- samplers ---------------------------------------------------------------------
@@ -230,14 +230,16 @@ def _split_interval(m):
 
 
 def build_plan(sub_mats, U=None, I=None, *, device=None, edge_weight=None, strict_pad=False, latdim=64,
-               row_block=None, padded_shape=None):
+               row_block=None, padded_shape=None, hot_rows=0):
     """Builds the device plan for ``T = len(sub_mats)`` interval graphs.
 
     sub_mats[k]: scipy sparse ``U x I`` matrix (``handler.subMat[k]``), or an ``[E,2]`` adjacency
     list as ``transToLsts`` returns it, or ``(row, col[, val])`` arrays / tensors, row-major sorted.
     edge_weight: None (reference-exact binary structure), ``"lightgcn"`` (1/sqrt(d_u d_i)) or a
     list of per-interval fp32 arrays in the adjacency list's order.
-    latdim: the embedding width the plan will mostly run with (sizes the shared-memory hot-row set).
+    latdim: the embedding width the plan will mostly run with (picks the kernel and its schedule).
+    hot_rows: stage that many highest-degree rows of every source table in shared memory
+    (``sagnn_plan_set_hot_rows``; default 0 -- measured slower on B200).
     strict_pad: raise like TF-CPU does when an interval's last populated row is more than 100
     rows before the end (model.py:87-91); by default such rows are simply zero (TF-GPU).
     row_block: ``(u_begin, u_end, i_begin, i_end)`` -- row sharding (``sagnn_plan_set_row_block``): the
@@ -301,6 +303,8 @@ def build_plan(sub_mats, U=None, I=None, *, device=None, edge_weight=None, stric
             _lib.check(lib.sagnn_plan_set_row_block(handle, *[int(x) for x in row_block]))
             plan.row_block = tuple(int(x) for x in row_block)
         _lib.check(lib.sagnn_plan_set_latdim_hint(handle, int(latdim)))
+        if hot_rows:
+            _lib.check(lib.sagnn_plan_set_hot_rows(handle, int(hot_rows)))
         _lib.check(lib.sagnn_plan_finalize(handle, mode, st))
     return plan
 

@@ -45,7 +45,7 @@ def run_gpu(plan, uE, iE, gU, gI, L, leaky=0.5, want_masks=False):
 
 
 def check_against_oracle(mats, d, L, leaky=0.5, seed=0, edge_weight=None, scale=1.0, tables=None,
-                         max_ties=8, latdim=None, report=None):
+                         max_ties=8, latdim=None, report=None, hot_rows=0):
     """Three-part parity (the derivative of LeakyReLU jumps at 0, so a pre-activation that is
     zero to within fp32 rounding may legitimately take the other branch):
       A. forward outputs vs the fp64 oracle                         <= 1e-5;
@@ -60,7 +60,7 @@ def check_against_oracle(mats, d, L, leaky=0.5, seed=0, edge_weight=None, scale=
         ew = [po.lightgcn_edge_weights(a, U, I) for a in adj]
         tew = [po.lightgcn_edge_weights(a, I, U) for a in tp]
     # latdim hint = d by default: plans hinted >= 128 run the v8 kernel, below that the packet-stream kernel
-    plan = sg.build_plan(mats, edge_weight=edge_weight, latdim=latdim or d)
+    plan = sg.build_plan(mats, edge_weight=edge_weight, latdim=latdim or d, hot_rows=hot_rows)
     uv, iv, du, di, gm = run_gpu(plan, uE, iE, gU, gI, L, leaky, want_masks=True)
     ref = c_oracle.propagate(adj, tp, uE, iE, gU, gI, L, leaky, np.float64, ew, tew,
                              mask_in=gm, mask_cmp=gm, tie_tol=1e-5)
@@ -262,6 +262,28 @@ def test_propagate_other_kernel_than_the_hint_would_pick(d, L, hint):
     """A plan hinted below 128 carries the packed task stream (v10 kernel), from 128 on the v8 task records:
     both kernels must serve every latdim."""
     check_against_oracle(random_interval_mats(3, 120, 80, 900, seed=d + L), d, L, seed=L, latdim=hint)
+
+
+@pytest.mark.parametrize("d,L,hot,weights", [(64, 2, 32, None), (64, 3, 500, None), (32, 2, 100, "lightgcn"),
+                                              (64, 2, 200, "lightgcn"), (128, 2, 64, None)])
+def test_propagate_hot_rows_staged_in_shared_memory(d, L, hot, weights):
+    """north_star's "TMA/shared-memory staging of hot item rows" (``sagnn_plan_set_hot_rows``, off by default):
+    the highest-degree source rows are read from their shared-memory copies, hot edges first inside every task --
+    power-law graphs with hubs, long (sliced) rows, more hot slots asked for than fit / than rows exist, and a
+    plan run at another latdim than its hint (slots that do not fit are read through their row ids)."""
+    rng = np.random.default_rng(hot)
+    U, I = 600, 260
+    mats = []
+    for k in range(3):
+        pu = 1.0 / np.arange(1, U + 1) ** 0.8; pi = 1.0 / np.arange(1, I + 1)
+        r = rng.choice(U, 9000, p=pu / pu.sum()); c = rng.choice(I, 9000, p=pi / pi.sum())
+        A = sp.coo_matrix((np.ones(9000, np.intc), (rng.permutation(U)[r], rng.permutation(I)[c])), shape=(U, I)).tocsr()
+        A.data[:] = 1
+        mats.append(A)
+    plan = check_against_oracle(mats, d, L, seed=hot, scale=0.1, edge_weight=weights, latdim=64 if d == 128 else d,
+                                hot_rows=hot)
+    st = plan.stats()
+    assert 0 < st["hot_rows"] <= hot and st["long_rows"] > 0
 
 
 def test_propagate_long_rows_chunked_reduction():
