@@ -24,6 +24,7 @@ replicated consumer that north_star names; --exchange none = compute only.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -497,10 +498,15 @@ def main():
         host = {}
         # the host entry point speaks the reference's [T,R,d] layout whatever layout the device step uses
         trd = lambda t: t if args.layout == "trd" else t.transpose(0, 1)
-        for name, src in (("uE", step.u_embed), ("iE", step.i_embed), ("gU", trd(step.g_user)), ("gI", trd(step.g_item))):
-            host[name] = src.contiguous().cpu().pin_memory()
-        for name, rows in (("uO", U), ("iO", I), ("dU", U), ("dI", I)):
-            host[name] = torch.empty((T, rows, d), dtype=torch.float32).pin_memory()
+        # pinned pages on the NUMA node the GPU hangs off (first touch while bound to its cores; affinity restored after)
+        numa = {}
+        from sagnn_b200 import hostmem
+        with (hostmem.near_gpu(dev.index, numa) if os.environ.get("SAGNN_NUMA_BIND", "1") != "0" else contextlib.nullcontext()):
+            for name, src in (("uE", step.u_embed), ("iE", step.i_embed), ("gU", trd(step.g_user)), ("gI", trd(step.g_item))):
+                host[name] = src.contiguous().cpu().pin_memory()
+            for name, rows in (("uO", U), ("iO", I), ("dU", U), ("dI", I)):
+                host[name] = torch.empty((T, rows, d), dtype=torch.float32).pin_memory()
+                host[name].zero_()
         h2d = sum(host[k].numel() * 4 for k in ("uE", "iE", "gU", "gI"))
         d2h = sum(host[k].numel() * 4 for k in ("uO", "iO", "dU", "dI"))
 
@@ -522,7 +528,8 @@ def main():
         chk = float(host["uO"][0, 0, 0])   # the device->host result is really there
         e2e = {"value": 4 * L * edges_all / e2e_s, "unit": "edge_traversals/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "probe": chk,
-               "api": "sagnn_propagate_host (C ABI, pinned host buffers)"}
+               "api": "sagnn_propagate_host (C ABI, pinned host buffers)",
+               "pinned_pages_numa_local": bool(numa.get("bound", False))}
 
     # ---- CPU baseline next to it (rank 0, N=1 only)
     cpu = None

@@ -116,11 +116,13 @@ __device__ __forceinline__ unsigned ticket_release_add(unsigned* p) {
   asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
   return old;
 }
-// same with acquire as well: the last arriver's later reads of the other slices' partials are ordered after it
-__device__ __forceinline__ unsigned ticket_acq_rel_add(unsigned* p) {
-  unsigned old;
-  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(p) : "memory");
-  return old;
+// acquire side of the ticket, executed by the LAST arriver of a group only (1 of up to 16 slices): its reads of the
+// other slices' partials are ordered after the ticket values it observed.  GPU-scope acquire costs an invalidation
+// of the SM's L1 (CCTL.IVALL) -- per group that is affordable, on every ticket (atom.acq_rel) it was not.
+__device__ __forceinline__ void ticket_acquire_fence() {
+#if !defined(SAGNN_NO_TICKET_ACQUIRE)
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
 }
 __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void st_stream(float* p, float4 v) {

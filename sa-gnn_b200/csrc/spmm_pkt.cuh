@@ -441,11 +441,11 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
 
     // ---- long rows: publish the slice sum; reduce through a fan-in-16 ticket tree -------------
     // The last arriver of every group of 16 slices (then of 16 groups, ...) sums them in slice
-    // order: deterministic, no float atomics.  Release-only tickets: the reducer reads the partials with
-    // L1-bypassing GPU-scope loads that depend on the ticket value.  (An acq_rel ticket or an acquire
-    // fence in the last arriver would be the formally complete pattern, but ptxas implements GPU-scope
-    // acquire as CCTL.IVALL: one invalidation of the SM's whole L1 per slice, which the gathers of
-    // high-degree graphs pay for.)  Lane groups run this independently (group-masked shuffles).
+    // order: deterministic, no float atomics.  Tickets are release increments; the last arriver of a group
+    // (only it) issues the matching acquire fence before reading the partials with L1-bypassing GPU-scope
+    // loads.  (An acq_rel ticket on EVERY slice was measured: ptxas implements GPU-scope acquire as
+    // CCTL.IVALL, one invalidation of the SM's whole L1 per slice, which the gathers of high-degree graphs
+    // pay for; one per group of 16 is not.)  Lane groups run this independently (group-masked shuffles).
     bool whole_row = valid;
 #if SAGNN_PKT_X == 3        // timing experiment: no slice publication / ticket tree
     if (multi) whole_row = false;
@@ -477,6 +477,7 @@ spmm_pkt_kernel(const __grid_constant__ SpmmParams p) {
         if (old != (unsigned)(members - 1)) {
           active = false;                              // someone else finishes this group
         } else {
+          ticket_acquire_fence();
           if (lane == leader) *my_tk = 0u;             // ready for the next launch
 #pragma unroll
           for (int i = 0; i < VPL; ++i) acc[i] = 0.f;

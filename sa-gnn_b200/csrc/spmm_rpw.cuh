@@ -424,8 +424,8 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
 
     // ---- long rows: publish the slice sum; reduce through a fan-in-16 ticket tree -------------
     // The last arriver of every group of 16 slices (then of 16 groups, ...) sums them in slice
-    // order: deterministic, no float atomics.  Release-only tickets; the reducer reads with
-    // L1-bypassing loads, so no acquire fence / L1 invalidate is needed.
+    // order: deterministic, no float atomics.  Release increments on every ticket, one acquire fence in
+    // the last arriver of a group before it reads the partials (L1-bypassing loads).
     bool finish = true;
     if (multi) {
       const uint32_t aux = (uint32_t)rec.w;            // global slice id
@@ -452,6 +452,7 @@ spmm_rpw_kernel(const __grid_constant__ SpmmParams p) {
         if (old != (unsigned)(members - 1)) {
           active = false;                              // someone else finishes this group
         } else {
+          ticket_acquire_fence();                      // pairs with the other slices' release increments
           if (lane == 0) *my_tk = 0u;                  // ready for the next launch
 #pragma unroll
           for (int i = 0; i < VPL; ++i) acc[i] = 0.f;

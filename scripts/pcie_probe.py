@@ -1,7 +1,16 @@
 """PCIe probe: H2D alone, D2H alone, both at once (pinned memory, 156 MB each: one step's worth of the host entry point)."""
-import time, torch
+# usage: python scripts/pcie_probe.py [device] [bind]   (bind: allocate the pinned buffers NUMA-local, sagnn_b200.hostmem)
+import contextlib, os, sys, time, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sagnn_b200 import hostmem
+devi = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+torch.cuda.set_device(devi)
+info = {}
 n = 155_556_864
-h_in = torch.empty(n, dtype=torch.uint8).pin_memory(); h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+with (hostmem.near_gpu(devi, info) if "bind" in sys.argv else contextlib.nullcontext()):
+    h_in = torch.empty(n, dtype=torch.uint8).pin_memory(); h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_in.zero_(); h_out.zero_()
+print("device %d, pinned pages bound near the GPU: %s" % (devi, info or "no"))
 d_in = torch.empty(n, dtype=torch.uint8, device="cuda"); d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 def run(h2d, d2h, reps=10):
