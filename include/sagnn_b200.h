@@ -281,6 +281,18 @@ int sagnn_pair_scores_bwd(const float* u_rows_dev, int64_t u_stride, const float
                           float leaky, const float* g_scores_dev, float* d_u_rows_dev, int64_t du_stride,
                           float* d_i_rows_dev, int64_t di_stride, sagnn_stream_t stream);
 
+/* The same accumulation WITHOUT atomics: the samples are radix-sorted by the row they scatter into (stable, so
+ * sample order inside a row is kept), the warp at the head of each run adds the run's terms in that order and
+ * updates the gradient row once -- bit-identical results run to run.  ws: device scratch of
+ * sagnn_pair_scores_bwd_ws_bytes(n) bytes.  Gradient tables 16-byte aligned, strides multiples of 4.
+ * Negative or out-of-range ids are not checked (as above). */
+int sagnn_pair_scores_bwd_ws_bytes(int64_t n, size_t* bytes);
+int sagnn_pair_scores_bwd_det(const float* u_rows_dev, int64_t u_stride, const float* i_rows_dev, int64_t i_stride,
+                              const int32_t* uids_dev, const int32_t* iids_dev, int64_t n, int d, int activation,
+                              float leaky, const float* g_scores_dev, float* d_u_rows_dev, int64_t du_stride,
+                              float* d_i_rows_dev, int64_t di_stride, void* ws_dev, size_t ws_bytes,
+                              sagnn_stream_t stream);
+
 /* ---- device-side sampleSslBatch (model.py:304-339) ---------------------------
  * For interval k and the batch users bat_ids_dev int32 [batch]: posset(u) = the items of user u in
  * A_k (read from the plan's CSR instead of densifying subMat[k][batIds].toarray()), s = min(ssl_num,
@@ -293,6 +305,14 @@ int sagnn_pair_scores_bwd(const float* u_rows_dev, int64_t u_stride, const float
 int sagnn_sample_ssl_batch(const sagnn_plan* plan, int k, const int32_t* bat_ids_dev, int batch, int ssl_num,
                            uint64_t seed, int32_t* u_locs_dev, int32_t* i_locs_dev, int32_t* u_locs_seq_dev,
                            int64_t* n_out_host, sagnn_stream_t stream);
+
+/* The same for EVERY interval of the plan in one call (what a training step needs: model.py:313 loops k over
+ * graphNum): outputs are [T, cap] int32 with cap = batch*2*ssl_num (interval k's entries start at k*cap),
+ * n_out_host int64 [T].  Same draws as T calls of sagnn_sample_ssl_batch with the same seed; two kernels, one scan
+ * and one stream synchronisation per step, scratch kept in the plan (one sampler call at a time per plan). */
+int sagnn_sample_ssl_batch_all(const sagnn_plan* plan, const int32_t* bat_ids_dev, int batch, int ssl_num,
+                               uint64_t seed, int32_t* u_locs_dev, int32_t* i_locs_dev, int32_t* u_locs_seq_dev,
+                               int64_t* n_out_host, sagnn_stream_t stream);
 
 /* ---- device-side sampleTrainBatch + negSamp (model.py:252-302, DataHandler.py:28-41) ----------
  * seq_ptr_dev int64 [U+1] / seq_items_dev int32: handler.sequence as CSR (a user's interactions in time order);

@@ -67,8 +67,14 @@ SIGNATURES = {
                                              ctypes.c_int, ctypes.c_float, vp, vp]),
     "sagnn_pair_scores_bwd": (ctypes.c_int, [vp, ctypes.c_int64, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, ctypes.c_int,
                                              ctypes.c_int, ctypes.c_float, vp, vp, ctypes.c_int64, vp, ctypes.c_int64, vp]),
+    "sagnn_pair_scores_bwd_ws_bytes": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(ctypes.c_size_t)]),
+    "sagnn_pair_scores_bwd_det": (ctypes.c_int, [vp, ctypes.c_int64, vp, ctypes.c_int64, vp, vp, ctypes.c_int64, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_float, vp, vp, ctypes.c_int64, vp, ctypes.c_int64, vp,
+                                                 ctypes.c_size_t, vp]),
     "sagnn_sample_ssl_batch": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, vp, vp, vp,
                                               c_i64p, vp]),
+    "sagnn_sample_ssl_batch_all": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, vp, vp, vp,
+                                                  c_i64p, vp]),
     "sagnn_sample_train_batch": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_int, ctypes.c_uint64, vp, vp, vp, vp, vp, vp, c_i64p, vp]),
     "sagnn_host_forward": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int]),

@@ -108,6 +108,8 @@ struct sagnn_plan {
   bool has_custom_w = false;
   bool finalized = false;
   int weight_mode = 0;
+  void* smp_scratch = nullptr;    // sampler scratch (counts, offsets, scan temp), grow-only
+  size_t smp_bytes = 0;
   int hot_rows_wanted = 0;        // sagnn_plan_set_hot_rows (before finalize)
   int hot_rows = 0;               // hot slots per source table the edge codes use (packet-stream kernel: what fits at latdim_hint)
   int latdim_hint = 64;

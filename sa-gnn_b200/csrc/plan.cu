@@ -449,6 +449,7 @@ extern "C" int sagnn_plan_destroy(sagnn_plan* p) {
   sagnn::free_host_cache(p);
   cudaFree(p->deg); cudaFree(p->rowptr); cudaFree(p->idx); cudaFree(p->val); cudaFree(p->w);
   cudaFree(p->valsum); cudaFree(p->chunk_base); cudaFree(p->chunk_lr); cudaFree(p->tasks);
+  cudaFree(p->smp_scratch);
   cudaFree(p->enc); cudaFree(p->w_enc); cudaFree(p->pkt_stream); cudaFree(p->pkt_dir); cudaFree(p->hot_ids); cudaFree(p->seg_dev); cudaFree(p->cta_dev); cudaFree(p->cta_int_dev);
   delete p;
   return SAGNN_OK;

@@ -64,6 +64,58 @@ struct SmpTmp {
   operator T*() const { return p; }
 };
 
+// all T intervals at once: grid.y = interval.  cnt / off are [T][batch + 1]; after ONE exclusive scan over the whole
+// array, off[k][b] - off[k][0] is user b's offset inside interval k's output and off[k][batch] - off[k][0] its total
+__global__ void ssl_count_all_kernel(const int32_t* __restrict__ deg, const int32_t* __restrict__ bat, int batch, int U,
+                                     int64_t N, int ssl_num, int64_t* __restrict__ cnt, int* __restrict__ bad) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (b > batch) return;
+  int64_t* c = cnt + (int64_t)k * (batch + 1);
+  if (b == batch) { c[b] = 0; return; }
+  const int u = bat[b];
+  if (u < 0 || u >= U) { atomicOr(bad, 1); c[b] = 0; return; }
+  const int half = deg[(int64_t)k * N + u] / 2;
+  c[b] = 2 * (int64_t)(half < ssl_num ? half : ssl_num);
+}
+
+__global__ void ssl_draw_all_kernel(const int32_t* __restrict__ deg, const int64_t* __restrict__ rowptr,
+                                    const int32_t* __restrict__ idx, const int32_t* __restrict__ bat, int batch, int U,
+                                    int64_t N, int ssl_num, uint64_t seed, const int64_t* __restrict__ off, int64_t cap,
+                                    int32_t* __restrict__ u_locs, int32_t* __restrict__ i_locs, int32_t* __restrict__ u_seq,
+                                    int64_t* __restrict__ totals) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  const int64_t* o_k = off + (int64_t)k * (batch + 1);
+  if (tid == 0) totals[k] = o_k[batch] - o_k[0];
+  const int b = (int)(tid / (2 * ssl_num)), j = (int)(tid % (2 * ssl_num));
+  if (b >= batch) return;
+  const int u = bat[b];
+  if (u < 0 || u >= U) return;
+  const int64_t row0 = (int64_t)k * N;
+  const int d = deg[row0 + u];
+  const int s = d / 2 < ssl_num ? d / 2 : ssl_num;
+  if (j >= 2 * s) return;
+  const uint64_t r = mix64(mix64(seed ^ ((uint64_t)b << 32 | (uint32_t)j)) + (uint64_t)row0);   // same draws as the per-interval call
+  const int pick = (int)(((r >> 32) * (uint64_t)d) >> 32);
+  const int64_t o = (int64_t)k * cap + (o_k[b] - o_k[0]) + (j < s ? 2 * j : 2 * (j - s) + 1);
+  i_locs[o] = idx[rowptr[row0 + u] + pick];
+  u_locs[o] = u;
+  u_seq[o] = b;
+}
+
+// grow-only sampler scratch kept in the plan (one user at a time per plan, like the propagation workspace)
+static int sampler_scratch(const sagnn_plan* cp, size_t bytes, char** out) {
+  sagnn_plan* p = const_cast<sagnn_plan*>(cp);
+  if (p->smp_bytes < bytes) {
+    cudaFree(p->smp_scratch); p->smp_scratch = nullptr; p->smp_bytes = 0;
+    SAGNN_CUDA(cudaMalloc(&p->smp_scratch, bytes));
+    p->smp_bytes = bytes;
+  }
+  *out = (char*)p->smp_scratch;
+  return SAGNN_OK;
+}
+
 }  // namespace sagnn
 
 using namespace sagnn;
@@ -85,27 +137,67 @@ extern "C" int sagnn_sample_ssl_batch(const sagnn_plan* p, int k, const int32_t*
   if (batch == 0) return SAGNN_OK;
   SAGNN_REQUIRE(bat_ids && u_locs && i_locs && u_locs_seq, SAGNN_INVALID_ARG, "sample_ssl_batch: NULL tensor");
   const int64_t row0 = (int64_t)k * p->N;                   // user rows of A_k in the global row space
-  SmpTmp<int64_t> cnt, off;
-  SmpTmp<int> bad;
-  SmpTmp<char> tmp;
-  SAGNN_CUDA(cnt.alloc(batch + 1)); SAGNN_CUDA(off.alloc(batch + 1)); SAGNN_CUDA(bad.alloc(1));
+  size_t tb = 0;
+  SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, (int64_t*)nullptr, (int64_t*)nullptr, batch + 1, st));
+  const size_t arr = align_up(sizeof(int64_t) * (batch + 1), 256);
+  char* base = nullptr;
+  if (int rc = sampler_scratch(p, 2 * arr + 256 + tb, &base)) return rc;
+  int64_t* cnt = (int64_t*)base; int64_t* off = (int64_t*)(base + arr);
+  int* bad = (int*)(base + 2 * arr); void* tmp = base + 2 * arr + 256;
   SAGNN_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
   ssl_count_kernel<<<(batch + 1 + 255) / 256, 256, 0, st>>>(p->deg, bat_ids, batch, p->U, row0, ssl_num, cnt, bad);
-  size_t tb = 0;
-  SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, batch + 1, st));
-  SAGNN_CUDA(tmp.alloc(tb));
-  SAGNN_CUDA(cub::DeviceScan::ExclusiveSum((void*)tmp.p, tb, cnt.p, off.p, batch + 1, st));
+  SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, off, batch + 1, st));
   const int64_t threads = (int64_t)batch * 2 * ssl_num;
   ssl_draw_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p->deg, p->rowptr, p->idx, bat_ids, batch, p->U, row0,
                                                                     ssl_num, seed, off, u_locs, i_locs, u_locs_seq);
   SAGNN_CUDA(cudaGetLastError());
   int hbad = 0;
   int64_t total = 0;
-  SAGNN_CUDA(cudaMemcpyAsync(&total, off.p + batch, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  SAGNN_CUDA(cudaMemcpyAsync(&total, off + batch, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   SAGNN_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   SAGNN_CUDA(cudaStreamSynchronize(st));
   SAGNN_REQUIRE(!hbad, SAGNN_OUT_OF_RANGE, "sample_ssl_batch: a batch id is outside [0,%d)", p->U);
   *n_out_host = total;
+  return SAGNN_OK;
+}
+
+// every interval of the plan in one call: outputs [T, cap] with cap = batch * 2 * ssl_num, n_out_host [T]; two kernels,
+// one scan and ONE stream synchronisation per training step instead of T of each (and no allocation)
+extern "C" int sagnn_sample_ssl_batch_all(const sagnn_plan* p, const int32_t* bat_ids, int batch, int ssl_num,
+                                          uint64_t seed, int32_t* u_locs, int32_t* i_locs, int32_t* u_locs_seq,
+                                          int64_t* n_out_host, sagnn_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  SAGNN_REQUIRE(p && n_out_host, SAGNN_INVALID_ARG, "sample_ssl_batch_all: NULL plan / n_out_host");
+  SAGNN_REQUIRE(p->finalized, SAGNN_NOT_FINALIZED, "sample_ssl_batch_all: plan not finalized");
+  SAGNN_REQUIRE(batch >= 0 && ssl_num >= 1 && ssl_num <= (1 << 20), SAGNN_INVALID_ARG,
+                "sample_ssl_batch_all: batch=%d sslNum=%d", batch, ssl_num);
+  const int T = p->T;
+  for (int k = 0; k < T; ++k) n_out_host[k] = 0;
+  if (batch == 0) return SAGNN_OK;
+  SAGNN_REQUIRE(bat_ids && u_locs && i_locs && u_locs_seq, SAGNN_INVALID_ARG, "sample_ssl_batch_all: NULL tensor");
+  SAGNN_REQUIRE(T <= 65535, SAGNN_INVALID_ARG, "sample_ssl_batch_all: T=%d", T);
+  const int64_t n = (int64_t)T * (batch + 1);
+  SAGNN_REQUIRE(n < ((int64_t)1 << 31), SAGNN_INVALID_ARG, "sample_ssl_batch_all: T*(batch+1) too large");
+  size_t tb = 0;
+  SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, (int64_t*)nullptr, (int64_t*)nullptr, (int)n, st));
+  const size_t arr = align_up(sizeof(int64_t) * n, 256), tot = align_up(sizeof(int64_t) * T, 256);
+  char* base = nullptr;
+  if (int rc = sampler_scratch(p, 2 * arr + tot + 256 + tb, &base)) return rc;
+  int64_t* cnt = (int64_t*)base; int64_t* off = (int64_t*)(base + arr); int64_t* totals = (int64_t*)(base + 2 * arr);
+  int* bad = (int*)(base + 2 * arr + tot); void* tmp = base + 2 * arr + tot + 256;
+  SAGNN_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), st));
+  ssl_count_all_kernel<<<dim3((batch + 1 + 255) / 256, T), 256, 0, st>>>(p->deg, bat_ids, batch, p->U, p->N, ssl_num, cnt, bad);
+  SAGNN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, off, (int)n, st));
+  const int64_t threads = (int64_t)batch * 2 * ssl_num, cap = threads;
+  ssl_draw_all_kernel<<<dim3((unsigned)((threads + 255) / 256), T), 256, 0, st>>>(
+      p->deg, p->rowptr, p->idx, bat_ids, batch, p->U, p->N, ssl_num, seed, off, cap, u_locs, i_locs, u_locs_seq, totals);
+  SAGNN_CUDA(cudaGetLastError());
+  int hbad = 0;
+  SAGNN_CUDA(cudaMemcpyAsync(n_out_host, totals, sizeof(int64_t) * T, cudaMemcpyDeviceToHost, st));
+  SAGNN_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SAGNN_CUDA(cudaStreamSynchronize(st));
+  if (hbad) for (int k = 0; k < T; ++k) n_out_host[k] = 0;
+  SAGNN_REQUIRE(!hbad, SAGNN_OUT_OF_RANGE, "sample_ssl_batch_all: a batch id is outside [0,%d)", p->U);
   return SAGNN_OK;
 }
 

@@ -125,15 +125,25 @@ class Plan:
         lib = _lib.load_library()
         bat = _as_dev_i32(bat_ids, self.device)
         batch, cap = int(bat.numel()), max(1, int(bat.numel()) * 2 * int(ssl_num))
-        out = []
         with torch.cuda.device(self.device):
-            for k in range(self.T):
-                u, i, s = (torch.empty(cap, dtype=torch.int32, device=self.device) for _ in range(3))
-                n = ctypes.c_int64()
-                _lib.check(lib.sagnn_sample_ssl_batch(self.handle, k, _ptr(bat), batch, int(ssl_num), int(seed) & (2**64 - 1),
-                                                      _ptr(u), _ptr(i), _ptr(s), ctypes.byref(n), _stream_ptr(self.device)))
-                out.append((u[:n.value], i[:n.value], s[:n.value]))
-        return out
+            # all T intervals in one call (one stream synchronisation per step): [T, cap] outputs, counts on the host
+            u, i, s = (torch.empty((self.T, cap), dtype=torch.int32, device=self.device) for _ in range(3))
+            n = (ctypes.c_int64 * self.T)()
+            _lib.check(lib.sagnn_sample_ssl_batch_all(self.handle, _ptr(bat), batch, int(ssl_num), int(seed) & (2**64 - 1),
+                                                      _ptr(u), _ptr(i), _ptr(s), n, _stream_ptr(self.device)))
+        return [(u[k, :n[k]], i[k, :n[k]], s[k, :n[k]]) for k in range(self.T)]
+
+    def sample_ssl_interval(self, k, bat_ids, ssl_num, seed=0):
+        """One interval of ``sample_ssl_batch`` (``sagnn_sample_ssl_batch``): same draws for the same seed."""
+        lib = _lib.load_library()
+        bat = _as_dev_i32(bat_ids, self.device)
+        batch, cap = int(bat.numel()), max(1, int(bat.numel()) * 2 * int(ssl_num))
+        with torch.cuda.device(self.device):
+            u, i, s = (torch.empty(cap, dtype=torch.int32, device=self.device) for _ in range(3))
+            n = ctypes.c_int64()
+            _lib.check(lib.sagnn_sample_ssl_batch(self.handle, int(k), _ptr(bat), batch, int(ssl_num), int(seed) & (2**64 - 1),
+                                                  _ptr(u), _ptr(i), _ptr(s), ctypes.byref(n), _stream_ptr(self.device)))
+        return u[:n.value], i[:n.value], s[:n.value]
 
     def sample_train_batch(self, bat_ids, sequences, tst_int=None, train_sample_num=40, pred_num=5, pos_length=200,
                            batch_pad=None, seed=0):
@@ -441,7 +451,7 @@ def message_propagate(srclats, plan, k, type="user", leaky=0.5):
 
 class _PairScores(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, user_vec, item_vec, k, uids, iids, activation, leaky, layout):
+    def forward(ctx, user_vec, item_vec, k, uids, iids, activation, leaky, layout, deterministic=True):
         lib = _lib.load_library()
         u, i = user_vec.contiguous(), item_vec.contiguous()
         d = u.shape[2]
@@ -452,23 +462,32 @@ class _PairScores(torch.autograd.Function):
             _lib.check(lib.sagnn_pair_scores_fwd(geo[0], geo[1], geo[2], geo[3], _ptr(uids), _ptr(iids), n, d,
                                                  activation, leaky, _ptr(scores), _stream_ptr(u.device)))
         ctx.save_for_backward(u, i, uids, iids)
-        ctx.args = (k, activation, leaky, layout, n, d)
+        ctx.args = (k, activation, leaky, layout, n, d, deterministic)
         return scores
 
     @staticmethod
     def backward(ctx, g):
         u, i, uids, iids = ctx.saved_tensors
-        k, activation, leaky, layout, n, d = ctx.args
+        k, activation, leaky, layout, n, d, deterministic = ctx.args
         lib = _lib.load_library()
         d_u = torch.zeros_like(u) if ctx.needs_input_grad[0] else None
         d_i = torch.zeros_like(i) if ctx.needs_input_grad[1] else None
         su = _pair_geometry(u, i, k, layout)                                  # the tables
         gu = _pair_geometry(d_u if d_u is not None else u, d_i if d_i is not None else i, k, layout)   # their gradients
         with torch.cuda.device(u.device):
-            _lib.check(lib.sagnn_pair_scores_bwd(su[0], su[1], su[2], su[3], _ptr(uids), _ptr(iids), n, d, activation,
-                                                 leaky, _ptr(g.contiguous()), gu[0] if d_u is not None else None, gu[1],
-                                                 gu[2] if d_i is not None else None, gu[3], _stream_ptr(u.device)))
-        return d_u, d_i, None, None, None, None, None, None
+            if deterministic:     # sorted by destination row, one writer per row: no float atomics, same bits every run
+                nb = ctypes.c_size_t()
+                _lib.check(lib.sagnn_pair_scores_bwd_ws_bytes(n, ctypes.byref(nb)))
+                ws = torch.empty(max(1, nb.value), dtype=torch.uint8, device=u.device)
+                _lib.check(lib.sagnn_pair_scores_bwd_det(su[0], su[1], su[2], su[3], _ptr(uids), _ptr(iids), n, d, activation,
+                                                         leaky, _ptr(g.contiguous()), gu[0] if d_u is not None else None, gu[1],
+                                                         gu[2] if d_i is not None else None, gu[3], _ptr(ws), nb.value,
+                                                         _stream_ptr(u.device)))
+            else:
+                _lib.check(lib.sagnn_pair_scores_bwd(su[0], su[1], su[2], su[3], _ptr(uids), _ptr(iids), n, d, activation,
+                                                     leaky, _ptr(g.contiguous()), gu[0] if d_u is not None else None, gu[1],
+                                                     gu[2] if d_i is not None else None, gu[3], _stream_ptr(u.device)))
+        return d_u, d_i, None, None, None, None, None, None, None
 
 
 def _pair_geometry(u, i, k, layout):
@@ -481,13 +500,16 @@ def _pair_geometry(u, i, k, layout):
             ctypes.c_void_p(i.data_ptr() + 4 * k * i.shape[1] * d), d)
 
 
-def pair_scores(user_vec, item_vec, k, uids, iids, activation="leakyRelu", leaky=0.5, layout="trd", check_ids=True):
+def pair_scores(user_vec, item_vec, k, uids, iids, activation="leakyRelu", leaky=0.5, layout="trd", check_ids=True,
+                deterministic=True):
     """``sum_c act(user_vec[k][uids] * item_vec[k][iids])`` over the propagation's outputs: the SSL
     scores ``preds_one`` of interval ``k`` (model.py:194-198; ``activation="leakyRelu"``) or a plain
     prediction dot product (model.py:171-173; ``activation=None``).  ``user_vec`` / ``item_vec`` are
     ``[T,U,d]`` / ``[T,I,d]`` (``layout="trd"``) or ``[U,T,d]`` / ``[I,T,d]`` (``"rtd"``); ``uids`` / ``iids`` int
     CUDA tensors of equal length (``suids[k]`` / ``siids[k]``).  Differentiable w.r.t. both tables: the
-    backward scatters the sparse gradient with a hand-written kernel (``sagnn_pair_scores_bwd``)."""
+    backward scatters the sparse gradient with a hand-written kernel: by default the atomic-free one
+    (``sagnn_pair_scores_bwd_det``: samples sorted by destination row, one writer per row, same bits every run);
+    ``deterministic=False`` uses float atomics (``sagnn_pair_scores_bwd``)."""
     if not (user_vec.is_cuda and item_vec.is_cuda and uids.is_cuda and iids.is_cuda):
         raise RuntimeError("sagnn_b200.pair_scores: tensors must be CUDA tensors (no CPU fallback)")
     if user_vec.dtype != torch.float32 or item_vec.dtype != torch.float32:
@@ -504,7 +526,7 @@ def pair_scores(user_vec, item_vec, k, uids, iids, activation="leakyRelu", leaky
         if int(uids.min()) < 0 or int(uids.max()) >= U or int(iids.min()) < 0 or int(iids.max()) >= I:
             raise IndexError("pair_scores: id out of range (tf.nn.embedding_lookup on CPU raises too)")
     act = 1 if activation == "leakyRelu" else 0
-    return _PairScores.apply(user_vec, item_vec, int(k), uids, iids, act, float(leaky), lay)
+    return _PairScores.apply(user_vec, item_vec, int(k), uids, iids, act, float(leaky), lay, bool(deterministic))
 
 
 def _host_ptr(a):

@@ -683,6 +683,8 @@ def test_sample_ssl_batch_contract():
         for a, b in zip(out[k], again[k]):
             assert torch.equal(a, b)
         assert not torch.equal(out[k][1], other[k][1])
+        for a, b in zip(out[k], plan.sample_ssl_interval(k, bat, ssl, seed=7)):  # the per-interval entry point draws the same
+            assert torch.equal(a, b)
     # uniformity: one user with many items, many draws -> every item drawn, counts within 5 sigma
     k, m = 0, sp.csr_matrix(g.sub_mat[0])
     hub = int(np.argmax(np.diff(m.indptr)))
@@ -783,6 +785,17 @@ def test_pair_scores_match_oracle(d, layout, act):
     for j in range(T):                                   # the other intervals get no gradient
         if j != k:
             assert not du[j].any() and not di[j].any()
+    # the default backward is the atomic-free one: bit-identical when repeated; the atomic variant agrees to rounding
+    first = (tu.grad.clone(), ti.grad.clone())
+    for det in (True, False):
+        tu.grad = None; ti.grad = None
+        sg.pair_scores(tu, ti, k, torch.from_numpy(uids).cuda(), torch.from_numpy(iids).cuda(), activation=act,
+                       leaky=0.5, layout=layout, deterministic=det).backward(torch.from_numpy(g).cuda())
+        if det:
+            assert torch.equal(tu.grad, first[0]) and torch.equal(ti.grad, first[1])
+        else:
+            du2 = tu.grad.transpose(0, 1) if layout == "rtd" else tu.grad
+            assert_parity(du2[k], ref_du, "d user_vector[k] (atomics)")
     with pytest.raises(IndexError):
         sg.pair_scores(tu, ti, k, torch.tensor([U], device="cuda"), torch.tensor([0], device="cuda"), layout=layout)
     empty = torch.empty(0, dtype=torch.int32, device="cuda")
