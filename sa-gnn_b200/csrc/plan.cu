@@ -679,12 +679,12 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   }
 
   const bool pkt = p->pkt;
-  if (!pkt || p->hot_rows > 0) {   // hot-first edge codes (and weights) per row; without hot slots a plain copy (v8)
+  if (p->hot_rows > 0) {   // hot-first edge codes (and weights) per row
     SAGNN_CUDA(cudaMalloc(&p->enc, sizeof(int32_t) * 2 * p->e_total));
     if (p->w) SAGNN_CUDA(cudaMalloc(&p->w_enc, sizeof(float) * 2 * p->e_total));
     sched_encode_kernel<<<blocks_for(R * 32), 256, 0, st>>>(p->rowptr, p->idx, p->w, slot_of, R, N, U, p->enc,
                                                             p->w_enc, nhot_row);
-  } else {      // packet stream without hot slots: the codes are read straight from the canonical CSR
+  } else {      // no hot slots (always so for the round-1 kernel): the codes ARE the canonical CSR, no second copy
     SAGNN_CUDA(cudaMemsetAsync(nhot_row, 0, sizeof(int32_t) * R, st));
   }
 

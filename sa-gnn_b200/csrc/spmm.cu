@@ -438,8 +438,8 @@ static size_t mask_layer_bytes(const sagnn_plan* p, int d) { return (size_t)p->n
 static void base_params(const sagnn_plan* p, SpmmParams& s) {
   s = SpmmParams{};
   s.pkt_dir = p->pkt_dir; s.pkt_stream = p->pkt_stream;
-  s.tasks = p->tasks; s.enc = p->enc;
-  s.w = p->pkt ? p->w : p->w_enc;   // packet stream: weights travel inside the packets, this is only the flag
+  s.tasks = p->tasks; s.enc = p->enc ? p->enc : p->idx;   // without hot slots the edge codes are the CSR's column ids
+  s.w = (p->pkt || !p->w_enc) ? p->w : p->w_enc;   // packet stream: weights travel inside the packets, this is only the flag
   s.chunk_base = p->chunk_base; s.chunk_lr = p->chunk_lr;
   s.hot_ids = p->hot_ids; s.seg = p->seg_dev; s.cta = p->cta_dev; s.cta_host = p->cta_host.data(); s.single_seg = -1;
   s.hot_rows = p->hot_rows;

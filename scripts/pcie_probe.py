@@ -3,7 +3,7 @@
 import contextlib, os, sys, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sagnn_b200 import hostmem
-devi = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+devi = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 0
 torch.cuda.set_device(devi)
 info = {}
 n = 155_556_864
@@ -21,7 +21,7 @@ def run(h2d, d2h, reps=10):
         if d2h:
             with torch.cuda.stream(s2): h_out.copy_(d_out, non_blocking=True)
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / reps
-for name, a, b in (("H2D alone", 1, 0), ("D2H alone", 0, 1), ("both at once", 1, 1)):
+for name, a, b in (() if "concurrent" in sys.argv else (("H2D alone", 1, 0), ("D2H alone", 0, 1), ("both at once", 1, 1))):
     run(a, b, 2); t = run(a, b)
     print("%-13s %.2f ms  %.1f GB/s per direction" % (name, t * 1e3, n / t / 1e9))
 c = n // 6
@@ -32,4 +32,27 @@ def chunked(reps=10):
             with torch.cuda.stream(s1): d_in[k*c:(k+1)*c].copy_(h_in[k*c:(k+1)*c], non_blocking=True)
             with torch.cuda.stream(s2): h_out[k*c:(k+1)*c].copy_(d_out[k*c:(k+1)*c], non_blocking=True)
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / reps
-chunked(2); t = chunked(); print("%-13s %.2f ms  %.1f GB/s per direction" % ("both, 6 chunks", t * 1e3, n / t / 1e9))
+if "concurrent" not in sys.argv: chunked(2); t = chunked(); print("%-13s %.2f ms  %.1f GB/s per direction" % ("both, 6 chunks", t * 1e3, n / t / 1e9))
+
+# ---- concurrent mode: python scripts/pcie_probe.py concurrent N  -> the same duplex copy on N GPUs at once
+# (children start at a common wall-clock time); shows whether the GPUs' host links are independent
+if "concurrent" in sys.argv:
+    import subprocess
+    if "child" in sys.argv:
+        t_start = float(sys.argv[sys.argv.index("child") + 1])
+        run(1, 1, 2)
+        while time.time() < t_start:
+            pass
+        t = run(1, 1, 40)
+        print("CHILD %d %.3f" % (devi, n / t / 1e9))
+    else:
+        N = int(sys.argv[sys.argv.index("concurrent") + 1])
+        t0 = time.time() + 25.0
+        ps = [subprocess.Popen([sys.executable, __file__, str(i), "concurrent", "child", repr(t0)], stdout=subprocess.PIPE, text=True)
+              for i in range(N)]
+        rates = []
+        for p in ps:
+            out = p.communicate()[0]
+            rates += [float(l.split()[2]) for l in out.splitlines() if l.startswith("CHILD")]
+        print("%d GPUs copying both ways at once: per GPU %s GB/s per direction, sum %.1f GB/s per direction"
+              % (N, " ".join("%.1f" % r for r in rates), sum(rates)))
