@@ -332,7 +332,7 @@ def main():
             rcv_u.zero_(); rcv_i.zero_()
             hdl_u.barrier(channel=0)
 
-            def ce_step():
+            def ce_step(with_barrier=False):
                 step.forward()
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
@@ -340,6 +340,8 @@ def main():
                         r = (rank + j) % world               # start with my own block, then round the ring
                         peer_u[r][rank].copy_(step.user_out_full[r * bu:(r + 1) * bu], non_blocking=True)
                         peer_i[r][rank].copy_(step.item_out_full[r * bi:(r + 1) * bi], non_blocking=True)
+                    if with_barrier:                         # arrival barrier behind the copies, under the backward
+                        hdl_u.barrier(channel=0)
                 step.backward()
                 torch.cuda.current_stream().wait_stream(side)
 
@@ -359,16 +361,48 @@ def main():
     # ordinary kernel arguments); the NCCL hand-offs keep direct launches
     use_graph = not args.no_graph and (not do_gather or fused)
     ce_graph = None
-    if use_graph and ce:
-        cap = torch.cuda.Stream()
-        cap.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(cap):
-            ce_step()
-        torch.cuda.current_stream().wait_stream(cap)
-        torch.cuda.synchronize()
-        ce_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(ce_graph):
-            ce_step()
+    barrier_in_graph = False
+
+    def fused_step(with_barrier=False):     # forward with the epilogue's peer stores, arrival barrier under the backward
+        step.forward()
+        if with_barrier:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                hdl_u.barrier(channel=0)
+        step.backward()
+        if with_barrier:
+            torch.cuda.current_stream().wait_stream(side)
+
+    if use_graph and fused:
+        # forward + hand-off + backward in ONE graph per rank; the symmetric-memory arrival barrier rides a side
+        # stream inside it (behind the copies / the forward's peer stores, concurrent with the backward), so a step
+        # no longer ends with a cross-rank rendezvous.  If the barrier cannot be captured it stays behind the graph.
+        body = ce_step if ce else fused_step
+        for in_graph in ((True, False) if os.environ.get("SAGNN_BARRIER_IN_GRAPH", "1") != "0" else (False,)):
+            try:
+                cap = torch.cuda.Stream()
+                cap.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(cap):
+                    body(in_graph)
+                    if not in_graph:
+                        hdl_u.barrier(channel=0)
+                torch.cuda.current_stream().wait_stream(cap)
+                torch.cuda.synchronize()
+                ce_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ce_graph):
+                    body(in_graph)
+                barrier_in_graph = in_graph
+                break
+            except Exception as e:
+                if not in_graph:
+                    raise
+                sys.stderr.write("[bench] rank %d: barrier not capturable (%s), keeping it behind the graph\n" % (rank, e))
+                ce_graph = None
+                torch.cuda.synchronize()
+        ok = torch.tensor([int(barrier_in_graph)], device=dev)      # every rank must run the same arrangement
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if barrier_in_graph and not bool(ok.item()):
+            raise RuntimeError("ranks disagree on the barrier arrangement")
     elif use_graph:
         step.capture()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -379,15 +413,13 @@ def main():
         flush = _NoFlush()
 
     def one_step():
-        if ce:
-            if ce_graph is not None:
-                ce_graph.replay()
-            else:
-                ce_step()
+        if fused and ce_graph is not None:
+            ce_graph.replay()                                       # rows land in the peers' buffers as they finish / by DMA
+            if not barrier_in_graph:
+                hdl_u.barrier(channel=0)                            # every rank is through: my receive slabs are complete
+        elif ce:
+            ce_step()
             hdl_u.barrier(channel=0)
-        elif fused and use_graph:
-            step.replay()                                           # rows land in the peers' buffers as they finish
-            hdl_u.barrier(channel=0)                                # every rank is through: my receive slabs are complete
         elif fused:
             step.forward()
             side.wait_stream(torch.cuda.current_stream())
@@ -572,7 +604,9 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, g, L, d, world),
-            "run": dict(run_config(args, world, stats, use_graph, do_gather), cta_split=split),
+            "run": dict(run_config(args, world, stats, use_graph, do_gather), cta_split=split,
+                        **({"arrival_barrier": "inside the graph, side stream, concurrent with the backward" if barrier_in_graph
+                            else "one launch behind the graph"} if fused else {})),
             "graph_edges_per_s": edges_all / (ms_per_step * 1e-3),
             "plan_build_ms": plan_ms, "wall_s_timed_region": wall,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
@@ -624,12 +658,14 @@ def run_config(args, world, stats, use_graph, gather):
                          "stream overlapping the backward",
             "fused": "no collective kernel: the last forward layer's epilogue stores every finished row into the "
                      "symmetric-memory receive buffer of the rank that owns its row block (peer stores over "
-                     "NVLink, sagnn_propagate_fwd_scatter); forward + backward replay from one CUDA graph, then one "
-                     "symmetric-memory barrier; verified bitwise against the NCCL all-to-all before timing",
+                     "NVLink, sagnn_propagate_fwd_scatter); forward + arrival barrier + backward replay from one CUDA graph "
+                     "(the symmetric-memory barrier on a side stream behind the forward, see arrival_barrier); verified "
+                     "bitwise against the NCCL all-to-all before timing",
             "ce": "no collective kernel and no SM: after the forward, one peer memcpy per row block (copy engines over "
                   "NVLink) fills the consumers' symmetric-memory receive buffers on a side stream while the backward runs; "
-                  "forward + copies + backward replay from one CUDA graph, then one symmetric-memory barrier; verified "
-                  "bitwise against the NCCL all-to-all before timing",
+                  "forward + copies + arrival barrier + backward replay from one CUDA graph (the symmetric-memory barrier "
+                  "on the side stream behind the copies, see arrival_barrier); verified bitwise against the NCCL "
+                  "all-to-all before timing",
             "none": "no hand-off collective (compute only)"}[args.exchange]
     return cfg
 

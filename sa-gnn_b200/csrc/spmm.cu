@@ -217,9 +217,15 @@ premask_kernel(const float4* __restrict__ in_u, const float4* __restrict__ in_i,
     const int64_t j = it ? i - n4_u : i;
     int64_t jin = j;
     if (rtd_T > 0) {      // (k, r, c) of the [T,R,d/4] range -> ((r*T + k0 + k)*q + c) of the whole [R,T,d/4] tensor
-      const int64_t rows = it ? rows_i : rows_u, rq = rows * q;
-      const int64_t k = j / rq, rem = j - k * rq, r = rem / q, c = rem - r * q;
-      jin = (r * rtd_T + k0 + k) * q + c;
+      // q = d/4 is a power of two for every supported latdim and T is small: shifts and a short subtract loop
+      // instead of two 64-bit divisions per element (they cost more than the memory traffic of this pass)
+      const int64_t rows = it ? rows_i : rows_u;
+      const int qs = 31 - __clz(q);
+      int64_t r = j >> qs;
+      const int64_t c = j & (q - 1);
+      int k = 0;
+      while (r >= rows) { r -= rows; ++k; }
+      jin = ((r * rtd_T + k0 + k) << qs) + c;
     }
     float4 x = it ? in_i[jin] : in_u[jin];
     const uint32_t b = it ? m_i[j] : m_u[j];
