@@ -29,7 +29,8 @@ sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True
 out = ["# SASS summary of sa-gnn_b200/lib/libsagnn_b200.so (cuobjdump -sass, sm_100a), round 2", "",
        "Opcode counts per kernel: `UBLKCP` = TMA bulk copy (cp.async.bulk), `SYNCS` = mbarrier arrive / try_wait, `LDGSTS` = cp.async,",
        "`FADD2` / `FFMA2` = packed fp32 pairs (sm_100 only), `LDG` / `STG` global, `LDS` shared, `ATOMG` global atomics (queue heads, tickets).", "",
-       "| kernel | instr | UBLKCP | SYNCS | LDGSTS | LDG | STG | LDS | FADD2 | FFMA2 | ATOMG | STL/LDL |", "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+       "`ACQBULK` / `PREEXIT` = griddepcontrol.wait / launch_dependents (programmatic dependent launch), `CCTL` = L1 invalidate (acquire fence of a slice group's last arriver).", "",
+       "| kernel | instr | UBLKCP | SYNCS | LDGSTS | LDG | STG | LDS | FADD2 | FFMA2 | ATOMG | ACQBULK+PREEXIT | CCTL | STL/LDL |", "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
 cur = None; counts = {}
 for line in sass.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -43,13 +44,15 @@ for line in sass.splitlines():
         counts[cur]["_n"] = counts[cur].get("_n", 0) + 1
 def demangle(n):
     return subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()
-want = [k for k in counts if re.search(r"spmm_pkt_kernelILi64ELi[012]ELb0ELb0|spmm_rpw_kernelILi4ELi[01]ELb0ELb0ELb0|premask|pkt_fill|sched_task", k)]
+want = [k for k in counts if re.search(r"spmm_pkt_kernelILi64ELi[012]ELb0ELb0ELb[01]|spmm_rpw_kernelILi4ELi[01]ELb0ELb0ELb0|premask|pkt_fill|sched_task", k)]
 for k in sorted(want):
     c = counts[k]
     g = lambda *ops: sum(c.get(o, 0) for o in ops)
-    out.append("| `%s` | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d |" % (
-        demangle(k)[:90], c.get("_n", 0), g("UBLKCP"), g("SYNCS"), g("LDGSTS"), g("LDG"), g("STG"), g("LDS"), g("FADD2"), g("FFMA2"), g("ATOMG", "ATOM"), g("STL", "LDL")))
-out += ["", "Default path: `spmm_pkt_kernel<64, MODE, false, false>` (latdim 64; MODE 0 forward, 1 backward, 2 messagePropagate): the packed task",
+    out.append("| `%s` | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d |" % (
+        demangle(k)[:90], c.get("_n", 0), g("UBLKCP"), g("SYNCS"), g("LDGSTS"), g("LDG"), g("STG"), g("LDS"), g("FADD2"), g("FFMA2"), g("ATOMG", "ATOM"),
+        g("ACQBULK", "PREEXIT"), g("CCTL"), g("STL", "LDL")))
+out += ["", "Default path: `spmm_pkt_kernel<64, MODE, false, false, false>` (latdim 64; MODE 0 forward, 1 backward, 2 messagePropagate; the last",
+        "`true` instances are the hot-row staging variant a plan asks for with `sagnn_plan_set_hot_rows`, more `UBLKCP` / `LDS`): the packed task",
         "stream arrives by `UBLKCP` (one per packet of four tasks, completion on an mbarrier: `SYNCS`), gathers are `LDG.E.128.CONSTANT`,",
         "accumulation is `FADD2`; no `LDGSTS`.  Plans hinted latdim >= 128 run `spmm_rpw_kernel<4, ...>` (v8: `LDGSTS` rings, no TMA)."]
 open(os.path.join(P, "r2_sass_summary.md"), "w").write("\n".join(out) + "\n")

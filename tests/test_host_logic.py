@@ -223,3 +223,21 @@ def test_product_never_imports_oracle():
         src = open(path).read()
         assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), path
         assert "sagnn_oracle" not in src, path
+
+
+def test_near_gpu_restores_affinity_and_degrades_without_nvml():
+    """hostmem.near_gpu: the with-block may narrow the thread's CPU affinity to the GPU's NUMA node (first-touch
+    placement of pinned pages); it must always put the old affinity back, and without a GPU / NVML it is a no-op."""
+    import os
+    from sagnn_b200 import hostmem
+    before = os.sched_getaffinity(0)
+    info = {}
+    with hostmem.near_gpu(0, info) as got:
+        assert got is info and "bound" in info
+        inside = os.sched_getaffinity(0)
+        assert inside <= before or not info["bound"]
+    assert os.sched_getaffinity(0) == before
+    with pytest.raises(RuntimeError):
+        with hostmem.near_gpu(0):
+            raise RuntimeError("body failed")
+    assert os.sched_getaffinity(0) == before
