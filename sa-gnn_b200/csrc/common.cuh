@@ -15,7 +15,6 @@ namespace sagnn {
 constexpr int kChunk = 64;        // max edges one warp gathers for one task
 constexpr int kPktTasks = 4;      // tasks per packet of the packed task stream (packet-stream kernel)
 constexpr int kHotRows = 768;     // max hot slots per source table (slot = degree rank); array stride
-constexpr int kHotBytes = 192 * 1024;   // (v7 legacy) shared memory given to staged hot rows
 constexpr int kSmemBudget = 226 * 1024; // dynamic shared memory a persistent CTA of the packet-stream kernel may use
 
 void set_error(const char* fmt, ...);
@@ -174,7 +173,6 @@ struct sagnn_plan {
 namespace sagnn {
 void free_host_cache(sagnn_plan* p);
 int apply_cta_split(sagnn_plan* p, const std::vector<double>& cost, cudaStream_t st);
-bool use_rpw();   // always true since the half-warp kernel (v7) was retired; kept for the call sites
 bool use_pkt();   // packet-stream kernel allowed (default); SAGNN_KERNEL=v8 forces the cp.async-ring kernel for every plan
 // which kernel a plan's schedule is built for: packet stream (v10) up to latdim 64, cp.async rings (v8) from 128 on --
 // measured on the ML-10M shape (d=128, mean user degree 143): v8 4.6 ms, v10 5.5-6.4 ms per step

@@ -246,7 +246,6 @@ static bool use_premask(const sagnn_plan* p) {
 // ---------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------
-bool use_rpw() { return true; }
 // SAGNN_KERNEL=v8 selects the cp.async-ring kernel (A/B runs); default: packet-stream kernel.
 // Read once: the plan's schedule (task records + codes vs packed stream) is built for one of them.
 bool use_pkt() {
@@ -433,7 +432,7 @@ static WsLayout ws_layout(const sagnn_plan* p, int n_layers, int d) {
   const int npm = n_layers < 2 ? n_layers : 2;
   for (int b = 0; b < 2; ++b) {   // backward: pre-masked copies of the upstream / running gradient
     w.pm_off[b] = off;
-    if (b < npm && use_rpw()) off = align_up(off + sizeof(float) * w.table_floats, 256);
+    if (b < npm) off = align_up(off + sizeof(float) * w.table_floats, 256);
   }
   w.total = off;
   return w;
@@ -510,7 +509,6 @@ static int fwd_impl(const sagnn_plan* p, int interval, const float* uE, const fl
   SAGNN_REQUIRE(0 <= l_begin && l_begin <= l_end && l_end <= L, SAGNN_INVALID_ARG,
                 "propagate_fwd: layer range [%d,%d) outside [0,%d]", l_begin, l_end, L);
   SAGNN_REQUIRE(!(flags & ~(unsigned)SAGNN_LAYOUT_RTD), SAGNN_INVALID_ARG, "propagate_fwd: unknown flags 0x%x", flags);
-  SAGNN_REQUIRE(!flags || use_rpw(), SAGNN_INVALID_ARG, "propagate_fwd: [R,T,d] outputs need the row-per-warp kernel");
   if (int rc = check_common(p, L, d, "propagate_fwd")) return rc;
   SAGNN_REQUIRE(interval < p->T, SAGNN_INVALID_ARG, "propagate_fwd: interval %d outside [0,%d)", interval, p->T);
   SAGNN_REQUIRE(uE && iE && uOut && iOut && ws, SAGNN_INVALID_ARG, "propagate_fwd: NULL tensor");
@@ -587,7 +585,6 @@ extern "C" int sagnn_propagate_fwd_scatter(const sagnn_plan* p, const float* uE,
   SAGNN_REQUIRE(user_recv && item_recv, SAGNN_INVALID_ARG, "propagate_fwd_scatter: NULL pointer table");
   for (int r = 0; r < world; ++r)
     SAGNN_REQUIRE(user_recv[r] && item_recv[r], SAGNN_INVALID_ARG, "propagate_fwd_scatter: NULL receive buffer of rank %d", r);
-  SAGNN_REQUIRE(use_rpw(), SAGNN_INVALID_ARG, "propagate_fwd_scatter: needs the row-per-warp kernel");
   PeerScatter ps{world, rank, user_recv, item_recv};
   return fwd_impl(p, -1, uE, iE, uOut, iOut, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream,
                   SAGNN_LAYOUT_RTD, 0, -1, &ps);
@@ -610,7 +607,6 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
   const int s_begin = ph_begin > 0 ? ph_begin - 1 : 0, s_end = ph_end - 1;
   if (ph_begin == ph_end) return SAGNN_OK;
   SAGNN_REQUIRE(!(flags & ~(unsigned)SAGNN_LAYOUT_RTD), SAGNN_INVALID_ARG, "propagate_bwd: unknown flags 0x%x", flags);
-  SAGNN_REQUIRE(!flags || use_rpw(), SAGNN_INVALID_ARG, "propagate_bwd: [R,T,d] upstream needs the row-per-warp kernel");
   if (int rc = check_common(p, L, d, "propagate_bwd")) return rc;
   SAGNN_REQUIRE(interval < p->T, SAGNN_INVALID_ARG, "propagate_bwd: interval %d outside [0,%d)", interval, p->T);
   SAGNN_REQUIRE(gU && gI && dU && dI && masks && ws, SAGNN_INVALID_ARG, "propagate_bwd: NULL tensor");
@@ -629,7 +625,6 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
   float* pmb[2] = {(float*)(base + w.pm_off[0]), (float*)(base + w.pm_off[1])};
   const size_t mlw = mask_layer_bytes(p, d);
   const size_t mu = (size_t)p->T * p->U * (d / 4);
-  const bool rpw = use_rpw();
   bool premasked = false;   // the pre-mask pass was launched by this call
   if (interval >= 0) { s.cta = p->cta_int_dev + (size_t)interval * p->num_sms; s.cta_host = p->cta_int_host.data() + (size_t)interval * p->num_sms; }
   for (int l = L - 1 - s_begin, step = s_begin; step < s_end || (step == 0 && ph_begin == 0); --l, ++step) {
@@ -640,7 +635,7 @@ static int bwd_impl(const sagnn_plan* p, int interval, const float* gU, const fl
     s.src_u = g_u; s.src_i = g_i;
     s.smask_u = (const uint8_t*)masks + (size_t)l * mlw;        // sigma'(Z0^l): masks user-table rows
     s.smask_i = (const uint8_t*)masks + (size_t)l * mlw + mu;   // sigma'(Z1^l): masks item-table rows
-    if (rpw) {
+    {
       // below the top level the source is the copy the level above already multiplied by sigma'(Z^l);
       // at the top level one streaming pass makes that copy of the upstream
       if (step == 0 && use_premask(p)) {
@@ -712,8 +707,7 @@ extern "C" int sagnn_propagate_fwd_layers(const sagnn_plan* p, int l_begin, int 
 extern "C" int sagnn_propagate_bwd_levels(const sagnn_plan* p, int ph_begin, int ph_end, const float* gU,
                                           const float* gI, float* dU, float* dI, int L, int d, float leaky,
                                           const void* masks, void* ws, size_t ws_bytes, sagnn_stream_t stream) {
-  SAGNN_REQUIRE(use_rpw() && use_premask(p), SAGNN_INVALID_ARG,
-                "propagate_bwd_levels: needs the row-per-warp kernel with pre-masked sources");
+  SAGNN_REQUIRE(use_premask(p), SAGNN_INVALID_ARG, "propagate_bwd_levels: needs pre-masked sources (SAGNN_BWD_PREMASK=0 is set)");
   return bwd_impl(p, -1, gU, gI, dU, dI, L, d, leaky, masks, ws, ws_bytes, (cudaStream_t)stream, 0, ph_begin, ph_end);
 }
 
@@ -723,7 +717,6 @@ extern "C" int sagnn_workspace_table(const sagnn_plan* p, int L, int d, int whic
   SAGNN_REQUIRE(offset_bytes && (which == 0 || which == 1) && index >= 0 && index < (which ? L : L - 1),
                 SAGNN_INVALID_ARG, "workspace_table: which=%d index=%d (forward: 0 <= index < n_layers-1, "
                 "backward: 0 <= index < n_layers; n_layers=%d)", which, index, L);
-  SAGNN_REQUIRE(which == 0 || use_rpw(), SAGNN_INVALID_ARG, "workspace_table: the v7 kernel has no pre-masked tables");
   WsLayout w = ws_layout(p, L, d);
   // forward: E^{index+1}, written by layer `index`; backward: the pre-masked gather source of level
   // step `index` (written by phase `index`: the pre-mask pass for 0, the level kernel of step index-1 after)
