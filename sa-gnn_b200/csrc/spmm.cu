@@ -211,29 +211,41 @@ premask_kernel(const float4* __restrict__ in_u, const float4* __restrict__ in_i,
                const uint8_t* __restrict__ m_i, float4* __restrict__ out_u, float4* __restrict__ out_i, int64_t n4_u,
                int64_t n4_i, float leaky, int rtd_T, int k0, int64_t rows_u, int64_t rows_i, int q) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the level kernel after me starts up under my tail
-  const int64_t n = n4_u + n4_i, step = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-    const bool it = i >= n4_u;
-    const int64_t j = it ? i - n4_u : i;
-    int64_t jin = j;
-    if (rtd_T > 0) {      // (k, r, c) of the [T,R,d/4] range -> ((r*T + k0 + k)*q + c) of the whole [R,T,d/4] tensor
-      // q = d/4 is a power of two for every supported latdim and T is small: shifts and a short subtract loop
-      // instead of two 64-bit divisions per element (they cost more than the memory traffic of this pass)
-      const int64_t rows = it ? rows_i : rows_u;
-      const int qs = 31 - __clz(q);
-      int64_t r = j >> qs;
-      const int64_t c = j & (q - 1);
-      int k = 0;
-      while (r >= rows) { r -= rows; ++k; }
-      jin = ((r * rtd_T + k0 + k) << qs) + c;
-    }
-    float4 x = it ? in_i[jin] : in_u[jin];
-    const uint32_t b = it ? m_i[j] : m_u[j];
+  const int64_t step = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  auto masked = [&](float4 x, uint32_t b) {
     x.x = (b & 1u) ? x.x : leaky * x.x;
     x.y = (b & 2u) ? x.y : leaky * x.y;
     x.z = (b & 4u) ? x.z : leaky * x.z;
     x.w = (b & 8u) ? x.w : leaky * x.w;
-    (it ? out_i : out_u)[j] = x;
+    return x;
+  };
+  if (rtd_T > 0) {
+    // [R,T,d] upstream: walk it in ITS order -- one thread per (row, float4 column), the row's intervals in an inner
+    // loop, so a warp reads whole contiguous T*d-float rows (q = d/4 is a power of two: shifts, no divisions);
+    // element (r, k0 + k, c) of the input goes to (k, r, c) of the [T,R,d] range the masks and the output use
+    const int qs = 31 - __clz(q);
+    const int nk_u = (int)(n4_u / (rows_u << qs)), nk_i = rows_i > 0 ? (int)(n4_i / (rows_i << qs)) : 0;
+    const int64_t nu = rows_u << qs, n = nu + (rows_i << qs);
+    for (int64_t i = i0; i < n; i += step) {
+      const bool it = i >= nu;
+      const int64_t j = it ? i - nu : i, r = j >> qs, c = j & (q - 1);
+      const int64_t rows = it ? rows_i : rows_u;
+      const float4* in = it ? in_i : in_u;
+      const uint8_t* m = it ? m_i : m_u;
+      float4* out = it ? out_i : out_u;
+      const int nk = it ? nk_i : nk_u;
+      for (int k = 0; k < nk; ++k) {
+        const int64_t o = (((int64_t)k * rows + r) << qs) + c;
+        out[o] = masked(in[((r * rtd_T + k0 + k) << qs) + c], m[o]);
+      }
+    }
+    return;
+  }
+  const int64_t n = n4_u + n4_i;
+  for (int64_t i = i0; i < n; i += step) {
+    const bool it = i >= n4_u;
+    const int64_t j = it ? i - n4_u : i;
+    (it ? out_i : out_u)[j] = masked(it ? in_i[j] : in_u[j], it ? m_i[j] : m_u[j]);
   }
 }
 
