@@ -10,10 +10,14 @@ Follows LIU-YUXI/SA-GNN ``model.py:135-155`` and ``Utils/attention.py:31-78``:
     ScaledDotProductAttention (attention.py:34-44: exp without max subtraction, + 1e-8 in the normaliser),
     tf.reduce_mean over the T axis (model.py:154-155).
 
-PARITY UNPINNED: nothing of the reference executes here (TF 1.14 is not importable) and, unlike the
-propagation, these lines were not run over the numpy shim; the per-op semantics below are the
-builder's reading of TF 1.14 (BasicLSTMCell: gate order i, j, f, o, forget_bias 1.0; layer_norm:
-begin_norm_axis=1, begin_params_axis=-1, epsilon 1e-12; tf.layers.dense: kernel + bias).
+PINNED TO THE REFERENCE TEXT (round 2): ``tests/golden/make_golden_downstream.py`` executes model.py:133-156,
+169-172 and 174-203 as they stand (with the reference's own Utils/attention.py and Utils/NNLayers.py) over the
+numpy TF stand-in and commits ``tests/golden/downstream_*.npz``; ``tests/test_fusion.py`` compares every function
+below with those fixtures.  Wiring, the shared LSTM cell, per-side Q / K / V kernels, exp-normalised attention,
+axes, stop_gradient placement and the positive | negative slicing therefore come from the reference; what stays
+the builder's statement is the per-op semantics of the TF 1.14 kernels inside the stand-in (BasicLSTMCell: gate
+order i, j, f, o, forget_bias 1.0; layer_norm: begin_norm_axis=1, begin_params_axis=-1, epsilon 1e-12;
+tf.layers.dense: kernel + bias).
 """
 from __future__ import annotations
 
@@ -67,3 +71,37 @@ def interval_fusion(x, p, heads):
     n = layer_norm(h, p["ln_gamma"], p["ln_beta"])
     a = multihead_self_attention(n, p["wq"], p["bq"], p["wk"], p["bk"], p["wv"], p["bv"], heads)
     return a.mean(axis=1)
+
+
+def _lrelu(x, leaky):
+    return np.maximum(leaky * x, x)
+
+
+def meta_user_weight(final_user, user_vector, w2, b2, w3, b3, leaky):
+    """model.py:178-184: per interval k, ``meta1 = concat([final * uv_k, final, uv_k], -1)``, ``meta2 =
+    lrelu(meta1 @ W2 + b2)``, ``weight_k = sigmoid(meta2 @ W3 + b3)`` squeezed to [U]; stacked to [T,U].
+    The same two FC layers (``reuse=True``) serve every interval."""
+    out = []
+    for k in range(user_vector.shape[0]):
+        m1 = np.concatenate([final_user * user_vector[k], final_user, user_vector[k]], axis=-1)
+        m2 = _lrelu(m1 @ w2 + b2, leaky)
+        out.append(_sigmoid(m2 @ w3 + b3)[:, 0])
+    return np.stack(out, axis=0)
+
+
+def ssl_hinge(final_user, final_item, user_vector, item_vector, user_weight, suids, siids, leaky):
+    """model.py:185-203: for every interval, the first half of (suids, siids) are the positive pairs, the second
+    half the negatives; ``S = w[pos users] * s_final[pos] - w[neg users] * s_final[neg]`` with the FINAL-vector
+    scores under stop_gradient, ``preds_one`` = the interval's own pair scores, loss = sum max(0, 1 - S * (pos - neg)).
+    Returns (sslloss, [preds_one per interval])."""
+    loss, preds = 0.0, []
+    for k in range(user_vector.shape[0]):
+        su, si = np.asarray(suids[k]), np.asarray(siids[k])
+        n = su.shape[0] // 2
+        s_final = _lrelu(final_user[su] * final_item[si], leaky).sum(axis=-1)
+        w = user_weight[k][su]
+        S = w[:n] * s_final[:n] - w[n:] * s_final[n:]
+        p1 = _lrelu(user_vector[k][su] * item_vector[k][si], leaky).sum(axis=-1)
+        loss = loss + np.maximum(0.0, 1.0 - S * (p1[:n] - p1[n:])).sum()
+        preds.append(p1)
+    return loss, preds

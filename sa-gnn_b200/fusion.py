@@ -12,7 +12,11 @@
 
 Same semantics as TF 1.14 for the ops involved (gate order i, j, f, o with forget_bias 1.0; layer norm over
 (T, d) with epsilon 1e-12; exp-normalised attention with 1e-8 in the denominator); checked against
-``oracle/fusion_oracle.py`` (the builder's restatement: parity unpinned for this consumer).
+``oracle/fusion_oracle.py`` and, through ``tests/golden/downstream_*.npz``, against the reference's own
+model.py:133-156 / Utils/attention.py text executed over a numpy TF stand-in (``tests/test_fusion.py``).
+
+  * ``SslHead``: the meta-weight network and the weighted hinge of the SSL objective (model.py:174-203) on top of
+    the pair scores ``sagnn_b200.pair_scores`` gathers from the path's outputs (dense framework-side ops as well).
 """
 from __future__ import annotations
 
@@ -79,6 +83,42 @@ class IntervalFusion(torch.nn.Module):
 
     def forward(self, user_rtd, item_rtd):
         return self.fuse(user_rtd, "user"), self.fuse(item_rtd, "item")
+
+
+class SslHead(torch.nn.Module):
+    """model.py:174-203 around the gathered pair scores: ``user_weight`` (two FC layers shared by all intervals:
+    ``meta2`` [3d, ssldim] + bias with LeakyReLU, ``meta3`` [ssldim, 1] + bias with sigmoid) and the hinge
+    ``sum max(0, 1 - S * (pos - neg))`` with ``S = w[pos] * s_final[pos] - w[neg] * s_final[neg]`` (final-vector
+    scores detached, like the reference's ``tf.stop_gradient``)."""
+
+    def __init__(self, d, ssldim=32, leaky=0.5, dtype=torch.float32, device=None, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+
+        def xavier(rows, cols):
+            a = math.sqrt(6.0 / (rows + cols))
+            return torch.nn.Parameter(((torch.rand((rows, cols), generator=g, dtype=torch.float64) * 2 - 1) * a).to(dtype=dtype, device=device))
+
+        self.leaky = leaky
+        self.meta2, self.meta2_bias = xavier(3 * d, ssldim), torch.nn.Parameter(torch.zeros(ssldim, dtype=dtype, device=device))
+        self.meta3, self.meta3_bias = xavier(ssldim, 1), torch.nn.Parameter(torch.zeros(1, dtype=dtype, device=device))
+
+    def user_weight(self, final_user, user_vector):
+        """final_user [U,d], user_vector [T,U,d] (the path's output) -> [T,U]   (model.py:178-184)."""
+        f = final_user.unsqueeze(0).expand_as(user_vector)
+        m1 = torch.cat([f * user_vector, f, user_vector], dim=-1)
+        z = m1 @ self.meta2 + self.meta2_bias
+        m2 = torch.maximum(self.leaky * z, z)                     # Activate(..., 'leakyRelu'), Utils/NNLayers.py:135-136
+        return torch.sigmoid(m2 @ self.meta3 + self.meta3_bias).squeeze(-1)
+
+    @staticmethod
+    def hinge(weight_at_suids, final_scores, interval_scores):
+        """One interval (model.py:186-202): all three are [2n] in the sampler's positives | negatives order;
+        ``final_scores`` = pair scores on the final vectors (detached here), ``interval_scores`` = ``preds_one``."""
+        n = interval_scores.shape[0] // 2
+        sf = final_scores.detach()
+        S = weight_at_suids[:n] * sf[:n] - weight_at_suids[n:] * sf[n:]
+        return torch.clamp_min(1.0 - S * (interval_scores[:n] - interval_scores[n:]), 0.0).sum()
 
 
 def slabs_to_rtd(slabs, owners, rank_rows=None):

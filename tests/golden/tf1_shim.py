@@ -15,6 +15,18 @@ semantics of the TF CPU kernels (each function says which):
   tf.nn.dropout (TF 1.14 positional keep_prob), tf.sparse.SparseTensor, tf.get_variable,
   tensorflow.contrib.layers.xavier_initializer.
 
+For the rows AFTER the path (interval fusion model.py:135-155 with Utils/attention.py:31-78,
+the prediction / SSL pair scores and the meta-weight hinge of model.py:170-173,175-201), used by
+make_golden_downstream.py, a second family of stand-ins (same rule: wiring from the reference text, per-op
+semantics stated here):
+
+  tf.contrib.rnn.BasicLSTMCell / DropoutWrapper / MultiRNNCell, tf.nn.dynamic_rnn, tf.layers.dense,
+  tf.contrib.layers.layer_norm, tf.matmul, tf.exp, tf.tanh, tf.reshape, tf.expand_dims, tf.tile, tf.concat,
+  tf.reduce_sum / reduce_mean, tf.shape, tf.stop_gradient, tf.nn.sigmoid / softmax, tf.random_uniform, tf.name_scope.
+
+Variables those create go through ``VarStore`` (creation order + names), so the generator can run the text once to
+discover them, move them off their trivial initial values and replay the same text with the stored values.
+
 Everything is eager: a ``Tensor`` wraps an ndarray and keeps its dtype (float32 like the
 reference, or float64 when the caller feeds float64 parameters for finite differences).
 """
@@ -52,7 +64,11 @@ class Tensor:
         return Tensor(self.a[k])
 
     def _b(self, o):
-        return o.a if isinstance(o, Tensor) else o
+        if isinstance(o, Tensor):
+            return o.a
+        if np.ndim(o) == 0 and np.issubdtype(self.a.dtype, np.floating):
+            return self.a.dtype.type(o)      # TF converts a Python / numpy scalar operand to the tensor's dtype
+        return o
 
     def __add__(self, o): return Tensor(self.a + self._b(o))
     def __radd__(self, o): return Tensor(self._b(o) + self.a)
@@ -84,6 +100,7 @@ class Stats:
 def tf_slice(x, begin, size):
     """tf.slice: size -1 = everything from ``begin`` to the end of that axis."""
     x = _a(x)
+    begin, size = [int(_a(b)) for b in begin], [int(_a(s)) for s in size]      # sizes may be shape-derived tensors
     idx = tuple(slice(b, None if s == -1 else b + s) for b, s in zip(begin, size))
     return Tensor(x[idx])
 
@@ -198,9 +215,180 @@ def xavier_initializer(uniform=True, seed=None, dtype=np.float32):
 
 
 def get_variable(name=None, shape=None, dtype=None, initializer=None, trainable=True, **kw):
-    if callable(initializer):
-        return Tensor(initializer(shape))
-    return Tensor(_a(initializer))
+    """tf.get_variable as Utils/NNLayers.defineParam calls it (an initializer callable + shape, or an initial
+    value); recorded in the VarStore defined below under its own name."""
+    return VarStore.get(name, (lambda: initializer(shape)) if callable(initializer) else (lambda: _a(initializer)))
+
+
+
+# ---- variables of the consumer rows (dense / LSTM / layer-norm weights) --------------------------
+class VarStore:
+    """Creation-ordered variable store.  mode "create": every request makes a fresh variable from its TF 1.14
+    initializer and records (name, value); mode "replay": the k-th request returns the k-th recorded value (the
+    generator perturbs them in between so that biases / gamma / beta are not at 0 / 1)."""
+    mode = "create"
+    names: list = []
+    values: list = []
+    cursor = 0
+
+    @classmethod
+    def reset(cls):
+        cls.mode, cls.names, cls.values, cls.cursor = "create", [], [], 0
+
+    @classmethod
+    def replay(cls, dtype=None):
+        cls.mode, cls.cursor = "replay", 0
+        if dtype is not None:
+            cls.values = [v.astype(dtype) for v in cls.values]
+
+    @classmethod
+    def get(cls, name, make):
+        if cls.mode == "replay":
+            assert cls.names[cls.cursor].split("#")[0] == name, (cls.names[cls.cursor], name)
+            v = cls.values[cls.cursor]
+            cls.cursor += 1
+            return Tensor(v)
+        v = np.asarray(make())
+        cls.names.append("%s#%d" % (name, len(cls.names)))
+        cls.values.append(v)
+        return Tensor(v)
+
+
+def _glorot_uniform(shape):
+    """The default initializer of tf.get_variable / tf.layers.dense / LSTM kernels in TF 1.14."""
+    lim = np.sqrt(6.0 / (shape[0] + shape[1]))
+    return _init_rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+def dense(inputs, units, kernel_initializer=None, use_bias=True, activation=None, name=None):
+    """tf.layers.dense: a NEW kernel [in, units] + zero-initialised bias [units] per call (no reuse), applied
+    to the last axis; no activation unless given."""
+    x = _a(inputs)
+    k = VarStore.get("dense/kernel", lambda: (kernel_initializer or _glorot_uniform)([x.shape[-1], units]))
+    y = x @ _a(k).astype(x.dtype)
+    if use_bias:
+        y = y + _a(VarStore.get("dense/bias", lambda: np.zeros(units, np.float32))).astype(x.dtype)
+    return Tensor(y if activation is None else _a(activation(Tensor(y))))
+
+
+def layer_norm(inputs, center=True, scale=True, begin_norm_axis=1, begin_params_axis=-1):
+    """tf.contrib.layers.layer_norm (TF 1.14): moments over axes begin_norm_axis..rank-1 (default: every axis
+    but the batch axis -- for a [R,T,d] input that is T AND d), beta (zeros) / gamma (ones) of the last axis'
+    shape, tf.nn.batch_normalization with variance_epsilon 1e-12."""
+    x = _a(inputs)
+    axes = tuple(range(begin_norm_axis % x.ndim, x.ndim))
+    pshape = x.shape[begin_params_axis:]
+    beta = _a(VarStore.get("LayerNorm/beta", lambda: np.zeros(pshape, np.float32))).astype(x.dtype)
+    gamma = _a(VarStore.get("LayerNorm/gamma", lambda: np.ones(pshape, np.float32))).astype(x.dtype)
+    mean = x.mean(axis=axes, keepdims=True)
+    var = np.mean(np.square(x - mean), axis=axes, keepdims=True)
+    inv = gamma / np.sqrt(var + 1e-12)          # batch_normalization: inv = rsqrt(var + eps) * scale
+    return Tensor(x * inv + (beta - mean * inv))
+
+
+def _sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+class BasicLSTMCell:
+    """tf.contrib.rnn.BasicLSTMCell(num_units): forget_bias 1.0, tanh, state (c, h); kernel
+    [input + num_units, 4 * num_units] applied to concat([inputs, h], 1), bias zeros; gates split in the order
+    i, j, f, o; new_c = c * sigmoid(f + forget_bias) + sigmoid(i) * tanh(j); new_h = tanh(new_c) * sigmoid(o).
+    A Layer builds its variables ONCE: a second dynamic_rnn over the same cell object reuses them."""
+
+    def __init__(self, num_units, forget_bias=1.0):
+        self.n, self.forget_bias, self.kernel, self.bias = int(num_units), forget_bias, None, None
+
+    def zero_state(self, batch, dtype):
+        return (np.zeros((batch, self.n), dtype), np.zeros((batch, self.n), dtype))
+
+    def __call__(self, x, state):
+        c, h = state
+        if self.kernel is None:
+            self.kernel = VarStore.get("basic_lstm_cell/kernel", lambda: _glorot_uniform([x.shape[1] + self.n, 4 * self.n]))
+            self.bias = VarStore.get("basic_lstm_cell/bias", lambda: np.zeros(4 * self.n, np.float32))
+        g = np.concatenate([x, h], axis=1) @ _a(self.kernel).astype(x.dtype) + _a(self.bias).astype(x.dtype)
+        i, j, f, o = np.split(g, 4, axis=1)
+        new_c = c * _sigmoid(f + self.forget_bias) + _sigmoid(i) * np.tanh(j)
+        new_h = np.tanh(new_c) * _sigmoid(o)
+        return new_h, (new_c, new_h)
+
+
+class DropoutWrapper:
+    """tf.contrib.rnn.DropoutWrapper(cell, output_keep_prob): dropout on the cell OUTPUT only (not the state)."""
+
+    def __init__(self, cell, input_keep_prob=1.0, output_keep_prob=1.0, state_keep_prob=1.0):
+        assert input_keep_prob == 1.0 and state_keep_prob == 1.0
+        self.cell, self.keep = cell, output_keep_prob
+
+    def zero_state(self, batch, dtype):
+        return self.cell.zero_state(batch, dtype)
+
+    def __call__(self, x, state):
+        out, st = self.cell(x, state)
+        if float(_a(self.keep)) < 1.0:
+            out = _a(dropout(out, self.keep))
+        return out, st
+
+
+class MultiRNNCell:
+    def __init__(self, cells, state_is_tuple=True):
+        assert state_is_tuple
+        self.cells = list(cells)
+
+    def zero_state(self, batch, dtype):
+        return tuple(c.zero_state(batch, dtype) for c in self.cells)
+
+    def __call__(self, x, state):
+        new = []
+        for c, s in zip(self.cells, state):
+            x, s2 = c(x, s)
+            new.append(s2)
+        return x, tuple(new)
+
+
+def dynamic_rnn(cell, inputs, dtype=None, time_major=False, sequence_length=None, initial_state=None):
+    """tf.nn.dynamic_rnn, batch-major [B, T, in]: zero initial state, steps t = 0..T-1, outputs stacked on axis 1."""
+    assert not time_major and sequence_length is None and initial_state is None
+    x = _a(inputs)
+    state = cell.zero_state(x.shape[0], x.dtype)
+    outs = []
+    for t in range(x.shape[1]):
+        o, state = cell(x[:, t], state)
+        outs.append(o)
+    return Tensor(np.stack(outs, axis=1)), state
+
+
+def matmul(a, b):
+    return Tensor(np.matmul(_a(a), _a(b)))
+
+
+def reshape(x, shape):
+    return Tensor(np.reshape(_a(x), [int(_a(s)) for s in shape]))
+
+
+def concat(ts, axis):
+    return Tensor(np.concatenate([_a(t) for t in ts], axis=axis))
+
+
+def reduce_sum(x, axis=None, keepdims=False):
+    return Tensor(np.sum(_a(x), axis=axis, keepdims=keepdims))
+
+
+def reduce_mean(x, axis=None, keepdims=False):
+    return Tensor(np.mean(_a(x), axis=axis, keepdims=keepdims))
+
+
+def softmax(x, axis=-1):
+    x = _a(x)
+    e = np.exp(x - x.max(axis=axis, keepdims=True))
+    return Tensor(e / e.sum(axis=axis, keepdims=True))
+
+
+class _Scope:
+    def __init__(self, *a, **k): pass
+    def __enter__(self): return self
+    def __exit__(self, *a): return False
 
 
 def _unsupported(name):
@@ -219,10 +407,26 @@ def install():
         zeros=lambda shape, dtype=np.float32: Tensor(np.zeros(shape, dtype)),
         ones=lambda shape, dtype=np.float32: Tensor(np.ones(shape, dtype)),
         placeholder=_unsupported("placeholder"), Variable=_unsupported("Variable"),
+        matmul=matmul, reshape=reshape, concat=concat, reduce_sum=reduce_sum, reduce_mean=reduce_mean,
+        exp=lambda x: Tensor(np.exp(_a(x))), tanh=lambda x: Tensor(np.tanh(_a(x))),
+        expand_dims=lambda x, axis: Tensor(np.expand_dims(_a(x), axis)),
+        tile=lambda x, m: Tensor(np.tile(_a(x), [int(_a(v)) for v in m])),
+        shape=lambda x: Tensor(np.asarray(_a(x).shape, np.int32)),
+        stop_gradient=lambda x: Tensor(_a(x)),
+        random_uniform=lambda shape, minval=0.0, maxval=1.0, dtype=np.float32:
+            Tensor(_init_rng.uniform(minval, maxval, size=shape).astype(np.float32)),
+        name_scope=_Scope, variable_scope=_Scope,
     )
     nn = types.ModuleType("tensorflow.nn")
     nn.embedding_lookup = embedding_lookup
     nn.dropout = dropout
+    nn.dynamic_rnn = dynamic_rnn
+    nn.sigmoid = lambda x: Tensor(_sigmoid(_a(x)))
+    nn.tanh = lambda x: Tensor(np.tanh(_a(x)))
+    nn.softmax = softmax
+    tf_layers = types.ModuleType("tensorflow.layers")
+    tf_layers.dense = dense
+    tf.layers = tf_layers
     math = types.ModuleType("tensorflow.math")
     math.segment_sum = segment_sum
     sparse = types.ModuleType("tensorflow.sparse")
@@ -232,7 +436,11 @@ def install():
     contrib = types.ModuleType("tensorflow.contrib")
     layers = types.ModuleType("tensorflow.contrib.layers")
     layers.xavier_initializer = xavier_initializer
+    layers.layer_norm = layer_norm
     contrib.layers = layers
+    rnn = types.ModuleType("tensorflow.contrib.rnn")
+    rnn.BasicLSTMCell, rnn.DropoutWrapper, rnn.MultiRNNCell = BasicLSTMCell, DropoutWrapper, MultiRNNCell
+    contrib.rnn = rnn
     tf.contrib = contrib
     core = types.ModuleType("tensorflow.core")
     protobuf = types.ModuleType("tensorflow.core.protobuf")
@@ -241,7 +449,8 @@ def install():
     core.protobuf = protobuf
     tf.core = core
     mods = {"tensorflow": tf, "tensorflow.nn": nn, "tensorflow.math": math, "tensorflow.sparse": sparse,
-            "tensorflow.contrib": contrib, "tensorflow.contrib.layers": layers, "tensorflow.core": core,
+            "tensorflow.contrib": contrib, "tensorflow.contrib.layers": layers,
+            "tensorflow.contrib.rnn": rnn, "tensorflow.layers": tf_layers, "tensorflow.core": core,
             "tensorflow.core.protobuf": protobuf, "tensorflow.core.protobuf.config_pb2": config_pb2}
     # model.py:4 imports a matplotlib helper it never uses; matplotlib is not installed here
     if "matplotlib" not in sys.modules:

@@ -73,3 +73,106 @@ def test_slabs_to_rtd_orders_intervals_by_owner():
             slabs[src, :, j] = full[k]
     x = slabs_to_rtd(slabs, owners, rank_rows=5)
     assert x.shape == (5, 5, d) and torch.equal(x, full.transpose(0, 1)[:5])
+
+
+# ---- pinned to the reference's own text: model.py:133-156, 169-172, 174-203 executed over the numpy TF stand-in
+#      (tests/golden/make_golden_downstream.py -> downstream_*.npz) ------------------------------------------------
+import glob
+import os
+
+_DOWNSTREAM = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "downstream_*.npz")))
+
+
+def _side_params(fx, side, dtype=np.float64):
+    """Variables in the order the reference text creates them: the ONE LSTM cell (kernel, bias); then per side
+    LayerNorm beta, gamma and the Q, K, V dense layers (kernel, bias each) -- user first; then meta2, meta3."""
+    names = [str(n).split("#")[0] for n in fx["var_names"]]
+    assert names[:4] == ["basic_lstm_cell/kernel", "basic_lstm_cell/bias", "LayerNorm/beta", "LayerNorm/gamma"]
+    assert names[4:10] == ["dense/kernel", "dense/bias"] * 3 and names[10:12] == ["LayerNorm/beta", "LayerNorm/gamma"]
+    assert names[18:] == ["meta2", "meta2Bias", "meta3", "meta3Bias"]
+    v = lambda j: fx["var%02d" % j].astype(dtype)
+    o = 2 if side == "user" else 10
+    return dict(lstm_kernel=v(0), lstm_bias=v(1), ln_beta=v(o), ln_gamma=v(o + 1), wq=v(o + 2), bq=v(o + 3),
+                wk=v(o + 4), bk=v(o + 5), wv=v(o + 6), bv=v(o + 7))
+
+
+def test_downstream_fixtures_present():
+    assert len(_DOWNSTREAM) >= 2
+
+
+@pytest.mark.parametrize("path", _DOWNSTREAM, ids=[os.path.basename(p)[11:-4] for p in _DOWNSTREAM])
+def test_fusion_oracle_matches_reference_model_py_executed(path):
+    fx = np.load(path)
+    heads = int(fx["heads"])
+    for side, x, want in (("user", fx["user_vector"], fx["final_user_vector"]), ("item", fx["item_vector"], fx["final_item_vector"])):
+        got = fo.interval_fusion(x.astype(np.float64).transpose(1, 0, 2), _side_params(fx, side), heads)
+        np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.parametrize("path", _DOWNSTREAM, ids=[os.path.basename(p)[11:-4] for p in _DOWNSTREAM])
+def test_fusion_module_matches_reference_model_py_executed(path):
+    """The product's consumer module (forward in fp64 and fp32, autograd input gradient) against the executed text
+    and its fp64 finite differences."""
+    fx = np.load(path)
+    d, heads = int(fx["d"]), int(fx["heads"])
+    for dtype, tol in ((torch.float64, 1e-10), (torch.float32, 2e-5)):
+        m = IntervalFusion(d, heads=heads, dtype=dtype)
+        with torch.no_grad():
+            for side in ("user", "item"):
+                for k, val in _side_params(fx, side).items():
+                    m.side_params(side)[k].copy_(torch.from_numpy(val))
+        u = torch.from_numpy(fx["user_vector"]).to(dtype).transpose(0, 1).contiguous().requires_grad_(True)
+        i = torch.from_numpy(fx["item_vector"]).to(dtype).transpose(0, 1).contiguous().requires_grad_(True)
+        fu, fi = m(u, i)
+        scale = np.abs(fx["final_user_vector"]).max()
+        assert np.abs(fu.detach().numpy() - fx["final_user_vector"]).max() <= tol * scale
+        assert np.abs(fi.detach().numpy() - fx["final_item_vector"]).max() <= tol * scale
+        if dtype == torch.float64:
+            ((fu * torch.from_numpy(fx["w_user"])).sum() + (fi * torch.from_numpy(fx["w_item"])).sum()).backward()
+            for got, want in ((u.grad, fx["d_user_vector"]), (i.grad, fx["d_item_vector"])):
+                got = got.transpose(0, 1).numpy()           # fixtures are [T,R,d]
+                assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("path", _DOWNSTREAM, ids=[os.path.basename(p)[11:-4] for p in _DOWNSTREAM])
+def test_pair_score_and_ssl_oracles_match_reference_model_py_executed(path):
+    """N2: ``preds`` (model.py:169-172), ``preds_one`` / ``user_weight`` / ``sslloss`` (model.py:174-203)."""
+    from oracle import propagate_oracle as po
+    fx = np.load(path)
+    T, leaky = int(fx["T"]), float(fx["leaky"])
+    uv, iv = fx["user_vector"].astype(np.float64), fx["item_vector"].astype(np.float64)
+    fu, fi = fx["final_user_vector"], fx["final_item_vector"]
+    s, _ = po.pair_scores(fu, fi, fx["uids"], fx["iids"], leaky, activation=False)
+    np.testing.assert_allclose(s, fx["preds"], rtol=1e-12, atol=1e-12)
+    for k in range(T):
+        s, _ = po.pair_scores(uv[k], iv[k], fx["suids%d" % k], fx["siids%d" % k], leaky, activation=True)
+        np.testing.assert_allclose(s, fx["preds_one%d" % k], rtol=1e-12, atol=1e-12)
+    v = lambda j: fx["var%02d" % j].astype(np.float64)
+    w = fo.meta_user_weight(fu, uv, v(18), v(19), v(20), v(21), leaky)
+    np.testing.assert_allclose(w, fx["user_weight"], rtol=1e-12, atol=1e-14)
+    loss, p1 = fo.ssl_hinge(fu, fi, uv, iv, w, [fx["suids%d" % k] for k in range(T)], [fx["siids%d" % k] for k in range(T)], leaky)
+    np.testing.assert_allclose(loss, float(fx["sslloss"]), rtol=1e-12)
+
+
+@pytest.mark.parametrize("path", _DOWNSTREAM, ids=[os.path.basename(p)[11:-4] for p in _DOWNSTREAM])
+def test_ssl_head_matches_reference_model_py_executed(path):
+    """The product's SslHead (meta-weight network + hinge) fed with gathered scores, against the executed text."""
+    from sagnn_b200.fusion import SslHead
+    fx = np.load(path)
+    T, d, leaky = int(fx["T"]), int(fx["d"]), float(fx["leaky"])
+    head = SslHead(d, ssldim=int(fx["ssldim"]), leaky=leaky, dtype=torch.float64)
+    with torch.no_grad():
+        for p, j in ((head.meta2, 18), (head.meta2_bias, 19), (head.meta3, 20), (head.meta3_bias, 21)):
+            p.copy_(torch.from_numpy(fx["var%02d" % j].astype(np.float64)).reshape(p.shape))
+    t = lambda a: torch.from_numpy(np.asarray(a, np.float64))
+    fu, fi, uv, iv = t(fx["final_user_vector"]), t(fx["final_item_vector"]), t(fx["user_vector"]), t(fx["item_vector"])
+    w = head.user_weight(fu, uv)
+    np.testing.assert_allclose(w.detach().numpy(), fx["user_weight"], rtol=1e-11, atol=1e-13)
+    lrelu = lambda x: torch.maximum(leaky * x, x)
+    loss = 0.0
+    for k in range(T):
+        su, si = torch.from_numpy(fx["suids%d" % k]).long(), torch.from_numpy(fx["siids%d" % k]).long()
+        final_scores = lrelu(fu[su] * fi[si]).sum(-1)              # what sagnn_b200.pair_scores gathers on the GPU
+        interval_scores = lrelu(uv[k][su] * iv[k][si]).sum(-1)
+        loss = loss + head.hinge(w[k][su], final_scores, interval_scores)
+    np.testing.assert_allclose(float(loss.detach()), float(fx["sslloss"]), rtol=1e-11)

@@ -802,6 +802,57 @@ def test_pair_scores_match_oracle(d, layout, act):
     assert sg.pair_scores(tu, ti, k, empty, empty, layout=layout).numel() == 0
 
 
+DOWNSTREAM = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "downstream_*.npz")))
+
+
+@pytest.mark.parametrize("path", DOWNSTREAM, ids=[os.path.basename(p)[11:-4] for p in DOWNSTREAM])
+def test_pair_scores_match_reference_model_py_executed(path):
+    """N2 pinned to the reference text: ``preds_one`` of every interval (model.py:197-199) and the plain ``preds``
+    (model.py:170-172) as the reference's own lines compute them (tests/golden/make_golden_downstream.py executes
+    model.py:133-156,169-172,174-203 over the numpy TF stand-in) vs ``sagnn_pair_scores_fwd`` on both layouts; then
+    the consumer chain on the GPU -- interval fusion, meta weights, the gathered scores, the hinge -- against the
+    executed ``sslloss``."""
+    from sagnn_b200.fusion import IntervalFusion, SslHead
+    fx = np.load(path)
+    T, d, heads, leaky = int(fx["T"]), int(fx["d"]), int(fx["heads"]), float(fx["leaky"])
+    uv, iv = torch.from_numpy(fx["user_vector"]).cuda(), torch.from_numpy(fx["item_vector"]).cuda()
+    ids = [(torch.from_numpy(fx["suids%d" % k]).cuda(), torch.from_numpy(fx["siids%d" % k]).cuda()) for k in range(T)]
+    for layout in ("trd", "rtd"):
+        tu, ti = (uv, iv) if layout == "trd" else (uv.transpose(0, 1).contiguous(), iv.transpose(0, 1).contiguous())
+        for k in range(T):
+            s = sg.pair_scores(tu, ti, k, ids[k][0], ids[k][1], activation="leakyRelu", leaky=leaky, layout=layout)
+            assert_parity(s, fx["preds_one%d" % k], "preds_one[%d] (%s)" % (k, layout))
+    fu = torch.from_numpy(fx["final_user_vector"].astype(np.float32)).cuda()[None].contiguous()
+    fi = torch.from_numpy(fx["final_item_vector"].astype(np.float32)).cuda()[None].contiguous()
+    s = sg.pair_scores(fu, fi, 0, torch.from_numpy(fx["uids"]).cuda(), torch.from_numpy(fx["iids"]).cuda(), activation=None)
+    assert_parity(s, fx["preds"], "preds")
+    # the whole consumer chain in fp32 on the GPU
+    m = IntervalFusion(d, heads=heads, device="cuda")
+    head = SslHead(d, ssldim=int(fx["ssldim"]), leaky=leaky, device="cuda")
+    v = lambda j: torch.from_numpy(fx["var%02d" % j])
+    order = ("ln_beta", "ln_gamma", "wq", "bq", "wk", "bk", "wv", "bv")
+    with torch.no_grad():
+        m.lstm_kernel.copy_(v(0)); m.lstm_bias.copy_(v(1))
+        for side, o in (("user", 2), ("item", 10)):
+            sp_ = m.side_params(side)
+            for j, name in enumerate(order):
+                sp_[name].copy_(v(o + j))
+        for p, j in ((head.meta2, 18), (head.meta2_bias, 19), (head.meta3, 20), (head.meta3_bias, 21)):
+            p.copy_(v(j).reshape(p.shape))
+    gu, gi = m(uv.transpose(0, 1).contiguous(), iv.transpose(0, 1).contiguous())
+    scale = float(np.abs(fx["final_user_vector"]).max())
+    assert float((gu.detach().cpu().double() - torch.from_numpy(fx["final_user_vector"])).abs().max()) <= 5e-5 * scale
+    assert float((gi.detach().cpu().double() - torch.from_numpy(fx["final_item_vector"])).abs().max()) <= 5e-5 * scale
+    w = head.user_weight(gu, uv)
+    loss = 0.0
+    for k in range(T):
+        su, si = ids[k]
+        final_scores = sg.pair_scores(gu[None].contiguous(), gi[None].contiguous(), 0, su, si, activation="leakyRelu", leaky=leaky)
+        interval_scores = sg.pair_scores(uv, iv, k, su, si, activation="leakyRelu", leaky=leaky)
+        loss = loss + head.hinge(w[k][su.long()], final_scores, interval_scores)
+    assert abs(float(loss.detach()) - float(fx["sslloss"])) <= 1e-4 * abs(float(fx["sslloss"]))
+
+
 def test_pair_scores_feed_the_propagation_backward():
     """End of the chain the reference builds (model.py:118-129 -> 194-198): the SSL scores of every
     interval on top of `propagate`, gradients w.r.t. the embedding tables through both hand-written
