@@ -333,6 +333,49 @@ int sagnn_sample_train_batch(const sagnn_plan* plan, const int64_t* seq_ptr_dev,
                              int32_t* i_locs_dev, int32_t* u_locs_seq_dev, int32_t* sequence_dev, float* mask_dev,
                              int32_t* choose_out_dev, int64_t* n_out_host, sagnn_stream_t stream);
 
+/* ---- stream-exact samplers, parity mode (model.py:252-339, DataHandler.py:28-41, main.py:21-22) ----
+ * The reference draws its samples from numpy's global RandomState and from CPython's `random` module, both
+ * MT19937, both seeded in main.py.  These HOST functions restate the two libraries' bounded-integer algorithms over
+ * caller-owned generator states, so that for the same seeds (or a state taken over from np.random.get_state() /
+ * random.getstate()) they emit the reference's samples bit for bit and leave the streams where the reference would.
+ * They read the caller's host CSR arrays (scipy's indptr / indices, canonical format: sorted, no duplicates) instead
+ * of densifying rows; no GPU is involved.  The device samplers above are the throughput mode.
+ *
+ * sagnn_mt19937: key + position, the layout of np.random.get_state()[1:3] and of random.getstate()[1]. */
+typedef struct sagnn_mt19937 { uint32_t key[624]; int32_t pos; } sagnn_mt19937;
+void sagnn_mt19937_seed_numpy(sagnn_mt19937* state, uint32_t seed);    /* np.random.seed(seed)   */
+void sagnn_mt19937_seed_python(sagnn_mt19937* state, uint64_t seed);   /* random.seed(seed), a non-negative int */
+uint32_t sagnn_mt19937_next32(sagnn_mt19937* state);
+/* out[i] = np.random.randint(low, high) (n draws; np.random.choice(m) == randint(0, m)) */
+int sagnn_np_randint(sagnn_mt19937* np_state, int64_t low, int64_t high, int64_t n, int64_t* out);
+/* out = np.random.permutation(n)   (model.py:342, the epoch's user order) */
+int sagnn_np_permutation(sagnn_mt19937* np_state, int64_t n, int64_t* out);
+/* *out = random.randint(a, b) */
+int sagnn_py_randint(sagnn_mt19937* py_state, int64_t a, int64_t b, int64_t* out);
+
+/* Recommender.sampleSslBatch(batIds, handler.subMat) (model.py:304-339).  indptr[k] / indices[k]: interval k's CSR
+ * (int32, [n_user+1] / [nnz_k]); nonzero (nullable, per-interval entries nullable): 1 where the stored value != 0
+ * (the reference tests `temLabel != 0`).  Outputs [T, cap] int32 with cap = batch*2*ssl_num (interval k starts at
+ * k*cap), n_out int64 [T]; entries (pos, neg) interleaved exactly like the reference's lists. */
+int sagnn_np_sample_ssl_batch(sagnn_mt19937* np_state, int T, const int32_t* const* indptr,
+                              const int32_t* const* indices, const uint8_t* const* nonzero, const int32_t* bat_ids,
+                              int batch, int ssl_num, int n_user, int n_item, int32_t* u_locs, int32_t* i_locs,
+                              int32_t* u_locs_seq, int64_t* n_out);
+
+/* Recommender.sampleTrainBatch(batIds, handler.trnMat, ...) + negSamp (model.py:252-302, DataHandler.py:28-41).
+ * seq_ptr int64 [n_user+1] / seq_items int32: handler.sequence as CSR; tst_int int32 [n_user], -1 = None (nullable);
+ * label_*: the CSR of labelMat (handler.trnMat) with the same `nonzero` convention.  `choose` comes from py_state
+ * (random.randint), the negatives from np_state (np.random.choice).  Outputs: u_locs / i_locs / u_locs_seq int32
+ * [2*batch*train_sample_num] (positives, then negatives; *n_out entries), sequence int64 / mask double
+ * [batch_pad, pos_length] (the reference's np.zeros(..., dtype=int) / np.zeros(...) rows), choose_out int32 [batch]
+ * (nullable).  A user with fewer than 3 interactions makes the reference raise (model.py:293): SAGNN_INVALID_ARG. */
+int sagnn_np_sample_train_batch(sagnn_mt19937* np_state, sagnn_mt19937* py_state, const int64_t* seq_ptr,
+                                const int32_t* seq_items, const int32_t* tst_int, const int32_t* label_indptr,
+                                const int32_t* label_indices, const uint8_t* label_nonzero, const int32_t* bat_ids,
+                                int batch, int batch_pad, int train_sample_num, int pred_num, int pos_length,
+                                int n_user, int n_item, int32_t* u_locs, int32_t* i_locs, int32_t* u_locs_seq,
+                                int64_t* sequence, double* mask, int32_t* choose_out, int64_t* n_out);
+
 /* Host-buffer entry point (what a non-torch caller binds): copies the embeddings (and,
  * when g_*_host != NULL, the upstream gradients) to the device, runs forward (+ backward),
  * copies the results back and synchronises.  Device buffers are cached inside the plan.

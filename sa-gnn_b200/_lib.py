@@ -77,6 +77,17 @@ SIGNATURES = {
                                                   c_i64p, vp]),
     "sagnn_sample_train_batch": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_int, ctypes.c_uint64, vp, vp, vp, vp, vp, vp, c_i64p, vp]),
+    "sagnn_mt19937_seed_numpy": (None, [vp, ctypes.c_uint32]),
+    "sagnn_mt19937_seed_python": (None, [vp, ctypes.c_uint64]),
+    "sagnn_mt19937_next32": (ctypes.c_uint32, [vp]),
+    "sagnn_np_randint": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, vp]),
+    "sagnn_np_permutation": (ctypes.c_int, [vp, ctypes.c_int64, vp]),
+    "sagnn_py_randint": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int64, c_i64p]),
+    "sagnn_np_sample_ssl_batch": (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                                 vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]),
+    "sagnn_np_sample_train_batch": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp,
+                                                   vp, vp]),
     "sagnn_host_forward": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int]),
     "sagnn_host_backward": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_float]),
     "sagnn_propagate_host": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,

@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SOURCES = ["csrc/plan.cu", "csrc/spmm.cu", "csrc/pairs.cu", "csrc/events.cu", "csrc/sampler.cu"]
+SOURCES = ["csrc/plan.cu", "csrc/spmm.cu", "csrc/pairs.cu", "csrc/events.cu", "csrc/sampler.cu", "csrc/np_stream.cu"]
 HEADERS = ["csrc/common.cuh", "csrc/spmm_rpw.cuh", "csrc/spmm_pkt.cuh", "../include/sagnn_b200.h"]
 LIB = os.path.join(HERE, "lib", "libsagnn_b200.so")
 
