@@ -144,14 +144,24 @@ __device__ __forceinline__ int64_t table_row0(uint32_t t, int64_t N, int U) {
 // inside a class).  Lock-step lane groups only need equal block counts, and a class that keeps its rows
 // in id order reads its own rows and writes its outputs as a forward-moving window over the tables
 // instead of scattered 256-byte rows (scripts/micro/l1tex_cost.cu "task mix": +20-30 % for scattered).
-__global__ void sched_key_kernel(const int32_t* __restrict__ deg, int64_t n_rows, int64_t N, int U, int bucket,
+//
+// window > 0 (SAGNN_SORT_WINDOW): the short rows are first cut into windows of `window` consecutive row ids and the
+// class sort happens INSIDE each window, so that all classes of a window run close in time: the own-row reads and the
+// output stores of the whole launch sweep every table ONCE, densely, instead of once per class and sparsely.  Lane
+// groups still meet equal classes except at the ~16 class boundaries of a window.
+__global__ void sched_key_kernel(const int32_t* __restrict__ deg, int64_t n_rows, int64_t N, int U, int bucket, int window,
                                  uint64_t* __restrict__ key, uint32_t* __restrict__ row) {
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_rows) return;
   const int d = deg[g];
   const int cls = d > kChunk ? d : (d + bucket - 1) / bucket;   // long rows keep their exact order and stay in front
-  const uint32_t sub = d > kChunk ? (uint32_t)(0x7fffffff - d) : (uint32_t)(0x7fffffff - cls) ;
-  key[g] = ((uint64_t)table_of(g, N, U) << 32) | sub;
+  const uint32_t t = table_of(g, N, U);
+  uint32_t sub = d > kChunk ? (uint32_t)(0x7fffffff - d) : (uint32_t)(0x7fffffff - cls);
+  if (window > 0 && d <= kChunk) {
+    const uint32_t win = (uint32_t)((g - table_row0(t, N, U)) / window);      // < 2^23: checked by the caller
+    sub = 0x80000000u | (win << 8) | (uint32_t)(255 - cls);                   // cls <= kChunk = 64
+  }
+  key[g] = ((uint64_t)t << 32) | sub;
   row[g] = (uint32_t)g;
 }
 
@@ -638,7 +648,10 @@ extern "C" int sagnn_plan_finalize(sagnn_plan* p, int weight_mode, sagnn_stream_
   SAGNN_CUDA(cudaMemsetAsync(p->hot_ids, 0, sizeof(int32_t) * 2 * p->T * kHotRows, st));
   int bucket = p->pkt ? 4 : 1;   // the packet kernel gathers in blocks of four slots
   if (const char* e = getenv("SAGNN_SORT_BUCKET")) bucket = atoi(e) > 0 ? atoi(e) : bucket;
-  sched_key_kernel<<<blocks_for(R), 256, 0, st>>>(p->deg, R, N, U, bucket, key_in, row_in);
+  int window = 0;                // 0: one class sort per table; W > 0: class sort inside windows of W row ids
+  if (const char* e = getenv("SAGNN_SORT_WINDOW")) window = atoi(e) > 0 ? atoi(e) : 0;
+  if (window > 0 && ((int64_t)(p->U > p->I ? p->U : p->I) / window) >= (1 << 23)) window = 0;
+  sched_key_kernel<<<blocks_for(R), 256, 0, st>>>(p->deg, R, N, U, bucket, window, key_in, row_in);
   {
     DevTmp<char> tmp; size_t tb = 0;
     const int end_bit = 32 + bits_for(2 * p->T);
