@@ -357,6 +357,23 @@ def test_repeated_calls_are_bitwise_deterministic():
         assert torch.equal(x, y)
 
 
+def test_windowed_schedule_order_is_bitwise_equal(monkeypatch):
+    """SAGNN_SORT_WINDOW (read at plan finalize) only permutes the task schedule: degree classes sorted inside
+    windows of consecutive row ids instead of over the whole table.  Every row is still summed by one task in its own
+    edge order, so outputs and gradients must not change by a bit (both kernels)."""
+    g = dh.make_named("small", seed=5)
+    uE, iE, gU, gI = random_tables(3, g.n_user, g.n_item, 64, seed=9)
+    for latdim in (64, 128):                             # 64: packet kernel schedule, 128: v8 schedule
+        monkeypatch.delenv("SAGNN_SORT_WINDOW", raising=False)
+        a = run_gpu(sg.build_plan(g.sub_mat, latdim=latdim), uE, iE, gU, gI, 2)
+        for w in ("64", "1000"):
+            monkeypatch.setenv("SAGNN_SORT_WINDOW", w)
+            b = run_gpu(sg.build_plan(g.sub_mat, latdim=latdim), uE, iE, gU, gI, 2)
+            for x, y in zip(a, b):
+                assert torch.equal(x, y)
+    monkeypatch.delenv("SAGNN_SORT_WINDOW", raising=False)
+
+
 def test_forward_only_and_partial_grad():
     mats = random_interval_mats(2, 50, 40, 300, seed=4)
     adj, tp = adj_lists(mats)
