@@ -241,3 +241,26 @@ def test_near_gpu_restores_affinity_and_degrades_without_nvml():
         with hostmem.near_gpu(0):
             raise RuntimeError("body failed")
     assert os.sched_getaffinity(0) == before
+
+
+def test_load_trn_mat_time_matches_reference_load_data():
+    """a1 pinned to the reference: tests/golden/make_golden_loaddata.py CALLED the reference's own
+    ``DataHandler().LoadData()`` (DataHandler.py:85-129) on tests/golden/dataset_tiny/ (the reference's on-disk layout)
+    and recorded what it keeps; the product's loader must keep the same interval matrices, shape and dtype."""
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    fx = np.load(os.path.join(gold, "loaddata_tiny.npz"))
+    h = dh.load_trn_mat_time(os.path.join(gold, "dataset_tiny", "trn_mat_time"))
+    assert (h.n_user, h.n_item, h.graph_num) == (int(fx["user"]), int(fx["item"]), int(fx["T"]))
+    for k, m in enumerate(h.sub_mat):
+        assert str(m.dtype) == str(fx["sub%d_dtype" % k])
+        np.testing.assert_array_equal(m.indptr, fx["sub%d_indptr" % k])
+        np.testing.assert_array_equal(m.indices, fx["sub%d_indices" % k])
+        np.testing.assert_array_equal(m.data, fx["sub%d_data" % k])
+    np.testing.assert_array_equal(h.time_mat.indices, fx["time_indices"])
+    np.testing.assert_array_equal(h.time_mat.data, fx["time_data"])
+    # --graphNum selects a prefix of the stored intervals (model.py:230-231)
+    assert dh.load_trn_mat_time(os.path.join(gold, "dataset_tiny", "trn_mat_time"), graph_num=2).graph_num == 2
+    # the adjacency lists of the loaded matrices = what prepareModel builds from handler.subMat (model.py:227-238)
+    for m in h.sub_mat:
+        idx, data, shape = dh.transToLsts(m, norm=True)
+        assert idx.shape == (m.nnz, 2) and shape == [h.n_user, h.n_item] or tuple(shape) == (h.n_user, h.n_item)
