@@ -38,7 +38,11 @@ template <int D_, bool WEIGHTED>
 struct PktGeo {
   static constexpr int D = D_;
   static constexpr int ROWB = D * 4;
+#ifdef SAGNN_PKT_LPT64   // experiment build: lane-group width at d = 64 (8: four tasks per warp, two float4 per lane)
+  static constexpr int LPT = D >= 128 ? 32 : (D == 64 ? SAGNN_PKT_LPT64 : D / 4);
+#else
   static constexpr int LPT = D >= 128 ? 32 : D / 4;   // lanes per task: one float4 per lane and chunk
+#endif
   static constexpr int G = 32 / LPT;                  // tasks a warp runs in lock step
   static constexpr int NV = D / (LPT * 4);            // float4 chunks per lane (2 at d=256)
   static constexpr int VPL = 4 * NV;                  // floats per lane
