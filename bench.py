@@ -197,6 +197,48 @@ def cpu_reference_run(g, L, d, steps, warmup, seed):
     return float(np.mean(times)), int(torch.get_num_threads())
 
 
+def cpu_extra_baselines(g, L, d, seed):
+    """SURVEY 8(d) b2 / b3 next to the stated baseline: the same TF1-graph restatement on ONE thread (one timed
+    step) and a scipy CSR @ dense forward-only sanity floor (one thread, fp32, residual + layer sum, no backward)."""
+    import torch
+    from oracle import propagate_oracle as po, tf1_mirror
+    from sagnn_b200 import data_handler as dh
+    T, U, I = g.graph_num, g.n_user, g.n_item
+    trav = 4 * L * sum(g.nnz)
+    out = {}
+    adj = [torch.from_numpy(po.trans_to_lsts(m)[0].astype(np.int64)) for m in g.sub_mat]
+    tp = [torch.from_numpy(po.trans_to_lsts(po.transpose(m))[0].astype(np.int64)) for m in g.sub_mat]
+    uE, iE = dh.xavier_embeddings(T, U, d, seed), dh.xavier_embeddings(T, I, d, seed + 1)
+    gen = torch.Generator().manual_seed(seed)
+    gU, gI = torch.randn((T, U, d), generator=gen), torch.randn((T, I, d), generator=gen)
+    n_before = torch.get_num_threads()
+    try:
+        torch.set_num_threads(1)
+        t0 = time.perf_counter()
+        tf1_mirror.propagate(adj, tp, torch.from_numpy(uE), torch.from_numpy(iE), gU, gI, L, 0.5)
+        dt = time.perf_counter() - t0
+        out["tf1_mirror_single_thread"] = {"value": trav / dt, "cores": 1, "ms_per_step": dt * 1e3,
+                                           "sample": "1 timed fwd+bwd step, no warm-up"}
+    finally:
+        torch.set_num_threads(n_before)
+    # forward only: binary structure @ dense table, LeakyReLU, residual, layer sum (model.py:118-127)
+    import scipy.sparse as sp
+    A = [sp.csr_matrix((np.ones(m.nnz, np.float32), m.indices, m.indptr), shape=m.shape) for m in g.sub_mat]
+    At = [sp.csr_matrix(a.T) for a in A]
+    t0 = time.perf_counter()
+    for k in range(T):
+        e0, e1 = uE[k], iE[k]
+        s0, s1 = e0.copy(), e1.copy()
+        for _ in range(L):
+            z0, z1 = A[k] @ e1, At[k] @ e0
+            e0, e1 = e0 + np.maximum(0.5 * z0, z0), e1 + np.maximum(0.5 * z1, z1)
+            s0 += e0; s1 += e1
+    dt = time.perf_counter() - t0
+    out["scipy_csr_forward_only"] = {"value": 2 * L * sum(g.nnz) / dt, "cores": 1, "ms_per_forward": dt * 1e3,
+                                     "note": "forward traversals only (2*L*E per pass), fp32, transposes prebuilt"}
+    return out
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -585,6 +627,10 @@ def main():
                                    "note": "oracle/csrc/sagnn_oracle.c (fused OpenMP fp32, incl. CSR build)"}
         except Exception as e:   # the C port is optional colour, never fatal
             cpu["fused_c_port"] = {"error": str(e)}
+        try:                     # single-thread restatement, scipy forward-only floor
+            cpu["others"] = cpu_extra_baselines(g, L, d, args.seed)
+        except Exception as e:   # optional colour as well
+            cpu["others"] = {"error": str(e)}
 
     # ---- the configurations north_star names for N GPUs (results only; the headline above is untouched)
     extras = None
