@@ -111,3 +111,71 @@ def test_sampler_edge_cases():
         rs.sample_train_batch(np.array([0, 1]), trn, [[1, 2], [3, 4, 5, 6]], [None, None], 3, pos_length=5)
     with pytest.raises(SagnnError):
         rs.sample_ssl_batch(np.array([U]), sub, ssl_num=2)          # user id out of range
+
+
+# ---- the samplers' numpy restatement (oracle/sampler_oracle.py): pinned by the same fixtures, then used as the
+#      live checker for many random cases ---------------------------------------------------------------------------
+from oracle import sampler_oracle as so
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[8:-4] for p in CASES])
+def test_sampler_oracle_reproduces_the_reference_fixtures(path):
+    fx = np.load(path)
+    sub, trn, seqs, tst = _mats(fx)
+    T = int(fx["T"])
+    np_rng, py_rng = np.random.RandomState(100), random.Random(100)
+    assert np.array_equal(np_rng.permutation(int(fx["U"])), fx["perm"])
+    for b in range(int(fx["n_batches"])):
+        bat = fx["bat%d" % b]
+        uL, iL, seq, mask, uLs = so.sample_train_batch(np_rng, py_rng, bat, trn, seqs, tst, int(fx["train_sample_num"]),
+                                                       int(fx["pred_num"]), int(fx["pos_length"]), int(fx["batch"]), int(fx["I"]))
+        assert np.array_equal(uL, fx["trn_uLocs%d" % b]) and np.array_equal(iL, fx["trn_iLocs%d" % b])
+        assert np.array_equal(uLs, fx["trn_uLocs_seq%d" % b])
+        assert np.array_equal(seq, fx["trn_sequence%d" % b]) and np.array_equal(mask, fx["trn_mask%d" % b])
+        suL, siL, suLs = so.sample_ssl_batch(np_rng, bat, sub, int(fx["sslNum"]), int(fx["I"]))
+        for k in range(T):
+            assert np.array_equal(suL[k], fx["ssl_uLocs%d_%d" % (b, k)]) and np.array_equal(siL[k], fx["ssl_iLocs%d_%d" % (b, k)])
+            assert np.array_equal(suLs[k], fx["ssl_uLocs_seq%d_%d" % (b, k)])
+        st = np_rng.get_state()
+        assert np.array_equal(st[1], fx["np_key%d" % b]) and st[2] == int(fx["np_pos%d" % b])
+        assert np.array_equal(np.array(py_rng.getstate()[1], dtype=np.uint32), fx["py_key%d" % b])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_samplers_equal_the_pinned_oracle_on_random_cases(seed):
+    """Random shapes, densities, batch compositions (repeated users, users with no items in an interval, dense
+    users for whom negSamp rejects most draws, stored zeros), seeds: C ABI == oracle, draws and stream positions."""
+    rng = np.random.default_rng(1000 + seed)
+    U, I, T = int(rng.integers(5, 80)), int(rng.integers(12, 120)), int(rng.integers(1, 6))
+    seqs, tst, rows, cols, ks = [], [], [], [], []
+    for u in range(U):
+        n = int(rng.integers(3, max(4, min(I - 3, 3 + int(rng.integers(0, I))))))      # up to nearly every item
+        items = rng.choice(I, size=n, replace=False)
+        seqs.append([int(x) for x in items])
+        tst.append(None if rng.random() < 0.4 else int(rng.integers(0, I)))
+        rows += [u] * n; cols += [int(x) for x in items]; ks += [int(x) for x in rng.integers(0, T, size=n)]
+    rows, cols, ks = np.asarray(rows), np.asarray(cols), np.asarray(ks)
+    vals = rng.integers(1, 1000, size=len(rows)).astype(np.intc)
+    if seed % 3 == 0:
+        vals[rng.random(len(vals)) < 0.2] = 0                                             # stored explicit zeros
+    sub = [sp.csr_matrix((vals[ks == k], (rows[ks == k], cols[ks == k])), shape=(U, I)) for k in range(T)]
+    trn = sp.csr_matrix((vals, (rows, cols)), shape=(U, I))
+    ssl_num, tsn, pred_num, pos_len = int(rng.integers(0, 8)), int(rng.integers(0, 9)), int(rng.integers(0, 7)), int(rng.integers(1, 20))
+    s1, s2 = int(rng.integers(0, 2**32)), int(rng.integers(0, 2**32))
+    rs = ReferenceStream(s1, s2)
+    np_rng, py_rng = np.random.RandomState(s1), random.Random(s2)
+    for _ in range(3):
+        bat = rng.integers(0, U, size=int(rng.integers(1, 25))).astype(np.int32)          # users may repeat
+        pad = len(bat) + int(rng.integers(0, 4))
+        got = rs.sample_train_batch(bat, trn, seqs, tst, tsn, pred_num=pred_num, pos_length=pos_len, batch_pad=pad)
+        want = so.sample_train_batch(np_rng, py_rng, bat, trn, seqs, tst, tsn, pred_num, pos_len, pad, I)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+        got = rs.sample_ssl_batch(bat, sub, ssl_num)
+        want = so.sample_ssl_batch(np_rng, bat, sub, ssl_num, I)
+        for gl, wl in zip(got, want):
+            for g, w in zip(gl, wl):
+                assert np.array_equal(g, w)
+        st = np_rng.get_state()
+        assert np.array_equal(rs.to_numpy()[1], st[1]) and rs.to_numpy()[2] == st[2]
+        assert rs.to_python() == py_rng.getstate()
