@@ -264,3 +264,25 @@ def test_load_trn_mat_time_matches_reference_load_data():
     for m in h.sub_mat:
         idx, data, shape = dh.transToLsts(m, norm=True)
         assert idx.shape == (m.nnz, 2) and shape == [h.n_user, h.n_item] or tuple(shape) == (h.n_user, h.n_item)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """``bench.py --impl reference`` (the CPU arm the driver runs next to the GPU arm): one JSON line with the
+    contract's keys, the same ``config`` builder as the GPU arm, no GPU needed."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "small",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["unit"] == "edge_traversals/s"
+    for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data",
+                "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    cfg = line["config"]
+    assert cfg["edge_traversals_per_step"] == 4 * cfg["layers"] * cfg["edges"] and "workload" in cfg
+    assert abs(line["value"] - cfg["edge_traversals_per_step"] / (line["ms_per_step"] * 1e-3)) <= 1e-6 * line["value"]
