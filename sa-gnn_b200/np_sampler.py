@@ -92,6 +92,24 @@ class ReferenceStream:
         _lib.check(self._lib.sagnn_py_randint(ctypes.byref(self._py), int(a), int(b), ctypes.byref(out)))
         return out.value
 
+    # -- static inputs are converted once (handler.subMat / trnMat / sequence / tstInt do not change in a run) ------
+    def _cached(self, obj, make):
+        if not hasattr(self, "_cache"):
+            self._cache = {}
+        hit = self._cache.get(id(obj))
+        if hit is None or hit[0] is not obj:
+            hit = (obj, make(obj))            # keeps obj alive, so its id cannot be reused
+            self._cache[id(obj)] = hit
+        return hit[1]
+
+    @staticmethod
+    def _seq_csr(sequences):
+        lens = np.fromiter((len(x) for x in sequences), dtype=np.int64, count=len(sequences))
+        ptr = np.zeros(len(sequences) + 1, dtype=np.int64)
+        np.cumsum(lens, out=ptr[1:])
+        flat = np.concatenate([np.asarray(x, dtype=np.int32) for x in sequences]) if ptr[-1] else np.zeros(0, np.int32)
+        return ptr, flat
+
     # -- the samplers ------------------------------------------------------------------------
     def sample_ssl_batch(self, bat_ids, sub_mats, ssl_num, n_item=None):
         """``sampleSslBatch(batIds, handler.subMat)`` with ``args.sslNum = ssl_num``, ``args.item = n_item``:
@@ -99,7 +117,7 @@ class ReferenceStream:
         T = len(sub_mats)
         U, I = sub_mats[0].shape
         n_item = I if n_item is None else int(n_item)
-        csr = [_csr_arrays(m) for m in sub_mats]
+        csr = [self._cached(m, _csr_arrays) for m in sub_mats]
         arr = lambda j: (ctypes.c_void_p * T)(*[_p(c[j]) for c in csr])
         bat = np.ascontiguousarray(bat_ids, dtype=np.int32)
         u, i, s = (np.empty((T, len(bat) * 2 * int(ssl_num)), dtype=np.int32) for _ in range(3))
@@ -115,15 +133,15 @@ class ReferenceStream:
         """``sampleTrainBatch(batIds, handler.trnMat, handler.timeMat, train_sample_num)`` with ``args.pred_num``,
         ``args.pos_length``, ``args.batch = batch_pad``, ``args.item = n_item``; ``sequences`` = ``handler.sequence``,
         ``tst_int`` = ``handler.tstInt`` (None entries allowed).  Returns ``(uLocs, iLocs, sequence, mask, uLocs_seq)``
-        like the reference (int32 index arrays; ``sequence`` int64 and ``mask`` float64 ``[batch_pad, pos_length]``)."""
+        like the reference (int32 index arrays; ``sequence`` int64 and ``mask`` float64 ``[batch_pad, pos_length]``).
+        The static inputs (matrices, sequences, tst_int) are converted to flat arrays on first use and cached by
+        object identity: pass the same objects every step, as the reference's handler does."""
         U, I = label_mat.shape
         n_item = I if n_item is None else int(n_item)
-        lens = np.fromiter((len(x) for x in sequences), dtype=np.int64, count=len(sequences))
-        ptr = np.zeros(len(sequences) + 1, dtype=np.int64)
-        np.cumsum(lens, out=ptr[1:])
-        flat = np.concatenate([np.asarray(x, dtype=np.int32) for x in sequences]) if ptr[-1] else np.zeros(0, np.int32)
-        tst = None if tst_int is None else np.array([-1 if x is None else int(x) for x in tst_int], dtype=np.int32)
-        indptr, indices, nz = _csr_arrays(label_mat)
+        ptr, flat = self._cached(sequences, self._seq_csr)
+        tst = None if tst_int is None else self._cached(
+            tst_int, lambda t: np.array([-1 if x is None else int(x) for x in t], dtype=np.int32))
+        indptr, indices, nz = self._cached(label_mat, _csr_arrays)
         bat = np.ascontiguousarray(bat_ids, dtype=np.int32)
         batch = len(bat)
         batch_pad = batch if batch_pad is None else int(batch_pad)
