@@ -10,8 +10,8 @@ Follows LIU-YUXI/SA-GNN ``model.py:135-155`` and ``Utils/attention.py:31-78``:
     ScaledDotProductAttention (attention.py:34-44: exp without max subtraction, + 1e-8 in the normaliser),
     tf.reduce_mean over the T axis (model.py:154-155).
 
-PINNED TO THE REFERENCE TEXT (round 2): ``tests/golden/make_golden_downstream.py`` executes model.py:133-156,
-169-172 and 174-203 as they stand (with the reference's own Utils/attention.py and Utils/NNLayers.py) over the
+PINNED TO THE REFERENCE TEXT (round 2): ``tests/golden/make_golden_downstream.py`` executes model.py:111-112 and
+133-203 as they stand (with the reference's own Utils/attention.py and Utils/NNLayers.py) over the
 numpy TF stand-in and commits ``tests/golden/downstream_*.npz``; ``tests/test_fusion.py`` compares every function
 below with those fixtures.  Wiring, the shared LSTM cell, per-side Q / K / V kernels, exp-normalised attention,
 axes, stop_gradient placement and the positive | negative slicing therefore come from the reference; what stays
@@ -75,6 +75,28 @@ def interval_fusion(x, p, heads):
 
 def _lrelu(x, leaky):
     return np.maximum(leaky * x, x)
+
+
+def sequence_attention(final_item, sequence, mask, pos_embed, ln_seq, ln_pos, layers, heads, leaky):
+    """model.py:111-112,157-168: the user's item sequence (right-aligned ids ``sequence`` [B,P], 0 / 1 ``mask`` [B,P])
+    collapses to ONE vector per user before any attention: ``mask @ final_item[sequence]`` ([B,1,P] x [B,P,d]),
+    layer-normed, plus the layer-normed masked sum of the position embeddings; then ``len(layers)`` rounds of
+    ``x = lrelu(MHSA(layer_norm(x))) + x`` over that length-1 axis, and ``att_user = sum over it`` -> [B,d].
+    ``ln_seq`` / ``ln_pos`` = (gamma, beta); ``layers`` = list of dicts ln_gamma, ln_beta, wq, bq, wk, bk, wv, bv."""
+    m = mask[:, None, :]
+    x = layer_norm(m @ final_item[sequence], *ln_seq) + layer_norm(m @ pos_embed[None, :, :], *ln_pos)
+    for p in layers:
+        a = multihead_self_attention(layer_norm(x, p["ln_gamma"], p["ln_beta"]), p["wq"], p["bq"], p["wk"], p["bk"],
+                                     p["wv"], p["bv"], heads)
+        x = _lrelu(a, leaky) + x
+    return x.sum(axis=1)
+
+
+def predictions(final_user, final_item, att_user, uids, iids, u_locs_seq, leaky):
+    """model.py:169-173: ``preds = <final_user[uids], final_item[iids]> + sum(lrelu(att_user[uLocs_seq]) *
+    final_item[iids])`` (``iEmbed_att`` IS ``final_item_vector``, model.py:156)."""
+    it = final_item[iids]
+    return (final_user[uids] * it).sum(-1) + (_lrelu(att_user[u_locs_seq], leaky) * it).sum(-1)
 
 
 def meta_user_weight(final_user, user_vector, w2, b2, w3, b3, leaky):

@@ -10,12 +10,12 @@ from . import data_handler                                            # noqa: F4
 from .data_handler import transToLsts, trans_to_lsts, transpose       # noqa: F401
 from .propagate import (Plan, build_plan, bucket_events, propagate, message_propagate, pair_scores,  # noqa: F401
                         propagate_host, host_forward, host_backward, IntervalPropagation)
-from .fusion import IntervalFusion, SslHead, slabs_to_rtd                       # noqa: F401
+from .fusion import IntervalFusion, SequenceAttention, SslHead, slabs_to_rtd                       # noqa: F401
 from .np_sampler import ReferenceStream                                # noqa: F401
 from ._lib import lib_path, load_library, SagnnError                  # noqa: F401
 
 __all__ = [
     "data_handler", "transToLsts", "trans_to_lsts", "transpose", "Plan", "build_plan", "bucket_events", "propagate",
     "message_propagate", "pair_scores", "propagate_host", "host_forward", "host_backward", "IntervalPropagation", "lib_path", "load_library",
-    "SagnnError", "IntervalFusion", "SslHead", "slabs_to_rtd", "ReferenceStream",
+    "SagnnError", "IntervalFusion", "SequenceAttention", "SslHead", "slabs_to_rtd", "ReferenceStream",
 ]

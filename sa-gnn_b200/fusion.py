@@ -15,6 +15,7 @@ Same semantics as TF 1.14 for the ops involved (gate order i, j, f, o with forge
 ``oracle/fusion_oracle.py`` and, through ``tests/golden/downstream_*.npz``, against the reference's own
 model.py:133-156 / Utils/attention.py text executed over a numpy TF stand-in (``tests/test_fusion.py``).
 
+  * ``SequenceAttention``: the sequence branch of the prediction (model.py:111-112, 157-168, 173).
   * ``SslHead``: the meta-weight network and the weighted hinge of the SSL objective (model.py:174-203) on top of
     the pair scores ``sagnn_b200.pair_scores`` gathers from the path's outputs (dense framework-side ops as well).
 """
@@ -23,6 +24,24 @@ from __future__ import annotations
 import math
 
 import torch
+
+
+def _layer_norm(x, gamma, beta):
+    """tf.contrib.layers.layer_norm on [R,T,d]: moments over (T, d), scale / shift over d, epsilon 1e-12."""
+    mean = x.mean(dim=(1, 2), keepdim=True)
+    var = x.var(dim=(1, 2), unbiased=False, keepdim=True)
+    return (x - mean) / torch.sqrt(var + 1e-12) * gamma + beta
+
+
+def _mhsa(n, p, heads):
+    """MultiHeadSelfAttention.attention (Utils/attention.py:46-78, 31-44): n [R,T,d] -> [R,T,d]; p: wq, bq, wk, bk, wv, bv."""
+    R, T, d = n.shape
+    dk = d // heads
+    split = lambda y: y.reshape(R, T, heads, dk).permute(0, 2, 1, 3)
+    q, k, v = split(n @ p["wq"] + p["bq"]), split(n @ p["wk"] + p["bk"]), split(n @ p["wv"] + p["bv"])
+    scores = torch.exp(q @ k.transpose(-1, -2) / math.sqrt(dk))
+    attn = scores / (scores.sum(dim=-1, keepdim=True) + 1e-8)
+    return (attn @ v).permute(0, 2, 1, 3).reshape(R, T, d)
 
 
 class IntervalFusion(torch.nn.Module):
@@ -69,20 +88,61 @@ class IntervalFusion(torch.nn.Module):
         """x [R,T,d] -> [R,d]   (model.py:146-155 for one side)."""
         p = self.side_params(side)
         R, T, d = x.shape
-        h = self.lstm(x)
-        mean = h.mean(dim=(1, 2), keepdim=True)
-        var = h.var(dim=(1, 2), unbiased=False, keepdim=True)
-        n = (h - mean) / torch.sqrt(var + 1e-12) * p["ln_gamma"] + p["ln_beta"]
-        dk = d // self.heads
-        split = lambda y: y.reshape(R, T, self.heads, dk).permute(0, 2, 1, 3)
-        q, k, v = split(n @ p["wq"] + p["bq"]), split(n @ p["wk"] + p["bk"]), split(n @ p["wv"] + p["bv"])
-        scores = torch.exp(q @ k.transpose(-1, -2) / math.sqrt(dk))
-        attn = scores / (scores.sum(dim=-1, keepdim=True) + 1e-8)
-        ctx = (attn @ v).permute(0, 2, 1, 3).reshape(R, T, d)
-        return ctx.mean(dim=1)
+        n = _layer_norm(self.lstm(x), p["ln_gamma"], p["ln_beta"])
+        return _mhsa(n, p, self.heads).mean(dim=1)
 
     def forward(self, user_rtd, item_rtd):
         return self.fuse(user_rtd, "user"), self.fuse(item_rtd, "item")
+
+
+class SequenceAttention(torch.nn.Module):
+    """The sequence branch of the prediction (model.py:111-112, 157-168, 173): a user's item sequence is collapsed to
+    the masked SUM of the final item vectors (plus the masked sum of position embeddings, both layer-normed), refined
+    by ``att_layers`` rounds of ``x = lrelu(MHSA(layer_norm(x))) + x`` over that length-1 axis -> ``att_user`` [B,d];
+    ``predict`` adds its term to the dot product of the final vectors (model.py:169-173)."""
+
+    def __init__(self, d, heads=16, att_layers=4, pos_length=200, leaky=0.5, dtype=torch.float32, device=None, seed=0):
+        super().__init__()
+        if d % heads:
+            raise ValueError("latdim must be a multiple of the number of attention heads (attention.py:49)")
+        self.d, self.heads, self.att_layers, self.leaky = d, heads, att_layers, leaky
+        g = torch.Generator().manual_seed(seed)
+        P = lambda t: torch.nn.Parameter(t.to(dtype=dtype, device=device))
+
+        def xavier(rows, cols):
+            a = math.sqrt(6.0 / (rows + cols))
+            return P((torch.rand((rows, cols), generator=g, dtype=torch.float64) * 2 - 1) * a)
+
+        self.pos_embed = xavier(pos_length, d)
+        for name in ["seq_ln", "pos_ln"] + ["l%d_ln" % l for l in range(att_layers)]:
+            setattr(self, name + "_gamma", P(torch.ones(d)))
+            setattr(self, name + "_beta", P(torch.zeros(d)))
+        for l in range(att_layers):
+            for n in ("q", "k", "v"):
+                setattr(self, "l%d_w%s" % (l, n), xavier(d, d))
+                setattr(self, "l%d_b%s" % (l, n), P(torch.zeros(d)))
+
+    def layer_params(self, l):
+        out = {"ln_gamma": getattr(self, "l%d_ln_gamma" % l), "ln_beta": getattr(self, "l%d_ln_beta" % l)}
+        out.update({k + n: getattr(self, "l%d_%s%s" % (l, k, n)) for n in ("q", "k", "v") for k in ("w", "b")})
+        return out
+
+    def forward(self, final_item, sequence, mask):
+        """final_item [I,d], sequence [B,P] item ids (right-aligned, 0-padded), mask [B,P] 0 / 1 -> att_user [B,d]."""
+        m = mask.to(final_item.dtype).unsqueeze(1)                                    # [B,1,P]
+        x = _layer_norm(m @ final_item[sequence], self.seq_ln_gamma, self.seq_ln_beta) + \
+            _layer_norm(m @ self.pos_embed.unsqueeze(0), self.pos_ln_gamma, self.pos_ln_beta)
+        for l in range(self.att_layers):
+            p = self.layer_params(l)
+            a = _mhsa(_layer_norm(x, p["ln_gamma"], p["ln_beta"]), p, self.heads)
+            x = torch.maximum(self.leaky * a, a) + x
+        return x.sum(dim=1)
+
+    def predict(self, final_user, final_item, att_user, uids, iids, u_locs_seq):
+        """model.py:169-173.  (On the GPU the first term is ``sagnn_b200.pair_scores(..., activation=None)``.)"""
+        it = final_item[iids]
+        s = att_user[u_locs_seq]
+        return (final_user[uids] * it).sum(-1) + (torch.maximum(self.leaky * s, s) * it).sum(-1)
 
 
 class SslHead(torch.nn.Module):

@@ -83,17 +83,35 @@ import os
 _DOWNSTREAM = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "downstream_*.npz")))
 
 
-def _side_params(fx, side, dtype=np.float64):
-    """Variables in the order the reference text creates them: the ONE LSTM cell (kernel, bias); then per side
-    LayerNorm beta, gamma and the Q, K, V dense layers (kernel, bias each) -- user first; then meta2, meta3."""
+def _layout(fx):
+    """Variables in the order the reference text creates them (checked against the recorded names): posEmbed; the ONE
+    LSTM cell (kernel, bias); per side LayerNorm (beta, gamma) + Q, K, V dense (kernel, bias each), user first; the
+    sequence branch: LayerNorm of the item sum, LayerNorm of the position sum, per attention layer LayerNorm + Q, K, V;
+    meta2, meta2Bias, meta3, meta3Bias."""
     names = [str(n).split("#")[0] for n in fx["var_names"]]
-    assert names[:4] == ["basic_lstm_cell/kernel", "basic_lstm_cell/bias", "LayerNorm/beta", "LayerNorm/gamma"]
-    assert names[4:10] == ["dense/kernel", "dense/bias"] * 3 and names[10:12] == ["LayerNorm/beta", "LayerNorm/gamma"]
-    assert names[18:] == ["meta2", "meta2Bias", "meta3", "meta3Bias"]
+    L = int(fx["att_layer"])
+    ln, qkv = ["LayerNorm/beta", "LayerNorm/gamma"], ["dense/kernel", "dense/bias"] * 3
+    want = ["posEmbed", "basic_lstm_cell/kernel", "basic_lstm_cell/bias"] + (ln + qkv) * 2 + ln + ln + (ln + qkv) * L + \
+        ["meta2", "meta2Bias", "meta3", "meta3Bias"]
+    assert names == want
+    return dict(pos=0, lstm=1, user=3, item=11, seq_ln=19, pos_ln=21, layers=[23 + 8 * l for l in range(L)], meta=23 + 8 * L)
+
+
+def _block(fx, o, dtype=np.float64):
+    """LayerNorm + Q, K, V starting at variable o."""
     v = lambda j: fx["var%02d" % j].astype(dtype)
-    o = 2 if side == "user" else 10
-    return dict(lstm_kernel=v(0), lstm_bias=v(1), ln_beta=v(o), ln_gamma=v(o + 1), wq=v(o + 2), bq=v(o + 3),
-                wk=v(o + 4), bk=v(o + 5), wv=v(o + 6), bv=v(o + 7))
+    return dict(ln_beta=v(o), ln_gamma=v(o + 1), wq=v(o + 2), bq=v(o + 3), wk=v(o + 4), bk=v(o + 5), wv=v(o + 6), bv=v(o + 7))
+
+
+def _side_params(fx, side, dtype=np.float64):
+    lay = _layout(fx)
+    v = lambda j: fx["var%02d" % j].astype(dtype)
+    return dict(lstm_kernel=v(lay["lstm"]), lstm_bias=v(lay["lstm"] + 1), **_block(fx, lay[side], dtype))
+
+
+def _meta(fx, dtype=np.float64):
+    o = _layout(fx)["meta"]
+    return [fx["var%02d" % (o + j)].astype(dtype) for j in range(4)]
 
 
 def test_downstream_fixtures_present():
@@ -143,12 +161,11 @@ def test_pair_score_and_ssl_oracles_match_reference_model_py_executed(path):
     uv, iv = fx["user_vector"].astype(np.float64), fx["item_vector"].astype(np.float64)
     fu, fi = fx["final_user_vector"], fx["final_item_vector"]
     s, _ = po.pair_scores(fu, fi, fx["uids"], fx["iids"], leaky, activation=False)
-    np.testing.assert_allclose(s, fx["preds"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(s, fx["preds_dot"], rtol=1e-12, atol=1e-12)
     for k in range(T):
         s, _ = po.pair_scores(uv[k], iv[k], fx["suids%d" % k], fx["siids%d" % k], leaky, activation=True)
         np.testing.assert_allclose(s, fx["preds_one%d" % k], rtol=1e-12, atol=1e-12)
-    v = lambda j: fx["var%02d" % j].astype(np.float64)
-    w = fo.meta_user_weight(fu, uv, v(18), v(19), v(20), v(21), leaky)
+    w = fo.meta_user_weight(fu, uv, *_meta(fx), leaky)
     np.testing.assert_allclose(w, fx["user_weight"], rtol=1e-12, atol=1e-14)
     loss, p1 = fo.ssl_hinge(fu, fi, uv, iv, w, [fx["suids%d" % k] for k in range(T)], [fx["siids%d" % k] for k in range(T)], leaky)
     np.testing.assert_allclose(loss, float(fx["sslloss"]), rtol=1e-12)
@@ -162,8 +179,8 @@ def test_ssl_head_matches_reference_model_py_executed(path):
     T, d, leaky = int(fx["T"]), int(fx["d"]), float(fx["leaky"])
     head = SslHead(d, ssldim=int(fx["ssldim"]), leaky=leaky, dtype=torch.float64)
     with torch.no_grad():
-        for p, j in ((head.meta2, 18), (head.meta2_bias, 19), (head.meta3, 20), (head.meta3_bias, 21)):
-            p.copy_(torch.from_numpy(fx["var%02d" % j].astype(np.float64)).reshape(p.shape))
+        for p, val in zip((head.meta2, head.meta2_bias, head.meta3, head.meta3_bias), _meta(fx)):
+            p.copy_(torch.from_numpy(val).reshape(p.shape))
     t = lambda a: torch.from_numpy(np.asarray(a, np.float64))
     fu, fi, uv, iv = t(fx["final_user_vector"]), t(fx["final_item_vector"]), t(fx["user_vector"]), t(fx["item_vector"])
     w = head.user_weight(fu, uv)
@@ -176,3 +193,40 @@ def test_ssl_head_matches_reference_model_py_executed(path):
         interval_scores = lrelu(uv[k][su] * iv[k][si]).sum(-1)
         loss = loss + head.hinge(w[k][su], final_scores, interval_scores)
     np.testing.assert_allclose(float(loss.detach()), float(fx["sslloss"]), rtol=1e-11)
+
+
+def _seq_params(fx, dtype=np.float64):
+    lay = _layout(fx)
+    v = lambda j: fx["var%02d" % j].astype(dtype)
+    ln = lambda o: (v(o + 1), v(o))                                   # (gamma, beta); created as beta, gamma
+    return v(lay["pos"]), ln(lay["seq_ln"]), ln(lay["pos_ln"]), [_block(fx, o, dtype) for o in lay["layers"]]
+
+
+@pytest.mark.parametrize("path", _DOWNSTREAM, ids=[os.path.basename(p)[11:-4] for p in _DOWNSTREAM])
+def test_sequence_branch_and_full_preds_match_reference_model_py_executed(path):
+    """model.py:111-112,157-168 (``att_user``) and the complete ``preds`` of model.py:169-173 -- what ``ours()``
+    returns next to ``sslloss`` -- oracle and product module against the executed text (padding rows included)."""
+    from sagnn_b200.fusion import SequenceAttention
+    fx = np.load(path)
+    d, heads, leaky = int(fx["d"]), int(fx["heads"]), float(fx["leaky"])
+    pos, ln_seq, ln_pos, layers = _seq_params(fx)
+    fu, fi = fx["final_user_vector"], fx["final_item_vector"]
+    att = fo.sequence_attention(fi, fx["sequence"], fx["mask"].astype(np.float64), pos, ln_seq, ln_pos, layers, heads, leaky)
+    np.testing.assert_allclose(att, fx["att_user"], rtol=1e-10, atol=1e-11)
+    preds = fo.predictions(fu, fi, att, fx["uids"], fx["iids"], fx["uLocs_seq"], leaky)
+    np.testing.assert_allclose(preds, fx["preds"], rtol=1e-10, atol=1e-11)
+    m = SequenceAttention(d, heads=heads, att_layers=int(fx["att_layer"]), pos_length=int(fx["pos_length"]), leaky=leaky,
+                          dtype=torch.float64)
+    t = lambda a: torch.from_numpy(np.asarray(a, np.float64))
+    with torch.no_grad():
+        m.pos_embed.copy_(t(pos))
+        m.seq_ln_gamma.copy_(t(ln_seq[0])); m.seq_ln_beta.copy_(t(ln_seq[1]))
+        m.pos_ln_gamma.copy_(t(ln_pos[0])); m.pos_ln_beta.copy_(t(ln_pos[1]))
+        for l, blk in enumerate(layers):
+            for k, val in blk.items():
+                m.layer_params(l)[k].copy_(t(val))
+    got = m(t(fi), torch.from_numpy(fx["sequence"]).long(), torch.from_numpy(fx["mask"]))
+    np.testing.assert_allclose(got.detach().numpy(), fx["att_user"], rtol=1e-10, atol=1e-11)
+    gp = m.predict(t(fu), t(fi), got, torch.from_numpy(fx["uids"]).long(), torch.from_numpy(fx["iids"]).long(),
+                   torch.from_numpy(fx["uLocs_seq"]).long())
+    np.testing.assert_allclose(gp.detach().numpy(), fx["preds"], rtol=1e-10, atol=1e-11)

@@ -842,20 +842,24 @@ def test_pair_scores_match_reference_model_py_executed(path):
     fu = torch.from_numpy(fx["final_user_vector"].astype(np.float32)).cuda()[None].contiguous()
     fi = torch.from_numpy(fx["final_item_vector"].astype(np.float32)).cuda()[None].contiguous()
     s = sg.pair_scores(fu, fi, 0, torch.from_numpy(fx["uids"]).cuda(), torch.from_numpy(fx["iids"]).cuda(), activation=None)
-    assert_parity(s, fx["preds"], "preds")
+    assert_parity(s, fx["preds_dot"], "preds (model.py:169-172)")
     # the whole consumer chain in fp32 on the GPU
     m = IntervalFusion(d, heads=heads, device="cuda")
     head = SslHead(d, ssldim=int(fx["ssldim"]), leaky=leaky, device="cuda")
     v = lambda j: torch.from_numpy(fx["var%02d" % j])
     order = ("ln_beta", "ln_gamma", "wq", "bq", "wk", "bk", "wv", "bv")
+    # creation order of the executed text: posEmbed, LSTM (1, 2), user block (3..10), item block (11..18), the sequence
+    # branch (2 + 2 + 8 per attention layer), then meta2, meta2Bias, meta3, meta3Bias (tests/test_fusion.py::_layout)
+    meta0 = 23 + 8 * int(fx["att_layer"])
+    assert str(fx["var_names"][meta0]).startswith("meta2") and str(fx["var_names"][1]).startswith("basic_lstm_cell/kernel")
     with torch.no_grad():
-        m.lstm_kernel.copy_(v(0)); m.lstm_bias.copy_(v(1))
-        for side, o in (("user", 2), ("item", 10)):
+        m.lstm_kernel.copy_(v(1)); m.lstm_bias.copy_(v(2))
+        for side, o in (("user", 3), ("item", 11)):
             sp_ = m.side_params(side)
             for j, name in enumerate(order):
                 sp_[name].copy_(v(o + j))
-        for p, j in ((head.meta2, 18), (head.meta2_bias, 19), (head.meta3, 20), (head.meta3_bias, 21)):
-            p.copy_(v(j).reshape(p.shape))
+        for j, p in enumerate((head.meta2, head.meta2_bias, head.meta3, head.meta3_bias)):
+            p.copy_(v(meta0 + j).reshape(p.shape))
     gu, gi = m(uv.transpose(0, 1).contiguous(), iv.transpose(0, 1).contiguous())
     scale = float(np.abs(fx["final_user_vector"]).max())
     assert float((gu.detach().cpu().double() - torch.from_numpy(fx["final_user_vector"])).abs().max()) <= 5e-5 * scale
