@@ -75,7 +75,7 @@ def test_slabs_to_rtd_orders_intervals_by_owner():
     assert x.shape == (5, 5, d) and torch.equal(x, full.transpose(0, 1)[:5])
 
 
-# ---- pinned to the reference's own text: model.py:133-156, 169-172, 174-203 executed over the numpy TF stand-in
+# ---- pinned to the reference's own text: model.py:111-112, 133-203 executed over the numpy TF stand-in
 #      (tests/golden/make_golden_downstream.py -> downstream_*.npz) ------------------------------------------------
 import glob
 import os

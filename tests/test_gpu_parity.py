@@ -826,7 +826,7 @@ DOWNSTREAM = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", 
 def test_pair_scores_match_reference_model_py_executed(path):
     """N2 pinned to the reference text: ``preds_one`` of every interval (model.py:197-199) and the plain ``preds``
     (model.py:170-172) as the reference's own lines compute them (tests/golden/make_golden_downstream.py executes
-    model.py:133-156,169-172,174-203 over the numpy TF stand-in) vs ``sagnn_pair_scores_fwd`` on both layouts; then
+    model.py:111-112,133-203 over the numpy TF stand-in) vs ``sagnn_pair_scores_fwd`` on both layouts; then
     the consumer chain on the GPU -- interval fusion, meta weights, the gathered scores, the hinge -- against the
     executed ``sslloss``."""
     from sagnn_b200.fusion import IntervalFusion, SslHead
