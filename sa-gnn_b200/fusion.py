@@ -145,6 +145,13 @@ class SequenceAttention(torch.nn.Module):
         return (final_user[uids] * it).sum(-1) + (torch.maximum(self.leaky * s, s) * it).sum(-1)
 
 
+def prediction_hinge(preds):
+    """model.py:241-244: ``preds`` holds the positives of all users, then their negatives (the sampler's order);
+    ``preLoss = mean(max(0, 1 - (pos - neg)))``."""
+    n = preds.shape[0] // 2
+    return torch.clamp_min(1.0 - (preds[:n] - preds[n:]), 0.0).mean()
+
+
 class SslHead(torch.nn.Module):
     """model.py:174-203 around the gathered pair scores: ``user_weight`` (two FC layers shared by all intervals:
     ``meta2`` [3d, ssldim] + bias with LeakyReLU, ``meta3`` [ssldim, 1] + bias with sigmoid) and the hinge

@@ -16,6 +16,7 @@ these line ranges of ``Recommender.ours()`` are exec'd as they stand, fed with a
     ``args.att_layer`` rounds of layer norm + ``MultiHeadSelfAttention`` + LeakyReLU residual -> ``att_user``
   * model.py:169-173  ``preds`` = dot product of the final vectors + the sequence-attention term               (N2)
     (``preds_dot`` in the fixtures is the first half alone, model.py:169-172)
+  * model.py:241-244  (prepareModel) the prediction hinge ``preLoss`` over positives | negatives of ``preds``
   * model.py:174-203  the meta-weight network (``FC`` of Utils/NNLayers.py), ``preds_one`` per interval on
     ``user_vector[i]`` / ``item_vector[i]``, the weighted hinge ``sslloss``                        (N2)
 
@@ -44,6 +45,8 @@ def blocks():
                                          "sequence_batch+=tf.contrib.layers.layer_norm(tf.matmul(tf.expand_dims(self.mask,axis=1),tf.nn.embedding_lookup(posEmbed,pos)))",
                                          "att_layer=Activate(att_layer1,\"leakyRelu\")+att_layer",
                                          "att_user=tf.reduce_sum(att_layer,axis=1)"]),
+        "preloss": ref_block(241, 244, ["sampNum = tf.shape(self.uids)[0] // 2",
+                                        "self.preLoss = tf.reduce_mean(tf.maximum(0.0, 1.0 - (self.posPred - self.negPred)))"]),
         "preds_full": ref_block(173, 173, ["preds += tf.reduce_sum(Activate(tf.nn.embedding_lookup(att_user,self.uLocs_seq),\"leakyRelu\")* pckIlat_att,axis=-1)"]),
         "fusion": ref_block(133, 156, ["user_vector_tensor=tf.transpose(user_vector, perm=[1, 0, 2])",
                                        "return tf.contrib.rnn.BasicLSTMCell(args.latdim)",
@@ -133,6 +136,9 @@ def main():
             ns, rec = run(shim, model, NNs, blk, uv.astype(dt), iv.astype(dt), ids, leaky)
             assert shim.VarStore.cursor == len(names), "replay consumed a different number of variables"
             outs.update({"preds_dot" + tag: ns["preds_dot"].a, "att_user" + tag: ns["att_user"].a})
+            rec.preds = ns["preds"]                                   # model.py:240: self.preds, self.sslloss = self.ours()
+            exec(blk["preloss"][0], ns)                               # model.py:241-244 (prepareModel)
+            outs["preLoss" + tag] = np.asarray(rec.preLoss.a)
             assert ns["final_user_vector"].a.dtype == dt
             outs.update({"final_user_vector" + tag: ns["final_user_vector"].a, "final_item_vector" + tag: ns["final_item_vector"].a,
                          "preds" + tag: ns["preds"].a, "user_weight" + tag: ns["user_weight"].a,

@@ -230,3 +230,5 @@ def test_sequence_branch_and_full_preds_match_reference_model_py_executed(path):
     gp = m.predict(t(fu), t(fi), got, torch.from_numpy(fx["uids"]).long(), torch.from_numpy(fx["iids"]).long(),
                    torch.from_numpy(fx["uLocs_seq"]).long())
     np.testing.assert_allclose(gp.detach().numpy(), fx["preds"], rtol=1e-10, atol=1e-11)
+    from sagnn_b200.fusion import prediction_hinge                   # model.py:241-244
+    np.testing.assert_allclose(float(prediction_hinge(gp).detach()), float(fx["preLoss"]), rtol=1e-10)
